@@ -1,0 +1,184 @@
+"""CPU tests: the oracle (oracle/mppi_oracle.py) against outputs of the unmodified reference
+(tests/golden/*.npz, produced by tests/golden/make_golden.py) and the SURVEY section-4 KATs."""
+import pytest
+import torch
+
+from oracle import mppi_oracle as orc
+from tests.golden_util import (case_names, frac_within, full_policy, load_npz, load_weights)
+
+torch.set_num_threads(max(1, min(8, torch.get_num_threads())))
+
+
+def _net(name):
+    W, b = load_weights(name)
+    return orc.Net(W, b)
+
+
+SURVEY_KAT = {
+    # SURVEY.md section 4 table (values printed by the reference in the survey container)
+    "franka": dict(z=[76.660835, 59.789768, 45.414402, 27.409927, 23.889229, 16.180807, 24.976217, 28.287218,
+                      26.959349], argmin=5,
+                   grad=[-45.852509, 37.691669, -33.084087, -7.053199, 4.890199, -0.326287, 0.088599, 3.592481,
+                         112.010201, 17.921404]),
+    "planar7": dict(z=[5.001369, 5.119025, 5.385324, 5.767498, 6.347265, 6.978477, 7.756307], argmin=0,
+                    grad=[-0.010012, -0.057813, 0.003840, 0.008133, -0.010020, -0.004597, -0.008497, 0.972665,
+                          -0.088714, 0.388395]),
+    "planar2": dict(z=[6.037664, 9.039477], argmin=0, grad=[-0.079455, -0.070966, 1.014340, -0.004995, 0.064275]),
+}
+
+
+@pytest.mark.parametrize("name", ["franka", "planar7", "planar2"])
+def test_kat_forward_and_vjp(name):
+    kat = load_npz("kat")
+    net = _net(name)
+    z, g, idx = orc.mlp_forward_grad(net, kat[f"{name}_x"])
+    ref = SURVEY_KAT[name]
+    assert int(idx[0]) == ref["argmin"]
+    torch.testing.assert_close(z[0], torch.tensor(ref["z"]), rtol=2e-6, atol=2e-5)
+    torch.testing.assert_close(g[0], torch.tensor(ref["grad"]), rtol=2e-5, atol=2e-5)
+    # batch of 64 random rows straight from the reference's functorch_vjp
+    zb, gb, ib = orc.mlp_forward_grad(net, kat[f"{name}_xb"])
+    assert torch.equal(ib, kat[f"{name}_ib"])
+    torch.testing.assert_close(zb, kat[f"{name}_zb"], rtol=1e-5, atol=1e-4)
+    torch.testing.assert_close(gb, kat[f"{name}_gb"], rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(orc.mlp_forward(net, kat[f"{name}_xb"]), kat[f"{name}_zb"], rtol=1e-5, atol=1e-4)
+
+
+@pytest.mark.parametrize("name", ["franka", "planar7", "planar2"])
+def test_distance_repulsion(name):
+    c = load_npz(f"distgrad_{name}")
+    net = _net(name)
+    dist, grad = orc.distance_repulsion(net, c["q"], c["obs"], int(c["K"]), c["ignored_links"].tolist())
+    assert frac_within(dist, c["distance"], 1e-5, 1e-6) == 1.0
+    assert frac_within(grad, c["nn_grad"], 1e-4, 1e-4 * c["nn_grad"].abs().max().item()) == 1.0
+
+
+def test_householder_matches_lapack_qr():
+    torch.manual_seed(0)
+    for d in (2, 3, 7):
+        g = torch.randn(200, d)
+        g[0] = torch.tensor([1.0] + [0.0] * (d - 1))
+        g[1] = -g[0]
+        A = torch.eye(d).repeat(200, 1, 1)
+        A[:, :, 0] = g
+        Q, _ = torch.linalg.qr(A)
+        Q[:, :, 0] = g / g.norm(2, 1).unsqueeze(1)
+        E = orc.householder_basis(g)
+        torch.testing.assert_close(E, Q, rtol=1e-5, atol=2e-6)
+        # orthonormal, first column e0
+        eye = torch.eye(d).expand(200, d, d)
+        torch.testing.assert_close(E.transpose(1, 2) @ E, eye, rtol=0, atol=1e-5)
+
+
+def _run_oracle_case(c, explicit_M=True):
+    net = _net(c["net"])
+    N, H = int(c["N"]), int(c["H"])
+    prm = orc.RolloutParams(dt=float(c["dt"]), dt_H=H, n_closest_obs=int(c["K"]), dst_thr=float(c["dst_thr"]),
+                            ignored_links=c["ignored_links"].tolist(), p=float(c["p"]), with_basis=True,
+                            explicit_M=explicit_M)
+    mu, sg, al = (full_policy(c, k, N) for k in ("mu_tmp", "sigma_tmp", "alpha_tmp"))
+    out = orc.rollout(net, c["q_cur"], c["qf"], c["obs"], mu, sg, al, int(c["nk"]), prm, N)
+    return net, out, (mu, sg, al)
+
+
+# The rollout is a chaotic map wherever samples sit inside the collision band (k=100 sigmoids, ReLU-kink
+# gradient flips): a 1e-7 distance difference grows ~30x per step in the planar-7 cases, so two correct
+# fp32 implementations disagree after ~6 steps.  Parity is therefore asserted (a) on the ONE-STEP map with
+# the reference's own states fed back in (teacher forcing, every step of every case, tight tolerance),
+# (b) on the full horizon for the cases that stay well-conditioned, (c) on cost and policy update given
+# the reference's own trajectories.
+STABLE_FULL_HORIZON = ["planar2", "planar2_nk0", "field2", "franka_shelf", "franka_shelf_b", "planar2_near"]
+
+
+def check(a, b, rtol, atol, name, min_frac=0.99, loose=20):
+    f = frac_within(a, b, rtol, atol)
+    assert f >= min_frac, f"{name}: only {f:.4f} within rtol={rtol}"
+    assert frac_within(a, b, loose * rtol, loose * atol) == 1.0, f"{name}: outliers beyond {loose}x tolerance"
+
+
+@pytest.mark.parametrize("tag", case_names())
+def test_one_step_map_teacher_forced(tag):
+    c = load_npz(f"case_{tag}")
+    net = _net(c["net"])
+    N, H, nk, dt = int(c["N"]), int(c["H"]), int(c["nk"]), float(c["dt"])
+    mu, sg, al = (full_policy(c, k, N) for k in ("mu_tmp", "sigma_tmp", "alpha_tmp"))
+    prm = orc.RolloutParams(dt=dt, dt_H=1, n_closest_obs=int(c["K"]), dst_thr=float(c["dst_thr"]),
+                            ignored_links=c["ignored_links"].tolist(), p=float(c["p"]))
+    for t in range(H):
+        q = c["all_traj"][:, t, :]
+        o = orc.rollout(net, q, c["qf"], c["obs"], mu, sg, al, nk, prm, N)
+        check(o.closest_dist_all[:, 0], c["closest_dist_all"][:, t], 1e-5, 2e-6, f"dist[{t}]")
+        check(o.dot_products[:, 0], c["dot_products"][:, t], 1e-5, 1e-5, f"dot[{t}]")
+        check(o.kernel_activations[:, 0], c["kernel_activations"][:, t], 1e-4, 1e-5, f"act[{t}]")
+        check(o.norm_basis[:, 0], c["norm_basis"][:, t], 1e-4, 1e-5, f"basis[{t}]")
+        if nk > 0:
+            check(o.kernel_val_all[:, 0, :nk], c["kernel_val_all"][:, t, :nk], 1e-4, 1e-6, f"kval[{t}]")
+        if t == 0:
+            check(o.qdot, c["qdot"], 1e-5, 1e-5, "qdot")
+        if t + 1 < H:
+            check(q + dt * o.qdot, c["all_traj"][:, t + 1, :], 1e-5, 1e-5, f"traj[{t + 1}]")
+
+
+@pytest.mark.parametrize("tag", case_names())
+def test_full_horizon_rollout(tag):
+    c = load_npz(f"case_{tag}")
+    nk = int(c["nk"])
+    net, out, _ = _run_oracle_case(c)
+    steps = int(c["H"]) if tag in STABLE_FULL_HORIZON else 3
+    check(out.closest_dist_all[:, :steps], c["closest_dist_all"][:, :steps], 1e-5, 2e-6, "closest_dist_all")
+    check(out.dot_products[:, :steps], c["dot_products"][:, :steps], 1e-5, 1e-5, "dot_products")
+    check(out.qdot, c["qdot"], 1e-5, 1e-5, "qdot")
+    check(out.all_traj[:, :steps], c["all_traj"][:, :steps], 1e-4, 1e-5, "all_traj")
+    check(out.kernel_activations[:, :steps], c["kernel_activations"][:, :steps], 1e-4, 1e-5, "kernel_activations")
+    if nk > 0:
+        check(out.kernel_val_all[:, :steps, :nk], c["kernel_val_all"][:, :steps, :nk], 1e-4, 1e-6, "kernel_val_all")
+    check(out.norm_basis[:, :steps], c["norm_basis"][:, :steps], 1e-4, 1e-5, "norm_basis")
+
+
+@pytest.mark.parametrize("tag", case_names())
+def test_cost_and_policy_update(tag):
+    c = load_npz(f"case_{tag}")
+    nk, N = int(c["nk"]), int(c["N"])
+    mu, sg, al = (full_policy(c, k, N) for k in ("mu_tmp", "sigma_tmp", "alpha_tmp"))
+    cost = orc.evaluate_costs(c["all_traj"], c["closest_dist_all"], c["qf"], c["dh_params"], c["q_min"], c["q_max"])
+    if not torch.isfinite(c["cost"]).all():
+        assert torch.equal(torch.isfinite(cost), torch.isfinite(c["cost"]))
+        return
+    check(cost, c["cost"], 1e-5, 1e-4, "cost")
+    kv = torch.zeros(N, int(c["H"]), 50)
+    kv[:, :, :max(nk, 1)] = c["kernel_val_all"]
+    mu1, sg1, al1, n_upd, _ = orc.policy_update(c["cost"], kv, c["kernel_activations"], mu, sg, al,
+                                                c["mu_c0"], c["sigma_c0"], c["alpha_c0"], nk, float(c["ker_thr"]))
+    assert n_upd == int(c["n_updated"])
+    check(mu1, c["mu_c1"], 1e-5, 1e-6, "mu_c")
+    check(sg1, c["sigma_c1"], 1e-5, 1e-6, "sigma_c")
+    check(al1, c["alpha_c1"], 1e-5, 1e-6, "alpha_c")
+
+
+@pytest.mark.parametrize("tag", ["planar2_near", "franka_shelf"])
+def test_rank1_modulation_equals_explicit_basis(tag):
+    """E D E^T == l_tau I + (l_n_vel - l_tau) e0 e0^T -- the form the GPU kernel uses."""
+    c = load_npz(f"case_{tag}")
+    _, a, _ = _run_oracle_case(c, explicit_M=True)
+    _, b, _ = _run_oracle_case(c, explicit_M=False)
+    assert frac_within(b.all_traj, a.all_traj, 1e-5, 1e-5) == 1.0
+    assert frac_within(b.qdot, a.qdot, 1e-5, 1e-5) == 1.0
+
+
+def test_policy_update_partials_sum_to_full_update():
+    """sharding the samples and summing the packed partial vectors reproduces the update."""
+    c = load_npz("case_planar7_near")
+    nk = int(c["nk"]); N = int(c["N"]); d = 7
+    mu, sg, al = (full_policy(c, k, N) for k in ("mu_tmp", "sigma_tmp", "alpha_tmp"))
+    kv = torch.zeros(N, int(c["H"]), 50); kv[:, :, :nk] = c["kernel_val_all"]
+    cost = c["cost"]
+    beta = cost.mean() / 50
+    halves = [slice(0, N // 2), slice(N // 2, N)]
+    tot = sum(orc.policy_update_partials(cost[s], kv[s], c["kernel_activations"][s], mu[s], sg[s], al[s], nk,
+                                         beta, owns_sample0=(i == 0)) for i, s in enumerate(halves))
+    mu1, sg1, al1, n_upd, w = orc.policy_update(cost, kv, c["kernel_activations"], mu, sg, al, c["mu_c0"],
+                                                c["sigma_c0"], c["alpha_c0"], nk, float(c["ker_thr"]))
+    wsum = tot[0]
+    mu_sum = tot[1:1 + nk * d].reshape(nk, d) / wsum
+    ref_mu_sum = torch.sum(w[:, None, None] * mu[:, :nk], 0)
+    torch.testing.assert_close(mu_sum, ref_mu_sum, rtol=1e-4, atol=1e-6)
