@@ -1,0 +1,196 @@
+/*
+ * dsmppi_b200.h -- C ABI of the B200-native ds_mppi MPPI rollout library (libdsmppi_b200.so).
+ *
+ * Drop-in boundary for ONE hot path of epfl-lasa/OptimalModulationDS: the MPPI rollout over N sampled
+ * policies x horizon H, its cost and its policy update.  The reference has no FFI (it is pure
+ * Python/PyTorch); each entry point below replaces a METHOD of the reference's Python objects, cited as
+ * file:line relative to /root/reference/python_scripts/ds_mppi/functions/.  The reference-side binding
+ * (a ctypes stub inside MPPI.py) is shown in INTEGRATION.md and implemented in
+ * optimalmodulationds_b200/_capi.py.
+ *
+ * Conventions
+ *   - plain C types only; every function returns 0 on success, non-zero on error, and
+ *     dsmppi_last_error() returns the message of the calling thread's last failure;
+ *   - `*_dev` pointers are DEVICE pointers owned by the caller (torch tensors), fp32, contiguous,
+ *     row-major; `*_host` pointers are host pointers; the library owns only the opaque context and the
+ *     scratch workspace inside it;
+ *   - all work is enqueued on the caller's `stream` (a cudaStream_t passed as void*); no call
+ *     synchronises the device except the `_host` variants, which must hand back host results;
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef DSMPPI_B200_H
+#define DSMPPI_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DSMPPI_N_KERNEL_MAX 50   /* policy.py:18 */
+#define DSMPPI_MAX_DOF 8
+#define DSMPPI_MAX_LINKS 16      /* network output channels O (<= 16) */
+#define DSMPPI_MAX_CLOSEST 8     /* n_closest_obs K (<= 8) */
+#define DSMPPI_HIDDEN 256        /* width of the shipped distance MLP */
+
+typedef struct dsmppi_ctx dsmppi_ctx;
+
+/* Network weights as torch stores them: W[l] is (out, in) row-major (mlp_learn/sdf/network_macros_mod.py
+ * 137-146 with skips=[]: 3(d+3) -> 256 -> 256 -> 256 -> 256 -> O, ReLU between).  HOST pointers. */
+typedef struct {
+  int32_t n_dof;                 /* d  */
+  int32_t n_out;                 /* O  */
+  const float* W_host[5];
+  const float* b_host[5];
+} dsmppi_net;
+
+/* Pass-1 precision: how the all-pairs forward pass that ranks obstacles (MPPI.py:231-253) is evaluated. */
+enum {
+  DSMPPI_PASS1_EXACT_FP32 = 0,   /* fp32 FFMA on every (sample, obstacle) pair                         */
+  DSMPPI_PASS1_TC_F16 = 1,       /* tcgen05 fp16 x fp16 -> fp32 prefilter + fp32 re-score of the band   */
+  DSMPPI_PASS1_TC_BF16 = 2,      /* same with bf16 operands                                             */
+  DSMPPI_PASS1_AUTO = 3          /* TC_F16 when M >= 64, else EXACT                                     */
+};
+
+typedef struct {
+  /* state / problem */
+  int32_t N;                     /* samples in this call (<= capacity)                                  */
+  int32_t H;                     /* horizon dt_H                                                        */
+  int32_t q_cur_is_batch;        /* 0: q_cur_dev is (d,), 1: (N, d)   (MPPI.py:99 broadcast)            */
+  int32_t n_kernels;             /* Policy.n_kernels                                                    */
+  int32_t n_closest;             /* n_closest_obs K                                                     */
+  uint32_t ignored_link_mask;    /* bit l set <=> l in MPPI.ignored_links (MPPI.py:62,241)              */
+  float dt;                      /* MPPI.dt                                                             */
+  float dst_thr;                 /* MPPI.dst_thr (MPPI.py:117)                                          */
+  float lin_thr;                 /* LinDS.lin_thr (LinDS.py:9)                                          */
+  float rbf_p;                   /* Policy.p (policy.py:41,186-199)                                     */
+  float q_goal[DSMPPI_MAX_DOF];  /* DS.q_goal == MPPI.qf                                                */
+  /* inputs (device) */
+  const float* q_cur_dev;
+  const float* mu_tmp_dev;       /* (N, 50, d)  Policy.mu_tmp                                           */
+  const float* sigma_tmp_dev;    /* (N, 50)     Policy.sigma_tmp                                        */
+  const float* alpha_tmp_dev;    /* (N, 50, d)  Policy.alpha_tmp                                        */
+  /* outputs (device) -- the attributes MPPI.propagate fills (MPPI.py:40-51, 224) */
+  float* all_traj_dev;           /* (N, H, d)                                                           */
+  float* closest_dist_all_dev;   /* (N, H)                                                              */
+  float* kernel_val_all_dev;     /* (N, H, 50); only columns [0, n_kernels) are written                 */
+  float* dot_products_dev;       /* (N, H)                                                              */
+  float* kernel_activations_dev; /* (N, H)                                                              */
+  float* qdot_dev;               /* (N, d)                                                              */
+  float* nn_grad_all_dev;        /* (N, H, d) blended distance gradient per state-step (basis source)   */
+  float* norm_basis_dev;         /* (N, H, d, d) or NULL (lazy: see dsmppi_norm_basis)                  */
+} dsmppi_rollout_args;
+
+typedef struct {
+  int32_t N, H;
+  float q_goal[DSMPPI_MAX_DOF];
+  float q_min[DSMPPI_MAX_DOF];   /* Cost.q_min / q_max (cost.py:10-11)                                  */
+  float q_max[DSMPPI_MAX_DOF];
+  const float* all_traj_dev;         /* (N, H, d) */
+  const float* closest_dist_all_dev; /* (N, H)    */
+  float* cost_dev;                   /* (N,)      */
+} dsmppi_cost_args;
+
+typedef struct {
+  int32_t N, H;
+  int32_t n_kernels;
+  int32_t owns_sample0;          /* 1 when this shard holds global sample 0 (the noise-free rollout)    */
+  int64_t N_global;              /* total samples over all shards (for the means)                       */
+  float ker_thr;                 /* MPPI.ker_thr                                                        */
+  float upd_rate;                /* MPPI.policy_upd_rate (MPPI.py:58,344)                               */
+  const float* cost_dev;         /* (N,)                                                                */
+  const float* kernel_val_all_dev;     /* (N, H, 50)                                                    */
+  const float* kernel_activations_dev; /* (N, H)                                                        */
+  const float* mu_tmp_dev;       /* (N, 50, d)                                                          */
+  const float* sigma_tmp_dev;    /* (N, 50)                                                             */
+  const float* alpha_tmp_dev;    /* (N, 50, d)                                                          */
+  float* mu_c_dev;               /* (50, d)  updated in place by _finalize                              */
+  float* sigma_c_dev;            /* (50,)                                                               */
+  float* alpha_c_dev;            /* (50, d)                                                             */
+} dsmppi_update_args;
+
+const char* dsmppi_last_error(void);
+int dsmppi_version(void);
+
+/* MPPI.__init__ (MPPI.py:22-73): packs the network (fp32 both orientations + fp16/bf16 UMMA smem images),
+ * the DH table (dh_params (d+1, 4) = [d, theta, a, alpha], HOST) and sizes the workspace for
+ * `capacity` samples.  `device` is the CUDA ordinal. */
+int dsmppi_ctx_create(dsmppi_ctx** out, const dsmppi_net* net, const float* dh_params_host,
+                      int32_t capacity, int32_t device);
+int dsmppi_ctx_destroy(dsmppi_ctx* ctx);
+int dsmppi_set_pass1_mode(dsmppi_ctx* ctx, int32_t mode, float guard_band);
+
+/* MPPI.update_obstacles (MPPI.py:347-350) and the obs argument of __init__: (M, 4) = [x, y, z, r]. */
+int dsmppi_set_obstacles(dsmppi_ctx* ctx, const float* obs_dev, int32_t M, void* stream);
+int dsmppi_set_obstacles_host(dsmppi_ctx* ctx, const float* obs_host, int32_t M, void* stream);
+
+/* MPPI.propagate (MPPI.py:97-224): the H-step rollout of all N samples. */
+int dsmppi_rollout(dsmppi_ctx* ctx, const dsmppi_rollout_args* args, void* stream);
+
+/* MPPI.distance_repulsion_nn (MPPI.py:227-282): q (n, d) -> distance (n,), nn_grad (n, d). */
+int dsmppi_distance_grad(dsmppi_ctx* ctx, const float* q_dev, int32_t n, int32_t n_closest,
+                         uint32_t ignored_link_mask, float* distance_dev, float* nn_grad_dev, void* stream);
+
+/* The Householder basis the reference stores in MPPI.norm_basis (MPPI.py:122-127), from the blended
+ * gradients: grad (n, d) -> basis (n, d, d). */
+int dsmppi_norm_basis(dsmppi_ctx* ctx, const float* grad_dev, int64_t n, float* basis_dev, void* stream);
+
+/* MPPI.get_cost -> Cost.evaluate_costs (MPPI.py:315-317, cost.py:13-46). */
+int dsmppi_cost(dsmppi_ctx* ctx, const dsmppi_cost_args* args, void* stream);
+
+/* MPPI.shift_policy_means -> TensorPolicyMPPI.update_policy (MPPI.py:331-345, policy.py:88-113), split in
+ * the three phases a sample-sharded job needs:
+ *   cost_stats : stats_dev[0..3] = { sum cost, min cost, argmin (as float), N }          -> allreduce #1
+ *   partial    : packed_dev[L], L = dsmppi_update_packed_len(nk, d)                      -> allreduce #2
+ *   finalize   : EMA of mu_c / sigma_c / alpha_c, n_updated_dev[0] = number of kernels updated.
+ * On one GPU call them back to back; `beta_dev` is cost mean / 50 computed by the caller or by
+ * dsmppi_update_beta from the (all-reduced) stats. */
+int32_t dsmppi_update_packed_len(int32_t n_kernels, int32_t n_dof);
+int dsmppi_update_cost_stats(dsmppi_ctx* ctx, const float* cost_dev, int32_t N, float* stats_dev, void* stream);
+int dsmppi_update_partial(dsmppi_ctx* ctx, const dsmppi_update_args* args, const float* stats_dev,
+                          float* packed_dev, void* stream);
+int dsmppi_update_finalize(dsmppi_ctx* ctx, const dsmppi_update_args* args, const float* packed_dev,
+                           int32_t* n_updated_dev, void* stream);
+
+/* One whole MPPI iteration with HOST buffers (what a CPU-tensor caller of the reference API pays):
+ * H2D of q_cur / sampled policy, rollout, cost, policy update, D2H of every output.  Host pointers may be
+ * pageable or pinned.  Synchronises `stream` before returning. */
+typedef struct {
+  dsmppi_rollout_args rollout;   /* the *_dev fields are ignored; shapes and scalars are used            */
+  float q_min[DSMPPI_MAX_DOF];
+  float q_max[DSMPPI_MAX_DOF];
+  float ker_thr, upd_rate;
+  const float* q_cur_host;       /* (d,) or (N, d)                                                      */
+  const float* mu_tmp_host;      /* (N, 50, d) */
+  const float* sigma_tmp_host;   /* (N, 50)    */
+  const float* alpha_tmp_host;   /* (N, 50, d) */
+  float* mu_c_host;              /* (50, d) in/out */
+  float* sigma_c_host;           /* (50,)   in/out */
+  float* alpha_c_host;           /* (50, d) in/out */
+  float* all_traj_host;          /* (N, H, d)  */
+  float* closest_dist_all_host;  /* (N, H)     */
+  float* kernel_val_all_host;    /* (N, H, 50) */
+  float* dot_products_host;      /* (N, H)     */
+  float* kernel_activations_host;/* (N, H)     */
+  float* qdot_host;              /* (N, d)     */
+  float* cost_host;              /* (N,)       */
+  int32_t* n_updated_host;       /* (1,)       */
+  int64_t h2d_bytes, d2h_bytes;  /* filled in: bytes moved by this call                                 */
+} dsmppi_iteration_host_args;
+int dsmppi_iteration_host(dsmppi_ctx* ctx, dsmppi_iteration_host_args* args, void* stream);
+
+/* Introspection used by bench.py / tests: launches issued by the library since ctx creation, pass-1
+ * statistics of the last rollout (re-scored pairs, band overflows), and the resolved pass-1 mode. */
+int64_t dsmppi_launch_count(const dsmppi_ctx* ctx);
+int dsmppi_pass1_stats(dsmppi_ctx* ctx, int64_t* rescored_pairs, int64_t* band_overflows, int32_t* mode,
+                       void* stream);
+/* Average device time (ms) of the dominant kernel over its launches in the last rollout; requires
+ * dsmppi_enable_kernel_timing(ctx, 1) beforehand (CUDA events on the launching stream). */
+int dsmppi_enable_kernel_timing(dsmppi_ctx* ctx, int32_t on);
+int dsmppi_kernel_timing(dsmppi_ctx* ctx, double* pass1_ms_per_launch, int32_t* pass1_launches,
+                         double* exact_ms_per_launch, int32_t* exact_launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DSMPPI_B200_H */

@@ -1,0 +1,414 @@
+"""Drop-in `MPPI` object: the reference's Python API over the sm_100a CUDA library.
+
+Mirror of the reference's ds_mppi/functions/MPPI.py:21-353 -- same constructor arguments, the same
+`propagate` / `get_cost` / `shift_policy_means` / `get_qdot` / `update_obstacles` / `switch_DS_idx` /
+`reset_DS` / `reset_tensors` / `update_kernel_normal_bases` / `distance_repulsion_nn` / `build_nn_input`
+call shapes, the same mutable attributes read at call time, torch tensors in and out on `q0.device`.
+Every numerical stage runs in libdsmppi_b200.so (include/dsmppi_b200.h); torch is used for device
+memory, streams and (optionally) torch.distributed.  There is NO CPU fallback: without the shared library
+or without a CUDA device the constructor raises.
+
+`from MPPI import *` in the reference's scripts also pulls torch, time, np, plt, pi, profile,
+record_function, ProfilerActivity, the fk helpers, the plot helpers, TensorPolicyMPPI, eval_rbf and Cost
+into the caller's namespace (MPPI.py:1-8); the same names are re-exported here.
+"""
+import os
+import time  # noqa: F401  (re-exported)
+from math import pi  # noqa: F401  (re-exported)
+
+import numpy as np  # noqa: F401  (re-exported)
+import torch
+from torch.profiler import ProfilerActivity, profile, record_function  # noqa: F401  (re-exported)
+
+from . import _capi
+from .cost import Cost
+from .fk_num import *  # noqa: F401,F403  (numeric_fk_model, numeric_fk_model_vec, dh_fk, plots, plt, np)
+from .policy import *  # noqa: F401,F403  (TensorPolicyMPPI, eval_rbf, ...)
+from .policy import TensorPolicyMPPI
+
+
+def generalized_sigmoid(x, y_min, y_max, x0, x1, k):
+    return y_min + (y_max - y_min) / (1 + torch.exp(k * (-x + (x0 + x1) / 2)))
+
+
+def _network_arrays(nn_model):
+    """The five (out, in) weight matrices and biases of nn_model.model as contiguous fp32 CPU tensors."""
+    lin = [m for m in nn_model.model.modules() if isinstance(m, torch.nn.Linear)]
+    if len(lin) != 5:
+        raise NotImplementedError(f"expected the 5-layer distance MLP (4 hidden + output), found {len(lin)} layers")
+    W = [m.weight.detach().to('cpu', torch.float32).contiguous() for m in lin]
+    b = [m.bias.detach().to('cpu', torch.float32).contiguous() for m in lin]
+    d = nn_model.in_channels - 3
+    if W[0].shape != (256, 3 * nn_model.in_channels) or any(w.shape != (256, 256) for w in W[1:4]) \
+            or W[4].shape != (nn_model.out_channels, 256):
+        raise NotImplementedError("only the shipped 3(d+3)-256-256-256-256-O layout (skips=[]) is supported")
+    return W, b, d
+
+
+class MPPI:
+    def __init__(self, q0: torch.Tensor, qf: torch.Tensor, dh_params: torch.Tensor, obs: torch.Tensor, dt: float,
+                 dt_H: int, N_traj: int, DS_ARRAY, dh_a, nn_model, n_closest_obs):
+        self.tensor_args = {'device': q0.device, 'dtype': q0.dtype}
+        if q0.dtype != torch.float32:
+            raise NotImplementedError("the CUDA path computes in fp32 (as every reference script does)")
+        if not torch.cuda.is_available():
+            raise RuntimeError("optimalmodulationds_b200.MPPI needs a CUDA device (B200); there is no CPU fallback")
+        self._lib = _capi.load()
+        if q0.is_cuda:
+            self._dev = q0.device
+        else:
+            self._dev = torch.device('cuda', int(os.environ.get('DSMPPI_DEVICE', os.environ.get('LOCAL_RANK', 0))))
+        self.n_dof = q0.shape[0]
+        self.Policy = TensorPolicyMPPI(N_traj, self.n_dof, self.tensor_args)
+        self.q0 = q0
+        self.DS_idx = 0
+        self.DS_ARRAY = DS_ARRAY
+        self.DS = DS_ARRAY[self.DS_idx]
+        self.qf = self.DS.q_goal.squeeze()
+        self.dh_params = dh_params
+        self.obs = obs
+        self.n_obs = obs.shape[0]
+        self.dt = dt
+        self.dt_H = dt_H
+        self.N_traj = N_traj
+        self.dh_a = dh_a
+        self.nn_model = nn_model
+        self.q_cur = q0
+        self.policy_upd_rate = 0.1
+        self.dst_thr = 0.5
+        self.ker_thr = 1e-3
+        self.ignored_links = [0, 1, 2] if self.n_dof >= 7 else []
+        self.n_closest_obs = n_closest_obs
+        self.traj_range = torch.arange(self.N_traj, device=q0.device)
+        self.kernel_obstacle_bases_tmp = torch.zeros((self.Policy.N_KERNEL_MAX, self.n_dof, self.n_dof),
+                                                     **self.tensor_args)
+        self._shard = None            # set by enable_sample_sharding
+        self._mirror = {}             # device copies of the last outputs, keyed by id() of what we returned
+        self._norm_basis = None
+        self._ctx = None
+        self._make_context()
+        self.Cost = Cost(self.qf, self.dh_params, backend=self)
+        self.reset_tensors()
+        self.qdot = torch.zeros((self.N_traj, self.n_dof), **self.tensor_args)
+        self.nn_grad = torch.zeros(N_traj, self.n_dof, **self.tensor_args)
+        self.ker_w = torch.zeros((N_traj, 0, 1), **self.tensor_args)
+        self.cur_cost = torch.zeros(N_traj, **self.tensor_args)
+        # one warm-up rollout sizes the workspace (the reference runs five, MPPI.py:69-73)
+        self.Policy.sample_policy()
+        self.propagate()
+
+    # ------------------------------------------------------------------ backend plumbing
+    def _make_context(self):
+        W, b, d = _network_arrays(self.nn_model)
+        if d != self.n_dof:
+            raise ValueError(f"network expects {d} joints, q0 has {self.n_dof}")
+        net = _capi.Net()
+        net.n_dof, net.n_out = self.n_dof, self.nn_model.out_channels
+        for i in range(5):
+            net.W_host[i] = W[i].data_ptr()
+            net.b_host[i] = b[i].data_ptr()
+        dh = self.dh_params.detach().to('cpu', torch.float32).contiguous()
+        if dh.shape != (self.n_dof + 1, 4):
+            raise ValueError("dh_params must be (n_dof + 1, 4) = [d, theta, a, alpha]")
+        handle = _capi.C.c_void_p()
+        with torch.cuda.device(self._dev):
+            _capi.check(self._lib.dsmppi_ctx_create(_capi.C.byref(handle), _capi.C.byref(net), dh.data_ptr(),
+                                                    int(self.N_traj), int(self._dev.index or 0)))
+        self._ctx = handle
+
+    def __del__(self):
+        ctx, self._ctx = getattr(self, '_ctx', None), None
+        if ctx:
+            try:
+                self._lib.dsmppi_ctx_destroy(ctx)
+            except Exception:  # noqa: BLE001 - interpreter shutdown
+                pass
+
+    def _stream(self):
+        return _capi.C.c_void_p(torch.cuda.current_stream(self._dev).cuda_stream)
+
+    def _d(self, t):
+        """Tensor on the compute device, fp32, contiguous (no copy when it already is)."""
+        return torch.as_tensor(t).detach().to(self._dev, torch.float32).contiguous()
+
+    def _u(self, t):
+        """Tensor on the caller's device."""
+        return t if t.device == self.tensor_args['device'] else t.to(self.tensor_args['device'])
+
+    def _dev_of(self, user_tensor):
+        """Device copy of a tensor we handed out earlier (identity match), else a fresh upload."""
+        hit = self._mirror.get(id(user_tensor))
+        if hit is not None and hit[0] is user_tensor and hit[1] == user_tensor._version:
+            return hit[2]
+        return self._d(user_tensor)
+
+    def _remember(self, user_tensor, dev_tensor):
+        # the version counter catches in-place edits the caller made after we uploaded the tensor
+        self._mirror[id(user_tensor)] = (user_tensor, user_tensor._version, dev_tensor)
+
+    def set_pass1_mode(self, mode='auto', guard_band=0.0):
+        """How obstacles are ranked: 'exact' (fp32 on every pair), 'tc_f16' / 'tc_bf16' (tcgen05 prefilter +
+        fp32 re-score of everything within `guard_band` metres of the K-th), or 'auto'."""
+        code = {'exact': _capi.PASS1_EXACT_FP32, 'tc_f16': _capi.PASS1_TC_F16, 'tc_bf16': _capi.PASS1_TC_BF16,
+                'auto': _capi.PASS1_AUTO}[mode]
+        _capi.check(self._lib.dsmppi_set_pass1_mode(self._ctx, code, float(guard_band)))
+
+    def _upload_obstacles(self):
+        obs = self._d(self.obs)
+        if obs.dim() != 2 or obs.shape[1] != 4:
+            raise ValueError("obs must be (M, 4) = [x, y, z, r]")
+        self.n_obs = obs.shape[0]
+        _capi.check(self._lib.dsmppi_set_obstacles(self._ctx, obs.data_ptr(), int(obs.shape[0]), self._stream()))
+        return obs
+
+    def _ignore_mask(self):
+        mask = 0
+        for link in self.ignored_links:
+            mask |= 1 << int(link)
+        return mask
+
+    # ------------------------------------------------------------------ reference API
+    def reset_DS(self, DS):
+        self.DS = DS
+        self.qf = DS.q_goal.squeeze()
+        self._rebuild_cost()
+
+    def switch_DS_idx(self, idx):
+        self.DS_idx = idx
+        self.DS = self.DS_ARRAY[idx]
+        self.qf = self.DS.q_goal.squeeze()
+        self._rebuild_cost()
+
+    def _rebuild_cost(self):
+        old = getattr(self, 'Cost', None)
+        self.Cost = Cost(self.qf, self.dh_params, backend=self)
+        if old is not None:                      # keep limits the caller assigned after construction
+            self.Cost.q_min, self.Cost.q_max = old.q_min, old.q_max
+
+    def reset_tensors(self):
+        N, H, d = self.N_traj, self.dt_H, self.n_dof
+        a = self.tensor_args
+        self.all_traj = torch.zeros(N, H, d, **a)
+        self.closest_dist_all = 100 + torch.zeros(N, H, **a)
+        self.kernel_val_all = torch.zeros(N, H, self.Policy.N_KERNEL_MAX, **a)
+        self.dot_products = torch.zeros(N, H, **a)
+        self.kernel_activations = torch.zeros(N, H, **a)
+
+    def build_nn_input(self, q_tens, obs_tens):
+        self.nn_input = torch.hstack((q_tens.tile(obs_tens.shape[0], 1), obs_tens.repeat_interleave(q_tens.shape[0], 0)))
+        return self.nn_input
+
+    def _rollout_args(self, N, H, nk, q_cur, mu, sigma, alpha, out):
+        a = _capi.RolloutArgs()
+        a.N, a.H, a.n_kernels, a.n_closest = N, H, nk, int(self.n_closest_obs)
+        a.q_cur_is_batch = 1 if q_cur.dim() == 2 else 0
+        a.ignored_link_mask = self._ignore_mask()
+        a.dt, a.dst_thr = float(self.dt), float(self.dst_thr)
+        if not hasattr(self.DS, 'lin_thr'):
+            raise NotImplementedError("only the LinDS nominal dynamics is implemented in the CUDA rollout")
+        a.lin_thr, a.rbf_p = float(self.DS.lin_thr), float(self.Policy.p)
+        goal = torch.as_tensor(self.DS.q_goal).detach().reshape(-1).to('cpu', torch.float32)
+        for i in range(self.n_dof):
+            a.q_goal[i] = float(goal[i])
+        a.q_cur_dev = q_cur.data_ptr()
+        a.mu_tmp_dev, a.sigma_tmp_dev, a.alpha_tmp_dev = mu.data_ptr(), sigma.data_ptr(), alpha.data_ptr()
+        a.all_traj_dev = out['all_traj'].data_ptr()
+        a.closest_dist_all_dev = out['closest'].data_ptr()
+        a.kernel_val_all_dev = out['kval'].data_ptr()
+        a.dot_products_dev = out['dots'].data_ptr()
+        a.kernel_activations_dev = out['acts'].data_ptr()
+        a.qdot_dev = out['qdot'].data_ptr()
+        a.nn_grad_all_dev = out['grads'].data_ptr()
+        a.norm_basis_dev = None
+        return a
+
+    def propagate(self):
+        N, H, d = self.N_traj, self.dt_H, self.n_dof
+        P = self.Policy
+        nk = int(P.n_kernels)
+        dev = self._dev
+        with torch.cuda.device(dev):
+            q_cur = self._d(self.q_cur)
+            if q_cur.shape not in ((d,), (N, d)):
+                raise ValueError(f"q_cur must be ({d},) or ({N}, {d}), got {tuple(q_cur.shape)}")
+            mu, sigma, alpha = self._d(P.mu_tmp), self._d(P.sigma_tmp), self._d(P.alpha_tmp)
+            if mu.shape != (N, P.N_KERNEL_MAX, d):
+                raise ValueError("Policy.mu_tmp must be (N_traj, 50, n_dof)")
+            self._upload_obstacles()
+            out = dict(all_traj=torch.empty(N, H, d, device=dev), closest=torch.empty(N, H, device=dev),
+                       kval=torch.zeros(N, H, P.N_KERNEL_MAX, device=dev), dots=torch.empty(N, H, device=dev),
+                       acts=torch.empty(N, H, device=dev), qdot=torch.empty(N, d, device=dev),
+                       grads=torch.empty(N, H, d, device=dev))
+            args = self._rollout_args(N, H, nk, q_cur, mu, sigma, alpha, out)
+            _capi.check(self._lib.dsmppi_rollout(self._ctx, _capi.C.byref(args), self._stream()))
+        self._mirror = {}
+        self._dev_last = dict(out, mu=mu, sigma=sigma, alpha=alpha, nk=nk)
+        self._norm_basis = None
+        if self.tensor_args['device'] == dev:
+            self.all_traj, self.closest_dist_all, self.kernel_val_all = out['all_traj'], out['closest'], out['kval']
+            self.dot_products, self.kernel_activations, self.qdot = out['dots'], out['acts'], out['qdot']
+        else:
+            self.all_traj, self.closest_dist_all = self._u(out['all_traj']), self._u(out['closest'])
+            self.dot_products, self.kernel_activations = self._u(out['dots']), self._u(out['acts'])
+            self.qdot = self._u(out['qdot'])
+            kv = torch.zeros(N, H, P.N_KERNEL_MAX, **self.tensor_args)
+            if nk > 0:
+                kv[:, :, :nk] = self._u(out['kval'][:, :, :nk])
+            self.kernel_val_all = kv
+        for user, key in ((self.all_traj, 'all_traj'), (self.closest_dist_all, 'closest'),
+                          (self.kernel_val_all, 'kval'), (self.kernel_activations, 'acts')):
+            self._remember(user, out[key])
+        self._remember(P.mu_tmp, mu), self._remember(P.sigma_tmp, sigma), self._remember(P.alpha_tmp, alpha)
+        self.nn_grad = self._u(out['grads'][:, H - 1, :])
+        self.ker_w = self.kernel_val_all[:, H - 1, :nk].unsqueeze(2)
+        return (self.all_traj, self.closest_dist_all, self.kernel_val_all[:, :, 0:nk], self.dot_products,
+                self.kernel_activations)
+
+    @property
+    def norm_basis(self):
+        """(N, H, d, d) Householder bases of every state-step (MPPI.py:122-127), materialised on first access
+        from the stored blended gradients (keeps 4*d*d bytes per state-step off the rollout)."""
+        if self._norm_basis is None:
+            g = self._dev_last['grads']
+            N, H, d = g.shape
+            with torch.cuda.device(self._dev):
+                E = torch.empty(N, H, d, d, device=self._dev)
+                _capi.check(self._lib.dsmppi_norm_basis(self._ctx, g.data_ptr(), N * H, E.data_ptr(), self._stream()))
+            self._norm_basis = self._u(E)
+        return self._norm_basis
+
+    @norm_basis.setter
+    def norm_basis(self, value):
+        self._norm_basis = value
+
+    def distance_repulsion_nn(self, q_prev, aot=False):
+        q = self._d(q_prev)
+        n = q.shape[0]
+        with torch.cuda.device(self._dev):
+            self._upload_obstacles()
+            dist = torch.empty(n, device=self._dev)
+            grad = torch.empty(n, self.n_dof, device=self._dev)
+            _capi.check(self._lib.dsmppi_distance_grad(self._ctx, q.data_ptr(), n, int(self.n_closest_obs),
+                                                       self._ignore_mask(), dist.data_ptr(), grad.data_ptr(),
+                                                       self._stream()))
+        self.nn_grad = self._u(grad)
+        return self._u(dist), self.nn_grad
+
+    def update_kernel_normal_bases(self):
+        nk = int(self.Policy.n_kernels)
+        if nk > 0:
+            _, grad = self.distance_repulsion_nn(self.Policy.mu_c[0:nk], aot=False)
+            g = self._d(grad)
+            with torch.cuda.device(self._dev):
+                E = torch.empty(nk, self.n_dof, self.n_dof, device=self._dev)
+                _capi.check(self._lib.dsmppi_norm_basis(self._ctx, g.data_ptr(), nk, E.data_ptr(), self._stream()))
+            self.Policy.kernel_obstacle_bases[0:nk] = E.to(self.Policy.kernel_obstacle_bases.device)
+        return 0
+
+    # ------------------------------------------------------------------ cost
+    def evaluate_costs(self, cost_obj, all_traj, closest_dist_all):
+        """Backend of Cost.evaluate_costs (cost.py:13-22)."""
+        N, H, d = all_traj.shape
+        a = _capi.CostArgs()
+        a.N, a.H = N, H
+        goal = torch.as_tensor(cost_obj.qf).detach().reshape(-1).to('cpu', torch.float32)
+        qmin = torch.as_tensor(cost_obj.q_min).detach().reshape(-1).to('cpu', torch.float32)
+        qmax = torch.as_tensor(cost_obj.q_max).detach().reshape(-1).to('cpu', torch.float32)
+        if qmin.numel() < d or qmax.numel() < d:
+            raise ValueError("Cost.q_min / q_max must have n_dof entries")
+        for i in range(d):
+            a.q_goal[i], a.q_min[i], a.q_max[i] = float(goal[i]), float(qmin[i]), float(qmax[i])
+        with torch.cuda.device(self._dev):
+            tr, cd = self._dev_of(all_traj), self._dev_of(closest_dist_all)
+            cost = torch.empty(N, device=self._dev)
+            a.all_traj_dev, a.closest_dist_all_dev, a.cost_dev = tr.data_ptr(), cd.data_ptr(), cost.data_ptr()
+            _capi.check(self._lib.dsmppi_cost(self._ctx, _capi.C.byref(a), self._stream()))
+        user = self._u(cost)
+        self._remember(user, cost)
+        return user
+
+    def get_cost(self):
+        self.cur_cost = self.Cost.evaluate_costs(self.all_traj, self.closest_dist_all)
+        return self.cur_cost
+
+    def get_qdot(self, mode='best'):
+        qdot = 0
+        if mode == 'best':
+            qdot = self.qdot[torch.argmin(self.cur_cost), :]
+        elif mode == 'weighted':
+            beta = self.cur_cost.mean() / 50
+            w = torch.exp(-1 / beta * self.cur_cost)
+            w = w / w.sum()
+            qdot = torch.sum(w.unsqueeze(1) * self.qdot, dim=0)
+        return qdot
+
+    # ------------------------------------------------------------------ policy update
+    def enable_sample_sharding(self, group=None):
+        """Sample-sharded MPPI: this object holds N_traj local samples of a job spread over the
+        ranks of `group`; shift_policy_means then all-reduces the cost statistics and the packed weighted
+        sums (two small NCCL all-reduces per iteration) so every rank applies the identical update."""
+        import torch.distributed as dist
+        self._shard = dict(group=group, rank=dist.get_rank(group), world=dist.get_world_size(group))
+
+    def shift_policy_means(self):
+        P = self.Policy
+        nk = int(P.n_kernels)
+        N, H, d = self.N_traj, self.dt_H, self.n_dof
+        dev = self._dev
+        with torch.cuda.device(dev):
+            a = _capi.UpdateArgs()
+            a.N, a.H, a.n_kernels = N, H, nk
+            a.owns_sample0, a.N_global = 1, N
+            a.ker_thr, a.upd_rate = float(self.ker_thr), float(self.policy_upd_rate)
+            cost = self._dev_of(self.cur_cost)
+            kv, acts = self._dev_of(self.kernel_val_all), self._dev_of(self.kernel_activations)
+            mu, sigma, alpha = self._dev_of(P.mu_tmp), self._dev_of(P.sigma_tmp), self._dev_of(P.alpha_tmp)
+            mu_c, sigma_c, alpha_c = (self._d(t).clone() for t in (P.mu_c, P.sigma_c, P.alpha_c))
+            a.cost_dev, a.kernel_val_all_dev, a.kernel_activations_dev = cost.data_ptr(), kv.data_ptr(), acts.data_ptr()
+            a.mu_tmp_dev, a.sigma_tmp_dev, a.alpha_tmp_dev = mu.data_ptr(), sigma.data_ptr(), alpha.data_ptr()
+            a.mu_c_dev, a.sigma_c_dev, a.alpha_c_dev = mu_c.data_ptr(), sigma_c.data_ptr(), alpha_c.data_ptr()
+            stats = torch.empty(4, device=dev)
+            packed = torch.empty(int(self._lib.dsmppi_update_packed_len(nk, d)), device=dev)
+            n_upd = torch.zeros(1, dtype=torch.int32, device=dev)
+            st = self._stream()
+            _capi.check(self._lib.dsmppi_update_cost_stats(self._ctx, cost.data_ptr(), N, stats.data_ptr(), st))
+            if self._shard is not None:
+                from .parallel import allreduce_cost_stats, allreduce_packed
+                a.owns_sample0 = 1 if self._shard['rank'] == 0 else 0
+                a.N_global = allreduce_cost_stats(stats, self._shard['group'])
+            _capi.check(self._lib.dsmppi_update_partial(self._ctx, _capi.C.byref(a), stats.data_ptr(),
+                                                        packed.data_ptr(), st))
+            if self._shard is not None:
+                allreduce_packed(packed, self._shard['group'])
+            _capi.check(self._lib.dsmppi_update_finalize(self._ctx, _capi.C.byref(a), packed.data_ptr(),
+                                                         n_upd.data_ptr(), st))
+        if nk > 0:      # in-place slice assignment keeps aliases of the mean tensors alive (policy.py:108-113)
+            P.mu_c[0:nk] = mu_c[0:nk].to(P.mu_c.device)
+            P.sigma_c[0:nk] = sigma_c[0:nk].to(P.sigma_c.device)
+            P.alpha_c[0:nk] = alpha_c[0:nk].to(P.alpha_c.device)
+        self._last_stats = stats
+        return 0, n_upd.to(self.tensor_args['device'])[0].to(torch.int64)
+
+    def update_obstacles(self, obs):
+        self.obs = obs
+        self.n_obs = obs.shape[0]
+        return 0
+
+    # ------------------------------------------------------------------ introspection (bench / tests)
+    def launch_count(self):
+        return int(self._lib.dsmppi_launch_count(self._ctx))
+
+    def pass1_stats(self):
+        a, b, m = _capi.C.c_int64(), _capi.C.c_int64(), _capi.C.c_int32()
+        _capi.check(self._lib.dsmppi_pass1_stats(self._ctx, _capi.C.byref(a), _capi.C.byref(b), _capi.C.byref(m),
+                                                 self._stream()))
+        return dict(rescored_pairs=a.value, band_overflows=b.value, mode=m.value)
+
+    def enable_kernel_timing(self, on=True):
+        _capi.check(self._lib.dsmppi_enable_kernel_timing(self._ctx, 1 if on else 0))
+
+    def kernel_timing(self):
+        p, pn, e, en = _capi.C.c_double(), _capi.C.c_int32(), _capi.C.c_double(), _capi.C.c_int32()
+        _capi.check(self._lib.dsmppi_kernel_timing(self._ctx, _capi.C.byref(p), _capi.C.byref(pn), _capi.C.byref(e),
+                                                   _capi.C.byref(en)))
+        return dict(pass1_ms=p.value, pass1_launches=pn.value, exact_ms=e.value, exact_launches=en.value)

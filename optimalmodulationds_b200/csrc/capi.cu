@@ -1,0 +1,441 @@
+// extern "C" surface of libdsmppi_b200.so (see include/dsmppi_b200.h) and the host-side orchestration of
+// one rollout: per step  [tensor-core prefilter -> candidate band ->] fp32 scoring -> ranking ->
+// fp32 forward+VJP on the K closest -> modulation/integration step.  Everything is stream-ordered; the
+// host never waits inside the horizon loop.
+#include <cstring>
+#include <vector>
+
+#include "internal.cuh"
+
+static thread_local std::string g_last_error;
+void dsmppi_set_error(const std::string& msg) { g_last_error = msg; }
+
+namespace {
+
+template <typename T>
+int grow(T*& p, size_t& cap, size_t need) {
+  if (need <= cap) return 0;
+  if (p) CUDA_TRY(cudaFree(p));
+  p = nullptr;
+  const size_t n = need + need / 8;
+  CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&p), n * sizeof(T)));
+  cap = n;
+  return 0;
+}
+
+template <typename T>
+int alloc(T*& p, size_t n) {
+  if (p) CUDA_TRY(cudaFree(p));
+  p = nullptr;
+  CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&p), (n ? n : 1) * sizeof(T)));
+  return 0;
+}
+
+int resolved_mode(const dsmppi_ctx* c) {
+  int m = c->pass1_mode;
+  if (m == DSMPPI_PASS1_AUTO) m = (c->M >= 64 && c->tc_blob) ? DSMPPI_PASS1_TC_F16 : DSMPPI_PASS1_EXACT_FP32;
+  if (m != DSMPPI_PASS1_EXACT_FP32 && !c->tc_blob) m = DSMPPI_PASS1_EXACT_FP32;
+  return m;
+}
+
+// records one event of a start/stop pair on the launching stream (no host synchronisation)
+int timing_mark(dsmppi_ctx* c, int kind, cudaStream_t st) {
+  if (!c->timing) return 0;
+  if (c->ev_used >= (int)c->ev.size()) {
+    cudaEvent_t e;
+    CUDA_TRY(cudaEventCreate(&e));
+    c->ev.push_back(e);
+  }
+  c->ev_kind = kind;
+  CUDA_TRY(cudaEventRecord(c->ev[c->ev_used++], st));
+  return 0;
+}
+
+}  // namespace
+
+int ensure_workspace(dsmppi_ctx* c, int n, int M) {
+  if (n <= c->ws_n && M <= c->ws_M) return 0;
+  const int nn = n > c->ws_n ? n : c->ws_n;
+  const int mm = M > c->ws_M ? M : c->ws_M;
+  const int d = c->d;
+  size_t cap;
+  if (nn > c->ws_n) {
+    if (alloc(c->q_work, (size_t)nn * d) || alloc(c->cand_obs, (size_t)nn * CAND_MAX) || alloc(c->cand_cnt, (size_t)nn) ||
+        alloc(c->row_base, (size_t)nn) || alloc(c->sel, (size_t)nn * MAXK) ||
+        alloc(c->sel_dist, (size_t)nn * MAXK) || alloc(c->sel_grad, (size_t)nn * MAXK * d) ||
+        alloc(c->dist_tmp, (size_t)nn) || alloc(c->grad_tmp, (size_t)nn * d))
+      return 1;
+  }
+  // rows scored in fp32: dense n*M when the prefilter is off, at most n*CAND_MAX when it is on.  Sized
+  // for the dense case only while that stays small; the tensor path needs n*CAND_MAX.
+  const int mode = resolved_mode(c);
+  size_t rows = (mode == DSMPPI_PASS1_EXACT_FP32) ? (size_t)nn * mm : (size_t)nn * CAND_MAX;
+  if (rows < (size_t)nn * CAND_MAX) rows = (size_t)nn * CAND_MAX;
+  if (grow(c->m_rows, c->m_rows_cap, rows)) return 1;
+  cap = c->rowlist_cap;
+  if (grow(c->row_sample, cap, (size_t)nn * CAND_MAX)) return 1;
+  if (grow(c->row_obs, c->rowlist_cap, (size_t)nn * CAND_MAX)) return 1;
+  if (mode != DSMPPI_PASS1_EXACT_FP32) {
+    if (grow(c->mdist, c->mdist_cap, (size_t)nn * mm)) return 1;
+  }
+  c->ws_n = nn;
+  c->ws_M = mm;
+  return 0;
+}
+
+extern "C" {
+
+const char* dsmppi_last_error(void) { return g_last_error.c_str(); }
+int dsmppi_version(void) { return 100; }
+
+int dsmppi_ctx_create(dsmppi_ctx** out, const dsmppi_net* net, const float* dh_params_host, int32_t capacity,
+                      int32_t device) {
+  REQUIRE(out && net && dh_params_host, "null argument");
+  REQUIRE(net->n_dof >= 1 && net->n_dof <= MAXD, "n_dof out of range (1..8)");
+  REQUIRE(net->n_out >= 1 && net->n_out <= MAXO, "n_out out of range (1..16)");
+  REQUIRE(capacity >= 1, "capacity must be positive");
+  int ndev = 0;
+  CUDA_TRY(cudaGetDeviceCount(&ndev));
+  REQUIRE(ndev > 0 && device < ndev, "no such CUDA device (this library has no CPU fallback)");
+  CUDA_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  REQUIRE(prop.major == 10, "libdsmppi_b200 is built for sm_100a (B200) only");
+  dsmppi_ctx* c = new dsmppi_ctx();
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  c->d = net->n_dof;
+  c->O = net->n_out;
+  c->nin = c->d + 3;
+  c->nenc = 3 * c->nin;
+  c->capacity = capacity;
+  for (int i = 0; i <= c->d; ++i)
+    for (int j = 0; j < 4; ++j) c->dh.v[i][j] = dh_params_host[i * 4 + j];
+  // fp32 weight blob: Wf[l] = W_l^T ([in][256]) and Wb[l] = W_l ([256][in]) for the hidden layers, W4, biases
+  const int in_dim[5] = {c->nenc, HID, HID, HID, HID};
+  auto pad = [](size_t x) { return (x + 63) / 64 * 64; };
+  size_t total = 0, off_f[4], off_b[4], off_w4, off_bias[5];
+  for (int l = 0; l < 4; ++l) { off_f[l] = total; total += pad((size_t)in_dim[l] * HID); }
+  for (int l = 0; l < 4; ++l) { off_b[l] = total; total += pad((size_t)in_dim[l] * HID); }
+  off_w4 = total; total += pad((size_t)c->O * HID);
+  for (int l = 0; l < 5; ++l) { off_bias[l] = total; total += pad(HID); }
+  std::vector<float> blob(total, 0.f);
+  for (int l = 0; l < 4; ++l) {
+    const float* W = net->W_host[l];
+    for (int o = 0; o < HID; ++o)
+      for (int k = 0; k < in_dim[l]; ++k) {
+        blob[off_f[l] + (size_t)k * HID + o] = W[(size_t)o * in_dim[l] + k];
+        blob[off_b[l] + (size_t)o * in_dim[l] + k] = W[(size_t)o * in_dim[l] + k];
+      }
+    std::memcpy(&blob[off_bias[l]], net->b_host[l], HID * sizeof(float));
+  }
+  std::memcpy(&blob[off_w4], net->W_host[4], (size_t)c->O * HID * sizeof(float));
+  std::memcpy(&blob[off_bias[4]], net->b_host[4], (size_t)c->O * sizeof(float));
+  if (cudaMalloc(reinterpret_cast<void**>(&c->weights_blob), total * sizeof(float)) != cudaSuccess) {
+    delete c;
+    dsmppi_set_error("cudaMalloc(weights) failed");
+    return 1;
+  }
+  CUDA_TRY(cudaMemcpy(c->weights_blob, blob.data(), total * sizeof(float), cudaMemcpyHostToDevice));
+  c->net.d = c->d; c->net.nin = c->nin; c->net.nenc = c->nenc; c->net.O = c->O;
+  c->net.scale = (c->O == 9) ? 0.01f : 1.f;            // MPPI.py:236-237
+  for (int l = 0; l < 4; ++l) {
+    c->net.Wf[l] = c->weights_blob + off_f[l];
+    c->net.Wb[l] = c->weights_blob + off_b[l];
+  }
+  c->net.W4 = c->weights_blob + off_w4;
+  for (int l = 0; l < 5; ++l) c->net.b[l] = c->weights_blob + off_bias[l];
+  if (tc_build_images(c, net)) { delete c; return 1; }
+  c->upd_blocks = c->sm_count * 2;
+  CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c->upd_partials),
+                      (size_t)c->upd_blocks * dsmppi_update_packed_len(NKMAX, MAXD) * sizeof(float)));
+  CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c->stats_tmp), 4 * sizeof(float)));
+  CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c->packed_tmp), dsmppi_update_packed_len(NKMAX, MAXD) * sizeof(float)));
+  CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c->counters), 8 * sizeof(int)));
+  CUDA_TRY(cudaMemset(c->counters, 0, 8 * sizeof(int)));
+  *out = c;
+  return 0;
+}
+
+int dsmppi_ctx_destroy(dsmppi_ctx* c) {
+  if (!c) return 0;
+  cudaSetDevice(c->device);
+  void* ptrs[] = {c->weights_blob, c->tc_blob, c->obs, c->obs_enc, c->q_work, c->m_rows, c->mdist, c->enc_q,
+                  c->cand_obs, c->cand_cnt, c->row_base, c->row_sample, c->row_obs, c->counters, c->sel,
+                  c->sel_dist, c->sel_grad, c->dist_tmp, c->grad_tmp, c->upd_partials, c->stats_tmp,
+                  c->packed_tmp, c->stage};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
+  delete c;
+  return 0;
+}
+
+int dsmppi_set_pass1_mode(dsmppi_ctx* c, int32_t mode, float guard_band) {
+  REQUIRE(c, "null ctx");
+  REQUIRE(mode >= 0 && mode <= 3, "bad pass-1 mode");
+  c->pass1_mode = mode;
+  if (guard_band > 0.f) c->guard_band = guard_band;
+  c->ws_n = 0;   // force re-sizing of the workspace for the new mode
+  c->ws_M = 0;
+  return 0;
+}
+
+int dsmppi_set_obstacles(dsmppi_ctx* c, const float* obs_dev, int32_t M, void* stream) {
+  REQUIRE(c && obs_dev, "null argument");
+  REQUIRE(M >= 1, "need at least one obstacle");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CUDA_TRY(cudaSetDevice(c->device));
+  if (M > c->obs_cap) {
+    if (c->obs) CUDA_TRY(cudaFree(c->obs));
+    c->obs = nullptr;
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c->obs), (size_t)M * 4 * sizeof(float)));
+    c->obs_cap = M;
+  }
+  CUDA_TRY(cudaMemcpyAsync(c->obs, obs_dev, (size_t)M * 4 * sizeof(float), cudaMemcpyDefault, st));
+  c->M = M;
+  if (c->tc_blob) return tc_set_obstacles(c, st);
+  return 0;
+}
+
+int dsmppi_set_obstacles_host(dsmppi_ctx* c, const float* obs_host, int32_t M, void* stream) {
+  return dsmppi_set_obstacles(c, obs_host, M, stream);   // cudaMemcpyDefault handles host sources
+}
+
+// distance + gradient of n states q (row stride q_stride floats) against the current obstacles:
+// fills c->sel_dist (n, K) and c->sel_grad (n, K, d)
+static int distance_pipeline(dsmppi_ctx* c, const float* q, int q_stride, int n, int K, uint32_t ignore_mask,
+                             cudaStream_t st) {
+  REQUIRE(c->M >= 1, "obstacles not set");
+  REQUIRE(K >= 1 && K <= MAXK, "n_closest_obs out of range (1..8)");
+  REQUIRE(K <= c->M, "n_closest_obs exceeds the number of obstacles");
+  if (ensure_workspace(c, n, c->M)) return 1;
+  const int mode = resolved_mode(c);
+  RowSrc src{};
+  src.M = c->M;
+  src.K = K;
+  if (mode == DSMPPI_PASS1_EXACT_FP32) {
+    src.mode = ROWS_DENSE;
+    src.n_rows = n * c->M;
+    if (timing_mark(c, 0, st)) return 1;
+    if (launch_exact_forward(c, q, q_stride, src, ignore_mask, c->m_rows, st)) return 1;
+    if (timing_mark(c, 0, st)) return 1;
+    if (launch_rank_dense(c, n, K, st)) return 1;
+  } else {
+    if (timing_mark(c, 1, st)) return 1;
+    if (tc_pass1(c, q, q_stride, n, ignore_mask, mode, st)) return 1;
+    if (timing_mark(c, 1, st)) return 1;
+    if (launch_select_candidates(c, n, K, c->guard_band, st)) return 1;
+    src.mode = ROWS_LIST;
+    src.n_rows = n * CAND_MAX;
+    src.n_rows_dev = c->counters;
+    src.row_sample = c->row_sample;
+    src.row_obs = c->row_obs;
+    if (launch_exact_forward(c, q, q_stride, src, ignore_mask, c->m_rows, st)) return 1;
+    if (launch_rank_candidates(c, n, K, st)) return 1;
+  }
+  RowSrc s2{};
+  s2.mode = ROWS_SELECTED;
+  s2.M = c->M;
+  s2.K = K;
+  s2.n_rows = n * K;
+  s2.sel = c->sel;
+  return launch_exact_fwdbwd(c, q, q_stride, s2, c->sel_dist, c->sel_grad, st);
+}
+
+int dsmppi_rollout(dsmppi_ctx* c, const dsmppi_rollout_args* a, void* stream) {
+  REQUIRE(c && a, "null argument");
+  REQUIRE(a->N >= 1 && a->H >= 1, "N and H must be positive");
+  REQUIRE(a->n_kernels >= 0 && a->n_kernels <= NKMAX, "n_kernels out of range");
+  REQUIRE(a->q_cur_dev && a->all_traj_dev && a->closest_dist_all_dev && a->kernel_val_all_dev &&
+              a->dot_products_dev && a->kernel_activations_dev && a->qdot_dev && a->nn_grad_all_dev,
+          "null device pointer");
+  REQUIRE(a->n_kernels == 0 || (a->mu_tmp_dev && a->sigma_tmp_dev && a->alpha_tmp_dev), "null policy pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CUDA_TRY(cudaSetDevice(c->device));
+  c->ev_used = 0;
+  CUDA_TRY(cudaMemsetAsync(c->counters + 1, 0, 3 * sizeof(int), st));
+  if (launch_init_traj(c, a, st)) return 1;
+  const int d = c->d;
+  for (int t = 1; t <= a->H; ++t) {
+    const float* q = a->all_traj_dev + (size_t)(t - 1) * d;          // q_prev = all_traj[:, t-1, :]
+    if (distance_pipeline(c, q, a->H * d, a->N, a->n_closest, a->ignored_link_mask, st)) return 1;
+    if (launch_step(c, a, t, st)) return 1;
+  }
+  if (a->norm_basis_dev)
+    if (launch_basis(c, a->nn_grad_all_dev, (int64_t)a->N * a->H, a->norm_basis_dev, st)) return 1;
+  return 0;
+}
+
+int dsmppi_distance_grad(dsmppi_ctx* c, const float* q_dev, int32_t n, int32_t n_closest, uint32_t ignored_link_mask,
+                         float* distance_dev, float* nn_grad_dev, void* stream) {
+  REQUIRE(c && q_dev && distance_dev && nn_grad_dev, "null argument");
+  REQUIRE(n >= 1, "n must be positive");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CUDA_TRY(cudaSetDevice(c->device));
+  if (distance_pipeline(c, q_dev, c->d, n, n_closest, ignored_link_mask, st)) return 1;
+  return launch_blend(c, n, n_closest, distance_dev, nn_grad_dev, st);
+}
+
+int dsmppi_norm_basis(dsmppi_ctx* c, const float* grad_dev, int64_t n, float* basis_dev, void* stream) {
+  REQUIRE(c && grad_dev && basis_dev, "null argument");
+  CUDA_TRY(cudaSetDevice(c->device));
+  return launch_basis(c, grad_dev, n, basis_dev, static_cast<cudaStream_t>(stream));
+}
+
+int dsmppi_cost(dsmppi_ctx* c, const dsmppi_cost_args* a, void* stream) {
+  REQUIRE(c && a && a->all_traj_dev && a->closest_dist_all_dev && a->cost_dev, "null argument");
+  CUDA_TRY(cudaSetDevice(c->device));
+  return launch_cost(c, a, static_cast<cudaStream_t>(stream));
+}
+
+int32_t dsmppi_update_packed_len(int32_t nk, int32_t d) { return 1 + nk * (2 * d + 3); }
+
+int dsmppi_update_cost_stats(dsmppi_ctx* c, const float* cost_dev, int32_t N, float* stats_dev, void* stream) {
+  REQUIRE(c && cost_dev && stats_dev, "null argument");
+  CUDA_TRY(cudaSetDevice(c->device));
+  return launch_cost_stats(c, cost_dev, N, stats_dev, static_cast<cudaStream_t>(stream));
+}
+
+int dsmppi_update_partial(dsmppi_ctx* c, const dsmppi_update_args* a, const float* stats_dev, float* packed_dev,
+                          void* stream) {
+  REQUIRE(c && a && stats_dev && packed_dev, "null argument");
+  REQUIRE(a->n_kernels >= 0 && a->n_kernels <= NKMAX, "n_kernels out of range");
+  CUDA_TRY(cudaSetDevice(c->device));
+  return launch_update_partial(c, a, stats_dev, packed_dev, static_cast<cudaStream_t>(stream));
+}
+
+int dsmppi_update_finalize(dsmppi_ctx* c, const dsmppi_update_args* a, const float* packed_dev,
+                           int32_t* n_updated_dev, void* stream) {
+  REQUIRE(c && a && packed_dev && n_updated_dev, "null argument");
+  CUDA_TRY(cudaSetDevice(c->device));
+  return launch_update_finalize(c, a, packed_dev, n_updated_dev, static_cast<cudaStream_t>(stream));
+}
+
+int dsmppi_iteration_host(dsmppi_ctx* c, dsmppi_iteration_host_args* h, void* stream) {
+  REQUIRE(c && h, "null argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CUDA_TRY(cudaSetDevice(c->device));
+  const dsmppi_rollout_args& r = h->rollout;
+  const size_t N = r.N, H = r.H, d = c->d;
+  REQUIRE(N >= 1 && H >= 1, "N and H must be positive");
+  const size_t nk = r.n_kernels;
+  // staging layout (floats)
+  size_t off = 0;
+  auto take = [&](size_t n) { size_t o = off; off += (n + 3) / 4 * 4; return o; };
+  const size_t o_q = take(r.q_cur_is_batch ? N * d : d), o_mu = take(N * NKMAX * d), o_sg = take(N * NKMAX),
+               o_al = take(N * NKMAX * d), o_tr = take(N * H * d), o_cd = take(N * H), o_kv = take(N * H * NKMAX),
+               o_dp = take(N * H), o_ka = take(N * H), o_qd = take(N * d), o_gr = take(N * H * d), o_co = take(N),
+               o_muc = take(NKMAX * d), o_sgc = take(NKMAX), o_alc = take(NKMAX * d), o_nu = take(4);
+  if (grow(c->stage, c->stage_cap, off)) return 1;
+  float* S = c->stage;
+  int64_t h2d = 0, d2h = 0;
+  auto up = [&](size_t o, const float* src, size_t n) {
+    h2d += (int64_t)(n * sizeof(float));
+    return cudaMemcpyAsync(S + o, src, n * sizeof(float), cudaMemcpyHostToDevice, st);
+  };
+  auto down = [&](float* dst, size_t o, size_t n) {
+    d2h += (int64_t)(n * sizeof(float));
+    return cudaMemcpyAsync(dst, S + o, n * sizeof(float), cudaMemcpyDeviceToHost, st);
+  };
+  CUDA_TRY(up(o_q, h->q_cur_host, r.q_cur_is_batch ? N * d : d));
+  if (nk > 0) {
+    // only the live kernel columns travel: (N, 50, d) rows are strided, so copy with a 2-D memcpy
+    CUDA_TRY(cudaMemcpy2DAsync(S + o_mu, NKMAX * d * sizeof(float), h->mu_tmp_host, NKMAX * d * sizeof(float),
+                               nk * d * sizeof(float), N, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpy2DAsync(S + o_al, NKMAX * d * sizeof(float), h->alpha_tmp_host, NKMAX * d * sizeof(float),
+                               nk * d * sizeof(float), N, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpy2DAsync(S + o_sg, NKMAX * sizeof(float), h->sigma_tmp_host, NKMAX * sizeof(float),
+                               nk * sizeof(float), N, cudaMemcpyHostToDevice, st));
+    h2d += (int64_t)(N * nk * (2 * d + 1) * sizeof(float));
+  }
+  CUDA_TRY(up(o_muc, h->mu_c_host, NKMAX * d));
+  CUDA_TRY(up(o_sgc, h->sigma_c_host, NKMAX));
+  CUDA_TRY(up(o_alc, h->alpha_c_host, NKMAX * d));
+  dsmppi_rollout_args a = r;
+  a.q_cur_dev = S + o_q; a.mu_tmp_dev = S + o_mu; a.sigma_tmp_dev = S + o_sg; a.alpha_tmp_dev = S + o_al;
+  a.all_traj_dev = S + o_tr; a.closest_dist_all_dev = S + o_cd; a.kernel_val_all_dev = S + o_kv;
+  a.dot_products_dev = S + o_dp; a.kernel_activations_dev = S + o_ka; a.qdot_dev = S + o_qd;
+  a.nn_grad_all_dev = S + o_gr; a.norm_basis_dev = nullptr;
+  if (dsmppi_rollout(c, &a, stream)) return 1;
+  dsmppi_cost_args ca{};
+  ca.N = r.N; ca.H = r.H;
+  for (int i = 0; i < MAXD; ++i) { ca.q_goal[i] = r.q_goal[i]; ca.q_min[i] = h->q_min[i]; ca.q_max[i] = h->q_max[i]; }
+  ca.all_traj_dev = a.all_traj_dev; ca.closest_dist_all_dev = a.closest_dist_all_dev; ca.cost_dev = S + o_co;
+  if (launch_cost(c, &ca, st)) return 1;
+  dsmppi_update_args ua{};
+  ua.N = r.N; ua.H = r.H; ua.n_kernels = r.n_kernels; ua.owns_sample0 = 1; ua.N_global = r.N;
+  ua.ker_thr = h->ker_thr; ua.upd_rate = h->upd_rate;
+  ua.cost_dev = S + o_co; ua.kernel_val_all_dev = a.kernel_val_all_dev;
+  ua.kernel_activations_dev = a.kernel_activations_dev;
+  ua.mu_tmp_dev = a.mu_tmp_dev; ua.sigma_tmp_dev = a.sigma_tmp_dev; ua.alpha_tmp_dev = a.alpha_tmp_dev;
+  ua.mu_c_dev = S + o_muc; ua.sigma_c_dev = S + o_sgc; ua.alpha_c_dev = S + o_alc;
+  if (launch_cost_stats(c, ua.cost_dev, r.N, c->stats_tmp, st)) return 1;
+  if (launch_update_partial(c, &ua, c->stats_tmp, c->packed_tmp, st)) return 1;
+  if (launch_update_finalize(c, &ua, c->packed_tmp, reinterpret_cast<int*>(S + o_nu), st)) return 1;
+  CUDA_TRY(down(h->all_traj_host, o_tr, N * H * d));
+  CUDA_TRY(down(h->closest_dist_all_host, o_cd, N * H));
+  if (nk > 0) {
+    CUDA_TRY(cudaMemcpy2DAsync(h->kernel_val_all_host, NKMAX * sizeof(float), S + o_kv, NKMAX * sizeof(float),
+                               nk * sizeof(float), N * H, cudaMemcpyDeviceToHost, st));
+    d2h += (int64_t)(N * H * nk * sizeof(float));
+  }
+  CUDA_TRY(down(h->dot_products_host, o_dp, N * H));
+  CUDA_TRY(down(h->kernel_activations_host, o_ka, N * H));
+  CUDA_TRY(down(h->qdot_host, o_qd, N * d));
+  CUDA_TRY(down(h->cost_host, o_co, N));
+  CUDA_TRY(down(h->mu_c_host, o_muc, NKMAX * d));
+  CUDA_TRY(down(h->sigma_c_host, o_sgc, NKMAX));
+  CUDA_TRY(down(h->alpha_c_host, o_alc, NKMAX * d));
+  CUDA_TRY(cudaMemcpyAsync(h->n_updated_host, S + o_nu, sizeof(int), cudaMemcpyDeviceToHost, st));
+  d2h += sizeof(int);
+  CUDA_TRY(cudaStreamSynchronize(st));
+  h->h2d_bytes = h2d;
+  h->d2h_bytes = d2h;
+  return 0;
+}
+
+int64_t dsmppi_launch_count(const dsmppi_ctx* c) { return c ? c->launches : 0; }
+
+int dsmppi_pass1_stats(dsmppi_ctx* c, int64_t* rescored_pairs, int64_t* band_overflows, int32_t* mode, void* stream) {
+  REQUIRE(c, "null ctx");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int host[4] = {0, 0, 0, 0};
+  CUDA_TRY(cudaMemcpyAsync(host, c->counters, sizeof(host), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  if (band_overflows) *band_overflows = host[1];
+  if (rescored_pairs) {
+    unsigned long long v;
+    std::memcpy(&v, &host[2], sizeof(v));
+    *rescored_pairs = (int64_t)v;
+  }
+  if (mode) *mode = resolved_mode(c);
+  return 0;
+}
+
+int dsmppi_enable_kernel_timing(dsmppi_ctx* c, int32_t on) {
+  REQUIRE(c, "null ctx");
+  c->timing = on;
+  return 0;
+}
+
+int dsmppi_kernel_timing(dsmppi_ctx* c, double* pass1_ms, int32_t* pass1_n, double* exact_ms, int32_t* exact_n) {
+  REQUIRE(c, "null ctx");
+  double tot = 0.0;
+  int n = 0;
+  for (int i = 0; i + 1 < c->ev_used; i += 2) {
+    CUDA_TRY(cudaEventSynchronize(c->ev[i + 1]));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, c->ev[i], c->ev[i + 1]));
+    tot += ms;
+    ++n;
+  }
+  const double avg = n ? tot / n : 0.0;
+  if (pass1_ms) *pass1_ms = c->ev_kind == 1 ? avg : 0.0;
+  if (pass1_n) *pass1_n = c->ev_kind == 1 ? n : 0;
+  if (exact_ms) *exact_ms = c->ev_kind == 0 ? avg : 0.0;
+  if (exact_n) *exact_n = c->ev_kind == 0 ? n : 0;
+  return 0;
+}
+
+}  // extern "C"

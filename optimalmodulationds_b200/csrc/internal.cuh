@@ -1,0 +1,137 @@
+// Internal declarations shared by the translation units of libdsmppi_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "dsmppi_b200.h"
+
+#define HID DSMPPI_HIDDEN
+#define MAXD DSMPPI_MAX_DOF
+#define MAXO DSMPPI_MAX_LINKS
+#define MAXK DSMPPI_MAX_CLOSEST
+#define NKMAX DSMPPI_N_KERNEL_MAX
+#define CAND_MAX 16            // candidates kept per sample by the tensor-core prefilter
+
+void dsmppi_set_error(const std::string& msg);
+
+#define CUDA_TRY(expr)                                                                     \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess) {                                                               \
+      dsmppi_set_error(std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" __FILE__ + \
+                       ":" + std::to_string(__LINE__) + ")");                              \
+      return 1;                                                                            \
+    }                                                                                      \
+  } while (0)
+
+#define REQUIRE(cond, msg)                                    \
+  do {                                                        \
+    if (!(cond)) {                                            \
+      dsmppi_set_error(std::string(msg) + " [" #cond "]");    \
+      return 2;                                               \
+    }                                                         \
+  } while (0)
+
+// Device-side view of the distance network (fp32).
+struct NetDev {
+  int d;        // joints
+  int nin;      // d + 3
+  int nenc;     // 3 * nin
+  int O;        // links
+  float scale;  // 0.01 when O == 9 (centimetres -> metres, MPPI.py:236-237), else 1
+  const float* Wf[4];   // layers 0..3, forward orientation [in][256]
+  const float* Wb[4];   // layers 0..3, torch orientation  [256][in]
+  const float* W4;      // output layer, torch orientation [O][256]
+  const float* b[5];
+};
+
+// How a kernel maps a row index to a (sample, obstacle) pair.
+enum { ROWS_DENSE = 0, ROWS_SELECTED = 1, ROWS_LIST = 2 };
+struct RowSrc {
+  int mode;
+  int M;                  // obstacles
+  int K;                  // ROWS_SELECTED: pairs per sample
+  int n_rows;             // host-known row count (upper bound when n_rows_dev != nullptr)
+  const int* n_rows_dev;  // ROWS_LIST: device row counter
+  const int* sel;         // ROWS_SELECTED: (n, K) obstacle index
+  const int* row_sample;  // ROWS_LIST
+  const int* row_obs;     // ROWS_LIST
+};
+
+struct DhTable { float v[MAXD + 1][4]; };   // rows [d, theta, a, alpha]
+
+struct dsmppi_ctx {
+  int device = 0;
+  int d = 0, O = 0, nin = 0, nenc = 0;
+  int capacity = 0;
+  int M = 0;
+  int pass1_mode = DSMPPI_PASS1_AUTO;
+  float guard_band = 0.f;
+  NetDev net{};
+  DhTable dh{};
+  float* weights_blob = nullptr;      // all fp32 weights
+  void* tc_blob = nullptr;            // tensor-core operand images (tc_pass1.cu)
+  size_t tc_blob_bytes = 0;
+  // obstacles
+  float* obs = nullptr; int obs_cap = 0;
+  void* obs_enc = nullptr;            // tensor path: per-obstacle packed encodings
+  // workspace (grown on demand)
+  int ws_n = 0, ws_M = 0;
+  float* q_work = nullptr;            // (n, d) states of the current step
+  float* m_rows = nullptr;            // exact masked min distance per scored row
+  size_t m_rows_cap = 0;
+  float* mdist = nullptr;             // tensor path: approximate (n, M)
+  size_t mdist_cap = 0;
+  void* enc_q = nullptr;              // tensor path: per-sample packed encodings
+  int* cand_obs = nullptr;            // (n, CAND_MAX)
+  int* cand_cnt = nullptr;            // (n)
+  int* row_base = nullptr;            // (n)
+  int* row_sample = nullptr; int* row_obs = nullptr; size_t rowlist_cap = 0;
+  int* counters = nullptr;            // [0] n_rows, [1] band overflows, [2..3] rescored pairs (u64)
+  int* sel = nullptr;                 // (n, K)
+  float* sel_dist = nullptr;          // (n, K) pass-2 distances
+  float* sel_grad = nullptr;          // (n, K, d)
+  float* dist_tmp = nullptr;          // (n)
+  float* grad_tmp = nullptr;          // (n, d)
+  // policy-update scratch
+  float* upd_partials = nullptr; int upd_blocks = 0;
+  float* stats_tmp = nullptr;         // 4 floats
+  float* packed_tmp = nullptr;
+  // host-buffer iteration staging
+  float* stage = nullptr; size_t stage_cap = 0;
+  int64_t launches = 0;
+  int sm_count = 148;
+  // kernel timing
+  int timing = 0;
+  std::vector<cudaEvent_t> ev;        // start/stop pairs around the scoring kernel of each step
+  int ev_used = 0;                    // events recorded by the last rollout
+  int ev_kind = 0;                    // 1: tensor-core pass 1, 0: fp32 dense scoring
+};
+
+// exact_mlp.cu
+// q points at the first state; consecutive samples are q_stride floats apart
+int launch_exact_forward(dsmppi_ctx* c, const float* q, int q_stride, const RowSrc& src, uint32_t ignore_mask,
+                         float* m_rows, cudaStream_t st);
+int launch_exact_fwdbwd(dsmppi_ctx* c, const float* q, int q_stride, const RowSrc& src, float* sel_dist,
+                        float* sel_grad, cudaStream_t st);
+// tc_pass1.cu
+int tc_build_images(dsmppi_ctx* c, const dsmppi_net* net);
+int tc_set_obstacles(dsmppi_ctx* c, cudaStream_t st);
+int tc_pass1(dsmppi_ctx* c, const float* q, int q_stride, int n, uint32_t ignore_mask, int mode, cudaStream_t st);
+// rollout_kernels.cu
+int launch_rank_dense(dsmppi_ctx* c, int n, int K, cudaStream_t st);
+int launch_select_candidates(dsmppi_ctx* c, int n, int K, float band, cudaStream_t st);
+int launch_rank_candidates(dsmppi_ctx* c, int n, int K, cudaStream_t st);
+int launch_blend(dsmppi_ctx* c, int n, int K, float* dist_out, float* grad_out, cudaStream_t st);
+int launch_step(dsmppi_ctx* c, const dsmppi_rollout_args* a, int t, cudaStream_t st);
+int launch_init_traj(dsmppi_ctx* c, const dsmppi_rollout_args* a, cudaStream_t st);
+int launch_cost(dsmppi_ctx* c, const dsmppi_cost_args* a, cudaStream_t st);
+int launch_basis(dsmppi_ctx* c, const float* grad, int64_t n, float* basis, cudaStream_t st);
+int launch_cost_stats(dsmppi_ctx* c, const float* cost, int N, float* stats, cudaStream_t st);
+int launch_update_partial(dsmppi_ctx* c, const dsmppi_update_args* a, const float* stats, float* packed,
+                          cudaStream_t st);
+int launch_update_finalize(dsmppi_ctx* c, const dsmppi_update_args* a, const float* packed, int* n_updated,
+                           cudaStream_t st);
+int ensure_workspace(dsmppi_ctx* c, int n, int M);

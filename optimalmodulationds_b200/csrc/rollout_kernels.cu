@@ -1,0 +1,730 @@
+// Per-sample stages of the MPPI rollout around the distance network: obstacle ranking, gradient blend,
+// modulation + policy blend + Euler step, cost with terminal FK, Householder basis, policy update.
+// One thread (or one warp, for ranking) per sample; every per-sample vector (d <= 8) lives in registers.
+#include <cfloat>
+
+#include "internal.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// Ranking: the K closest obstacles per sample, ascending by (distance, obstacle index)
+// (MPPI.py:243-247: sort over obstacles, first K).  One warp per sample.
+// ------------------------------------------------------------------------------------------------
+__global__ void rank_kernel(const float* __restrict__ m_rows, const int* __restrict__ row_base,
+                            const int* __restrict__ cnt, const int* __restrict__ row_obs, int M, int n, int K,
+                            int* __restrict__ sel) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= n) return;
+  const int base = row_base ? row_base[w] : w * M;
+  const int c = cnt ? cnt[w] : M;
+  float last_v = -FLT_MAX;
+  int last_j = -1;
+  bool first = true;
+  for (int kk = 0; kk < K; ++kk) {
+    float bv = FLT_MAX;
+    int bj = 0x7fffffff;
+    for (int t = lane; t < c; t += 32) {
+      const float v = m_rows[base + t];
+      const int j = row_obs ? row_obs[base + t] : t;
+      const bool after = first || v > last_v || (v == last_v && j > last_j);
+      if (after && (v < bv || (v == bv && j < bj))) { bv = v; bj = j; }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
+      const int oj = __shfl_xor_sync(0xffffffffu, bj, off);
+      if (ov < bv || (ov == bv && oj < bj)) { bv = ov; bj = oj; }
+    }
+    if (bj == 0x7fffffff) bj = last_j < 0 ? 0 : last_j;   // fewer than K candidates: repeat the last one
+    if (lane == 0) sel[w * K + kk] = bj;
+    last_v = bv; last_j = bj; first = false;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Candidate band from the approximate (tensor-core) distances: every obstacle within `band` of the
+// K-th smallest approximate distance is re-scored in fp32.  One warp per sample.
+// ------------------------------------------------------------------------------------------------
+__global__ void select_candidates_kernel(const float* __restrict__ mdist, int M, int n, int K, float band,
+                                         int* __restrict__ cand_cnt, int* __restrict__ row_base,
+                                         int* __restrict__ row_sample, int* __restrict__ row_obs,
+                                         int* __restrict__ counters) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= n) return;
+  const float* md = mdist + (size_t)w * M;
+  // K-th smallest approximate value (with multiplicity)
+  float last_v = -FLT_MAX;
+  int last_j = -1;
+  bool first = true;
+  for (int kk = 0; kk < K; ++kk) {
+    float bv = FLT_MAX;
+    int bj = 0x7fffffff;
+    for (int t = lane; t < M; t += 32) {
+      const float v = md[t];
+      const bool after = first || v > last_v || (v == last_v && t > last_j);
+      if (after && (v < bv || (v == bv && t < bj))) { bv = v; bj = t; }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
+      const int oj = __shfl_xor_sync(0xffffffffu, bj, off);
+      if (ov < bv || (ov == bv && oj < bj)) { bv = ov; bj = oj; }
+    }
+    last_v = bv; last_j = bj; first = false;
+  }
+  const float thr = last_v + band;
+  // count, reserve a contiguous row range, then fill (ascending obstacle index within the sample)
+  int mine = 0;
+  for (int t = lane; t < M; t += 32) mine += (md[t] <= thr) ? 1 : 0;
+  int total = mine;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) total += __shfl_xor_sync(0xffffffffu, total, off);
+  int keep = total;
+  float thr_use = thr;
+  if (total > CAND_MAX) {
+    // band overflow: fall back to the CAND_MAX smallest approximate values (counted, reported)
+    if (lane == 0) atomicAdd(&counters[1], 1);
+    float lv = -FLT_MAX; int lj = -1; bool fst = true;
+    for (int kk = 0; kk < CAND_MAX; ++kk) {
+      float bv = FLT_MAX; int bj = 0x7fffffff;
+      for (int t = lane; t < M; t += 32) {
+        const float v = md[t];
+        const bool after = fst || v > lv || (v == lv && t > lj);
+        if (after && (v < bv || (v == bv && t < bj))) { bv = v; bj = t; }
+      }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
+        const int oj = __shfl_xor_sync(0xffffffffu, bj, off);
+        if (ov < bv || (ov == bv && oj < bj)) { bv = ov; bj = oj; }
+      }
+      lv = bv; lj = bj; fst = false;
+    }
+    thr_use = lv;
+    keep = CAND_MAX;
+  }
+  int base = 0;
+  if (lane == 0) {
+    base = atomicAdd(&counters[0], keep);
+    atomicAdd(reinterpret_cast<unsigned long long*>(&counters[2]), (unsigned long long)keep);
+    cand_cnt[w] = keep;
+    row_base[w] = base;
+  }
+  base = __shfl_sync(0xffffffffu, base, 0);
+  int written = 0;
+  for (int t0 = 0; t0 < M && written < keep; t0 += 32) {
+    const int t = t0 + lane;
+    const bool in = t < M && md[t] <= thr_use;
+    const unsigned bal = __ballot_sync(0xffffffffu, in);
+    const int pos = written + __popc(bal & ((1u << lane) - 1u));
+    if (in && pos < keep) {
+      row_sample[base + pos] = w;
+      row_obs[base + pos] = t;
+    }
+    written += __popc(bal);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Gradient blend (MPPI.py:270-280): w = softmax(-10 * dist_k), grad = sum_k w_k grad_k, distance = dist_0
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void blend(const float* __restrict__ sd, const float* __restrict__ sg, int K, int d,
+                                      float& dist, float (&g)[MAXD]) {
+  float mx = -FLT_MAX;
+  for (int k = 0; k < K; ++k) mx = fmaxf(mx, -10.f * sd[k]);
+  float wk[MAXK];
+  float den = 0.f;
+  for (int k = 0; k < K; ++k) { wk[k] = expf(-10.f * sd[k] - mx); den += wk[k]; }
+#pragma unroll
+  for (int a = 0; a < MAXD; ++a) g[a] = 0.f;
+  for (int k = 0; k < K; ++k) {
+    const float w = wk[k] / den;
+#pragma unroll
+    for (int a = 0; a < MAXD; ++a)
+      if (a < d) g[a] += sg[k * d + a] * w;
+  }
+  dist = sd[0];
+}
+
+__global__ void blend_kernel(const float* __restrict__ sel_dist, const float* __restrict__ sel_grad, int n, int K,
+                             int d, float* __restrict__ dist_out, float* __restrict__ grad_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float dist, g[MAXD];
+  blend(sel_dist + (size_t)i * K, sel_grad + (size_t)i * K * d, K, d, dist, g);
+  dist_out[i] = dist;
+  for (int a = 0; a < d; ++a) grad_out[(size_t)i * d + a] = g[a];
+}
+
+// ------------------------------------------------------------------------------------------------
+// One rollout step for all samples: nominal DS, modulation, RBF policy blend, integration
+// (MPPI.py:101-223, LinDS.py:11-21, policy.py:186-199).
+// ------------------------------------------------------------------------------------------------
+struct StepArgs {
+  int N, H, d, t, nk, K;
+  float dt, dst_thr, lin_thr, p;
+  float goal[MAXD];
+  const float* sel_dist; const float* sel_grad;
+  const float* mu; const float* sigma; const float* alpha;
+  float* traj; float* closest; float* kval; float* dots; float* acts; float* qdot; float* grads;
+};
+
+__device__ __forceinline__ float gsigmoid(float x, float y_min, float y_max, float mid, float k) {
+  // MPPI.py:352-353 with mid = (x0 + x1) / 2 folded on the host side of the expression
+  return y_min + (y_max - y_min) / (1.f + expf(k * (-x + mid)));
+}
+
+__device__ __forceinline__ float nan_to_num(float v) {
+  if (isnan(v)) return 0.f;
+  if (isinf(v)) return v > 0.f ? FLT_MAX : -FLT_MAX;
+  return v;
+}
+
+__global__ void __launch_bounds__(128) step_kernel(StepArgs s) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= s.N) return;
+  const int d = s.d;
+  const size_t st = (size_t)i * s.H + (s.t - 1);     // state-step index
+  float q[MAXD], v[MAXD], vhat[MAXD], e0[MAXD], g[MAXD], u[MAXD], vt[MAXD], m[MAXD];
+  // S0 nominal DS (LinDS.py:11-21) and its norm (MPPI.py:106-108)
+  float ss = 0.f;
+#pragma unroll
+  for (int a = 0; a < MAXD; ++a) {
+    q[a] = a < d ? s.traj[st * d + a] : 0.f;
+    v[a] = a < d ? -(q[a] - s.goal[a]) : 0.f;
+    ss += v[a] * v[a];
+  }
+  const float dst = sqrtf(ss);
+  if (dst > s.lin_thr) {
+#pragma unroll
+    for (int a = 0; a < MAXD; ++a) v[a] = v[a] / dst;
+  }
+  ss = 0.f;
+#pragma unroll
+  for (int a = 0; a < MAXD; ++a) ss += v[a] * v[a];
+  const float vn = sqrtf(ss);
+#pragma unroll
+  for (int a = 0; a < MAXD; ++a) vhat[a] = a < d ? v[a] / vn : 0.f;
+
+  // S2e blended distance / gradient
+  float dist;
+  blend(s.sel_dist + (size_t)i * s.K, s.sel_grad + (size_t)i * s.K * d, s.K, d, dist, g);
+  dist -= s.dst_thr;                                  // MPPI.py:117
+  s.closest[st] = dist;
+  ss = 0.f;
+#pragma unroll
+  for (int a = 0; a < MAXD; ++a) {
+    if (a < d) s.grads[st * d + a] = g[a];
+    ss += g[a] * g[a];
+  }
+  const float gn = sqrtf(ss);
+  float dot = 0.f;
+#pragma unroll
+  for (int a = 0; a < MAXD; ++a) {
+    e0[a] = a < d ? g[a] / gn : 0.f;                  // MPPI.py:126
+    dot += e0[a] * vhat[a];                           // MPPI.py:129
+  }
+  s.dots[st] = dot;
+  // S3 modulation coefficients (MPPI.py:132,149-155)
+  const float l_vel = gsigmoid(dot, 0.f, 1.f, -0.5f, 10.f);
+  const float l_n = gsigmoid(dist, 0.f, 1.f, 0.05f, 100.f);
+  const float l_tau = gsigmoid(dist, 5.f, 1.f, 0.05f, 100.f);
+  const float l_nv = l_vel * 1.f + (1.f - l_vel) * l_n;
+
+  // S4 RBF policy (policy.py:186-199, MPPI.py:165-186)
+#pragma unroll
+  for (int a = 0; a < MAXD; ++a) u[a] = 0.f;
+  for (int k = 0; k < s.nk; ++k) {
+    const float* mu = s.mu + ((size_t)i * NKMAX + k) * d;
+    float acc = 0.f;
+    if (s.p == 2.f) {
+#pragma unroll
+      for (int a = 0; a < MAXD; ++a)
+        if (a < d) { const float df = q[a] - mu[a]; acc += df * df; }
+      acc = sqrtf(acc);
+    } else {
+#pragma unroll
+      for (int a = 0; a < MAXD; ++a)
+        if (a < d) acc += powf(fabsf(q[a] - mu[a]), s.p);
+      acc = powf(acc, 1.f / s.p);
+    }
+    const float num = acc * acc;                       // norm ** 2
+    const float phi = expf(-s.sigma[(size_t)i * NKMAX + k] * num);
+    s.kval[st * NKMAX + k] = phi;                      // MPPI.py:184
+    const float* al = s.alpha + ((size_t)i * NKMAX + k) * d;
+#pragma unroll
+    for (int a = 0; a < MAXD; ++a)
+      if (a < d) u[a] += al[a] * phi;                  // MPPI.py:174-177
+  }
+  // activations (MPPI.py:191-196)
+  float ga = 0.f;
+#pragma unroll
+  for (int a = 0; a < MAXD; ++a)
+    if (a < d) ga += sqrtf(fabsf(q[a] - s.goal[a]));
+  ga = ga * ga;                                        // (sum |x|^0.5)^(1/0.5)
+  ga = fminf(fmaxf(ga, 0.f), 1.f);
+  if (ga < 0.5f) ga = 0.f;
+  const float act = (1.f - l_n) * (1.f - l_vel) * ga;
+  s.acts[st] = act;
+  // total velocity and modulation M = l_tau I + (l_nv - l_tau) e0 e0^T  (MPPI.py:158-161,197-209)
+  float proj = 0.f;
+#pragma unroll
+  for (int a = 0; a < MAXD; ++a) {
+    vt[a] = v[a] + act * u[a] * vn;
+    proj += e0[a] * vt[a];
+  }
+  ss = 0.f;
+#pragma unroll
+  for (int a = 0; a < MAXD; ++a) {
+    m[a] = l_tau * vt[a] + (l_nv - l_tau) * e0[a] * proj;
+    if (a >= d) m[a] = 0.f;
+    ss += m[a] * m[a];
+  }
+  float mn = sqrtf(ss);
+  if (mn <= 0.5f) mn = 1.f;                            // MPPI.py:211-212
+  const bool coll = dist < 0.f;
+#pragma unroll
+  for (int a = 0; a < MAXD; ++a) {
+    float mv = nan_to_num(m[a] / mn);                  // MPPI.py:213
+    if (coll) mv = mv * 0.1f + e0[a] * vn * 0.1f;      // MPPI.py:215-217
+    m[a] = mv;
+  }
+  if (s.t < s.H) {
+#pragma unroll
+    for (int a = 0; a < MAXD; ++a)
+      if (a < d) s.traj[(st + 1) * d + a] = q[a] + s.dt * m[a];   // MPPI.py:220-221
+  }
+  if (s.t == 1) {
+#pragma unroll
+    for (int a = 0; a < MAXD; ++a)
+      if (a < d) s.qdot[(size_t)i * d + a] = m[a];                // MPPI.py:222-223
+  }
+}
+
+__global__ void init_traj_kernel(const float* __restrict__ q_cur, int is_batch, int N, int H, int d,
+                                 float* __restrict__ traj) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= N * d) return;
+  const int i = idx / d, a = idx - i * d;
+  traj[(size_t)i * H * d + a] = is_batch ? q_cur[idx] : q_cur[a];   // MPPI.py:99
+}
+
+// ------------------------------------------------------------------------------------------------
+// Cost (cost.py:13-46) with the terminal forward kinematics (fk_num.py:7-75)
+// ------------------------------------------------------------------------------------------------
+struct CostArgs {
+  int N, H, d;
+  float goal[MAXD], qmin[MAXD], qmax[MAXD];
+  DhTable dh;
+  const float* traj; const float* closest; float* cost;
+};
+
+// link end points P_link = T_{link+1}[:3,3] + T_{link+1}[:3,0] * a_{link+1}
+__device__ __forceinline__ void fk_points(const float* q, int d, const DhTable& dh, float (*pts)[3]) {
+  float Rm[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+  float tv[3] = {0, 0, 0};
+#pragma unroll
+  for (int i = 0; i < MAXD; ++i) {
+    if (i < d) {
+      const float dd = dh.v[i][0], th = dh.v[i][1], aa = dh.v[i][2], al = dh.v[i][3];
+      const float sa = sinf(al), ca = cosf(al), sq = sinf(q[i] + th), cq = cosf(q[i] + th);
+      // modified-DH transform (fk_num.py:17-26)
+      const float A[3][4] = {{cq, -sq, 0.f, aa}, {sq * ca, cq * ca, -sa, -dd * sa}, {sq * sa, cq * sa, ca, dd * ca}};
+      float Rn[3][3], tn[3];
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) Rn[r][c] = Rm[r][0] * A[0][c] + Rm[r][1] * A[1][c] + Rm[r][2] * A[2][c];
+        tn[r] = Rm[r][0] * A[0][3] + Rm[r][1] * A[1][3] + Rm[r][2] * A[2][3] + tv[r];
+      }
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) Rm[r][c] = Rn[r][c];
+        tv[r] = tn[r];
+      }
+      const float an = dh.v[i + 1][2];
+#pragma unroll
+      for (int r = 0; r < 3; ++r) pts[i][r] = Rm[r][0] * an + tv[r];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128) cost_kernel(CostArgs c) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c.N) return;
+  const int d = c.d, H = c.H;
+  const float* tr = c.traj + (size_t)i * H * d;
+  float qT[MAXD], q0[MAXD];
+  float sg = 0.f, s0 = 0.f;
+#pragma unroll
+  for (int a = 0; a < MAXD; ++a) {
+    qT[a] = a < d ? tr[(size_t)(H - 1) * d + a] : 0.f;
+    q0[a] = a < d ? tr[a] : 0.f;
+    const float dg = a < d ? qT[a] - c.goal[a] : 0.f;
+    const float d0 = a < d ? q0[a] - qT[a] : 0.f;
+    sg += dg * dg;
+    s0 += d0 * d0;
+  }
+  const float goal_cost = 10.f * sqrtf(sg);                           // cost.py:14
+  int ncoll = 0, nviol = 0;
+  for (int t = 0; t < H; ++t) {
+    ncoll += c.closest[(size_t)i * H + t] < 0.f ? 1 : 0;              // cost.py:33-34
+    for (int a = 0; a < d; ++a) {
+      const float x = tr[(size_t)t * d + a];
+      nviol += (x < c.qmin[a]) ? 1 : 0;
+      nviol += (x > c.qmax[a]) ? 1 : 0;                               // cost.py:36-39
+    }
+  }
+  const float coll_cost = 100.f * (float)ncoll;
+  const float jl_cost = 100.f * (nviol > 0 ? 1.f : 0.f);
+  float inv = 1.f / sqrtf(s0);
+  if (isnan(inv)) inv = 0.f;                                          // nan_to_num(0): nan -> 0,
+  else if (isinf(inv)) inv = inv > 0.f ? FLT_MAX : -FLT_MAX;          // +-inf -> +-FLT_MAX
+  const float stag_cost = 10.f * goal_cost * inv;                     // cost.py:17,41-43
+  float pT[MAXD][3], pG[MAXD][3];
+  fk_points(qT, d, c.dh, pT);
+  fk_points(c.goal, d, c.dh, pG);
+  float fk = 0.f;
+#pragma unroll
+  for (int l = 0; l < MAXD; ++l)
+    if (l < d) {
+      const float dx = pT[l][0] - pG[l][0], dy = pT[l][1] - pG[l][1], dz = pT[l][2] - pG[l][2];
+      fk += sqrtf(dx * dx + dy * dy + dz * dz);                        // cost.py:27-31
+    }
+  c.cost[i] = goal_cost + coll_cost + jl_cost + stag_cost + 10.f * fk; // cost.py:21
+}
+
+// ------------------------------------------------------------------------------------------------
+// Householder basis: Q of the unblocked QR (geqr2 + org2r) of [g | e_2 .. e_d], column 0 := g/|g|
+// (MPPI.py:122-127).  One thread per state-step, D compile-time so the d x d tiles stay in registers.
+// ------------------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(128) basis_kernel(const float* __restrict__ grad, long long n,
+                                                    float* __restrict__ basis) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float A[D][D], tau[D], g[D];
+#pragma unroll
+  for (int r = 0; r < D; ++r) {
+    g[r] = grad[i * D + r];
+#pragma unroll
+    for (int c = 0; c < D; ++c) A[r][c] = (r == c) ? 1.f : 0.f;
+  }
+#pragma unroll
+  for (int r = 0; r < D; ++r) A[r][0] = g[r];
+#pragma unroll
+  for (int k = 0; k < D; ++k) {
+    // slarfg
+    const float alpha = A[k][k];
+    float xs = 0.f;
+#pragma unroll
+    for (int r = k + 1; r < D; ++r) xs += A[r][k] * A[r][k];
+    const float xnorm = sqrtf(xs);
+    if (xnorm == 0.f) {
+      tau[k] = 0.f;
+    } else {
+      const float beta = -copysignf(sqrtf(alpha * alpha + xnorm * xnorm), alpha);
+      tau[k] = (beta - alpha) / beta;
+      const float sc = 1.f / (alpha - beta);
+#pragma unroll
+      for (int r = k + 1; r < D; ++r) A[r][k] *= sc;
+      A[k][k] = beta;
+    }
+    // apply H_k to the trailing columns
+#pragma unroll
+    for (int c = k + 1; c < D; ++c) {
+      float w = A[k][c];
+#pragma unroll
+      for (int r = k + 1; r < D; ++r) w += A[r][k] * A[r][c];
+      w *= tau[k];
+      A[k][c] -= w;
+#pragma unroll
+      for (int r = k + 1; r < D; ++r) A[r][c] -= A[r][k] * w;
+    }
+  }
+  // org2r: Q = H_0 ... H_{D-1} applied to I, backwards
+  float Q[D][D];
+#pragma unroll
+  for (int r = 0; r < D; ++r)
+#pragma unroll
+    for (int c = 0; c < D; ++c) Q[r][c] = (r == c) ? 1.f : 0.f;
+#pragma unroll
+  for (int k = D - 1; k >= 0; --k) {
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+      float w = Q[k][c];
+#pragma unroll
+      for (int r = k + 1; r < D; ++r) w += A[r][k] * Q[r][c];
+      w *= tau[k];
+      Q[k][c] -= w;
+#pragma unroll
+      for (int r = k + 1; r < D; ++r) Q[r][c] -= A[r][k] * w;
+    }
+  }
+  float ss = 0.f;
+#pragma unroll
+  for (int r = 0; r < D; ++r) ss += g[r] * g[r];
+  const float gn = sqrtf(ss);
+#pragma unroll
+  for (int r = 0; r < D; ++r) Q[r][0] = g[r] / gn;                    // MPPI.py:126
+  float* out = basis + i * D * D;
+#pragma unroll
+  for (int r = 0; r < D; ++r)
+#pragma unroll
+    for (int c = 0; c < D; ++c) out[r * D + c] = Q[r][c];
+}
+
+// ------------------------------------------------------------------------------------------------
+// Policy update (MPPI.py:331-345, policy.py:88-113) as three reductions
+// ------------------------------------------------------------------------------------------------
+// stats = { sum cost, min cost, argmin, N }.  Single CTA, fixed order => deterministic.
+__global__ void __launch_bounds__(1024) cost_stats_kernel(const float* __restrict__ cost, int N,
+                                                          float* __restrict__ stats) {
+  __shared__ float ssum[32], smin[32];
+  __shared__ int sidx[32];
+  float s = 0.f, mn = FLT_MAX;
+  int mi = 0x7fffffff;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    const float c = cost[i];
+    s += c;
+    if (c < mn || (c == mn && i < mi)) { mn = c; mi = i; }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, off);
+    const float om = __shfl_xor_sync(0xffffffffu, mn, off);
+    const int oi = __shfl_xor_sync(0xffffffffu, mi, off);
+    if (om < mn || (om == mn && oi < mi)) { mn = om; mi = oi; }
+  }
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { ssum[w] = s; smin[w] = mn; sidx[w] = mi; }
+  __syncthreads();
+  if (w == 0) {
+    const int nw = blockDim.x >> 5;
+    s = lane < nw ? ssum[lane] : 0.f;
+    mn = lane < nw ? smin[lane] : FLT_MAX;
+    mi = lane < nw ? sidx[lane] : 0x7fffffff;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, off);
+      const float om = __shfl_xor_sync(0xffffffffu, mn, off);
+      const int oi = __shfl_xor_sync(0xffffffffu, mi, off);
+      if (om < mn || (om == mn && oi < mi)) { mn = om; mi = oi; }
+    }
+    if (lane == 0) { stats[0] = s; stats[1] = mn; stats[2] = (float)mi; stats[3] = (float)N; }
+  }
+}
+
+struct UpdArgs {
+  int N, H, d, nk, owns0, L;
+  const float* cost; const float* kval; const float* acts; const float* mu; const float* sigma; const float* alpha;
+  const float* stats;
+  float* partials;
+};
+
+constexpr int UPD_T = 256;
+constexpr int UPD_E = (1 + NKMAX * (2 * MAXD + 3) + UPD_T - 1) / UPD_T;   // packed elements per thread
+
+// packed = [ sum w | sum w mu (nk*d) | sum w sigma (nk) | sum w alpha (nk*d) | sum_i max_t kv*act (nk) |
+//            mean_t kv[sample 0] (nk) ],  w = exp(-cost / beta),  beta = mean(cost) / 50
+__global__ void __launch_bounds__(UPD_T) update_partial_kernel(UpdArgs u) {
+  const int nk = u.nk, d = u.d, H = u.H;
+  const int o_mu = 1, o_sg = o_mu + nk * d, o_al = o_sg + nk, o_mx = o_al + nk * d, o_b0 = o_mx + nk;
+  const float beta = (u.stats[0] / u.stats[3]) / 50.f;               // MPPI.py:332
+  const float nib = -1.f / beta;
+  float acc[UPD_E];
+#pragma unroll
+  for (int e = 0; e < UPD_E; ++e) acc[e] = 0.f;
+  for (int i = blockIdx.x; i < u.N; i += gridDim.x) {
+    const float w = expf(nib * u.cost[i]);                            // MPPI.py:333
+#pragma unroll
+    for (int e = 0; e < UPD_E; ++e) {
+      const int idx = threadIdx.x + e * UPD_T;
+      if (idx >= u.L) break;
+      float val;
+      if (idx == 0) val = w;
+      else if (idx < o_sg) val = w * u.mu[(size_t)i * NKMAX * d + (idx - o_mu)];
+      else if (idx < o_al) val = w * u.sigma[(size_t)i * NKMAX + (idx - o_sg)];
+      else if (idx < o_mx) val = w * u.alpha[(size_t)i * NKMAX * d + (idx - o_al)];
+      else if (idx < o_b0) {
+        const int k = idx - o_mx;
+        float mx = -FLT_MAX;
+        for (int t = 0; t < H; ++t)
+          mx = fmaxf(mx, u.kval[((size_t)i * H + t) * NKMAX + k] * u.acts[(size_t)i * H + t]);   // MPPI.py:336
+        val = mx;
+      } else {
+        val = 0.f;
+        if (i == 0 && u.owns0) {
+          const int k = idx - o_b0;
+          float sm = 0.f;
+          for (int t = 0; t < H; ++t) sm += u.kval[(size_t)t * NKMAX + k];
+          val = sm / (float)H;                                        // MPPI.py:341
+        }
+      }
+      acc[e] += val;
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < UPD_E; ++e) {
+    const int idx = threadIdx.x + e * UPD_T;
+    if (idx < u.L) u.partials[(size_t)blockIdx.x * u.L + idx] = acc[e];
+  }
+}
+
+__global__ void update_block_sum_kernel(const float* __restrict__ partials, int blocks, int L,
+                                        float* __restrict__ packed) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= L) return;
+  float s = 0.f;
+  for (int b = 0; b < blocks; ++b) s += partials[(size_t)b * L + idx];
+  packed[idx] = s;
+}
+
+__global__ void update_finalize_kernel(const float* __restrict__ packed, int nk, int d, float n_global,
+                                       float ker_thr, float rate, float* __restrict__ mu_c,
+                                       float* __restrict__ sigma_c, float* __restrict__ alpha_c,
+                                       int* __restrict__ n_updated) {
+  const int o_mu = 1, o_sg = o_mu + nk * d, o_al = o_sg + nk, o_mx = o_al + nk * d, o_b0 = o_mx + nk;
+  const float wsum = packed[0];
+  int cnt = 0;
+  for (int k = threadIdx.x; k < nk; k += blockDim.x) {
+    const bool on = (packed[o_mx + k] / n_global > ker_thr) && (packed[o_b0 + k] > ker_thr);   // MPPI.py:338-342
+    const float r = on ? rate : 0.f;                                   // policy.py:97-99
+    for (int a = 0; a < d; ++a) {
+      mu_c[k * d + a] = (1.f - r) * mu_c[k * d + a] + r * (packed[o_mu + k * d + a] / wsum);
+      alpha_c[k * d + a] = (1.f - r) * alpha_c[k * d + a] + r * (packed[o_al + k * d + a] / wsum);
+    }
+    sigma_c[k] = (1.f - r) * sigma_c[k] + r * (packed[o_sg + k] / wsum);
+    cnt += on ? 1 : 0;
+  }
+  __shared__ int total;
+  if (threadIdx.x == 0) total = 0;
+  __syncthreads();
+  if (cnt) atomicAdd(&total, cnt);
+  __syncthreads();
+  if (threadIdx.x == 0) n_updated[0] = total;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// host launchers
+// ------------------------------------------------------------------------------------------------
+#define LAUNCH_CHECK(c)              \
+  do {                               \
+    CUDA_TRY(cudaGetLastError());    \
+    (c)->launches++;                 \
+  } while (0)
+
+int launch_rank_dense(dsmppi_ctx* c, int n, int K, cudaStream_t st) {
+  const int threads = 128, warps = threads / 32;
+  rank_kernel<<<(n + warps - 1) / warps, threads, 0, st>>>(c->m_rows, nullptr, nullptr, nullptr, c->M, n, K, c->sel);
+  LAUNCH_CHECK(c);
+  return 0;
+}
+
+int launch_select_candidates(dsmppi_ctx* c, int n, int K, float band, cudaStream_t st) {
+  CUDA_TRY(cudaMemsetAsync(c->counters, 0, sizeof(int), st));   // row counter only; stats accumulate
+  const int threads = 128, warps = threads / 32;
+  select_candidates_kernel<<<(n + warps - 1) / warps, threads, 0, st>>>(
+      c->mdist, c->M, n, K, band, c->cand_cnt, c->row_base, c->row_sample, c->row_obs, c->counters);
+  LAUNCH_CHECK(c);
+  return 0;
+}
+
+int launch_rank_candidates(dsmppi_ctx* c, int n, int K, cudaStream_t st) {
+  const int threads = 128, warps = threads / 32;
+  rank_kernel<<<(n + warps - 1) / warps, threads, 0, st>>>(c->m_rows, c->row_base, c->cand_cnt, c->row_obs, c->M, n,
+                                                          K, c->sel);
+  LAUNCH_CHECK(c);
+  return 0;
+}
+
+int launch_blend(dsmppi_ctx* c, int n, int K, float* dist_out, float* grad_out, cudaStream_t st) {
+  blend_kernel<<<(n + 127) / 128, 128, 0, st>>>(c->sel_dist, c->sel_grad, n, K, c->d, dist_out, grad_out);
+  LAUNCH_CHECK(c);
+  return 0;
+}
+
+int launch_init_traj(dsmppi_ctx* c, const dsmppi_rollout_args* a, cudaStream_t st) {
+  const int total = a->N * c->d;
+  init_traj_kernel<<<(total + 255) / 256, 256, 0, st>>>(a->q_cur_dev, a->q_cur_is_batch, a->N, a->H, c->d,
+                                                       a->all_traj_dev);
+  LAUNCH_CHECK(c);
+  return 0;
+}
+
+int launch_step(dsmppi_ctx* c, const dsmppi_rollout_args* a, int t, cudaStream_t st) {
+  StepArgs s;
+  s.N = a->N; s.H = a->H; s.d = c->d; s.t = t; s.nk = a->n_kernels; s.K = a->n_closest;
+  s.dt = a->dt; s.dst_thr = a->dst_thr; s.lin_thr = a->lin_thr; s.p = a->rbf_p;
+  for (int i = 0; i < MAXD; ++i) s.goal[i] = a->q_goal[i];
+  s.sel_dist = c->sel_dist; s.sel_grad = c->sel_grad;
+  s.mu = a->mu_tmp_dev; s.sigma = a->sigma_tmp_dev; s.alpha = a->alpha_tmp_dev;
+  s.traj = a->all_traj_dev; s.closest = a->closest_dist_all_dev; s.kval = a->kernel_val_all_dev;
+  s.dots = a->dot_products_dev; s.acts = a->kernel_activations_dev; s.qdot = a->qdot_dev;
+  s.grads = a->nn_grad_all_dev;
+  step_kernel<<<(a->N + 127) / 128, 128, 0, st>>>(s);
+  LAUNCH_CHECK(c);
+  return 0;
+}
+
+int launch_cost(dsmppi_ctx* c, const dsmppi_cost_args* a, cudaStream_t st) {
+  CostArgs k;
+  k.N = a->N; k.H = a->H; k.d = c->d;
+  for (int i = 0; i < MAXD; ++i) { k.goal[i] = a->q_goal[i]; k.qmin[i] = a->q_min[i]; k.qmax[i] = a->q_max[i]; }
+  k.dh = c->dh;
+  k.traj = a->all_traj_dev; k.closest = a->closest_dist_all_dev; k.cost = a->cost_dev;
+  cost_kernel<<<(a->N + 127) / 128, 128, 0, st>>>(k);
+  LAUNCH_CHECK(c);
+  return 0;
+}
+
+int launch_basis(dsmppi_ctx* c, const float* grad, int64_t n, float* basis, cudaStream_t st) {
+  const unsigned grid = (unsigned)((n + 127) / 128);
+  if (n <= 0) return 0;
+  switch (c->d) {
+#define CASE(D) case D: basis_kernel<D><<<grid, 128, 0, st>>>(grad, (long long)n, basis); break;
+    CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8)
+#undef CASE
+    default: dsmppi_set_error("unsupported n_dof"); return 2;
+  }
+  LAUNCH_CHECK(c);
+  return 0;
+}
+
+int launch_cost_stats(dsmppi_ctx* c, const float* cost, int N, float* stats, cudaStream_t st) {
+  cost_stats_kernel<<<1, 1024, 0, st>>>(cost, N, stats);
+  LAUNCH_CHECK(c);
+  return 0;
+}
+
+int launch_update_partial(dsmppi_ctx* c, const dsmppi_update_args* a, const float* stats, float* packed,
+                          cudaStream_t st) {
+  UpdArgs u;
+  u.N = a->N; u.H = a->H; u.d = c->d; u.nk = a->n_kernels; u.owns0 = a->owns_sample0;
+  u.L = dsmppi_update_packed_len(a->n_kernels, c->d);
+  u.cost = a->cost_dev; u.kval = a->kernel_val_all_dev; u.acts = a->kernel_activations_dev;
+  u.mu = a->mu_tmp_dev; u.sigma = a->sigma_tmp_dev; u.alpha = a->alpha_tmp_dev; u.stats = stats;
+  u.partials = c->upd_partials;
+  int blocks = c->upd_blocks;
+  if (blocks > a->N) blocks = a->N;
+  if (blocks < 1) blocks = 1;
+  update_partial_kernel<<<blocks, UPD_T, 0, st>>>(u);
+  LAUNCH_CHECK(c);
+  update_block_sum_kernel<<<(u.L + 127) / 128, 128, 0, st>>>(c->upd_partials, blocks, u.L, packed);
+  LAUNCH_CHECK(c);
+  return 0;
+}
+
+int launch_update_finalize(dsmppi_ctx* c, const dsmppi_update_args* a, const float* packed, int* n_updated,
+                           cudaStream_t st) {
+  update_finalize_kernel<<<1, 64, 0, st>>>(packed, a->n_kernels, c->d, (float)a->N_global, a->ker_thr, a->upd_rate,
+                                          a->mu_c_dev, a->sigma_c_dev, a->alpha_c_dev, n_updated);
+  LAUNCH_CHECK(c);
+  return 0;
+}

@@ -1,0 +1,44 @@
+"""Builds product MPPI objects (optimalmodulationds_b200) from golden-case dictionaries."""
+import torch
+
+from optimalmodulationds_b200 import MPPI, LinDS
+from optimalmodulationds_b200.sdf.robot_sdf import RobotSdfCollisionNet
+from tests.golden_util import full_policy, load_weights
+
+NET_SHAPES = {"planar2": (2, 2), "planar7": (7, 7), "franka": (7, 9)}
+
+
+def make_net(name):
+    dof, out = NET_SHAPES[name]
+    net = RobotSdfCollisionNet(in_channels=dof + 3, out_channels=out, layers=[256] * 4, skips=[])
+    W, b = load_weights(name)
+    net.load_arrays(W, b)
+    return net
+
+
+def make_mppi(c, device="cpu", H=None, N=None, q_cur=None, pass1="exact", copy_policy=True):
+    """device: where the CALLER's tensors live ('cpu' like the reference's scripts, or 'cuda')."""
+    dev = torch.device(device)
+    t = lambda x: x.to(dev)  # noqa: E731
+    N = int(c["N"]) if N is None else N
+    H = int(c["H"]) if H is None else H
+    net = make_net(c["net"])
+    DS = [LinDS(t(c["qf"])), LinDS(t(c["q0"]))]
+    m = MPPI(t(c["q0"]), t(c["qf"]), t(c["dh_params"]), t(c["obs"]), float(c["dt"]), H, N, DS, t(c["dh_a"]), net,
+             int(c["K"]))
+    m.set_pass1_mode(pass1)
+    m.Policy.p = float(c["p"])
+    m.dst_thr = float(c["dst_thr"])
+    m.ker_thr = float(c["ker_thr"])
+    m.ignored_links = c["ignored_links"].tolist()
+    m.Cost.q_min, m.Cost.q_max = t(c["q_min"]), t(c["q_max"])
+    nk = int(c["nk"])
+    P = m.Policy
+    P.n_kernels = nk
+    P.mu_c.copy_(t(c["mu_c0"])); P.sigma_c.copy_(t(c["sigma_c0"])); P.alpha_c.copy_(t(c["alpha_c0"]))
+    if copy_policy and N == int(c["N"]):
+        P.mu_tmp.copy_(t(full_policy(c, "mu_tmp", N)))
+        P.sigma_tmp.copy_(t(full_policy(c, "sigma_tmp", N)))
+        P.alpha_tmp.copy_(t(full_policy(c, "alpha_tmp", N)))
+    m.q_cur = t(c["q_cur"]) if q_cur is None else t(q_cur)
+    return m

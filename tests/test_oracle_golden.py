@@ -92,6 +92,7 @@ STABLE_FULL_HORIZON = ["planar2", "planar2_nk0", "field2", "franka_shelf", "fran
 
 def check(a, b, rtol, atol, name, min_frac=0.99, loose=20):
     f = frac_within(a, b, rtol, atol)
+    min_frac = min(min_frac, 1.0 - 1.0 / max(a.numel(), 1)) if min_frac < 1.0 else 1.0   # always allow one outlier
     assert f >= min_frac, f"{name}: only {f:.4f} within rtol={rtol}"
     assert frac_within(a, b, loose * rtol, loose * atol) == 1.0, f"{name}: outliers beyond {loose}x tolerance"
 
