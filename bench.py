@@ -1,0 +1,372 @@
+#!/usr/bin/env python
+"""bench.py -- MPPI rollout state-steps/s (samples x horizon per MPPI iteration) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl reference]
+
+A "step" is one MPPI iteration of the hot path (propagate + get_cost + shift_policy_means; sampling the
+policy noise is excluded) over one batch of synthetic input.  Default workload =
+BASELINE.json configs[2] / the metric's named config: Franka Panda 7-DoF, shelf point cloud of 2064 spheres
+("~2k points"), 4096 samples x 50 steps per GPU (weak scaling; configs[4] is the same sharded), K = 5,
+10 policy kernels, shipped Franka checkpoint (tests/golden/weights/franka.npz).
+
+Prints ONE JSON line (rank 0).  `value` = whole-job state-steps/s with inputs resident in HBM, CUDA-event
+timed, max over ranks; `e2e` = the same through the C ABI host-buffer entry point with pinned host tensors
+(H2D + D2H inside the timed region); `roofline` = tensor-core prefilter kernel vs the measured bf16 peak;
+`cpu_baseline` = the oracle port (torch CPU, all host threads) on a bounded sample.
+`--impl reference` times that CPU port alone (the reference is pure Python/torch and is not shipped to
+the GPU box; the oracle restates it op for op -- oracle/mppi_oracle.py).
+"""
+import argparse
+import json
+import math
+import os
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (net, shelf n_pts or None, N per GPU, H, K, nk, dt, dst_thr, ker_thr, alpha_s, sigma, ignored)
+    "franka_shelf_2064": dict(net="franka", n_pts=32, N=4096, H=50, K=5, nk=10, dt=0.5, dst_thr=0.01, ker_thr=0.1,
+                              alpha_s=3.0, sigma=1.0, ignored=[0, 1, 2]),
+    "franka_shelf_294": dict(net="franka", n_pts=12, N=4096, H=50, K=5, nk=10, dt=0.5, dst_thr=0.01, ker_thr=0.1,
+                             alpha_s=3.0, sigma=1.0, ignored=[0, 1, 2]),
+    "planar7": dict(net="planar7", n_pts=None, N=1000, H=30, K=1, nk=10, dt=0.3, dst_thr=0.25, ker_thr=1e-3,
+                    alpha_s=0.75, sigma=0.5, ignored=[]),
+}
+
+
+def shelf(n_pts):
+    """Shelf point cloud of the reference's obstacle streamer (obstacleStreamer.py:87-108), restated."""
+    r = 0.03
+    length = max(1, 2 * n_pts - 2) * r * 1.5
+    posA = torch.tensor([0.45, 0.0, 0.15 + length, r])
+    posB = posA + torch.tensor([length / 3, 0.0, 0.0, 0.0])
+    line = posA + torch.linspace(0, 1, n_pts // 2).reshape(-1, 1) * (posB - posA)
+    out = line
+    span = torch.linspace(0, 1, n_pts).reshape(-1, 1)
+    for s in line:
+        down = s + span * (torch.tensor([0, 0, -length, 0]))
+        left = s + torch.tensor([0, -length / 2, -length / 2, 0])
+        right = s + torch.tensor([0, length / 2, -length / 2, 0])
+        lr = left + span * (right - left)
+        out = torch.vstack((out, down, lr, lr + torch.tensor([0, 0, length / 2, 0]),
+                            lr + torch.tensor([0, 0, -length / 2, 0])))
+    return out
+
+
+def problem(name):
+    w = WORKLOADS[name]
+    pi = math.pi
+    if w["net"] == "franka":
+        dh_a = torch.tensor([0, 0, 0, 0.0825, -0.0825, 0, 0.088, 0])
+        dh_d = torch.tensor([0.333, 0, 0.316, 0, 0.384, 0, 0, 0.107])
+        dh_alpha = torch.tensor([0, -pi / 2, pi / 2, pi / 2, -pi / 2, pi / 2, pi / 2, 0])
+        dh = torch.vstack((dh_d, dh_a * 0, dh_a, dh_alpha)).T.contiguous()
+        q0 = torch.tensor([-0.88, 0.38, 0.5, -1, 0.45, 1.9, 0.31])
+        qf = torch.tensor([-1.24, 1.53, 1.22, -1.21, -0.21, 1.55, 0.08])
+        obs = shelf(w["n_pts"])
+        qlim = (torch.tensor([-2.8973, -1.7628, -2.8973, -3.0718, -2.8973, -0.0175, -2.8973]),
+                torch.tensor([2.8973, 1.7628, 2.8973, -0.0698, 2.8973, 3.7525, 2.8973]))
+        dof, out = 7, 9
+    else:
+        dof, out = 7, 7
+        dh_a = torch.zeros(dof + 1); dh_a[1:] = 1
+        dh = torch.vstack((dh_a * 0, dh_a * 0, dh_a, dh_a * 0)).T.contiguous()
+        q0 = torch.zeros(dof); q0[0] = pi / 2
+        qf = torch.zeros(dof); qf[0] = -pi / 2
+        obs = torch.tensor([[6, 2, 0, .5], [4., -1, 0, .5], [5, 0, 0, .5], [6, 6, 6, .1]])
+        qlim = (-3.2 * torch.ones(dof), 3.2 * torch.ones(dof))
+    return dict(w, dof=dof, out=out, dh=dh, dh_a=dh_a, q0=q0, qf=qf, obs=obs, qlim=qlim)
+
+
+def flops_per_state_step(p):
+    d, O, M, K = p["dof"], p["out"], p["obs"].shape[0], p["K"]
+    f_fwd = 2 * (3 * (d + 3) * 256 + 3 * 256 * 256 + 256 * O)
+    f_bwd = 2 * (3 * 256 * 256 + 3 * (d + 3) * 256)
+    return f_fwd, f_bwd, M * f_fwd + K * (f_fwd + f_bwd)
+
+
+def load_net_arrays(name):
+    import numpy as np
+    path = os.path.join(ROOT, "tests", "golden", "weights", name + ".npz")
+    if os.path.exists(path):
+        z = np.load(path)
+        return [torch.from_numpy(z[f"W{i}"]) for i in range(5)], [torch.from_numpy(z[f"b{i}"]) for i in range(5)], "shipped"
+    torch.manual_seed(0)
+    d, O = (7, 9) if name == "franka" else (7, 7)
+    dims = [3 * (d + 3), 256, 256, 256, 256, O]
+    lin = [torch.nn.Linear(dims[i], dims[i + 1]) for i in range(5)]
+    return [l.weight.detach() for l in lin], [l.bias.detach() for l in lin], "random-init"
+
+
+def seeded_policy(p, N, seed):
+    """nk kernels pre-placed along q0 + 0.1 k and one Gaussian draw of the weights."""
+    g = torch.Generator().manual_seed(seed)
+    nk, d = p["nk"], p["dof"]
+    mu_c = torch.zeros(50, d); sigma_c = torch.zeros(50); alpha_c = torch.zeros(50, d)
+    for k in range(nk):
+        mu_c[k] = p["q0"] + 0.1 * k
+    sigma_c[:nk] = p["sigma"]
+    alpha_c[:nk] = 0.5 * torch.randn(nk, d, generator=g)
+    mu_tmp = torch.zeros(N, 50, d); sigma_tmp = torch.zeros(N, 50); alpha_tmp = torch.zeros(N, 50, d)
+    mu_tmp[:, :nk] = mu_c[:nk]
+    sigma_tmp[:, :nk] = sigma_c[:nk]
+    alpha_tmp[:, :nk] = alpha_c[:nk] + p["alpha_s"] * torch.randn(N, nk, d, generator=g)
+    alpha_tmp[0, :nk] = alpha_c[:nk]
+    return mu_c, sigma_c, alpha_c, mu_tmp, sigma_tmp, alpha_tmp
+
+
+# ---------------------------------------------------------------------------------------- CPU arm
+def cpu_port_rate(p, target_seconds, steps=1, warmup=0):
+    """state-steps/s of the oracle port (torch CPU, all host threads) on a bounded sample of the workload."""
+    from oracle import mppi_oracle as orc
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    W, b, _ = load_net_arrays(p["net"])
+    net = orc.Net(W, b)
+    prm = lambda H: orc.RolloutParams(dt=p["dt"], dt_H=H, n_closest_obs=p["K"], dst_thr=p["dst_thr"],  # noqa: E731
+                                      ignored_links=p["ignored"], p=2.0, with_basis=False)
+
+    def one(N, H, seed):
+        mu_c, sigma_c, alpha_c, mu, sg, al = seeded_policy(p, N, seed)
+        t0 = time.perf_counter()
+        o = orc.rollout(net, p["q0"], p["qf"], p["obs"], mu, sg, al, p["nk"], prm(H), N)
+        cost = orc.evaluate_costs(o.all_traj, o.closest_dist_all, p["qf"], p["dh"], p["qlim"][0], p["qlim"][1])
+        orc.policy_update(cost, o.kernel_val_all, o.kernel_activations, mu, sg, al, mu_c, sigma_c, alpha_c, p["nk"],
+                          p["ker_thr"])
+        return time.perf_counter() - t0
+
+    one(4, 1, 0)                                   # thread-pool / allocator warm-up
+    t = one(8, 2, 1)
+    rate = 16 / t
+    H = min(p["H"], 10)
+    N = int(max(8, min(p["N"], rate * target_seconds / H)))
+    for _ in range(warmup):
+        one(N, H, 2)
+    times = [one(N, H, 3 + i) for i in range(steps)]
+    t = sum(times) / len(times)
+    return dict(value=N * H / t, ms_per_step=t * 1e3, cores=cores, N=N, H=H,
+                sample=f"{N} samples x {H} steps of the same workload (M={p['obs'].shape[0]}, K={p['K']}, "
+                       f"nk={p['nk']}), propagate+cost+update, torch CPU {cores} threads")
+
+
+# ---------------------------------------------------------------------------------------- clocks
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:  # noqa: BLE001
+            self.nv = None
+
+    NAMES = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+             0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x10: "sync_boost"}
+
+    def run(self):
+        if self.nv is None:
+            return
+        while not self.stop_flag:
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                mask = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, name in self.NAMES.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return dict(sm_mhz=(s[len(s) // 2] if s else None), sm_max_mhz=self.max_mhz, reasons=sorted(self.reasons),
+                    samples=len(s))
+
+
+# ---------------------------------------------------------------------------------------- GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="franka_shelf_2064", choices=sorted(WORKLOADS))
+    ap.add_argument("--samples", type=int, default=0, help="samples per GPU (default: the workload's)")
+    ap.add_argument("--pass1", default="auto", choices=["auto", "exact", "tc_f16", "tc_bf16"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    p = problem(args.workload)
+    if args.samples:
+        p["N"] = args.samples
+    N, H = p["N"], p["H"]
+    M = p["obs"].shape[0]
+    f_fwd, f_bwd, f_step = flops_per_state_step(p)
+    config = dict(workload=args.workload, robot="franka_panda_7dof" if p["net"] == "franka" else "planar_7dof",
+                  n_obstacles=M, samples_per_gpu=N, horizon=H, n_closest_obs=p["K"], n_kernels=p["nk"],
+                  weights="tests/golden/weights (shipped checkpoint)", sharding=f"samples x{world}",
+                  l2="flushed between timed steps (256 MiB write, outside the per-step event pairs)")
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        K = max(1, args.steps)
+        r = cpu_port_rate(p, target_seconds=max(2.0, 60.0 / (K + args.warmup)), steps=K, warmup=min(args.warmup, 1))
+        line = dict(metric="mppi_rollout_state_steps_per_sec", value=r["value"], unit="state-steps/s", n_gpus=0,
+                    steps=K, warmup=min(args.warmup, 1), ms_per_step=r["ms_per_step"], higher_is_better=True,
+                    scaling="weak", vs_baseline=None, dtype="f32", data="synthetic", config=config, impl="reference",
+                    cpu_baseline=dict(value=r["value"], unit="state-steps/s", cores=r["cores"], kind="port",
+                                      sample=r["sample"]),
+                    e2e=dict(value=r["value"], unit="state-steps/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+        print(json.dumps(line))
+        return
+
+    import torch.distributed as dist
+    from optimalmodulationds_b200 import MPPI, LinDS
+    from optimalmodulationds_b200.sdf.robot_sdf import RobotSdfCollisionNet
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    W, b, wsrc = load_net_arrays(p["net"])
+    config["weights"] = wsrc
+    net = RobotSdfCollisionNet(in_channels=p["dof"] + 3, out_channels=p["out"], layers=[256] * 4, skips=[])
+    net.load_arrays(W, b)
+    t = lambda x: x.to(dev)  # noqa: E731
+    DS = [LinDS(t(p["qf"])), LinDS(t(p["q0"]))]
+    mppi = MPPI(t(p["q0"]), t(p["qf"]), t(p["dh"]), t(p["obs"]), p["dt"], H, N, DS, t(p["dh_a"]), net, p["K"])
+    mppi.set_pass1_mode(args.pass1)
+    mppi.dst_thr, mppi.ker_thr, mppi.ignored_links = p["dst_thr"], p["ker_thr"], list(p["ignored"])
+    mppi.Cost.q_min, mppi.Cost.q_max = t(p["qlim"][0]), t(p["qlim"][1])
+    if world > 1:
+        mppi.enable_sample_sharding()
+    mu_c, sigma_c, alpha_c, mu_tmp, sigma_tmp, alpha_tmp = seeded_policy(p, N, 100 + rank)
+    P = mppi.Policy
+    P.n_kernels = p["nk"]
+    P.mu_c.copy_(t(mu_c)); P.sigma_c.copy_(t(sigma_c)); P.alpha_c.copy_(t(alpha_c))
+    P.mu_tmp.copy_(t(mu_tmp)); P.sigma_tmp.copy_(t(sigma_tmp)); P.alpha_tmp.copy_(t(alpha_tmp))
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
+
+    def step():
+        mppi.propagate()
+        mppi.get_cost()
+        mppi.shift_policy_means()
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    sync_all()
+    mppi.enable_kernel_timing(True)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = mppi.launch_count()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kt_ms, kt_n = 0.0, 0
+    sync_all()
+    for a, bq in evs:
+        flush.fill_(1.0)
+        a.record()
+        step()
+        bq.record()
+        bq.synchronize()
+        kt = mppi.kernel_timing()
+        key = "pass1" if kt["pass1_launches"] else "exact"
+        kt_ms += kt[key + "_ms"] * kt[key + "_launches"]
+        kt_n += kt[key + "_launches"]
+    sync_all()
+    total_ms = sum(a.elapsed_time(bq) for a, bq in evs)
+    launches = mppi.launch_count() - launches0
+    sampler.stop_flag = True
+    sampler.join()
+    ms = torch.tensor([total_ms / args.steps], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_per_step = float(ms)
+    value = world * N * H / (ms_per_step * 1e-3)
+    stats = mppi.pass1_stats()
+    mppi.enable_kernel_timing(False)
+
+    # ---- e2e: the same iteration through the C ABI with pinned HOST buffers (H2D + D2H inside the timed region)
+    pin = lambda x: x.contiguous().pin_memory()  # noqa: E731
+    d = p["dof"]
+    host = dict(q_cur=pin(p["q0"]), mu_tmp=pin(mu_tmp), sigma_tmp=pin(sigma_tmp), alpha_tmp=pin(alpha_tmp),
+                mu_c=pin(mu_c), sigma_c=pin(sigma_c), alpha_c=pin(alpha_c),
+                all_traj=pin(torch.empty(N, H, d)), closest_dist_all=pin(torch.empty(N, H)),
+                kernel_val_all=pin(torch.zeros(N, H, 50)), dot_products=pin(torch.empty(N, H)),
+                kernel_activations=pin(torch.empty(N, H)), qdot=pin(torch.empty(N, d)), cost=pin(torch.empty(N)),
+                n_updated=pin(torch.zeros(1, dtype=torch.int32)))
+    saved = mppi._shard
+    mppi._shard = None            # the host-buffer entry point is a single-GPU call: every rank runs its own shard
+    for _ in range(2):
+        h2d, d2h = mppi.iteration_host(host)
+    sync_all()
+    e_steps = max(2, min(args.steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(e_steps):
+        h2d, d2h = mppi.iteration_host(host)
+    torch.cuda.synchronize(dev)
+    e_ms = torch.tensor([(time.perf_counter() - t0) * 1e3 / e_steps], device=dev)
+    if world > 1:
+        dist.all_reduce(e_ms, op=dist.ReduceOp.MAX)
+    mppi._shard = saved
+    e2e_value = world * N * H / (float(e_ms) * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:  # noqa: BLE001
+        pass
+    peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+    peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (measured)" if peaks else "fallback 1.4 PFLOP/s sustained"
+    mode = {0: "exact_fp32", 1: "tc_f16", 2: "tc_bf16"}.get(stats["mode"], str(stats["mode"]))
+    if stats["mode"] == 0:
+        peak_tf, peak_src = 74.0, "FFMA nominal 74 TFLOP/s (fp32 scoring kernel; no tensor cores in this mode)"
+    kern_ms = kt_ms / max(kt_n, 1)
+    achieved = (N * M * f_fwd) / (kern_ms * 1e-3) / 1e12 if kern_ms > 0 else 0.0
+    roofline = dict(bound="tensor", kernel="tc_pass1_kernel" if stats["mode"] else "exact_mlp_kernel<fwd>",
+                    achieved=achieved, peak=peak_tf, unit="TFLOP/s", frac=achieved / peak_tf, traffic=None,
+                    peak_source=peak_src, flops_per_launch=N * M * f_fwd, ms_per_launch=kern_ms, launches_timed=kt_n,
+                    share_of_step=kern_ms * H / ms_per_step)
+    line = dict(metric="mppi_rollout_state_steps_per_sec", value=value, unit="state-steps/s", n_gpus=world,
+                steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=ms_per_step, higher_is_better=True,
+                scaling="weak", vs_baseline=None, dtype="f32 (obstacle-ranking prefilter: f16 tcgen05, f32 accumulate)",
+                data="synthetic", config=dict(config, pass1=mode, rescored_pairs_per_state_step=stats[
+                    "rescored_pairs"] / (N * H), band_overflows=stats["band_overflows"],
+                    flops_per_state_step=f_step),
+                clocks=sampler.summary(),
+                e2e=dict(value=e2e_value, unit="state-steps/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
+                         ms_per_step=float(e_ms), api="dsmppi_iteration_host (C ABI, pinned host buffers)"),
+                gpu_launches=launches, roofline=roofline,
+                ms_per_mppi_iteration=ms_per_step)
+    if world == 1 and not args.no_cpu_baseline:
+        r = cpu_port_rate(p, target_seconds=15.0)
+        line["cpu_baseline"] = dict(value=r["value"], unit="state-steps/s", cores=r["cores"], kind="port",
+                                    sample=r["sample"])
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

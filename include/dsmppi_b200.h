@@ -131,6 +131,11 @@ int dsmppi_rollout(dsmppi_ctx* ctx, const dsmppi_rollout_args* args, void* strea
 int dsmppi_distance_grad(dsmppi_ctx* ctx, const float* q_dev, int32_t n, int32_t n_closest,
                          uint32_t ignored_link_mask, float* distance_dev, float* nn_grad_dev, void* stream);
 
+/* Test hook: the per-pair masked minimum link distance of pass 1 (MPPI.py:235-243), (n, M) row-major, from
+ * the fp32 path (mode = DSMPPI_PASS1_EXACT_FP32) or the tensor-core prefilter (TC_F16 / TC_BF16). */
+int dsmppi_debug_pass1(dsmppi_ctx* ctx, const float* q_dev, int32_t n, uint32_t ignored_link_mask, int32_t mode,
+                       float* out_dev, void* stream);
+
 /* The Householder basis the reference stores in MPPI.norm_basis (MPPI.py:122-127), from the blended
  * gradients: grad (n, d) -> basis (n, d, d). */
 int dsmppi_norm_basis(dsmppi_ctx* ctx, const float* grad_dev, int64_t n, float* basis_dev, void* stream);

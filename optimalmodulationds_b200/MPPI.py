@@ -389,6 +389,34 @@ class MPPI:
         self._last_stats = stats
         return 0, n_upd.to(self.tensor_args['device'])[0].to(torch.int64)
 
+    def iteration_host(self, host):
+        """One whole MPPI iteration through the C ABI's host-buffer entry point (dsmppi_iteration_host):
+        `host` is a dict of CPU tensors (ideally pinned) -- inputs q_cur, mu_tmp, sigma_tmp, alpha_tmp, in/out
+        mu_c, sigma_c, alpha_c, outputs all_traj, closest_dist_all, kernel_val_all, dot_products,
+        kernel_activations, qdot, cost, n_updated (int32).  Returns (h2d_bytes, d2h_bytes)."""
+        N, H, d = self.N_traj, self.dt_H, self.n_dof
+        P = self.Policy
+        a = _capi.IterationHostArgs()
+        dummy = torch.empty(1, device=self._dev)
+        out = {k: dummy for k in ('all_traj', 'closest', 'kval', 'dots', 'acts', 'qdot', 'grads')}
+        r = self._rollout_args(N, H, int(P.n_kernels), host['q_cur'], dummy, dummy, dummy, out)
+        a.rollout = r
+        qmin = torch.as_tensor(self.Cost.q_min).reshape(-1).float()
+        qmax = torch.as_tensor(self.Cost.q_max).reshape(-1).float()
+        for i in range(d):
+            a.q_min[i], a.q_max[i] = float(qmin[i]), float(qmax[i])
+        a.ker_thr, a.upd_rate = float(self.ker_thr), float(self.policy_upd_rate)
+        for name in ('q_cur', 'mu_tmp', 'sigma_tmp', 'alpha_tmp', 'mu_c', 'sigma_c', 'alpha_c', 'all_traj',
+                     'closest_dist_all', 'kernel_val_all', 'dot_products', 'kernel_activations', 'qdot', 'cost',
+                     'n_updated'):
+            t = host[name]
+            assert t.device.type == 'cpu' and t.is_contiguous(), name
+            setattr(a, name + '_host', t.data_ptr())
+        with torch.cuda.device(self._dev):
+            self._upload_obstacles()
+            _capi.check(self._lib.dsmppi_iteration_host(self._ctx, _capi.C.byref(a), self._stream()))
+        return int(a.h2d_bytes), int(a.d2h_bytes)
+
     def update_obstacles(self, obs):
         self.obs = obs
         self.n_obs = obs.shape[0]
@@ -403,6 +431,17 @@ class MPPI:
         _capi.check(self._lib.dsmppi_pass1_stats(self._ctx, _capi.C.byref(a), _capi.C.byref(b), _capi.C.byref(m),
                                                  self._stream()))
         return dict(rescored_pairs=a.value, band_overflows=b.value, mode=m.value)
+
+    def debug_pass1(self, q, mode='exact'):
+        """Test hook: (n, M) masked minimum link distances of pass 1 from the fp32 or the tensor-core path."""
+        code = {'exact': _capi.PASS1_EXACT_FP32, 'tc_f16': _capi.PASS1_TC_F16, 'tc_bf16': _capi.PASS1_TC_BF16}[mode]
+        qd = self._d(q)
+        with torch.cuda.device(self._dev):
+            obs = self._upload_obstacles()
+            out = torch.empty(qd.shape[0], obs.shape[0], device=self._dev)
+            _capi.check(self._lib.dsmppi_debug_pass1(self._ctx, qd.data_ptr(), int(qd.shape[0]), self._ignore_mask(),
+                                                     code, out.data_ptr(), self._stream()))
+        return out
 
     def enable_kernel_timing(self, on=True):
         _capi.check(self._lib.dsmppi_enable_kernel_timing(self._ctx, 1 if on else 0))

@@ -160,7 +160,8 @@ int dsmppi_ctx_create(dsmppi_ctx** out, const dsmppi_net* net, const float* dh_p
 int dsmppi_ctx_destroy(dsmppi_ctx* c) {
   if (!c) return 0;
   cudaSetDevice(c->device);
-  void* ptrs[] = {c->weights_blob, c->tc_blob, c->obs, c->obs_enc, c->q_work, c->m_rows, c->mdist, c->enc_q,
+  tc_free_images(c);
+  void* ptrs[] = {c->weights_blob, c->obs, c->obs_enc, c->q_work, c->m_rows, c->mdist, c->enc_q,
                   c->cand_obs, c->cand_cnt, c->row_base, c->row_sample, c->row_obs, c->counters, c->sel,
                   c->sel_dist, c->sel_grad, c->dist_tmp, c->grad_tmp, c->upd_partials, c->stats_tmp,
                   c->packed_tmp, c->stage};
@@ -225,7 +226,10 @@ static int distance_pipeline(dsmppi_ctx* c, const float* q, int q_stride, int n,
     if (timing_mark(c, 1, st)) return 1;
     if (tc_pass1(c, q, q_stride, n, ignore_mask, mode, st)) return 1;
     if (timing_mark(c, 1, st)) return 1;
-    if (launch_select_candidates(c, n, K, c->guard_band, st)) return 1;
+    // default guard band = ~2.5x the largest fp16 prefilter error measured on the shipped nets
+    float band = c->guard_band;
+    if (band <= 0.f) band = (c->O == 9 ? 0.006f : 0.05f) * (mode == DSMPPI_PASS1_TC_BF16 ? 6.f : 1.f);
+    if (launch_select_candidates(c, n, K, band, st)) return 1;
     src.mode = ROWS_LIST;
     src.n_rows = n * CAND_MAX;
     src.n_rows_dev = c->counters;
@@ -275,6 +279,33 @@ int dsmppi_distance_grad(dsmppi_ctx* c, const float* q_dev, int32_t n, int32_t n
   CUDA_TRY(cudaSetDevice(c->device));
   if (distance_pipeline(c, q_dev, c->d, n, n_closest, ignored_link_mask, st)) return 1;
   return launch_blend(c, n, n_closest, distance_dev, nn_grad_dev, st);
+}
+
+int dsmppi_debug_pass1(dsmppi_ctx* c, const float* q_dev, int32_t n, uint32_t ignored_link_mask, int32_t mode,
+                       float* out_dev, void* stream) {
+  REQUIRE(c && q_dev && out_dev, "null argument");
+  REQUIRE(c->M >= 1, "obstacles not set");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CUDA_TRY(cudaSetDevice(c->device));
+  const int saved = c->pass1_mode;
+  c->pass1_mode = mode;
+  c->ws_n = c->ws_M = 0;
+  const int rc = ensure_workspace(c, n, c->M);
+  c->pass1_mode = saved;
+  if (rc) return rc;
+  const size_t bytes = (size_t)n * c->M * sizeof(float);
+  if (mode == DSMPPI_PASS1_EXACT_FP32) {
+    RowSrc src{};
+    src.mode = ROWS_DENSE; src.M = c->M; src.n_rows = n * c->M;
+    if (launch_exact_forward(c, q_dev, c->d, src, ignored_link_mask, c->m_rows, st)) return 1;
+    CUDA_TRY(cudaMemcpyAsync(out_dev, c->m_rows, bytes, cudaMemcpyDeviceToDevice, st));
+  } else {
+    REQUIRE(c->tc_blob, "tensor-core path unavailable for this network");
+    if (tc_pass1(c, q_dev, c->d, n, ignored_link_mask, mode, st)) return 1;
+    CUDA_TRY(cudaMemcpyAsync(out_dev, c->mdist, bytes, cudaMemcpyDeviceToDevice, st));
+  }
+  c->ws_n = c->ws_M = 0;   // the next rollout re-sizes for its own mode
+  return 0;
 }
 
 int dsmppi_norm_basis(dsmppi_ctx* c, const float* grad_dev, int64_t n, float* basis_dev, void* stream) {

@@ -76,7 +76,7 @@ struct dsmppi_ctx {
   size_t tc_blob_bytes = 0;
   // obstacles
   float* obs = nullptr; int obs_cap = 0;
-  void* obs_enc = nullptr;            // tensor path: per-obstacle packed encodings
+  void* obs_enc = nullptr; size_t obs_enc_cap = 0;   // tensor path: per-obstacle packed encodings
   // workspace (grown on demand)
   int ws_n = 0, ws_M = 0;
   float* q_work = nullptr;            // (n, d) states of the current step
@@ -84,7 +84,7 @@ struct dsmppi_ctx {
   size_t m_rows_cap = 0;
   float* mdist = nullptr;             // tensor path: approximate (n, M)
   size_t mdist_cap = 0;
-  void* enc_q = nullptr;              // tensor path: per-sample packed encodings
+  void* enc_q = nullptr; size_t enc_q_cap = 0;       // tensor path: per-sample packed encodings
   int* cand_obs = nullptr;            // (n, CAND_MAX)
   int* cand_cnt = nullptr;            // (n)
   int* row_base = nullptr;            // (n)
@@ -118,6 +118,7 @@ int launch_exact_fwdbwd(dsmppi_ctx* c, const float* q, int q_stride, const RowSr
                         float* sel_grad, cudaStream_t st);
 // tc_pass1.cu
 int tc_build_images(dsmppi_ctx* c, const dsmppi_net* net);
+void tc_free_images(dsmppi_ctx* c);
 int tc_set_obstacles(dsmppi_ctx* c, cudaStream_t st);
 int tc_pass1(dsmppi_ctx* c, const float* q, int q_stride, int n, uint32_t ignore_mask, int mode, cudaStream_t st);
 // rollout_kernels.cu

@@ -1,8 +1,627 @@
-// placeholder: the tcgen05 prefilter is added in a later commit; until then every mode resolves to fp32.
+// Tensor-core prefilter for obstacle ranking (pass 1 of MPPI.distance_repulsion_nn, MPPI.py:231-247).
+//
+// Every (sample, obstacle) pair is pushed through the 5-layer distance MLP on the 5th-generation tensor
+// cores (tcgen05.mma, kind::f16, fp32 accumulation in TMEM) to get an APPROXIMATE masked minimum link
+// distance; the exact fp32 path (exact_mlp.cu) then re-scores only the obstacles inside a guard band of
+// the K-th smallest, so the final ranking, distances and gradients are fp32-exact.
+//
+// Design (B200, one CTA pair per TPC, persistent):
+//   * cta_group::2 MMAs with M = 256 (128 pair-rows per CTA): each CTA keeps HALF of every weight matrix
+//     resident in shared memory for the whole kernel (16 + 3*64 + 8 KB of fp16 + 4 KB of biases = 220 KB),
+//     loaded once with bulk TMA copies (cp.async.bulk, UBLKCP) -- no weight traffic afterwards.
+//   * activations never touch shared memory or HBM: the A operand of every layer lives in TMEM
+//     (tcgen05.mma "ts" form); the epilogue warps read the fp32 accumulator with tcgen05.ld, add bias, ReLU,
+//     convert to fp16 pairs and write the next layer's A operand back with tcgen05.st.
+//   * TMEM (512 columns): A operands of two row tiles X,Y (2 x 128 columns) + two 128-column accumulator
+//     halves D_lo/D_hi shared by both tiles.  While the epilogue warps of X drain D_lo/D_hi, the tensor core
+//     already works on Y, so in steady state the MMA pipe never waits for an epilogue.
+//   * layer 1 consumes [enc_hi | enc_lo] (two fp16 halves of the fp32 encoding, K = 64) so the only
+//     quantisation is in weights/activations; the per-sample and per-obstacle parts of the encoding are
+//     pre-packed (128 B each) and OR-ed together per pair.
+//   * warp roles: warps 0-3 rows of tile X, warps 4-7 rows of tile Y (TMEM lane quarter = warp % 4),
+//     warp 8 = TMEM allocator + weight loader + MMA issuer (one elected thread, leader CTA only).
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
 #include "internal.cuh"
-int tc_build_images(dsmppi_ctx* c, const dsmppi_net*) { c->tc_blob = nullptr; return 0; }
-int tc_set_obstacles(dsmppi_ctx*, cudaStream_t) { return 0; }
-int tc_pass1(dsmppi_ctx*, const float*, int, int, uint32_t, int, cudaStream_t) {
-  dsmppi_set_error("tensor-core pass 1 not built");
-  return 3;
+
+namespace {
+
+constexpr int ROWS = 128;                 // pair-rows per CTA per tile slot
+constexpr int K0 = 64;                    // layer-1 K: 32 "hi" + 32 "lo" halves of the encoding
+constexpr int NROWTHREADS = 256;          // 8 row warps
+constexpr int NTHREADS = NROWTHREADS + 32;
+
+// ---- shared-memory map (bytes); the weight part is a verbatim copy of the per-CTA global image
+constexpr int OFF_W1 = 0;                          // 2 halves x (64 rows x K0) fp16
+constexpr int SZ_W1H = 64 * K0 * 2;                // 8 KB per half
+constexpr int OFF_WH = OFF_W1 + 2 * SZ_W1H;        // layers 2..4: 3 x 2 halves x (64 rows x 256) fp16
+constexpr int SZ_WHH = 64 * HID * 2;               // 32 KB per half
+constexpr int OFF_W5 = OFF_WH + 3 * 2 * SZ_WHH;    // output layer: 16 rows x 256 fp16
+constexpr int SZ_W5 = 16 * HID * 2;                // 8 KB
+constexpr int OFF_BIAS = OFF_W5 + SZ_W5;           // 4 x 256 fp32 + 16 fp32
+constexpr int SZ_BIAS = (4 * HID + 16) * 4;
+constexpr int IMG_BYTES = OFF_BIAS + SZ_BIAS;      // 225344
+constexpr int OFF_BAR = IMG_BYTES;                 // mbarriers (8 B each)
+constexpr int NBAR = 12;
+constexpr int OFF_TMEMPTR = OFF_BAR + NBAR * 8;
+constexpr int SMEM_BYTES = OFF_TMEMPTR + 16;
+static_assert(IMG_BYTES % 16 == 0, "bulk copies need 16-byte granularity");
+static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB shared-memory budget");
+
+// barrier indices
+enum { BAR_W = 0, BAR_AREADY0 = 1, BAR_AREADY1 = 2, BAR_DFREE0 = 3, BAR_DFREE1 = 4,
+       BAR_DFULL00 = 5, BAR_DFULL01 = 6, BAR_DFULL10 = 7, BAR_DFULL11 = 8 };
+
+// TMEM columns
+constexpr uint32_t TM_A0 = 0, TM_A1 = 128, TM_DLO = 256, TM_DHI = 384;
+
+// debug switches for bring-up (env DSMPPI_TC_FLAGS): alternative readings of the operand layouts
+enum { F_SWAP_LBO_SBO = 1, F_SWAP_CTA_HALVES = 2, F_SWAP_PACK = 4 };
+
+struct TcImages {
+  uint8_t* img[2];        // device images, one per CTA rank
+  int flags;
+  int fmt_bf16;           // 0: fp16, 1: bf16
+};
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Spin with a watchdog: a protocol bug must surface as a trapped kernel, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("tc_pass1: mbarrier timeout (block %d thread %d bar-offset %u parity %u)\n", blockIdx.x, threadIdx.x,
+             bar, parity);
+      __trap();
+    }
+  }
+}
+// arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar),
+      "r"(rank)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc_512(uint32_t dst_smem) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(dst_smem) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_free_512(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(taddr) : "memory");
+}
+
+// D[tmem] (+)= A[tmem] * B[smem]^T, M = 256 over the CTA pair, issued by one thread of the leader CTA
+__device__ __forceinline__ void mma_ts_2cta(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// completion of all MMAs issued so far by this thread -> arrive on the barrier at this offset in BOTH CTAs
+__device__ __forceinline__ void mma_commit_2cta(uint32_t bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+      "h"((uint16_t)3)
+      : "memory");
+}
+
+#define R8(v, o) "=r"(v[o + 0]), "=r"(v[o + 1]), "=r"(v[o + 2]), "=r"(v[o + 3]), "=r"(v[o + 4]), "=r"(v[o + 5]), "=r"(v[o + 6]), "=r"(v[o + 7])
+#define W8(v, o) "r"(v[o + 0]), "r"(v[o + 1]), "r"(v[o + 2]), "r"(v[o + 3]), "r"(v[o + 4]), "r"(v[o + 5]), "r"(v[o + 6]), "r"(v[o + 7])
+
+// 32 consecutive accumulator columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : R8(v, 0), R8(v, 8), R8(v, 16), R8(v, 24)
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : R8(v, 0), R8(v, 8)
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%32], "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31};" ::
+          W8(v, 0), W8(v, 8), W8(v, 16), W8(v, 24), "r"(taddr)
+      : "memory");
+}
+
+template <bool BF16>
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  uint32_t r;
+  if (BF16) asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  else asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
+// K-major, no-swizzle UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor, version 1)
+__device__ __forceinline__ uint64_t make_b_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;   // descriptor version (Blackwell)
+  return d;                 // base_offset 0, lbo_mode 0, layout_type 0 = SWIZZLE_NONE
+}
+__host__ __device__ constexpr uint32_t make_idesc(int fmt /*0 f16, 1 bf16*/, int M, int N) {
+  return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);   // fp32 accumulate, K-major A and B, dense
+}
+
+// ------------------------------------------------------------------------------------------------
+// Encoding tables: per sample / per obstacle 64 halves = [hi(32) | lo(32)] of enc = [x, sin x, cos x]
+// with zeros at the positions the other table fills (row operand = bitwise OR of the two)
+// ------------------------------------------------------------------------------------------------
+template <bool BF16>
+__device__ __forceinline__ void split_store(uint16_t* row, int pos, float v) {
+  if (BF16) {
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+    row[pos] = __bfloat16_as_ushort(h);
+    row[32 + pos] = __bfloat16_as_ushort(l);
+  } else {
+    const __half h = __float2half_rn(v);
+    const __half l = __float2half_rn(v - __half2float(h));
+    row[pos] = __half_as_ushort(h);
+    row[32 + pos] = __half_as_ushort(l);
+  }
+}
+
+template <bool BF16>
+__global__ void encode_kernel(const float* __restrict__ x, int x_stride, int x_off, int n, int ncomp, int comp0, int nin,
+                              uint16_t* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint16_t row[64];
+#pragma unroll
+  for (int k = 0; k < 64; ++k) row[k] = 0;
+  for (int c = 0; c < ncomp; ++c) {
+    const float v = x[(size_t)i * x_stride + x_off + c];
+    split_store<BF16>(row, comp0 + c, v);
+    split_store<BF16>(row, nin + comp0 + c, sinf(v));
+    split_store<BF16>(row, 2 * nin + comp0 + c, cosf(v));
+  }
+  uint4* o = reinterpret_cast<uint4*>(out + (size_t)i * 64);
+  const uint4* r = reinterpret_cast<const uint4*>(row);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) o[k] = r[k];
+}
+
+// ------------------------------------------------------------------------------------------------
+// The prefilter kernel
+// ------------------------------------------------------------------------------------------------
+struct TcArgs {
+  const uint8_t* img0; const uint8_t* img1;    // per-CTA-rank weight images
+  const uint4* encq; const uint4* encp;        // (n, 8) and (M, 8) uint4
+  const float* obs;                            // (M, 4)
+  float* mdist;                                // (n * M)
+  long long n_rows;                            // n * M
+  int M, O;
+  uint32_t ignore_mask;
+  float inv_scale_div;                         // 100 for the 9-link net else 1
+  int flags;
+};
+
+template <bool BF16>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_pass1_kernel(TcArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bar0 = sbase + OFF_BAR;
+  auto BAR = [&](int i) { return bar0 + (uint32_t)i * 8u; };
+  const float* bias = reinterpret_cast<const float*>(smem + OFF_BIAS);
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + OFF_TMEMPTR);
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+
+  // ---- one-time setup: barriers, TMEM, resident weights
+  if (warp == 8) {
+    if (lane == 0) {
+      mbar_init(BAR(BAR_W), 1);
+      mbar_init(BAR(BAR_AREADY0), 8);     // 4 row warps x 2 CTAs (used in the leader CTA)
+      mbar_init(BAR(BAR_AREADY1), 8);
+      mbar_init(BAR(BAR_DFREE0), 8);
+      mbar_init(BAR(BAR_DFREE1), 8);
+      for (int i = BAR_DFULL00; i <= BAR_DFULL11; ++i) mbar_init(BAR(i), 1);   // tcgen05.commit arrives
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    tmem_alloc_512(smem_u32((const void*)tmem_ptr_smem));
+    if (lane == 0) {
+      const uint8_t* img = rank == 0 ? a.img0 : a.img1;
+      mbar_expect_tx(BAR(BAR_W), IMG_BYTES);
+      constexpr int CH = 32768;
+      for (int off = 0; off < IMG_BYTES; off += CH) {
+        const int n = IMG_BYTES - off < CH ? IMG_BYTES - off : CH;
+        bulk_g2s(sbase + off, img + off, n, BAR(BAR_W));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  mbar_wait(BAR(BAR_W), 0);            // this CTA's weights have landed
+  cluster_sync_all();                  // ... and so have the peer's; barrier inits visible cluster-wide
+
+  const long long n_tiles = (a.n_rows + 2 * ROWS - 1) / (2 * ROWS);     // 256 pair-rows per tile
+
+  if (warp < 8) {
+    // =================================== row warps ===================================
+    const int slot = warp >> 2;                          // 0: tile X, 1: tile Y
+    const int row = ((warp & 3) << 5) | lane;            // TMEM lane == row within the CTA's 128
+    const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t tA = tmem_base + lane_addr + (slot ? TM_A1 : TM_A0);
+    const uint32_t tD[2] = {tmem_base + lane_addr + TM_DLO, tmem_base + lane_addr + TM_DHI};
+    const uint32_t bar_aready = BAR(slot ? BAR_AREADY1 : BAR_AREADY0);
+    const uint32_t bar_dfull[2] = {BAR(slot ? BAR_DFULL10 : BAR_DFULL00), BAR(slot ? BAR_DFULL11 : BAR_DFULL01)};
+    const uint32_t bar_dfree[2] = {BAR(BAR_DFREE0), BAR(BAR_DFREE1)};
+    uint32_t ph_full[2] = {0, 0};
+    const bool swap_pack = (a.flags & F_SWAP_PACK) != 0;
+
+    // builds the layer-1 operand of row `r` (or zeros) and publishes it
+    auto stage_input = [&](long long r) {
+      uint32_t v[32];
+      if (r < a.n_rows) {
+        const long long i = r / a.M;
+        const int j = (int)(r - i * a.M);
+        const uint4* eq = a.encq + i * 8;
+        const uint4* ep = a.encp + (size_t)j * 8;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint4 x = __ldg(eq + k), y = __ldg(ep + k);
+          v[4 * k + 0] = x.x | y.x; v[4 * k + 1] = x.y | y.y; v[4 * k + 2] = x.z | y.z; v[4 * k + 3] = x.w | y.w;
+        }
+        if (swap_pack) {
+#pragma unroll
+          for (int k = 0; k < 32; ++k) v[k] = (v[k] >> 16) | (v[k] << 16);
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 32; ++k) v[k] = 0u;
+      }
+      tmem_st32(tA, v);
+      tc_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(bar_aready, 0);
+    };
+
+    long long tile = (long long)slot * npairs + pair;              // first tile of this slot
+    long long r_cur = tile * (2 * ROWS) + (long long)rank * ROWS + row;
+    if ((long long)pair < n_tiles) stage_input(tile < n_tiles ? r_cur : a.n_rows);
+    for (long long it = 0;; ++it) {
+      const long long tX = (it * 2) * npairs + pair;
+      if (tX >= n_tiles) break;
+      // hidden layers 1..4 (layer index l = 0..3): D_h -> bias, ReLU, fp16 pairs -> next A operand
+#pragma unroll 1
+      for (int l = 0; l < 4; ++l) {
+        uint32_t packed[128];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          mbar_wait(bar_dfull[h], ph_full[h]);
+          ph_full[h] ^= 1;
+          tc_fence_after();
+#pragma unroll
+          for (int cchunk = 0; cchunk < 4; ++cchunk) {
+            uint32_t v[32];
+            tmem_ld32(tD[h] + cchunk * 32, v);
+            tc_wait_ld();
+            const float4* b4 = reinterpret_cast<const float4*>(bias + l * HID + h * 128 + cchunk * 32);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const float4 bb = b4[k];
+              const float f0 = fmaxf(__uint_as_float(v[4 * k + 0]) + bb.x, 0.f);
+              const float f1 = fmaxf(__uint_as_float(v[4 * k + 1]) + bb.y, 0.f);
+              const float f2 = fmaxf(__uint_as_float(v[4 * k + 2]) + bb.z, 0.f);
+              const float f3 = fmaxf(__uint_as_float(v[4 * k + 3]) + bb.w, 0.f);
+              packed[h * 64 + cchunk * 16 + 2 * k + 0] = swap_pack ? pack2<BF16>(f1, f0) : pack2<BF16>(f0, f1);
+              packed[h * 64 + cchunk * 16 + 2 * k + 1] = swap_pack ? pack2<BF16>(f3, f2) : pack2<BF16>(f2, f3);
+            }
+          }
+          // this accumulator half is drained: the tensor core may overwrite it (other tile / next layer)
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(bar_dfree[h], 0);
+        }
+        // both halves complete => every MMA that reads the old A operand has retired: overwrite it
+#pragma unroll
+        for (int cchunk = 0; cchunk < 4; ++cchunk) tmem_st32(tA + cchunk * 32, packed + cchunk * 32);
+        tc_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(bar_aready, 0);
+      }
+      // output layer: 16 columns of D_lo -> masked minimum link distance (MPPI.py:236-242)
+      {
+        mbar_wait(bar_dfull[0], ph_full[0]);
+        ph_full[0] ^= 1;
+        tc_fence_after();
+        uint32_t v[16];
+        tmem_ld16(tD[0], v);
+        tc_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(bar_dfree[0], 0);
+        if (r_cur < a.n_rows && tile < n_tiles) {
+          const int j = (int)(r_cur % a.M);
+          const float rad = __ldg(a.obs + (size_t)j * 4 + 3);
+          float m = 3.0e38f;
+#pragma unroll
+          for (int o = 0; o < 16; ++o) {
+            if (o < a.O) {
+              float y = __uint_as_float(v[o]) + bias[4 * HID + o];
+              y = y / a.inv_scale_div - rad;
+              if ((a.ignore_mask >> o) & 1u) y = 1e6f;
+              m = fminf(m, y);
+            }
+          }
+          a.mdist[r_cur] = m;
+        }
+      }
+      // next tile of this slot
+      tile += 2LL * npairs;
+      r_cur = tile * (2 * ROWS) + (long long)rank * ROWS + row;
+      const long long tX_next = ((it + 1) * 2) * npairs + pair;
+      if (tX_next < n_tiles) stage_input(tile < n_tiles ? r_cur : a.n_rows);
+    }
+  } else if (rank == 0 && lane == 0) {
+    // =================================== MMA issuer (leader CTA, one thread) ===================================
+    const bool swap = (a.flags & F_SWAP_LBO_SBO) != 0;
+    const int fmt = BF16 ? 1 : 0;
+    const uint32_t idesc128 = make_idesc(fmt, 256, 128);
+    const uint32_t idesc32 = make_idesc(fmt, 256, 32);
+    uint32_t ph_a[2] = {0, 0}, ph_free[2] = {0, 0};
+    const uint32_t tAs[2] = {tmem_base + TM_A0, tmem_base + TM_A1};
+    const uint32_t tDs[2] = {tmem_base + TM_DLO, tmem_base + TM_DHI};
+    for (long long it = 0;; ++it) {
+      const long long tX = (it * 2) * npairs + pair;
+      if (tX >= n_tiles) break;
+#pragma unroll 1
+      for (int l = 0; l < 5; ++l) {
+#pragma unroll 1
+        for (int s = 0; s < 2; ++s) {
+          mbar_wait(BAR(s ? BAR_AREADY1 : BAR_AREADY0), ph_a[s]);
+          ph_a[s] ^= 1;
+          tc_fence_after();
+          const int nh = l == 4 ? 1 : 2;
+          for (int h = 0; h < nh; ++h) {
+            mbar_wait(BAR(h ? BAR_DFREE1 : BAR_DFREE0), ph_free[h] ^ 1);
+            ph_free[h] ^= 1;
+            tc_fence_after();
+            uint32_t boff, lbo, ksteps, idesc;
+            if (l == 0) { boff = OFF_W1 + h * SZ_W1H; lbo = 64 * 16; ksteps = K0 / 16; idesc = idesc128; }
+            else if (l < 4) { boff = OFF_WH + ((l - 1) * 2 + h) * SZ_WHH; lbo = 64 * 16; ksteps = HID / 16; idesc = idesc128; }
+            else { boff = OFF_W5; lbo = 16 * 16; ksteps = HID / 16; idesc = idesc32; }
+            const uint32_t sbo = 128;
+            for (uint32_t ks = 0; ks < ksteps; ++ks) {
+              const uint32_t baddr = sbase + boff + ks * 2 * lbo;
+              const uint64_t bdesc = swap ? make_b_desc(baddr, sbo, lbo) : make_b_desc(baddr, lbo, sbo);
+              mma_ts_2cta(tDs[h], tAs[s] + ks * 8, bdesc, idesc, ks > 0 ? 1u : 0u);
+            }
+            mma_commit_2cta(BAR(BAR_DFULL00 + s * 2 + h));
+          }
+        }
+      }
+    }
+  }
+  // ---- teardown
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 8) {
+    __syncwarp();
+    tmem_free_512(tmem_base);
+  }
+}
+
+// host: fp16/bf16 conversion (round to nearest even), no device needed
+uint16_t f2h(float f) {
+  __half h = __float2half_rn(f);
+  uint16_t u;
+  std::memcpy(&u, &h, 2);
+  return u;
+}
+uint16_t f2bf(float f) {
+  __nv_bfloat16 h = __float2bfloat16_rn(f);
+  uint16_t u;
+  std::memcpy(&u, &h, 2);
+  return u;
+}
+
+// canonical K-major no-swizzle placement of element (n, k) inside a slab of `rows` rows:
+//   core matrix = 8 rows x 16 bytes, contiguous 128 B; core matrices of one K-chunk are consecutive (SBO = 128),
+//   K-chunks are rows*16 bytes apart (LBO)
+inline size_t canon(int n, int k, int rows) {
+  return (size_t)(k / 8) * rows * 16 + (size_t)(n / 8) * 128 + (size_t)(n % 8) * 16 + (size_t)(k % 8) * 2;
+}
+
+}  // namespace
+
+int tc_build_images(dsmppi_ctx* c, const dsmppi_net* net) {
+  c->tc_blob = nullptr;
+  if (c->nenc > 32 || c->O > 16) return 0;          // layer-1 operand is fixed at K = 2 x 32; fall back to fp32
+  const char* dis = std::getenv("DSMPPI_DISABLE_TC");
+  if (dis && dis[0] == '1') return 0;
+  const char* fl = std::getenv("DSMPPI_TC_FLAGS");
+  const int flags = fl ? std::atoi(fl) : 0;
+  TcImages* t = new TcImages();
+  t->flags = flags;
+  t->fmt_bf16 = 0;
+  // two formats x two CTA ranks
+  uint8_t* dev = nullptr;
+  if (cudaMalloc(reinterpret_cast<void**>(&dev), (size_t)4 * IMG_BYTES) != cudaSuccess) {
+    dsmppi_set_error("cudaMalloc(tc images) failed");
+    delete t;
+    return 1;
+  }
+  std::vector<uint8_t> host((size_t)4 * IMG_BYTES, 0);
+  const int nenc = c->nenc;
+  for (int fmt = 0; fmt < 2; ++fmt)
+    for (int rank = 0; rank < 2; ++rank) {
+      uint8_t* img = host.data() + (size_t)(fmt * 2 + rank) * IMG_BYTES;
+      auto put = [&](size_t off, float v) {
+        const uint16_t u = fmt ? f2bf(v) : f2h(v);
+        std::memcpy(img + off, &u, 2);
+      };
+      const int r_eff = (flags & F_SWAP_CTA_HALVES) ? 1 - rank : rank;
+      for (int h = 0; h < 2; ++h)
+        for (int n = 0; n < 64; ++n) {
+          const int feat = 128 * h + 64 * r_eff + n;       // output feature held by this CTA in half h
+          // layer 1: K = [hi(32) | lo(32)], both multiply the same weight column
+          for (int k = 0; k < K0; ++k) {
+            const int e = k & 31;
+            const float w = e < nenc ? net->W_host[0][(size_t)feat * nenc + e] : 0.f;
+            put(OFF_W1 + h * SZ_W1H + canon(n, k, 64), w);
+          }
+          for (int l = 1; l < 4; ++l)
+            for (int k = 0; k < HID; ++k)
+              put(OFF_WH + ((l - 1) * 2 + h) * SZ_WHH + canon(n, k, 64), net->W_host[l][(size_t)feat * HID + k]);
+        }
+      for (int n = 0; n < 16; ++n) {
+        const int o = 16 * r_eff + n;                      // N = 32 over the pair: links 0..15 | 16..31 (padding)
+        for (int k = 0; k < HID; ++k)
+          put(OFF_W5 + canon(n, k, 16), o < c->O ? net->W_host[4][(size_t)o * HID + k] : 0.f);
+      }
+      float* bias = reinterpret_cast<float*>(img + OFF_BIAS);
+      for (int l = 0; l < 4; ++l)
+        for (int k = 0; k < HID; ++k) bias[l * HID + k] = net->b_host[l][k];
+      for (int o = 0; o < 16; ++o) bias[4 * HID + o] = o < c->O ? net->b_host[4][o] : 0.f;
+    }
+  CUDA_TRY(cudaMemcpy(dev, host.data(), host.size(), cudaMemcpyHostToDevice));
+  t->img[0] = dev;
+  t->img[1] = nullptr;
+  c->tc_blob = t;
+  c->tc_blob_bytes = host.size();
+  CUDA_TRY(cudaFuncSetAttribute(tc_pass1_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  CUDA_TRY(cudaFuncSetAttribute(tc_pass1_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  if (c->guard_band <= 0.f) c->guard_band = 0.f;
+  return 0;
+}
+
+void tc_free_images(dsmppi_ctx* c) {
+  if (!c->tc_blob) return;
+  TcImages* t = static_cast<TcImages*>(c->tc_blob);
+  if (t->img[0]) cudaFree(t->img[0]);
+  delete t;
+  c->tc_blob = nullptr;
+}
+
+int tc_set_obstacles(dsmppi_ctx* c, cudaStream_t st) {
+  // per-obstacle packed encodings, both formats (fp16 at [0, M), bf16 at [M, 2M))
+  const size_t need = (size_t)2 * c->M * 128;
+  if (need > c->obs_enc_cap) {
+    if (c->obs_enc) CUDA_TRY(cudaFree(c->obs_enc));
+    c->obs_enc = nullptr;
+    CUDA_TRY(cudaMalloc(&c->obs_enc, need));
+    c->obs_enc_cap = need;
+  }
+  uint16_t* out = static_cast<uint16_t*>(c->obs_enc);
+  const int th = 128, bl = (c->M + th - 1) / th;
+  encode_kernel<false><<<bl, th, 0, st>>>(c->obs, 4, 0, c->M, 3, c->d, c->nin, out);
+  encode_kernel<true><<<bl, th, 0, st>>>(c->obs, 4, 0, c->M, 3, c->d, c->nin, out + (size_t)c->M * 64);
+  CUDA_TRY(cudaGetLastError());
+  c->launches += 2;
+  return 0;
+}
+
+int tc_pass1(dsmppi_ctx* c, const float* q, int q_stride, int n, uint32_t ignore_mask, int mode, cudaStream_t st) {
+  REQUIRE(c->tc_blob, "tensor-core images not built");
+  TcImages* t = static_cast<TcImages*>(c->tc_blob);
+  const bool bf16 = mode == DSMPPI_PASS1_TC_BF16;
+  const size_t need = (size_t)n * 128;
+  if (need > c->enc_q_cap) {
+    if (c->enc_q) CUDA_TRY(cudaFree(c->enc_q));
+    c->enc_q = nullptr;
+    CUDA_TRY(cudaMalloc(&c->enc_q, need));
+    c->enc_q_cap = need;
+  }
+  uint16_t* eq = static_cast<uint16_t*>(c->enc_q);
+  const int th = 128, bl = (n + th - 1) / th;
+  if (bf16) encode_kernel<true><<<bl, th, 0, st>>>(q, q_stride, 0, n, c->d, 0, c->nin, eq);
+  else encode_kernel<false><<<bl, th, 0, st>>>(q, q_stride, 0, n, c->d, 0, c->nin, eq);
+  CUDA_TRY(cudaGetLastError());
+  c->launches++;
+  TcArgs a;
+  const uint8_t* base = t->img[0] + (size_t)(bf16 ? 2 : 0) * IMG_BYTES;
+  a.img0 = base;
+  a.img1 = base + IMG_BYTES;
+  a.encq = reinterpret_cast<const uint4*>(eq);
+  a.encp = reinterpret_cast<const uint4*>(static_cast<uint16_t*>(c->obs_enc) + (bf16 ? (size_t)c->M * 64 : 0));
+  a.obs = c->obs;
+  a.mdist = c->mdist;
+  a.n_rows = (long long)n * c->M;
+  a.M = c->M;
+  a.O = c->O;
+  a.ignore_mask = ignore_mask;
+  a.inv_scale_div = (c->O == 9) ? 100.f : 1.f;
+  a.flags = t->flags;
+  const long long n_tiles = (a.n_rows + 2 * ROWS - 1) / (2 * ROWS);
+  long long pairs = c->sm_count / 2;
+  if (pairs > (n_tiles + 1) / 2) pairs = (n_tiles + 1) / 2;     // each pair takes two tiles per iteration
+  if (pairs < 1) pairs = 1;
+  const dim3 grid((unsigned)(2 * pairs));
+  if (bf16) tc_pass1_kernel<true><<<grid, NTHREADS, SMEM_BYTES, st>>>(a);
+  else tc_pass1_kernel<false><<<grid, NTHREADS, SMEM_BYTES, st>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  c->launches++;
+  return 0;
 }

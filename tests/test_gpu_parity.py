@@ -187,6 +187,46 @@ def test_gradient_error_vs_fp64(name, factory):
     assert gpu_err_g <= 4 * ref_err_g + 1e-6 * g64.abs().max().item()
 
 
+def test_tensor_core_prefilter_error_bound(factory):
+    """tcgen05 fp16 pass 1 vs fp32 pass 1 on the Franka shelf: the error must stay well inside the default
+    6 mm guard band (measured max 1.3 mm / 2.3 mm emulated over 2e5 random pairs)."""
+    c = load_npz("case_franka_shelf")
+    m = factory.make_mppi(c, device="cuda", N=32, H=1)
+    torch.manual_seed(0)
+    q = c["q0"].cuda() + 0.5 * torch.randn(700, 7, device="cuda")        # 700*294 rows: ragged last tile
+    ex = m.debug_pass1(q, "exact")
+    for mode, bound in (("tc_f16", 3e-3), ("tc_bf16", 1.8e-2)):
+        tc = m.debug_pass1(q, mode)
+        err = (tc - ex).abs().max().item()
+        print(f"{mode}: max |d_tc - d_fp32| = {err:.3e} m over {ex.numel()} pairs")
+        assert err < bound
+
+
+@pytest.mark.parametrize("tag,N,H", [("franka_shelf", 777, 6), ("franka_shelf_b", 300, 4)])
+def test_tensor_core_mode_is_bitwise_identical_to_fp32_mode(tag, N, H, factory):
+    """The prefilter only prunes; ranking, distances and gradients come from the fp32 path, so a rollout in
+    tc mode must reproduce the fp32-mode rollout BIT FOR BIT (and never overflow the candidate band)."""
+    c = load_npz(f"case_{tag}")
+    torch.manual_seed(5)
+    outs = {}
+    q_cur = c["q0"] + 0.2 * torch.randn(N, 7)
+    for mode in ("exact", "tc_f16"):
+        m = factory.make_mppi(c, device="cuda", N=N, H=H, q_cur=q_cur, pass1=mode, copy_policy=False)
+        P = m.Policy
+        P.alpha_s = 3.0
+        torch.manual_seed(11)
+        P.sample_policy()
+        traj, dist, kv, dots, acts = m.propagate()
+        cost = m.get_cost()
+        outs[mode] = (traj.clone(), dist.clone(), dots.clone(), acts.clone(), cost.clone())
+        if mode == "tc_f16":
+            st = m.pass1_stats()
+            assert st["mode"] == 1 and st["band_overflows"] == 0, st
+            print(f"{tag}: re-scored pairs per state-step = {st['rescored_pairs'] / (N * H):.2f} (K = {int(c['K'])})")
+    for a, b2 in zip(outs["exact"], outs["tc_f16"]):
+        assert torch.equal(a, b2)
+
+
 def test_constructor_rejects_missing_cuda_path(monkeypatch, factory):
     """The product must fail loudly rather than fall back when the shared library is unavailable."""
     from optimalmodulationds_b200 import _capi
