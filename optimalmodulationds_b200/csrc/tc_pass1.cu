@@ -33,8 +33,8 @@ namespace {
 
 constexpr int ROWS = 128;                 // pair-rows per CTA per tile slot
 constexpr int K0 = 64;                    // layer-1 K: 32 "hi" + 32 "lo" halves of the encoding
-constexpr int NROWTHREADS = 256;          // 8 row warps
-constexpr int NTHREADS = NROWTHREADS + 32;
+constexpr int MMA_WARP = 8;               // warps 0..7: rows (2 tile slots x 4 TMEM lane quarters)
+constexpr int NTHREADS = (MMA_WARP + 1) * 32;
 
 // ---- shared-memory map (bytes); the weight part is a verbatim copy of the per-CTA global image
 constexpr int OFF_W1 = 0;                          // 2 halves x (64 rows x K0) fp16
@@ -60,13 +60,8 @@ enum { BAR_W = 0, BAR_AREADY0 = 1, BAR_AREADY1 = 2, BAR_DFREE0 = 3, BAR_DFREE1 =
 // TMEM columns
 constexpr uint32_t TM_A0 = 0, TM_A1 = 128, TM_DLO = 256, TM_DHI = 384;
 
-// debug switches for bring-up (env DSMPPI_TC_FLAGS): alternative readings of the operand layouts
-enum { F_SWAP_LBO_SBO = 1, F_SWAP_CTA_HALVES = 2, F_SWAP_PACK = 4 };
-
 struct TcImages {
   uint8_t* img[2];        // device images, one per CTA rank
-  int flags;
-  int fmt_bf16;           // 0: fp16, 1: bf16
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -110,12 +105,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
   }
 }
-// arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t rank) {
+// arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster.  Only TMEM traffic is
+// ordered through these barriers (tcgen05.fence before/after), so the default .release.cta arrive is enough;
+// the .release.cluster form costs a MEMBAR + ERRBAR per arrival (17% of all stall samples in the first profile).
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) {
   asm volatile(
       "{\n\t.reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar),
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar),
       "r"(rank)
       : "memory");
 }
@@ -174,11 +171,13 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
       : "r"(taddr)
       : "memory");
 }
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* v) {
+template <int OFF, int N>
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[N]) {
+  static_assert(OFF + 32 <= N, "out of range");
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x32.b32 [%32], "
       "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31};" ::
-          W8(v, 0), W8(v, 8), W8(v, 16), W8(v, 24), "r"(taddr)
+          W8(v, OFF + 0), W8(v, OFF + 8), W8(v, OFF + 16), W8(v, OFF + 24), "r"(taddr)
       : "memory");
 }
 
@@ -255,8 +254,24 @@ struct TcArgs {
   int M, O;
   uint32_t ignore_mask;
   float inv_scale_div;                         // 100 for the 9-link net else 1
-  int flags;
 };
+
+// bias + ReLU + fp16/bf16 pair packing of 32 accumulator columns into pk[OFF .. OFF+16)
+template <bool BF16, int OFF>
+__device__ __forceinline__ void relu_pack32(const uint32_t (&v)[32], const float* __restrict__ bias32,
+                                            uint32_t (&pk)[64]) {
+  const float4* b4 = reinterpret_cast<const float4*>(bias32);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float4 bb = b4[k];
+    const float f0 = fmaxf(__uint_as_float(v[4 * k + 0]) + bb.x, 0.f);
+    const float f1 = fmaxf(__uint_as_float(v[4 * k + 1]) + bb.y, 0.f);
+    const float f2 = fmaxf(__uint_as_float(v[4 * k + 2]) + bb.z, 0.f);
+    const float f3 = fmaxf(__uint_as_float(v[4 * k + 3]) + bb.w, 0.f);
+    pk[OFF + 2 * k + 0] = pack2<BF16>(f0, f1);
+    pk[OFF + 2 * k + 1] = pack2<BF16>(f2, f3);
+  }
+}
 
 template <bool BF16>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_pass1_kernel(TcArgs a) {
@@ -273,12 +288,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_pass
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
 
   // ---- one-time setup: barriers, TMEM, resident weights
-  if (warp == 8) {
+  if (warp == MMA_WARP) {
     if (lane == 0) {
       mbar_init(BAR(BAR_W), 1);
-      mbar_init(BAR(BAR_AREADY0), 8);     // 4 row warps x 2 CTAs (used in the leader CTA)
+      mbar_init(BAR(BAR_AREADY0), 8);     // 4 row warps of the slot x 2 CTAs (used in the leader CTA)
       mbar_init(BAR(BAR_AREADY1), 8);
-      mbar_init(BAR(BAR_DFREE0), 8);
+      mbar_init(BAR(BAR_DFREE0), 8);      // 4 draining warps x 2 CTAs
       mbar_init(BAR(BAR_DFREE1), 8);
       for (int i = BAR_DFULL00; i <= BAR_DFULL11; ++i) mbar_init(BAR(i), 1);   // tcgen05.commit arrives
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -304,22 +319,27 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_pass
 
   const long long n_tiles = (a.n_rows + 2 * ROWS - 1) / (2 * ROWS);     // 256 pair-rows per tile
 
-  if (warp < 8) {
+  if (warp < MMA_WARP) {
     // =================================== row warps ===================================
+    // warp = slot*4 + quarter.  Per hidden layer a thread drains its row of D_lo while the tensor core still
+    // computes D_hi (packed fp16 pairs wait in 64 registers), then drains D_hi and rewrites the A operand.
+    // TMEM loads are double-buffered (two 32-column buffers) so their latency overlaps the bias/ReLU/pack math.
     const int slot = warp >> 2;                          // 0: tile X, 1: tile Y
     const int row = ((warp & 3) << 5) | lane;            // TMEM lane == row within the CTA's 128
     const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
     const uint32_t tA = tmem_base + lane_addr + (slot ? TM_A1 : TM_A0);
-    const uint32_t tD[2] = {tmem_base + lane_addr + TM_DLO, tmem_base + lane_addr + TM_DHI};
+    const uint32_t tDlo = tmem_base + lane_addr + TM_DLO, tDhi = tmem_base + lane_addr + TM_DHI;
     const uint32_t bar_aready = BAR(slot ? BAR_AREADY1 : BAR_AREADY0);
-    const uint32_t bar_dfull[2] = {BAR(slot ? BAR_DFULL10 : BAR_DFULL00), BAR(slot ? BAR_DFULL11 : BAR_DFULL01)};
-    const uint32_t bar_dfree[2] = {BAR(BAR_DFREE0), BAR(BAR_DFREE1)};
-    uint32_t ph_full[2] = {0, 0};
-    const bool swap_pack = (a.flags & F_SWAP_PACK) != 0;
+    const uint32_t bar_full_lo = BAR(slot ? BAR_DFULL10 : BAR_DFULL00);
+    const uint32_t bar_full_hi = BAR(slot ? BAR_DFULL11 : BAR_DFULL01);
 
-    // builds the layer-1 operand of row `r` (or zeros) and publishes it
-    auto stage_input = [&](long long r) {
-      uint32_t v[32];
+    auto signal = [&](uint32_t bar) {       // one arrival per warp on the leader CTA's barrier
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(bar, 0);
+    };
+    // layer-1 operand of pair-row r: [enc_hi | enc_lo] = per-sample part OR per-obstacle part
+    auto load_input = [&](long long r, uint32_t (&v)[32]) {
       if (r < a.n_rows) {
         const long long i = r / a.M;
         const int j = (int)(r - i * a.M);
@@ -330,102 +350,101 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_pass
           const uint4 x = __ldg(eq + k), y = __ldg(ep + k);
           v[4 * k + 0] = x.x | y.x; v[4 * k + 1] = x.y | y.y; v[4 * k + 2] = x.z | y.z; v[4 * k + 3] = x.w | y.w;
         }
-        if (swap_pack) {
-#pragma unroll
-          for (int k = 0; k < 32; ++k) v[k] = (v[k] >> 16) | (v[k] << 16);
-        }
       } else {
 #pragma unroll
         for (int k = 0; k < 32; ++k) v[k] = 0u;
       }
-      tmem_st32(tA, v);
-      tc_wait_st();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(bar_aready, 0);
     };
 
-    long long tile = (long long)slot * npairs + pair;              // first tile of this slot
+    long long tile = (long long)slot * npairs + pair;              // this slot's tile in iteration 0
     long long r_cur = tile * (2 * ROWS) + (long long)rank * ROWS + row;
-    if ((long long)pair < n_tiles) stage_input(tile < n_tiles ? r_cur : a.n_rows);
+    if ((long long)pair < n_tiles) {
+      uint32_t v[32];
+      load_input(tile < n_tiles ? r_cur : a.n_rows, v);
+      tmem_st32<0>(tA, v);
+      tc_wait_st();
+      signal(bar_aready);
+    }
     for (long long it = 0;; ++it) {
       const long long tX = (it * 2) * npairs + pair;
       if (tX >= n_tiles) break;
-      // hidden layers 1..4 (layer index l = 0..3): D_h -> bias, ReLU, fp16 pairs -> next A operand
 #pragma unroll 1
       for (int l = 0; l < 4; ++l) {
-        uint32_t packed[128];
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          mbar_wait(bar_dfull[h], ph_full[h]);
-          ph_full[h] ^= 1;
-          tc_fence_after();
-#pragma unroll
-          for (int cchunk = 0; cchunk < 4; ++cchunk) {
-            uint32_t v[32];
-            tmem_ld32(tD[h] + cchunk * 32, v);
-            tc_wait_ld();
-            const float4* b4 = reinterpret_cast<const float4*>(bias + l * HID + h * 128 + cchunk * 32);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              const float4 bb = b4[k];
-              const float f0 = fmaxf(__uint_as_float(v[4 * k + 0]) + bb.x, 0.f);
-              const float f1 = fmaxf(__uint_as_float(v[4 * k + 1]) + bb.y, 0.f);
-              const float f2 = fmaxf(__uint_as_float(v[4 * k + 2]) + bb.z, 0.f);
-              const float f3 = fmaxf(__uint_as_float(v[4 * k + 3]) + bb.w, 0.f);
-              packed[h * 64 + cchunk * 16 + 2 * k + 0] = swap_pack ? pack2<BF16>(f1, f0) : pack2<BF16>(f0, f1);
-              packed[h * 64 + cchunk * 16 + 2 * k + 1] = swap_pack ? pack2<BF16>(f3, f2) : pack2<BF16>(f2, f3);
-            }
-          }
-          // this accumulator half is drained: the tensor core may overwrite it (other tile / next layer)
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(bar_dfree[h], 0);
-        }
-        // both halves complete => every MMA that reads the old A operand has retired: overwrite it
-#pragma unroll
-        for (int cchunk = 0; cchunk < 4; ++cchunk) tmem_st32(tA + cchunk * 32, packed + cchunk * 32);
-        tc_wait_st();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(bar_aready, 0);
-      }
-      // output layer: 16 columns of D_lo -> masked minimum link distance (MPPI.py:236-242)
-      {
-        mbar_wait(bar_dfull[0], ph_full[0]);
-        ph_full[0] ^= 1;
+        const float* bl = bias + l * HID;
+        uint32_t pk[64], va[32], vb[32];
+        // ---- D_lo (features 0..127) while the tensor core is still producing D_hi
+        mbar_wait(bar_full_lo, (uint32_t)((it + l) & 1));          // phase 5*it + l of this slot's D_lo
         tc_fence_after();
-        uint32_t v[16];
-        tmem_ld16(tD[0], v);
+        tmem_ld32(tDlo, va);
+        tmem_ld32(tDlo + 32, vb);
         tc_wait_ld();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(bar_dfree[0], 0);
-        if (r_cur < a.n_rows && tile < n_tiles) {
-          const int j = (int)(r_cur % a.M);
-          const float rad = __ldg(a.obs + (size_t)j * 4 + 3);
-          float m = 3.0e38f;
-#pragma unroll
-          for (int o = 0; o < 16; ++o) {
-            if (o < a.O) {
-              float y = __uint_as_float(v[o]) + bias[4 * HID + o];
-              y = y / a.inv_scale_div - rad;
-              if ((a.ignore_mask >> o) & 1u) y = 1e6f;
-              m = fminf(m, y);
-            }
-          }
-          a.mdist[r_cur] = m;
-        }
+        relu_pack32<BF16, 0>(va, bl, pk);
+        tmem_ld32(tDlo + 64, va);
+        relu_pack32<BF16, 16>(vb, bl + 32, pk);
+        tmem_ld32(tDlo + 96, vb);
+        tc_wait_ld();
+        signal(BAR(BAR_DFREE0));                                    // D_lo drained: the other tile may use it
+        relu_pack32<BF16, 32>(va, bl + 64, pk);
+        relu_pack32<BF16, 48>(vb, bl + 96, pk);
+        // ---- D_hi (features 128..255); its completion also retires every MMA that read the old A operand
+        mbar_wait(bar_full_hi, (uint32_t)(l & 1));                 // phase 4*it + l of this slot's D_hi
+        tc_fence_after();
+        tmem_ld32(tDhi, va);
+        tmem_ld32(tDhi + 32, vb);
+        tmem_st32<0>(tA, pk);
+        tmem_st32<32>(tA + 32, pk);
+        tc_wait_ld();
+        relu_pack32<BF16, 0>(va, bl + 128, pk);
+        tmem_ld32(tDhi + 64, va);
+        relu_pack32<BF16, 16>(vb, bl + 160, pk);
+        tmem_ld32(tDhi + 96, vb);
+        tmem_st32<0>(tA + 64, pk);
+        tc_wait_ld();
+        signal(BAR(BAR_DFREE1));                                    // D_hi drained
+        relu_pack32<BF16, 32>(va, bl + 192, pk);
+        relu_pack32<BF16, 48>(vb, bl + 224, pk);
+        tmem_st32<32>(tA + 96, pk);
+        tc_wait_st();
+        signal(bar_aready);                                         // next layer's A operand is in TMEM
       }
-      // next tile of this slot
-      tile += 2LL * npairs;
-      r_cur = tile * (2 * ROWS) + (long long)rank * ROWS + row;
-      const long long tX_next = ((it + 1) * 2) * npairs + pair;
-      if (tX_next < n_tiles) stage_input(tile < n_tiles ? r_cur : a.n_rows);
+      // ---- prefetch the next tile's layer-1 operand, then the output layer of this one
+      const long long tile_next = tile + 2LL * npairs;
+      const long long r_next = tile_next * (2 * ROWS) + (long long)rank * ROWS + row;
+      const bool more = ((it + 1) * 2) * npairs + pair < n_tiles;
+      uint32_t vin[32];
+      if (more) load_input(tile_next < n_tiles ? r_next : a.n_rows, vin);
+      float rad = 0.f;
+      const bool valid = r_cur < a.n_rows && tile < n_tiles;
+      if (valid) rad = __ldg(a.obs + (size_t)(r_cur % a.M) * 4 + 3);
+      mbar_wait(bar_full_lo, (uint32_t)((it + 4) & 1));
+      tc_fence_after();
+      uint32_t v[16];
+      tmem_ld16(tDlo, v);
+      if (more) tmem_st32<0>(tA, vin);          // the output-layer MMA has retired: A may be overwritten
+      tc_wait_ld();
+      signal(BAR(BAR_DFREE0));
+      if (more) {
+        tc_wait_st();
+        signal(bar_aready);
+      }
+      if (valid) {                           // masked minimum link distance (MPPI.py:236-242)
+        float m = 3.0e38f;
+#pragma unroll
+        for (int o = 0; o < 16; ++o) {
+          if (o < a.O) {
+            float y = __uint_as_float(v[o]) + bias[4 * HID + o];
+            y = y / a.inv_scale_div - rad;
+            if ((a.ignore_mask >> o) & 1u) y = 1e6f;
+            m = fminf(m, y);
+          }
+        }
+        a.mdist[r_cur] = m;
+      }
+      tile = tile_next;
+      r_cur = r_next;
     }
   } else if (rank == 0 && lane == 0) {
     // =================================== MMA issuer (leader CTA, one thread) ===================================
-    const bool swap = (a.flags & F_SWAP_LBO_SBO) != 0;
     const int fmt = BF16 ? 1 : 0;
     const uint32_t idesc128 = make_idesc(fmt, 256, 128);
     const uint32_t idesc32 = make_idesc(fmt, 256, 32);
@@ -454,7 +473,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_pass
             const uint32_t sbo = 128;
             for (uint32_t ks = 0; ks < ksteps; ++ks) {
               const uint32_t baddr = sbase + boff + ks * 2 * lbo;
-              const uint64_t bdesc = swap ? make_b_desc(baddr, sbo, lbo) : make_b_desc(baddr, lbo, sbo);
+              const uint64_t bdesc = make_b_desc(baddr, lbo, sbo);
               mma_ts_2cta(tDs[h], tAs[s] + ks * 8, bdesc, idesc, ks > 0 ? 1u : 0u);
             }
             mma_commit_2cta(BAR(BAR_DFULL00 + s * 2 + h));
@@ -467,7 +486,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_pass
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();
-  if (warp == 8) {
+  if (warp == MMA_WARP) {
     __syncwarp();
     tmem_free_512(tmem_base);
   }
@@ -501,11 +520,7 @@ int tc_build_images(dsmppi_ctx* c, const dsmppi_net* net) {
   if (c->nenc > 32 || c->O > 16) return 0;          // layer-1 operand is fixed at K = 2 x 32; fall back to fp32
   const char* dis = std::getenv("DSMPPI_DISABLE_TC");
   if (dis && dis[0] == '1') return 0;
-  const char* fl = std::getenv("DSMPPI_TC_FLAGS");
-  const int flags = fl ? std::atoi(fl) : 0;
   TcImages* t = new TcImages();
-  t->flags = flags;
-  t->fmt_bf16 = 0;
   // two formats x two CTA ranks
   uint8_t* dev = nullptr;
   if (cudaMalloc(reinterpret_cast<void**>(&dev), (size_t)4 * IMG_BYTES) != cudaSuccess) {
@@ -522,7 +537,7 @@ int tc_build_images(dsmppi_ctx* c, const dsmppi_net* net) {
         const uint16_t u = fmt ? f2bf(v) : f2h(v);
         std::memcpy(img + off, &u, 2);
       };
-      const int r_eff = (flags & F_SWAP_CTA_HALVES) ? 1 - rank : rank;
+      const int r_eff = rank;
       for (int h = 0; h < 2; ++h)
         for (int n = 0; n < 64; ++n) {
           const int feat = 128 * h + 64 * r_eff + n;       // output feature held by this CTA in half h
@@ -613,7 +628,6 @@ int tc_pass1(dsmppi_ctx* c, const float* q, int q_stride, int n, uint32_t ignore
   a.O = c->O;
   a.ignore_mask = ignore_mask;
   a.inv_scale_div = (c->O == 9) ? 100.f : 1.f;
-  a.flags = t->flags;
   const long long n_tiles = (a.n_rows + 2 * ROWS - 1) / (2 * ROWS);
   long long pairs = c->sm_count / 2;
   if (pairs > (n_tiles + 1) / 2) pairs = (n_tiles + 1) / 2;     // each pair takes two tiles per iteration
