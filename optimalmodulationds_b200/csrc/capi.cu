@@ -31,6 +31,8 @@ int alloc(T*& p, size_t n) {
   return 0;
 }
 
+constexpr int FUSE_M_MAX = 16;   // up to this many obstacles the fp32 path differentiates every pair in one launch
+
 int resolved_mode(const dsmppi_ctx* c) {
   int m = c->pass1_mode;
   if (m == DSMPPI_PASS1_AUTO) m = (c->M >= 64 && c->tc_blob) ? DSMPPI_PASS1_TC_F16 : DSMPPI_PASS1_EXACT_FP32;
@@ -62,8 +64,7 @@ int ensure_workspace(dsmppi_ctx* c, int n, int M) {
   if (nn > c->ws_n) {
     if (alloc(c->q_work, (size_t)nn * d) || alloc(c->cand_obs, (size_t)nn * CAND_MAX) || alloc(c->cand_cnt, (size_t)nn) ||
         alloc(c->row_base, (size_t)nn) || alloc(c->sel, (size_t)nn * MAXK) ||
-        alloc(c->sel_dist, (size_t)nn * MAXK) || alloc(c->sel_grad, (size_t)nn * MAXK * d) ||
-        alloc(c->dist_tmp, (size_t)nn) || alloc(c->grad_tmp, (size_t)nn * d))
+        alloc(c->sel_rows, (size_t)nn * MAXK) || alloc(c->dist_tmp, (size_t)nn) || alloc(c->grad_tmp, (size_t)nn * d))
       return 1;
   }
   // rows scored in fp32: dense n*M when the prefilter is off, at most n*CAND_MAX when it is on.  Sized
@@ -72,6 +73,11 @@ int ensure_workspace(dsmppi_ctx* c, int n, int M) {
   size_t rows = (mode == DSMPPI_PASS1_EXACT_FP32) ? (size_t)nn * mm : (size_t)nn * CAND_MAX;
   if (rows < (size_t)nn * CAND_MAX) rows = (size_t)nn * CAND_MAX;
   if (grow(c->m_rows, c->m_rows_cap, rows)) return 1;
+  // rows that get a distance + gradient: all candidates (fused single launch) or the K selected
+  size_t drows = (size_t)nn * CAND_MAX;
+  if (mm <= FUSE_M_MAX && (size_t)nn * mm > drows) drows = (size_t)nn * mm;
+  if (grow(c->row_dist, c->row_dist_cap, drows)) return 1;
+  if (grow(c->row_grad, c->row_grad_cap, drows * d)) return 1;
   cap = c->rowlist_cap;
   if (grow(c->row_sample, cap, (size_t)nn * CAND_MAX)) return 1;
   if (grow(c->row_obs, c->rowlist_cap, (size_t)nn * CAND_MAX)) return 1;
@@ -163,7 +169,7 @@ int dsmppi_ctx_destroy(dsmppi_ctx* c) {
   tc_free_images(c);
   void* ptrs[] = {c->weights_blob, c->obs, c->obs_enc, c->q_work, c->m_rows, c->mdist, c->enc_q,
                   c->cand_obs, c->cand_cnt, c->row_base, c->row_sample, c->row_obs, c->counters, c->sel,
-                  c->sel_dist, c->sel_grad, c->dist_tmp, c->grad_tmp, c->upd_partials, c->stats_tmp,
+                  c->sel_rows, c->row_dist, c->row_grad, c->dist_tmp, c->grad_tmp, c->upd_partials, c->stats_tmp,
                   c->packed_tmp, c->stage};
   for (void* p : ptrs)
     if (p) cudaFree(p);
@@ -203,8 +209,8 @@ int dsmppi_set_obstacles_host(dsmppi_ctx* c, const float* obs_host, int32_t M, v
   return dsmppi_set_obstacles(c, obs_host, M, stream);   // cudaMemcpyDefault handles host sources
 }
 
-// distance + gradient of n states q (row stride q_stride floats) against the current obstacles:
-// fills c->sel_dist (n, K) and c->sel_grad (n, K, d)
+// distance + gradient of n states q (row stride q_stride floats) against the current obstacles: fills
+// c->row_dist / c->row_grad and the ranked row indices c->sel_rows (n, K)
 static int distance_pipeline(dsmppi_ctx* c, const float* q, int q_stride, int n, int K, uint32_t ignore_mask,
                              cudaStream_t st) {
   REQUIRE(c->M >= 1, "obstacles not set");
@@ -215,36 +221,47 @@ static int distance_pipeline(dsmppi_ctx* c, const float* q, int q_stride, int n,
   RowSrc src{};
   src.M = c->M;
   src.K = K;
+  if (mode == DSMPPI_PASS1_EXACT_FP32 && c->M <= FUSE_M_MAX) {
+    // few obstacles: one launch scores AND differentiates every (sample, obstacle) pair
+    src.mode = ROWS_DENSE;
+    src.n_rows = n * c->M;
+    if (timing_mark(c, 0, st)) return 1;
+    if (launch_exact_fwdbwd(c, q, q_stride, src, ignore_mask, c->m_rows, c->row_dist, c->row_grad, st)) return 1;
+    if (timing_mark(c, 0, st)) return 1;
+    return launch_rank_dense(c, n, K, true, st);
+  }
   if (mode == DSMPPI_PASS1_EXACT_FP32) {
+    // many obstacles, no tensor-core prefilter: fp32 forward on every pair, then forward + VJP on the K closest
     src.mode = ROWS_DENSE;
     src.n_rows = n * c->M;
     if (timing_mark(c, 0, st)) return 1;
     if (launch_exact_forward(c, q, q_stride, src, ignore_mask, c->m_rows, st)) return 1;
     if (timing_mark(c, 0, st)) return 1;
-    if (launch_rank_dense(c, n, K, st)) return 1;
-  } else {
-    if (timing_mark(c, 1, st)) return 1;
-    if (tc_pass1(c, q, q_stride, n, ignore_mask, mode, st)) return 1;
-    if (timing_mark(c, 1, st)) return 1;
-    // default guard band = ~2.5x the largest fp16 prefilter error measured on the shipped nets
-    float band = c->guard_band;
-    if (band <= 0.f) band = (c->O == 9 ? 0.006f : 0.05f) * (mode == DSMPPI_PASS1_TC_BF16 ? 6.f : 1.f);
-    if (launch_select_candidates(c, n, K, band, st)) return 1;
-    src.mode = ROWS_LIST;
-    src.n_rows = n * CAND_MAX;
-    src.n_rows_dev = c->counters;
-    src.row_sample = c->row_sample;
-    src.row_obs = c->row_obs;
-    if (launch_exact_forward(c, q, q_stride, src, ignore_mask, c->m_rows, st)) return 1;
-    if (launch_rank_candidates(c, n, K, st)) return 1;
+    if (launch_rank_dense(c, n, K, false, st)) return 1;
+    RowSrc s2{};
+    s2.mode = ROWS_SELECTED;
+    s2.M = c->M;
+    s2.K = K;
+    s2.n_rows = n * K;
+    s2.sel = c->sel;
+    if (launch_exact_fwdbwd(c, q, q_stride, s2, ignore_mask, nullptr, c->row_dist, c->row_grad, st)) return 1;
+    return launch_identity_rows(c, n, K, st);
   }
-  RowSrc s2{};
-  s2.mode = ROWS_SELECTED;
-  s2.M = c->M;
-  s2.K = K;
-  s2.n_rows = n * K;
-  s2.sel = c->sel;
-  return launch_exact_fwdbwd(c, q, q_stride, s2, c->sel_dist, c->sel_grad, st);
+  // tensor-core prefilter -> candidate band -> one fp32 launch (ranking key + distance + gradient) -> rank
+  if (timing_mark(c, 1, st)) return 1;
+  if (tc_pass1(c, q, q_stride, n, ignore_mask, mode, st)) return 1;
+  if (timing_mark(c, 1, st)) return 1;
+  // default guard band = ~2.5x the largest fp16 prefilter error measured on the shipped nets
+  float band = c->guard_band;
+  if (band <= 0.f) band = (c->O == 9 ? 0.006f : 0.05f) * (mode == DSMPPI_PASS1_TC_BF16 ? 6.f : 1.f);
+  if (launch_select_candidates(c, n, K, band, st)) return 1;
+  src.mode = ROWS_LIST;
+  src.n_rows = n * CAND_MAX;
+  src.n_rows_dev = c->counters;
+  src.row_sample = c->row_sample;
+  src.row_obs = c->row_obs;
+  if (launch_exact_fwdbwd(c, q, q_stride, src, ignore_mask, c->m_rows, c->row_dist, c->row_grad, st)) return 1;
+  return launch_rank_candidates(c, n, K, st);
 }
 
 int dsmppi_rollout(dsmppi_ctx* c, const dsmppi_rollout_args* a, void* stream) {

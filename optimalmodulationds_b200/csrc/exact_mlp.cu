@@ -154,19 +154,27 @@ exact_mlp_kernel(NetDev net, RowSrc src, const float* __restrict__ q, int q_stri
     return;
   }
 
-  // ---- pass 2: l* = argmin of the RAW output (robot_sdf.py:155), distance of that link (MPPI.py:265-274)
+  // ---- pass 2: l* = argmin of the RAW output (robot_sdf.py:155), distance of that link (MPPI.py:265-274);
+  //      optionally also the pass-1 ranking key (masked minimum) so one launch serves both passes
   if (tid < R) {
     int best = 0;
     float bv = zs[tid * MAXO];
-    for (int o = 1; o < O; ++o) {
+    float m = 3.0e38f;
+    for (int o = 0; o < O; ++o) {
       const float v = zs[tid * MAXO + o];
       if (v < bv) { bv = v; best = o; }
+      float y = v;
+      if (net.scale != 1.f) y = y / 100.f;
+      y -= rad[tid];
+      if ((ignore_mask >> o) & 1u) y = 1e6f;
+      m = fminf(m, y);
     }
     lst[tid] = best;
     if (row0 + tid < n_rows) {
       float y = bv;
       if (net.scale != 1.f) y = y / 100.f;
       out_dist[row0 + tid] = y - rad[tid];
+      if (out_m) out_m[row0 + tid] = m;
     }
   }
   __syncthreads();
@@ -243,7 +251,7 @@ int launch_exact_forward(dsmppi_ctx* c, const float* q, int q_stride, const RowS
   return launch<false>(c, q, q_stride, src, ignore_mask, m_rows, nullptr, nullptr, st);
 }
 
-int launch_exact_fwdbwd(dsmppi_ctx* c, const float* q, int q_stride, const RowSrc& src, float* sel_dist,
-                        float* sel_grad, cudaStream_t st) {
-  return launch<true>(c, q, q_stride, src, 0u, nullptr, sel_dist, sel_grad, st);
+int launch_exact_fwdbwd(dsmppi_ctx* c, const float* q, int q_stride, const RowSrc& src, uint32_t ignore_mask,
+                        float* m_rows, float* row_dist, float* row_grad, cudaStream_t st) {
+  return launch<true>(c, q, q_stride, src, ignore_mask, m_rows, row_dist, row_grad, st);
 }

@@ -90,9 +90,11 @@ struct dsmppi_ctx {
   int* row_base = nullptr;            // (n)
   int* row_sample = nullptr; int* row_obs = nullptr; size_t rowlist_cap = 0;
   int* counters = nullptr;            // [0] n_rows, [1] band overflows, [2..3] rescored pairs (u64)
-  int* sel = nullptr;                 // (n, K)
-  float* sel_dist = nullptr;          // (n, K) pass-2 distances
-  float* sel_grad = nullptr;          // (n, K, d)
+  int* sel = nullptr;                 // (n, K) selected obstacle indices (two-launch fp32 path)
+  int* sel_rows = nullptr;            // (n, K) rows of row_dist / row_grad holding the K closest, ranked
+  float* row_dist = nullptr;          // pass-2 distance of every differentiated row
+  float* row_grad = nullptr;          // (rows, d)
+  size_t row_dist_cap = 0, row_grad_cap = 0;
   float* dist_tmp = nullptr;          // (n)
   float* grad_tmp = nullptr;          // (n, d)
   // policy-update scratch
@@ -114,15 +116,17 @@ struct dsmppi_ctx {
 // q points at the first state; consecutive samples are q_stride floats apart
 int launch_exact_forward(dsmppi_ctx* c, const float* q, int q_stride, const RowSrc& src, uint32_t ignore_mask,
                          float* m_rows, cudaStream_t st);
-int launch_exact_fwdbwd(dsmppi_ctx* c, const float* q, int q_stride, const RowSrc& src, float* sel_dist,
-                        float* sel_grad, cudaStream_t st);
+// forward + VJP; when m_rows != nullptr also writes the pass-1 ranking key of every row
+int launch_exact_fwdbwd(dsmppi_ctx* c, const float* q, int q_stride, const RowSrc& src, uint32_t ignore_mask,
+                        float* m_rows, float* row_dist, float* row_grad, cudaStream_t st);
 // tc_pass1.cu
 int tc_build_images(dsmppi_ctx* c, const dsmppi_net* net);
 void tc_free_images(dsmppi_ctx* c);
 int tc_set_obstacles(dsmppi_ctx* c, cudaStream_t st);
 int tc_pass1(dsmppi_ctx* c, const float* q, int q_stride, int n, uint32_t ignore_mask, int mode, cudaStream_t st);
 // rollout_kernels.cu
-int launch_rank_dense(dsmppi_ctx* c, int n, int K, cudaStream_t st);
+int launch_rank_dense(dsmppi_ctx* c, int n, int K, bool rows_out, cudaStream_t st);
+int launch_identity_rows(dsmppi_ctx* c, int n, int K, cudaStream_t st);
 int launch_select_candidates(dsmppi_ctx* c, int n, int K, float band, cudaStream_t st);
 int launch_rank_candidates(dsmppi_ctx* c, int n, int K, cudaStream_t st);
 int launch_blend(dsmppi_ctx* c, int n, int K, float* dist_out, float* grad_out, cudaStream_t st);

@@ -13,33 +13,34 @@ namespace {
 // ------------------------------------------------------------------------------------------------
 __global__ void rank_kernel(const float* __restrict__ m_rows, const int* __restrict__ row_base,
                             const int* __restrict__ cnt, const int* __restrict__ row_obs, int M, int n, int K,
-                            int* __restrict__ sel) {
+                            int rows_out, int* __restrict__ sel) {
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (w >= n) return;
   const int base = row_base ? row_base[w] : w * M;
   const int c = cnt ? cnt[w] : M;
   float last_v = -FLT_MAX;
-  int last_j = -1;
+  int last_j = -1, last_t = 0;
   bool first = true;
   for (int kk = 0; kk < K; ++kk) {
     float bv = FLT_MAX;
-    int bj = 0x7fffffff;
+    int bj = 0x7fffffff, bt = 0;
     for (int t = lane; t < c; t += 32) {
       const float v = m_rows[base + t];
       const int j = row_obs ? row_obs[base + t] : t;
       const bool after = first || v > last_v || (v == last_v && j > last_j);
-      if (after && (v < bv || (v == bv && j < bj))) { bv = v; bj = j; }
+      if (after && (v < bv || (v == bv && j < bj))) { bv = v; bj = j; bt = t; }
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
       const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
       const int oj = __shfl_xor_sync(0xffffffffu, bj, off);
-      if (ov < bv || (ov == bv && oj < bj)) { bv = ov; bj = oj; }
+      const int ot = __shfl_xor_sync(0xffffffffu, bt, off);
+      if (ov < bv || (ov == bv && oj < bj)) { bv = ov; bj = oj; bt = ot; }
     }
-    if (bj == 0x7fffffff) bj = last_j < 0 ? 0 : last_j;   // fewer than K candidates: repeat the last one
-    if (lane == 0) sel[w * K + kk] = bj;
-    last_v = bv; last_j = bj; first = false;
+    if (bj == 0x7fffffff) { bj = last_j < 0 ? 0 : last_j; bt = last_t; }   // fewer than K candidates: repeat
+    if (lane == 0) sel[w * K + kk] = rows_out ? base + bt : bj;
+    last_v = bv; last_j = bj; last_t = bt; first = false;
   }
 }
 
@@ -131,30 +132,46 @@ __global__ void select_candidates_kernel(const float* __restrict__ mdist, int M,
 // ------------------------------------------------------------------------------------------------
 // Gradient blend (MPPI.py:270-280): w = softmax(-10 * dist_k), grad = sum_k w_k grad_k, distance = dist_0
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void blend(const float* __restrict__ sd, const float* __restrict__ sg, int K, int d,
-                                      float& dist, float (&g)[MAXD]) {
+// rows[k] = row of row_dist / row_grad holding the k-th closest obstacle of this sample
+__device__ __forceinline__ void blend(const float* __restrict__ row_dist, const float* __restrict__ row_grad,
+                                      const int* __restrict__ rows, int K, int d, float& dist, float (&g)[MAXD]) {
+  float sd[MAXK];
+  int rr[MAXK];
   float mx = -FLT_MAX;
-  for (int k = 0; k < K; ++k) mx = fmaxf(mx, -10.f * sd[k]);
+#pragma unroll
+  for (int k = 0; k < MAXK; ++k)
+    if (k < K) { rr[k] = rows[k]; sd[k] = row_dist[rr[k]]; mx = fmaxf(mx, -10.f * sd[k]); }
   float wk[MAXK];
   float den = 0.f;
-  for (int k = 0; k < K; ++k) { wk[k] = expf(-10.f * sd[k] - mx); den += wk[k]; }
+#pragma unroll
+  for (int k = 0; k < MAXK; ++k)
+    if (k < K) { wk[k] = expf(-10.f * sd[k] - mx); den += wk[k]; }
 #pragma unroll
   for (int a = 0; a < MAXD; ++a) g[a] = 0.f;
-  for (int k = 0; k < K; ++k) {
-    const float w = wk[k] / den;
 #pragma unroll
-    for (int a = 0; a < MAXD; ++a)
-      if (a < d) g[a] += sg[k * d + a] * w;
-  }
+  for (int k = 0; k < MAXK; ++k)
+    if (k < K) {
+      const float w = wk[k] / den;
+      const float* sg = row_grad + (size_t)rr[k] * d;
+#pragma unroll
+      for (int a = 0; a < MAXD; ++a)
+        if (a < d) g[a] += sg[a] * w;
+    }
   dist = sd[0];
 }
 
-__global__ void blend_kernel(const float* __restrict__ sel_dist, const float* __restrict__ sel_grad, int n, int K,
-                             int d, float* __restrict__ dist_out, float* __restrict__ grad_out) {
+__global__ void identity_rows_kernel(int total, int* __restrict__ rows) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < total) rows[i] = i;
+}
+
+__global__ void blend_kernel(const float* __restrict__ row_dist, const float* __restrict__ row_grad,
+                             const int* __restrict__ sel_rows, int n, int K, int d, float* __restrict__ dist_out,
+                             float* __restrict__ grad_out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float dist, g[MAXD];
-  blend(sel_dist + (size_t)i * K, sel_grad + (size_t)i * K * d, K, d, dist, g);
+  blend(row_dist, row_grad, sel_rows + (size_t)i * K, K, d, dist, g);
   dist_out[i] = dist;
   for (int a = 0; a < d; ++a) grad_out[(size_t)i * d + a] = g[a];
 }
@@ -167,7 +184,7 @@ struct StepArgs {
   int N, H, d, t, nk, K;
   float dt, dst_thr, lin_thr, p;
   float goal[MAXD];
-  const float* sel_dist; const float* sel_grad;
+  const float* row_dist; const float* row_grad; const int* sel_rows;
   const float* mu; const float* sigma; const float* alpha;
   float* traj; float* closest; float* kval; float* dots; float* acts; float* qdot; float* grads;
 };
@@ -211,7 +228,7 @@ __global__ void __launch_bounds__(128) step_kernel(StepArgs s) {
 
   // S2e blended distance / gradient
   float dist;
-  blend(s.sel_dist + (size_t)i * s.K, s.sel_grad + (size_t)i * s.K * d, s.K, d, dist, g);
+  blend(s.row_dist, s.row_grad, s.sel_rows + (size_t)i * s.K, s.K, d, dist, g);
   dist -= s.dst_thr;                                  // MPPI.py:117
   s.closest[st] = dist;
   ss = 0.f;
@@ -620,9 +637,16 @@ __global__ void update_finalize_kernel(const float* __restrict__ packed, int nk,
     (c)->launches++;                 \
   } while (0)
 
-int launch_rank_dense(dsmppi_ctx* c, int n, int K, cudaStream_t st) {
+int launch_rank_dense(dsmppi_ctx* c, int n, int K, bool rows_out, cudaStream_t st) {
   const int threads = 128, warps = threads / 32;
-  rank_kernel<<<(n + warps - 1) / warps, threads, 0, st>>>(c->m_rows, nullptr, nullptr, nullptr, c->M, n, K, c->sel);
+  rank_kernel<<<(n + warps - 1) / warps, threads, 0, st>>>(c->m_rows, nullptr, nullptr, nullptr, c->M, n, K,
+                                                          rows_out ? 1 : 0, rows_out ? c->sel_rows : c->sel);
+  LAUNCH_CHECK(c);
+  return 0;
+}
+
+int launch_identity_rows(dsmppi_ctx* c, int n, int K, cudaStream_t st) {
+  identity_rows_kernel<<<(n * K + 255) / 256, 256, 0, st>>>(n * K, c->sel_rows);
   LAUNCH_CHECK(c);
   return 0;
 }
@@ -639,13 +663,14 @@ int launch_select_candidates(dsmppi_ctx* c, int n, int K, float band, cudaStream
 int launch_rank_candidates(dsmppi_ctx* c, int n, int K, cudaStream_t st) {
   const int threads = 128, warps = threads / 32;
   rank_kernel<<<(n + warps - 1) / warps, threads, 0, st>>>(c->m_rows, c->row_base, c->cand_cnt, c->row_obs, c->M, n,
-                                                          K, c->sel);
+                                                          K, 1, c->sel_rows);
   LAUNCH_CHECK(c);
   return 0;
 }
 
 int launch_blend(dsmppi_ctx* c, int n, int K, float* dist_out, float* grad_out, cudaStream_t st) {
-  blend_kernel<<<(n + 127) / 128, 128, 0, st>>>(c->sel_dist, c->sel_grad, n, K, c->d, dist_out, grad_out);
+  blend_kernel<<<(n + 127) / 128, 128, 0, st>>>(c->row_dist, c->row_grad, c->sel_rows, n, K, c->d, dist_out,
+                                                grad_out);
   LAUNCH_CHECK(c);
   return 0;
 }
@@ -663,7 +688,7 @@ int launch_step(dsmppi_ctx* c, const dsmppi_rollout_args* a, int t, cudaStream_t
   s.N = a->N; s.H = a->H; s.d = c->d; s.t = t; s.nk = a->n_kernels; s.K = a->n_closest;
   s.dt = a->dt; s.dst_thr = a->dst_thr; s.lin_thr = a->lin_thr; s.p = a->rbf_p;
   for (int i = 0; i < MAXD; ++i) s.goal[i] = a->q_goal[i];
-  s.sel_dist = c->sel_dist; s.sel_grad = c->sel_grad;
+  s.row_dist = c->row_dist; s.row_grad = c->row_grad; s.sel_rows = c->sel_rows;
   s.mu = a->mu_tmp_dev; s.sigma = a->sigma_tmp_dev; s.alpha = a->alpha_tmp_dev;
   s.traj = a->all_traj_dev; s.closest = a->closest_dist_all_dev; s.kval = a->kernel_val_all_dev;
   s.dots = a->dot_products_dev; s.acts = a->kernel_activations_dev; s.qdot = a->qdot_dev;
