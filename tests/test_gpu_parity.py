@@ -227,6 +227,56 @@ def test_tensor_core_mode_is_bitwise_identical_to_fp32_mode(tag, N, H, factory):
         assert torch.equal(a, b2)
 
 
+def test_sharded_update_kernels_match_unsharded(factory):
+    """SURVEY 8(e) on one GPU: run the cost-stats / partial kernels on two sample shards, add the packed
+    vectors (what the NCCL all-reduce does), finalize -> same policy as the unsharded update."""
+    from optimalmodulationds_b200 import _capi
+    c = load_npz("case_franka_shelf")
+    N, H, nk, d = int(c["N"]), int(c["H"]), int(c["nk"]), 7
+    m = factory.make_mppi(c, device="cuda")
+    m.propagate(); m.get_cost()
+    P = m.Policy
+    ref_mu, ref_sg, ref_al = P.mu_c.clone(), P.sigma_c.clone(), P.alpha_c.clone()
+    mu0, sg0, al0 = P.mu_c.clone(), P.sigma_c.clone(), P.alpha_c.clone()
+    _, n_ref = m.shift_policy_means()
+    ref_mu, ref_sg, ref_al = P.mu_c.clone(), P.sigma_c.clone(), P.alpha_c.clone()
+    lib, ctx, st = m._lib, m._ctx, m._stream()
+    L = int(lib.dsmppi_update_packed_len(nk, d))
+    halves = [(0, N // 2), (N // 2, N)]
+    stats = []
+    for lo, hi in halves:
+        s_ = torch.empty(4, device="cuda")
+        _capi.check(lib.dsmppi_update_cost_stats(ctx, m.cur_cost[lo:hi].contiguous().data_ptr(), hi - lo, s_.data_ptr(), st))
+        stats.append(s_)
+    g = torch.stack((stats[0][0] + stats[1][0], torch.minimum(stats[0][1], stats[1][1]), stats[0][2],
+                     stats[0][3] + stats[1][3]))
+    assert int(g[3]) == N
+    total = torch.zeros(L, device="cuda")
+    args = None
+    for r, (lo, hi) in enumerate(halves):
+        a = _capi.UpdateArgs()
+        a.N, a.H, a.n_kernels, a.owns_sample0, a.N_global = hi - lo, H, nk, 1 if r == 0 else 0, N
+        a.ker_thr, a.upd_rate = float(m.ker_thr), float(m.policy_upd_rate)
+        keep = [m.cur_cost[lo:hi].contiguous(), m.kernel_val_all[lo:hi].contiguous(),
+                m.kernel_activations[lo:hi].contiguous(), P.mu_tmp[lo:hi].contiguous(),
+                P.sigma_tmp[lo:hi].contiguous(), P.alpha_tmp[lo:hi].contiguous()]
+        (a.cost_dev, a.kernel_val_all_dev, a.kernel_activations_dev, a.mu_tmp_dev, a.sigma_tmp_dev,
+         a.alpha_tmp_dev) = [t.data_ptr() for t in keep]
+        packed = torch.empty(L, device="cuda")
+        _capi.check(lib.dsmppi_update_partial(ctx, _capi.C.byref(a), g.data_ptr(), packed.data_ptr(), st))
+        torch.cuda.synchronize()
+        total += packed
+        args = a
+    args.mu_c_dev, args.sigma_c_dev, args.alpha_c_dev = mu0.data_ptr(), sg0.data_ptr(), al0.data_ptr()
+    n_upd = torch.zeros(1, dtype=torch.int32, device="cuda")
+    _capi.check(lib.dsmppi_update_finalize(ctx, _capi.C.byref(args), total.data_ptr(), n_upd.data_ptr(), st))
+    torch.cuda.synchronize()
+    assert int(n_upd) == int(n_ref)
+    check(mu0, ref_mu, 1e-5, 1e-6, "mu_c", min_frac=1.0)
+    check(sg0, ref_sg, 1e-5, 1e-6, "sigma_c", min_frac=1.0)
+    check(al0, ref_al, 1e-5, 1e-6, "alpha_c", min_frac=1.0)
+
+
 def test_constructor_rejects_missing_cuda_path(monkeypatch, factory):
     """The product must fail loudly rather than fall back when the shared library is unavailable."""
     from optimalmodulationds_b200 import _capi
