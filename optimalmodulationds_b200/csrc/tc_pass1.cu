@@ -25,6 +25,8 @@
 
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
+#include <utility>
 #include <vector>
 
 #include "internal.cuh"
@@ -34,7 +36,12 @@ namespace {
 constexpr int ROWS = 128;                 // pair-rows per CTA per tile slot
 constexpr int K0 = 64;                    // layer-1 K: 32 "hi" + 32 "lo" halves of the encoding
 constexpr int MMA_WARP = 8;               // warps 0..7: rows (2 tile slots x 4 TMEM lane quarters)
-constexpr int NTHREADS = (MMA_WARP + 1) * 32;
+// Three warpgroups: two of row warps and one holding the MMA issuer (warp 8; warps 9..11 only exist so that the
+// third warpgroup is complete and can hand its registers over with setmaxnreg).  A 9-warp CTA would leave the
+// row warps 168 registers (three warps on one scheduler) -- not enough to keep a whole 128-column accumulator
+// half in flight, which is what frees D_lo / D_hi early enough for the other tile's MMAs.
+constexpr int NTHREADS = 12 * 32;
+constexpr int ROW_REGS = 232, ISSUER_REGS = 40;   // 128*(168-40) freed == 2*128*(232-168) claimed
 
 // ---- shared-memory map (bytes); the weight part is a verbatim copy of the per-CTA global image
 constexpr int OFF_W1 = 0;                          // 2 halves x (64 rows x K0) fp16
@@ -98,11 +105,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {
-      printf("tc_pass1: mbarrier timeout (block %d thread %d bar-offset %u parity %u)\n", blockIdx.x, threadIdx.x,
-             bar, parity);
-      __trap();
-    }
+    if (clock64() - t0 > 4000000000LL) __trap();
   }
 }
 // arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster.  Only TMEM traffic is
@@ -143,6 +146,40 @@ __device__ __forceinline__ void mma_ts_2cta(uint32_t d_tmem, uint32_t a_tmem, ui
       "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
       "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+// The issuer's form: everything that is known at compile time (TMEM column offsets, the descriptor's offset
+// from the start of shared memory, LBO, the instruction descriptor, the accumulate flag) is an immediate inside
+// the asm block, so per MMA only two adds feed the instruction and the compiler has nothing to hoist out of the
+// tile loop (a first unrolled version precomputed 240 descriptors and spilled them).
+//   sb4      = shared-memory base address >> 4
+//   DESC_IMM = (byte offset of the B slab >> 4) + (LBO >> 4 << 16), added to sb4 -> low descriptor word
+template <uint32_t D_COL, uint32_t A_COL, uint32_t DESC_IMM, uint32_t DESC_HI, uint32_t IDESC, bool ACC>
+__device__ __forceinline__ void mma_ts_2cta_imm(uint32_t tmem_base, uint32_t sb4) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 bd;\n\t.reg .b32 dl, td, ta;\n\t"
+      "add.u32 td, %0, %2;\n\t"
+      "add.u32 ta, %0, %3;\n\t"
+      "add.u32 dl, %1, %4;\n\t"
+      "mov.b64 bd, {dl, %5};\n\t"
+      "setp.ne.b32 p, %7, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [td], [ta], bd, %6, p;\n\t}" ::"r"(tmem_base),
+      "r"(sb4), "n"(D_COL), "n"(A_COL), "n"(DESC_IMM), "n"(DESC_HI), "n"(IDESC), "n"(ACC ? 1 : 0)
+      : "memory");
+}
+template <uint32_t D_COL, uint32_t A_COL, uint32_t B_OFF, uint32_t LBO, uint32_t IDESC, int... KS>
+__device__ __forceinline__ void mma_group(uint32_t tmem_base, uint32_t sb4, std::integer_sequence<int, KS...>) {
+  constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);          // SBO = 128 B, descriptor version 1
+  (mma_ts_2cta_imm<D_COL, A_COL + KS * 8, (B_OFF >> 4) + ((LBO >> 4) << 16) + KS * ((2 * LBO) >> 4), DESC_HI, IDESC,
+                   (KS > 0)>(tmem_base, sb4), ...);
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
 }
 // completion of all MMAs issued so far by this thread -> arrive on the barrier at this offset in BOTH CTAs
 __device__ __forceinline__ void mma_commit_2cta(uint32_t bar) {
@@ -251,10 +288,24 @@ struct TcArgs {
   const float* obs;                            // (M, 4)
   float* mdist;                                // (n * M)
   long long n_rows;                            // n * M
-  int M, O;
+  int n, M, O;
   uint32_t ignore_mask;
   float inv_scale_div;                         // 100 for the 9-link net else 1
+  long long* prof;                             // DSMPPI_TC_PROF builds only: [block][warp][8] cycle counters
 };
+
+// Per-phase cycle accounting of the kernel's own pipeline (tools/tc_microbench.cu builds with
+// -DDSMPPI_TC_PROF); compiled out of the product library.
+#ifdef DSMPPI_TC_PROF
+#define PROF_DECL long long _pt = clock64(); long long _pc[8] = {0, 0, 0, 0, 0, 0, 0, 0}
+#define PROF_ADD(i) do { const long long _n = clock64(); _pc[i] += _n - _pt; _pt = _n; } while (0)
+#define PROF_FLUSH(a, w) do { if ((a).prof && (threadIdx.x & 31) == 0) for (int _i = 0; _i < 8; ++_i) \
+    (a).prof[((size_t)blockIdx.x * 9 + (w)) * 8 + _i] = _pc[_i]; } while (0)
+#else
+#define PROF_DECL do { } while (0)
+#define PROF_ADD(i) do { } while (0)
+#define PROF_FLUSH(a, w) do { } while (0)
+#endif
 
 // bias + ReLU + fp16/bf16 pair packing of 32 accumulator columns into pk[OFF .. OFF+16)
 template <bool BF16, int OFF>
@@ -321,9 +372,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_pass
 
   if (warp < MMA_WARP) {
     // =================================== row warps ===================================
-    // warp = slot*4 + quarter.  Per hidden layer a thread drains its row of D_lo while the tensor core still
-    // computes D_hi (packed fp16 pairs wait in 64 registers), then drains D_hi and rewrites the A operand.
-    // TMEM loads are double-buffered (two 32-column buffers) so their latency overlaps the bias/ReLU/pack math.
+    // warp = slot*4 + quarter; a thread owns one pair-row (TMEM lane).  Per hidden layer it pulls a whole
+    // 128-column accumulator half into registers with four back-to-back tcgen05.ld, releases that half to the
+    // tensor core at once (the other tile's MMAs are waiting for it), and only then does bias / ReLU / fp16
+    // packing; the packed low half waits in registers until the D_hi MMAs have retired the old A operand.
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(ROW_REGS));
     const int slot = warp >> 2;                          // 0: tile X, 1: tile Y
     const int row = ((warp & 3) << 5) | lane;            // TMEM lane == row within the CTA's 128
     const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
@@ -338,12 +391,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_pass
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(bar, 0);
     };
-    // layer-1 operand of pair-row r: [enc_hi | enc_lo] = per-sample part OR per-obstacle part
-    auto load_input = [&](long long r, uint32_t (&v)[32]) {
-      if (r < a.n_rows) {
-        const long long i = r / a.M;
-        const int j = (int)(r - i * a.M);
-        const uint4* eq = a.encq + i * 8;
+    // layer-1 operand of pair (sample i, obstacle j): [enc_hi | enc_lo] = per-sample part OR per-obstacle part
+    auto load_input = [&](int i, int j, uint32_t (&v)[32]) {
+      if (i < a.n) {
+        const uint4* eq = a.encq + (size_t)i * 8;
         const uint4* ep = a.encp + (size_t)j * 8;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
@@ -356,68 +407,79 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_pass
       }
     };
 
-    long long tile = (long long)slot * npairs + pair;              // this slot's tile in iteration 0
-    long long r_cur = tile * (2 * ROWS) + (long long)rank * ROWS + row;
+    // pair-row of this thread: r = tile*256 + rank*128 + row = i*M + j, advanced by a constant stride per
+    // iteration (no 64-bit division inside the loop)
+    const long long stride = 2LL * npairs * (2 * ROWS);
+    const int di = (int)(stride / a.M), dj = (int)(stride % a.M);
+    const long long r0 = ((long long)slot * npairs + pair) * (2 * ROWS) + (long long)rank * ROWS + row;
+    int i_cur = (int)min(r0 / a.M, (long long)a.n), j_cur = (int)(r0 % a.M);
+    uint32_t vin[32];
     if ((long long)pair < n_tiles) {
-      uint32_t v[32];
-      load_input(tile < n_tiles ? r_cur : a.n_rows, v);
-      tmem_st32<0>(tA, v);
+      load_input(i_cur, j_cur, vin);
+      tmem_st32<0>(tA, vin);
       tc_wait_st();
       signal(bar_aready);
     }
+    PROF_DECL;
     for (long long it = 0;; ++it) {
       const long long tX = (it * 2) * npairs + pair;
       if (tX >= n_tiles) break;
-#pragma unroll 1
-      for (int l = 0; l < 4; ++l) {
+      const bool more = ((it + 1) * 2) * npairs + pair < n_tiles;
+      int i_next = min(i_cur + di, a.n), j_next = j_cur + dj;
+      if (j_next >= a.M) { j_next -= a.M; i_next = min(i_next + 1, a.n); }
+#pragma unroll
+      for (int l = 0; l < 4; ++l) {          // unrolled: the prefetch registers of layer 4 must not be loop-carried
         const float* bl = bias + l * HID;
-        uint32_t pk[64], va[32], vb[32];
+        uint32_t pk[64], raw[4][32];
+        PROF_ADD(7);
         // ---- D_lo (features 0..127) while the tensor core is still producing D_hi
         mbar_wait(bar_full_lo, (uint32_t)((it + l) & 1));          // phase 5*it + l of this slot's D_lo
         tc_fence_after();
-        tmem_ld32(tDlo, va);
-        tmem_ld32(tDlo + 32, vb);
-        tc_wait_ld();
-        relu_pack32<BF16, 0>(va, bl, pk);
-        tmem_ld32(tDlo + 64, va);
-        relu_pack32<BF16, 16>(vb, bl + 32, pk);
-        tmem_ld32(tDlo + 96, vb);
+        PROF_ADD(0);
+        tmem_ld32(tDlo, raw[0]);
+        tmem_ld32(tDlo + 32, raw[1]);
+        tmem_ld32(tDlo + 64, raw[2]);
+        tmem_ld32(tDlo + 96, raw[3]);
         tc_wait_ld();
         signal(BAR(BAR_DFREE0));                                    // D_lo drained: the other tile may use it
-        relu_pack32<BF16, 32>(va, bl + 64, pk);
-        relu_pack32<BF16, 48>(vb, bl + 96, pk);
+        PROF_ADD(1);
+        relu_pack32<BF16, 0>(raw[0], bl, pk);
+        relu_pack32<BF16, 16>(raw[1], bl + 32, pk);
+        relu_pack32<BF16, 32>(raw[2], bl + 64, pk);
+        relu_pack32<BF16, 48>(raw[3], bl + 96, pk);
+        PROF_ADD(2);
         // ---- D_hi (features 128..255); its completion also retires every MMA that read the old A operand
         mbar_wait(bar_full_hi, (uint32_t)(l & 1));                 // phase 4*it + l of this slot's D_hi
         tc_fence_after();
-        tmem_ld32(tDhi, va);
-        tmem_ld32(tDhi + 32, vb);
+        PROF_ADD(3);
+        tmem_ld32(tDhi, raw[0]);
+        tmem_ld32(tDhi + 32, raw[1]);
+        tmem_ld32(tDhi + 64, raw[2]);
+        tmem_ld32(tDhi + 96, raw[3]);
         tmem_st32<0>(tA, pk);
         tmem_st32<32>(tA + 32, pk);
         tc_wait_ld();
-        relu_pack32<BF16, 0>(va, bl + 128, pk);
-        tmem_ld32(tDhi + 64, va);
-        relu_pack32<BF16, 16>(vb, bl + 160, pk);
-        tmem_ld32(tDhi + 96, vb);
-        tmem_st32<0>(tA + 64, pk);
-        tc_wait_ld();
         signal(BAR(BAR_DFREE1));                                    // D_hi drained
-        relu_pack32<BF16, 32>(va, bl + 192, pk);
-        relu_pack32<BF16, 48>(vb, bl + 224, pk);
+        PROF_ADD(4);
+        if (l == 3 && more) load_input(i_next, j_next, vin);        // next tile's layer-1 operand, latency hidden below
+        relu_pack32<BF16, 0>(raw[0], bl + 128, pk);
+        relu_pack32<BF16, 16>(raw[1], bl + 160, pk);
+        relu_pack32<BF16, 32>(raw[2], bl + 192, pk);
+        relu_pack32<BF16, 48>(raw[3], bl + 224, pk);
+        tmem_st32<0>(tA + 64, pk);
         tmem_st32<32>(tA + 96, pk);
         tc_wait_st();
         signal(bar_aready);                                         // next layer's A operand is in TMEM
+        PROF_ADD(5);
       }
-      // ---- prefetch the next tile's layer-1 operand, then the output layer of this one
-      const long long tile_next = tile + 2LL * npairs;
-      const long long r_next = tile_next * (2 * ROWS) + (long long)rank * ROWS + row;
-      const bool more = ((it + 1) * 2) * npairs + pair < n_tiles;
-      uint32_t vin[32];
-      if (more) load_input(tile_next < n_tiles ? r_next : a.n_rows, vin);
+      // ---- output layer of this tile
+      const bool valid = i_cur < a.n;
       float rad = 0.f;
-      const bool valid = r_cur < a.n_rows && tile < n_tiles;
-      if (valid) rad = __ldg(a.obs + (size_t)(r_cur % a.M) * 4 + 3);
+      if (valid) rad = __ldg(a.obs + (size_t)j_cur * 4 + 3);
+      PROF_ADD(6);
       mbar_wait(bar_full_lo, (uint32_t)((it + 4) & 1));
       tc_fence_after();
+      PROF_ADD(0);
       uint32_t v[16];
       tmem_ld16(tDlo, v);
       if (more) tmem_st32<0>(tA, vin);          // the output-layer MMA has retired: A may be overwritten
@@ -438,49 +500,73 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_pass
             m = fminf(m, y);
           }
         }
-        a.mdist[r_cur] = m;
+        a.mdist[(size_t)i_cur * a.M + j_cur] = m;
       }
-      tile = tile_next;
-      r_cur = r_next;
+      i_cur = i_next;
+      j_cur = j_next;
+      PROF_ADD(6);
     }
-  } else if (rank == 0 && lane == 0) {
-    // =================================== MMA issuer (leader CTA, one thread) ===================================
-    const int fmt = BF16 ? 1 : 0;
-    const uint32_t idesc128 = make_idesc(fmt, 256, 128);
-    const uint32_t idesc32 = make_idesc(fmt, 256, 32);
+    PROF_FLUSH(a, warp);
+  } else {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(ISSUER_REGS));
+  }
+  if (warp == MMA_WARP && rank == 0) {
+    // =================================== MMA issuer (warp 8 of the leader CTA) ===================================
+    // The whole warp runs this loop convergently and one elected lane issues: every operand is then warp-uniform
+    // and the (layer, slot, half) groups are fully unrolled, so one MMA costs a handful of issue slots.  (The
+    // first version issued from a single divergent thread inside rolled loops: ~18 dependent instructions per
+    // MMA, and the issue loop -- not the tensor pipe, not the epilogue -- set the pace of the whole kernel.)
+    constexpr int fmt = BF16 ? 1 : 0;
+    constexpr uint32_t idesc128 = make_idesc(fmt, 256, 128);
+    constexpr uint32_t idesc32 = make_idesc(fmt, 256, 32);
+    const uint32_t sb4 = sbase >> 4;
     uint32_t ph_a[2] = {0, 0}, ph_free[2] = {0, 0};
-    const uint32_t tAs[2] = {tmem_base + TM_A0, tmem_base + TM_A1};
-    const uint32_t tDs[2] = {tmem_base + TM_DLO, tmem_base + TM_DHI};
+    PROF_DECL;
+    // one (layer L, slot S, half H) group: wait for the operands, issue its K-steps, commit
+    auto group = [&](auto L, auto S, auto H) {
+      constexpr int l = decltype(L)::value, s = decltype(S)::value, h = decltype(H)::value;
+      PROF_ADD(2);
+      mbar_wait(BAR(h ? BAR_DFREE1 : BAR_DFREE0), ph_free[h] ^ 1);
+      ph_free[h] ^= 1;
+      tc_fence_after();
+      PROF_ADD(1);
+      constexpr uint32_t boff = l == 0 ? OFF_W1 + h * SZ_W1H : (l < 4 ? OFF_WH + ((l - 1) * 2 + h) * SZ_WHH : OFF_W5);
+      constexpr uint32_t lbo = l < 4 ? 64 * 16 : 16 * 16;
+      constexpr int ksteps = l == 0 ? K0 / 16 : HID / 16;
+      constexpr uint32_t idesc = l < 4 ? idesc128 : idesc32;
+      constexpr uint32_t dcol = h ? TM_DHI : TM_DLO, acol = s ? TM_A1 : TM_A0;
+      if (elect_one()) {
+        mma_group<dcol, acol, boff, lbo, idesc>(tmem_base, sb4, std::make_integer_sequence<int, ksteps>{});
+        mma_commit_2cta(BAR(BAR_DFULL00 + s * 2 + h));
+      }
+      __syncwarp();
+    };
+    auto layer = [&](auto L) {
+      constexpr int l = decltype(L)::value;
+      auto slot = [&](auto S) {
+        constexpr int s = decltype(S)::value;
+        PROF_ADD(2);
+        mbar_wait(BAR(s ? BAR_AREADY1 : BAR_AREADY0), ph_a[s]);
+        ph_a[s] ^= 1;
+        tc_fence_after();
+        PROF_ADD(0);
+        group(L, S, std::integral_constant<int, 0>{});
+        if constexpr (l < 4) group(L, S, std::integral_constant<int, 1>{});
+      };
+      slot(std::integral_constant<int, 0>{});
+      slot(std::integral_constant<int, 1>{});
+    };
     for (long long it = 0;; ++it) {
       const long long tX = (it * 2) * npairs + pair;
       if (tX >= n_tiles) break;
-#pragma unroll 1
-      for (int l = 0; l < 5; ++l) {
-#pragma unroll 1
-        for (int s = 0; s < 2; ++s) {
-          mbar_wait(BAR(s ? BAR_AREADY1 : BAR_AREADY0), ph_a[s]);
-          ph_a[s] ^= 1;
-          tc_fence_after();
-          const int nh = l == 4 ? 1 : 2;
-          for (int h = 0; h < nh; ++h) {
-            mbar_wait(BAR(h ? BAR_DFREE1 : BAR_DFREE0), ph_free[h] ^ 1);
-            ph_free[h] ^= 1;
-            tc_fence_after();
-            uint32_t boff, lbo, ksteps, idesc;
-            if (l == 0) { boff = OFF_W1 + h * SZ_W1H; lbo = 64 * 16; ksteps = K0 / 16; idesc = idesc128; }
-            else if (l < 4) { boff = OFF_WH + ((l - 1) * 2 + h) * SZ_WHH; lbo = 64 * 16; ksteps = HID / 16; idesc = idesc128; }
-            else { boff = OFF_W5; lbo = 16 * 16; ksteps = HID / 16; idesc = idesc32; }
-            const uint32_t sbo = 128;
-            for (uint32_t ks = 0; ks < ksteps; ++ks) {
-              const uint32_t baddr = sbase + boff + ks * 2 * lbo;
-              const uint64_t bdesc = make_b_desc(baddr, lbo, sbo);
-              mma_ts_2cta(tDs[h], tAs[s] + ks * 8, bdesc, idesc, ks > 0 ? 1u : 0u);
-            }
-            mma_commit_2cta(BAR(BAR_DFULL00 + s * 2 + h));
-          }
-        }
-      }
+      layer(std::integral_constant<int, 0>{});
+      layer(std::integral_constant<int, 1>{});
+      layer(std::integral_constant<int, 2>{});
+      layer(std::integral_constant<int, 3>{});
+      layer(std::integral_constant<int, 4>{});
     }
+    PROF_ADD(2);
+    PROF_FLUSH(a, MMA_WARP);
   }
   // ---- teardown
   tc_fence_before();
@@ -624,10 +710,15 @@ int tc_pass1(dsmppi_ctx* c, const float* q, int q_stride, int n, uint32_t ignore
   a.obs = c->obs;
   a.mdist = c->mdist;
   a.n_rows = (long long)n * c->M;
+  a.n = n;
   a.M = c->M;
   a.O = c->O;
   a.ignore_mask = ignore_mask;
   a.inv_scale_div = (c->O == 9) ? 100.f : 1.f;
+  a.prof = nullptr;
+#ifdef DSMPPI_TC_PROF
+  a.prof = reinterpret_cast<long long*>(c->stage);   // the micro-benchmark parks its counter buffer here
+#endif
   const long long n_tiles = (a.n_rows + 2 * ROWS - 1) / (2 * ROWS);
   long long pairs = c->sm_count / 2;
   if (pairs > (n_tiles + 1) / 2) pairs = (n_tiles + 1) / 2;     // each pair takes two tiles per iteration
