@@ -225,6 +225,24 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
   else asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
+// max(x, 0) folded into the conversion (round-to-nearest keeps the sign, so relu commutes with the rounding)
+template <bool BF16>
+__device__ __forceinline__ uint32_t pack2_relu(uint32_t lo, uint32_t hi) {
+  uint32_t r;
+  if (BF16) asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(__uint_as_float(hi)), "f"(__uint_as_float(lo)));
+  else asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(__uint_as_float(hi)), "f"(__uint_as_float(lo)));
+  return r;
+}
+// two fp32 additions in one issue slot (Blackwell packed fp32 pipe); bit-identical to two add.rn.f32
+__device__ __forceinline__ void add2(uint32_t a0, uint32_t a1, float b0, float b1, uint32_t& s0, uint32_t& s1) {
+  asm("{\n\t.reg .b64 x, y, z;\n\t"
+      "mov.b64 x, {%2, %3};\n\t"
+      "mov.b64 y, {%4, %5};\n\t"
+      "add.rn.f32x2 z, x, y;\n\t"
+      "mov.b64 {%0, %1}, z;\n\t}"
+      : "=r"(s0), "=r"(s1)
+      : "r"(a0), "r"(a1), "r"(__float_as_uint(b0)), "r"(__float_as_uint(b1)));
+}
 
 // K-major, no-swizzle UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor, version 1)
 __device__ __forceinline__ uint64_t make_b_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -307,7 +325,8 @@ struct TcArgs {
 #define PROF_FLUSH(a, w) do { } while (0)
 #endif
 
-// bias + ReLU + fp16/bf16 pair packing of 32 accumulator columns into pk[OFF .. OFF+16)
+// bias + ReLU + fp16/bf16 pair packing of 32 accumulator columns into pk[OFF .. OFF+16): per pair of columns one
+// packed fp32 add and one converting ReLU (the epilogue's issue slots are what the two tile slots compete for)
 template <bool BF16, int OFF>
 __device__ __forceinline__ void relu_pack32(const uint32_t (&v)[32], const float* __restrict__ bias32,
                                             uint32_t (&pk)[64]) {
@@ -315,12 +334,11 @@ __device__ __forceinline__ void relu_pack32(const uint32_t (&v)[32], const float
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     const float4 bb = b4[k];
-    const float f0 = fmaxf(__uint_as_float(v[4 * k + 0]) + bb.x, 0.f);
-    const float f1 = fmaxf(__uint_as_float(v[4 * k + 1]) + bb.y, 0.f);
-    const float f2 = fmaxf(__uint_as_float(v[4 * k + 2]) + bb.z, 0.f);
-    const float f3 = fmaxf(__uint_as_float(v[4 * k + 3]) + bb.w, 0.f);
-    pk[OFF + 2 * k + 0] = pack2<BF16>(f0, f1);
-    pk[OFF + 2 * k + 1] = pack2<BF16>(f2, f3);
+    uint32_t s0, s1, s2, s3;
+    add2(v[4 * k + 0], v[4 * k + 1], bb.x, bb.y, s0, s1);
+    add2(v[4 * k + 2], v[4 * k + 3], bb.z, bb.w, s2, s3);
+    pk[OFF + 2 * k + 0] = pack2_relu<BF16>(s0, s1);
+    pk[OFF + 2 * k + 1] = pack2_relu<BF16>(s2, s3);
   }
 }
 
