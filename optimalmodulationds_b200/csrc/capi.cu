@@ -226,7 +226,7 @@ static int distance_pipeline(dsmppi_ctx* c, const float* q, int q_stride, int n,
     src.mode = ROWS_DENSE;
     src.n_rows = n * c->M;
     if (timing_mark(c, 0, st)) return 1;
-    if (launch_exact_fwdbwd(c, q, q_stride, src, ignore_mask, c->m_rows, c->row_dist, c->row_grad, st)) return 1;
+    if (launch_exact_fwdbwd(c, q, q_stride, src, ignore_mask, c->m_rows, c->row_dist, c->row_grad, 0, st)) return 1;
     if (timing_mark(c, 0, st)) return 1;
     return launch_rank_dense(c, n, K, true, st);
   }
@@ -244,7 +244,7 @@ static int distance_pipeline(dsmppi_ctx* c, const float* q, int q_stride, int n,
     s2.K = K;
     s2.n_rows = n * K;
     s2.sel = c->sel;
-    if (launch_exact_fwdbwd(c, q, q_stride, s2, ignore_mask, nullptr, c->row_dist, c->row_grad, st)) return 1;
+    if (launch_exact_fwdbwd(c, q, q_stride, s2, ignore_mask, nullptr, c->row_dist, c->row_grad, 0, st)) return 1;
     return launch_identity_rows(c, n, K, st);
   }
   // tensor-core prefilter -> candidate band -> one fp32 launch (ranking key + distance + gradient) -> rank
@@ -260,7 +260,10 @@ static int distance_pipeline(dsmppi_ctx* c, const float* q, int q_stride, int n,
   src.n_rows_dev = c->counters;
   src.row_sample = c->row_sample;
   src.row_obs = c->row_obs;
-  if (launch_exact_fwdbwd(c, q, q_stride, src, ignore_mask, c->m_rows, c->row_dist, c->row_grad, st)) return 1;
+  // the candidate count lives on the device; K + 1 per sample is what the guard band typically lets through
+  if (launch_exact_fwdbwd(c, q, q_stride, src, ignore_mask, c->m_rows, c->row_dist, c->row_grad,
+                          (long long)n * (K + 1), st))
+    return 1;
   return launch_rank_candidates(c, n, K, st);
 }
 

@@ -1,20 +1,31 @@
 // fp32-exact evaluation of the learned distance network on (sample, obstacle) rows.
 //
-//   exact_mlp_kernel<false>: forward only  -> masked minimum link distance per row  (MPPI.py:235-242)
-//   exact_mlp_kernel<true> : forward + analytic VJP at argmin_l of the raw output   (robot_sdf.py:153-158)
+//   exact_mlp_kernel<false, RPT>: forward only  -> masked minimum link distance per row  (MPPI.py:235-242)
+//   exact_mlp_kernel<true,  RPT>: forward + analytic VJP at argmin_l of the raw output   (robot_sdf.py:153-158)
 //
-// One CTA owns 64 rows.  Activations live in shared memory feature-major (act[k][row]) and are updated in
-// place layer by layer; each of the 256 threads owns an 8-row x 8-feature register tile, so a layer is
-// 256 rank-1 updates of 64 FFMAs.  ReLU masks stay in registers (the forward and backward tilings
-// coincide), so the backward pass needs no extra memory.  All arithmetic is IEEE fp32 (no fast-math):
-// this is the path that has to agree with the reference's torch-CPU numbers to ~1e-6.
+// One CTA of 4 warps owns R = 4*RPT rows (RPT = 8, 4 or 2).  Activations live in shared memory feature-major
+// (act[k][row]) and are updated in place layer by layer.  A warp owns an R-row x 64-feature block of the layer
+// output, its lanes form a 4 x 8 grid and each thread keeps an RPT-row x 8-feature register tile, so one k-step of a
+// warp is 8*RPT FFMAs fed by single-wavefront shared-memory loads (broadcast over the row / feature groups).
+// The weights of all seven GEMMs (4 forward, 3 backward) are one stream of 8-row stages that the CTA pulls from L2
+// through a 4-deep cp.async ring, three stages (24 k-steps) ahead of the FFMAs and straight across layer
+// boundaries: a lone CTA on an SM is then FFMA-bound instead of waiting ~500 cycles for L2 every four k-steps,
+// which is what set the pace of the first versions whenever there were few rows.  ReLU masks stay in
+// registers as bit masks (the forward and backward tilings coincide), so the backward pass needs no extra memory.
+// The host picks RPT per launch from the (estimated) row count: big tiles amortise the weight stream, small tiles
+// fill the 148 SMs when there are few rows and shorten the tail of the last wave (pick_rpt below).
+// All arithmetic is IEEE fp32 (no fast-math): this is the path that has to agree with the reference's torch-CPU
+// numbers to ~1e-6.
+#include <cstdlib>
+
 #include "internal.cuh"
 
 namespace {
 
-constexpr int R = 64;     // rows per CTA
-constexpr int NT = 256;   // threads per CTA
+constexpr int NT = 128;   // threads per CTA: 4 warps, one per 64-feature quarter
 constexpr int XS = 12;    // padded row stride of the raw-input scratch (nin <= 11)
+constexpr int WS = 8;     // k-rows of weights per pipeline stage (8 KB)
+constexpr int NSTAGE = 4; // ring depth
 
 __device__ __forceinline__ bool row_lookup(const RowSrc& s, int r, int n_rows, int& i, int& j) {
   if (r >= n_rows) return false;
@@ -31,45 +42,136 @@ __device__ __forceinline__ bool row_lookup(const RowSrc& s, int r, int n_rows, i
   return true;
 }
 
-// acc[i][j] = sum_k act[k][rg*8+i] * W[k*256 + fg*8+j]
-__device__ __forceinline__ void gemm_tile(const float* __restrict__ W, int K, const float (*act)[R], int rg, int fg,
-                                          float (&acc)[8][8]) {
+// Thread tile: rows r0 .. r0+RPT-1, features {fa .. fa+3} (j = 0..3) and {fa+32 .. fa+35} (j = 4..7).
+struct Tile {
+  int r0, fa;
+  __device__ __forceinline__ int feat(int j) const { return fa + (j & 3) + ((j >> 2) << 5); }
+};
+
+template <int RPT>
+__device__ __forceinline__ void load_rows(const float* p, float (&a)[RPT]) {
+  if constexpr (RPT == 8) {
+    const float4 a0 = *reinterpret_cast<const float4*>(p), a1 = *reinterpret_cast<const float4*>(p + 4);
+    a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+  } else if constexpr (RPT == 4) {
+    const float4 a0 = *reinterpret_cast<const float4*>(p);
+    a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w;
+  } else {
+    const float2 a0 = *reinterpret_cast<const float2*>(p);
+    a[0] = a0.x; a[1] = a0.y;
+  }
+}
+
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// The weight stream: GEMM g = 0..3 are the forward layers (Wf[g], K = nenc or 256), g = 4..6 the backward ones
+// (Wb[3], Wb[2], Wb[1]); stage indices run through all of them.
+struct WeightStream {
+  const NetDev* net;
+  float* ring;            // [NSTAGE][WS][HID]
+  int n0;                 // stages of GEMM 0 = ceil(nenc / WS)
+  int total;              // stages in the whole stream
+  int issued;             // next stage to request
+
+  __device__ __forceinline__ void locate(int stage, const float*& src, int& rows) const {
+    int g, st;
+    if (stage < n0) { g = 0; st = stage; }
+    else { g = 1 + (stage - n0) / (HID / WS); st = (stage - n0) % (HID / WS); }
+    const int K = g == 0 ? net->nenc : HID;
+    const float* W = g < 4 ? net->Wf[g] : net->Wb[7 - g];
+    src = W + (size_t)st * WS * HID;
+    rows = min(WS, K - st * WS);
+  }
+  // every thread requests its share of the next stage (or nothing past the end) and closes one group
+  __device__ __forceinline__ void request_next() {
+    if (issued < total) {
+      const float* src;
+      int rows;
+      locate(issued, src, rows);
+      float* dst = ring + (size_t)(issued % NSTAGE) * WS * HID;
+      for (int c = threadIdx.x; c < rows * (HID / 4); c += NT) cp_async16(dst + c * 4, src + c * 4);
+    }
+    ++issued;
+    cp_async_commit();
+  }
+};
+
+// acc[i][j] = sum_k act[k][r0+i] * W[k*256 + feat(j)], W arriving through the ring; `stage` is the stream position
+// of this GEMM's first stage and is advanced past its last one
+template <int RPT>
+__device__ __forceinline__ void gemm_tile(WeightStream& ws, int& stage, int K, const float (*act)[4 * RPT], const Tile& t,
+                                          float (&acc)[RPT][8]) {
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < RPT; ++i)
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-  const float4* wp = reinterpret_cast<const float4*>(W + fg * 8);
-#pragma unroll 4
-  for (int k = 0; k < K; ++k) {
-    const float4 a0 = *reinterpret_cast<const float4*>(&act[k][rg * 8]);
-    const float4 a1 = *reinterpret_cast<const float4*>(&act[k][rg * 8 + 4]);
-    const float4 w0 = __ldg(wp + k * (HID / 4));
-    const float4 w1 = __ldg(wp + k * (HID / 4) + 1);
-    const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-    const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+  for (int k0 = 0; k0 < K; k0 += WS, ++stage) {
+    cp_async_wait<NSTAGE - 2>();          // this thread's share of `stage` has landed ...
+    __syncthreads();                      // ... and everybody's; the buffer of stage-1 is free again
+    ws.request_next();                    // refill it with stage + NSTAGE - 1
+    const float* wb = ws.ring + (size_t)(stage % NSTAGE) * WS * HID + t.fa;
+    const int rows = min(WS, K - k0);
+    if (rows == WS) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+      for (int kk = 0; kk < WS; ++kk) {
+        float a[RPT];
+        load_rows<RPT>(&act[k0 + kk][t.r0], a);
+        const float4 w0 = *reinterpret_cast<const float4*>(wb + kk * HID);
+        const float4 w1 = *reinterpret_cast<const float4*>(wb + kk * HID + 32);
+        const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+        for (int i = 0; i < RPT; ++i)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+      }
+    } else {
+      for (int kk = 0; kk < rows; ++kk) {
+        float a[RPT];
+        load_rows<RPT>(&act[k0 + kk][t.r0], a);
+        const float4 w0 = *reinterpret_cast<const float4*>(wb + kk * HID);
+        const float4 w1 = *reinterpret_cast<const float4*>(wb + kk * HID + 32);
+        const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+        for (int i = 0; i < RPT; ++i)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+      }
+    }
   }
 }
 
-__device__ __forceinline__ void store_tile(float (*act)[R], int rg, int fg, const float (&v)[8][8]) {
+template <int RPT>
+__device__ __forceinline__ void store_tile(float (*act)[4 * RPT], const Tile& t, const float (&v)[RPT][8]) {
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    *reinterpret_cast<float4*>(&act[fg * 8 + j][rg * 8]) = make_float4(v[0][j], v[1][j], v[2][j], v[3][j]);
-    *reinterpret_cast<float4*>(&act[fg * 8 + j][rg * 8 + 4]) = make_float4(v[4][j], v[5][j], v[6][j], v[7][j]);
+    float* p = &act[t.feat(j)][t.r0];
+    if constexpr (RPT == 8) {
+      *reinterpret_cast<float4*>(p) = make_float4(v[0][j], v[1][j], v[2][j], v[3][j]);
+      *reinterpret_cast<float4*>(p + 4) = make_float4(v[4][j], v[5][j], v[6][j], v[7][j]);
+    } else if constexpr (RPT == 4) {
+      *reinterpret_cast<float4*>(p) = make_float4(v[0][j], v[1][j], v[2][j], v[3][j]);
+    } else {
+      *reinterpret_cast<float2*>(p) = make_float2(v[0][j], v[1][j]);
+    }
   }
 }
 
-template <bool BWD>
-__global__ void __launch_bounds__(NT, 2)
+template <bool BWD, int RPT>
+__global__ void __launch_bounds__(NT, RPT == 8 ? 4 : (RPT == 4 ? 6 : 8))
 exact_mlp_kernel(NetDev net, RowSrc src, const float* __restrict__ q, int q_stride, const float* __restrict__ obs,
                  uint32_t ignore_mask, float* __restrict__ out_m, float* __restrict__ out_dist,
                  float* __restrict__ out_grad) {
+  constexpr int R = 4 * RPT;
   extern __shared__ __align__(16) float smem[];
   float (*act)[R] = reinterpret_cast<float (*)[R]>(smem);   // [256][R]
-  float* xs = smem + HID * R;                               // [R][XS]  raw inputs x = [q, p]
+  float* ring = smem + HID * R;                             // [NSTAGE][WS][256] weight stages
+  float* xs = ring + NSTAGE * WS * HID;                     // [R][XS]  raw inputs x = [q, p]
   float* zs = xs + R * XS;                                  // [R][MAXO] raw outputs
   float* rad = zs + R * MAXO;                               // [R]
   int* lst = reinterpret_cast<int*>(rad + R);               // [R] argmin link
@@ -78,52 +180,59 @@ exact_mlp_kernel(NetDev net, RowSrc src, const float* __restrict__ q, int q_stri
   const int row0 = blockIdx.x * R;
   if (row0 >= n_rows) return;
   const int tid = threadIdx.x;
-  const int rg = tid >> 5;      // warp = group of 8 rows
-  const int fg = tid & 31;      // lane = group of 8 features
+  Tile t;
+  t.r0 = ((tid & 31) >> 3) * RPT;                     // lane / 8: one of four RPT-row groups
+  t.fa = (tid >> 5) * 64 + (tid & 7) * 4;             // warp: 64-feature quarter; lane % 8: 4-feature group
   const int d = net.d, nin = net.nin, nenc = net.nenc, O = net.O;
 
+  // start the weight stream before anything else: the first three stages fly while the inputs are encoded
+  WeightStream ws;
+  ws.net = &net;
+  ws.ring = ring;
+  ws.n0 = (nenc + WS - 1) / WS;
+  ws.total = ws.n0 + (BWD ? 6 : 3) * (HID / WS);
+  ws.issued = 0;
+#pragma unroll
+  for (int i = 0; i < NSTAGE - 1; ++i) ws.request_next();
+  int stage = 0;
+
   // ---- rows -> encoded inputs [x, sin x, cos x]  (network_macros_mod.py:139-140)
-  if (tid < R) {
+  for (int idx = tid; idx < R * nin; idx += NT) {
+    const int r = idx % R, c = idx / R;
     int i = 0, j = 0;
-    const bool valid = row_lookup(src, row0 + tid, n_rows, i, j);
-    for (int c = 0; c < nin; ++c) {
-      float x = 0.f;
-      if (valid) x = (c < d) ? q[(size_t)i * q_stride + c] : obs[j * 4 + (c - d)];
-      xs[tid * XS + c] = x;
-      act[c][tid] = x;
-      act[nin + c][tid] = sinf(x);
-      act[2 * nin + c][tid] = cosf(x);
-    }
-    rad[tid] = valid ? obs[j * 4 + 3] : 0.f;
+    const bool valid = row_lookup(src, row0 + r, n_rows, i, j);
+    float x = 0.f;
+    if (valid) x = (c < d) ? q[(size_t)i * q_stride + c] : obs[j * 4 + (c - d)];
+    xs[r * XS + c] = x;
+    act[c][r] = x;
+    act[nin + c][r] = sinf(x);
+    act[2 * nin + c][r] = cosf(x);
+    if (c == 0) rad[r] = valid ? obs[j * 4 + 3] : 0.f;
   }
   __syncthreads();
 
-  uint32_t mk[4][2];
-  float acc[8][8];
+  uint64_t mk[4];          // ReLU masks of this thread's tile, bit i*8+j
+  float acc[RPT][8];
   // ---- hidden layers: h = relu(W h + b)
 #pragma unroll 1
   for (int l = 0; l < 4; ++l) {
-    gemm_tile(net.Wf[l], l == 0 ? nenc : HID, act, rg, fg, acc);
+    gemm_tile<RPT>(ws, stage, l == 0 ? nenc : HID, act, t, acc);
     __syncthreads();
-    const float4 b0 = __ldg(reinterpret_cast<const float4*>(net.b[l] + fg * 8));
-    const float4 b1 = __ldg(reinterpret_cast<const float4*>(net.b[l] + fg * 8) + 1);
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(net.b[l] + t.fa));
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(net.b[l] + t.fa + 32));
     const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-    uint32_t m0 = 0, m1 = 0;
+    uint64_t m = 0;
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < RPT; ++i)
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float v = acc[i][j] + bb[j];
         const bool on = v > 0.f;
-        if (BWD) {
-          if (i < 4) m0 |= (on ? 1u : 0u) << (i * 8 + j);
-          else m1 |= (on ? 1u : 0u) << ((i - 4) * 8 + j);
-        }
+        if (BWD) m |= (uint64_t)(on ? 1u : 0u) << (i * 8 + j);
         acc[i][j] = on ? v : 0.f;
       }
-    mk[l][0] = m0;
-    mk[l][1] = m1;
-    store_tile(act, rg, fg, acc);
+    mk[l] = m;
+    store_tile<RPT>(act, t, acc);
     __syncthreads();
   }
 
@@ -181,28 +290,28 @@ exact_mlp_kernel(NetDev net, RowSrc src, const float* __restrict__ q, int q_stri
 
   // g4 = W5[l*, :] * s4
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const float* w = net.W4 + lst[rg * 8 + i] * HID + fg * 8;
-    const uint32_t bits = (i < 4 ? mk[3][0] >> (i * 8) : mk[3][1] >> ((i - 4) * 8)) & 0xffu;
+  for (int i = 0; i < RPT; ++i) {
+    const float* w = net.W4 + lst[t.r0 + i] * HID;
+    const uint32_t bits = (uint32_t)(mk[3] >> (i * 8)) & 0xffu;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j] = ((bits >> j) & 1u) ? __ldg(w + j) : 0.f;
+    for (int j = 0; j < 8; ++j) acc[i][j] = ((bits >> j) & 1u) ? __ldg(w + t.feat(j)) : 0.f;
   }
-  store_tile(act, rg, fg, acc);
+  store_tile<RPT>(act, t, acc);
   __syncthreads();
 
   // g_{l-1} = (W_l^T g_l) * s_{l-1},  l = 3, 2, 1   (Wb[l] is torch's [out][in]: out = k, in = n)
 #pragma unroll 1
   for (int l = 3; l >= 1; --l) {
-    gemm_tile(net.Wb[l], HID, act, rg, fg, acc);
+    gemm_tile<RPT>(ws, stage, HID, act, t, acc);
     __syncthreads();
-    const uint32_t m0 = mk[l - 1][0], m1 = mk[l - 1][1];
+    const uint64_t m = mk[l - 1];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const uint32_t bits = (i < 4 ? m0 >> (i * 8) : m1 >> ((i - 4) * 8)) & 0xffu;
+    for (int i = 0; i < RPT; ++i) {
+      const uint32_t bits = (uint32_t)(m >> (i * 8)) & 0xffu;
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[i][j] = ((bits >> j) & 1u) ? acc[i][j] : 0.f;
     }
-    store_tile(act, rg, fg, acc);
+    store_tile<RPT>(act, t, acc);
     __syncthreads();
   }
 
@@ -224,34 +333,58 @@ exact_mlp_kernel(NetDev net, RowSrc src, const float* __restrict__ q, int q_stri
   }
 }
 
-constexpr size_t kSmemBytes = (size_t)(HID * R + R * XS + R * MAXO + R + R) * sizeof(float);
+constexpr size_t smem_bytes(int R) {
+  return (size_t)(HID * R + NSTAGE * WS * HID + R * XS + R * MAXO + R + R) * sizeof(float);
+}
 
-template <bool BWD>
-int launch(dsmppi_ctx* c, const float* q, int q_stride, const RowSrc& src, uint32_t ignore_mask, float* out_m,
-           float* out_dist, float* out_grad, cudaStream_t st) {
-  static bool attr_set[2] = {false, false};
-  if (!attr_set[BWD]) {
-    CUDA_TRY(cudaFuncSetAttribute(exact_mlp_kernel<BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)kSmemBytes));
-    attr_set[BWD] = true;
-  }
-  if (src.n_rows <= 0) return 0;
-  const int grid = (src.n_rows + R - 1) / R;
-  exact_mlp_kernel<BWD><<<grid, NT, kSmemBytes, st>>>(c->net, src, q, q_stride, c->obs, ignore_mask, out_m,
-                                                       out_dist, out_grad);
+// Rows-per-thread for a launch over about `rows` rows.  Measured on B200 (Franka shelf, ~24.6k candidate rows per
+// step: 171.8 / 177.0 / 187.1 ms per iteration for RPT = 8 / 4 / 2; planar-7, 4000 rows: 6.32 / 6.02 / 6.81 ms):
+// 32-row tiles win as soon as they give every SM two CTAs to overlap, 16-row tiles when rows are scarce; 8-row
+// tiles re-read the weights from shared memory too often (LSU-bound) and are only kept for experiments.
+int pick_rpt(const dsmppi_ctx* c, long long rows) {
+  const char* force = std::getenv("DSMPPI_EXACT_RPT");
+  if (force) { const int f = std::atoi(force); if (f == 8 || f == 4 || f == 2) return f; }
+  return (rows + 31) / 32 >= 2LL * c->sm_count ? 8 : 4;
+}
+
+template <bool BWD, int RPT>
+int launch_variant(dsmppi_ctx* c, const float* q, int q_stride, const RowSrc& src, uint32_t ignore_mask, float* out_m,
+                   float* out_dist, float* out_grad, cudaStream_t st) {
+  constexpr int R = 4 * RPT;
+  const long long grid = ((long long)src.n_rows + R - 1) / R;
+  exact_mlp_kernel<BWD, RPT><<<(unsigned)grid, NT, smem_bytes(R), st>>>(c->net, src, q, q_stride, c->obs, ignore_mask,
+                                                                       out_m, out_dist, out_grad);
   CUDA_TRY(cudaGetLastError());
   c->launches++;
   return 0;
+}
+
+template <bool BWD>
+int launch(dsmppi_ctx* c, const float* q, int q_stride, const RowSrc& src, uint32_t ignore_mask, float* out_m,
+           float* out_dist, float* out_grad, long long rows_estimate, cudaStream_t st) {
+  static bool init[2] = {false, false};
+  if (!init[BWD]) {
+    CUDA_TRY(cudaFuncSetAttribute(exact_mlp_kernel<BWD, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(32)));
+    CUDA_TRY(cudaFuncSetAttribute(exact_mlp_kernel<BWD, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(16)));
+    init[BWD] = true;
+  }
+  if (src.n_rows <= 0) return 0;
+  if (rows_estimate <= 0 || rows_estimate > src.n_rows) rows_estimate = src.n_rows;
+  switch (pick_rpt(c, rows_estimate)) {
+    case 8: return launch_variant<BWD, 8>(c, q, q_stride, src, ignore_mask, out_m, out_dist, out_grad, st);
+    case 4: return launch_variant<BWD, 4>(c, q, q_stride, src, ignore_mask, out_m, out_dist, out_grad, st);
+    default: return launch_variant<BWD, 2>(c, q, q_stride, src, ignore_mask, out_m, out_dist, out_grad, st);
+  }
 }
 
 }  // namespace
 
 int launch_exact_forward(dsmppi_ctx* c, const float* q, int q_stride, const RowSrc& src, uint32_t ignore_mask,
                          float* m_rows, cudaStream_t st) {
-  return launch<false>(c, q, q_stride, src, ignore_mask, m_rows, nullptr, nullptr, st);
+  return launch<false>(c, q, q_stride, src, ignore_mask, m_rows, nullptr, nullptr, 0, st);
 }
 
 int launch_exact_fwdbwd(dsmppi_ctx* c, const float* q, int q_stride, const RowSrc& src, uint32_t ignore_mask,
-                        float* m_rows, float* row_dist, float* row_grad, cudaStream_t st) {
-  return launch<true>(c, q, q_stride, src, ignore_mask, m_rows, row_dist, row_grad, st);
+                        float* m_rows, float* row_dist, float* row_grad, long long rows_estimate, cudaStream_t st) {
+  return launch<true>(c, q, q_stride, src, ignore_mask, m_rows, row_dist, row_grad, rows_estimate, st);
 }

@@ -117,8 +117,9 @@ struct dsmppi_ctx {
 int launch_exact_forward(dsmppi_ctx* c, const float* q, int q_stride, const RowSrc& src, uint32_t ignore_mask,
                          float* m_rows, cudaStream_t st);
 // forward + VJP; when m_rows != nullptr also writes the pass-1 ranking key of every row
+// rows_estimate: expected row count when src.n_rows is only an upper bound (device-side counter), else 0
 int launch_exact_fwdbwd(dsmppi_ctx* c, const float* q, int q_stride, const RowSrc& src, uint32_t ignore_mask,
-                        float* m_rows, float* row_dist, float* row_grad, cudaStream_t st);
+                        float* m_rows, float* row_dist, float* row_grad, long long rows_estimate, cudaStream_t st);
 // tc_pass1.cu
 int tc_build_images(dsmppi_ctx* c, const dsmppi_net* net);
 void tc_free_images(dsmppi_ctx* c);

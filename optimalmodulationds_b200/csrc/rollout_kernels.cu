@@ -48,37 +48,58 @@ __global__ void rank_kernel(const float* __restrict__ m_rows, const int* __restr
 // Candidate band from the approximate (tensor-core) distances: every obstacle within `band` of the
 // K-th smallest approximate distance is re-scored in fp32.  One warp per sample.
 // ------------------------------------------------------------------------------------------------
-__global__ void select_candidates_kernel(const float* __restrict__ mdist, int M, int n, int K, float band,
-                                         int* __restrict__ cand_cnt, int* __restrict__ row_base,
-                                         int* __restrict__ row_sample, int* __restrict__ row_obs,
-                                         int* __restrict__ counters) {
+__global__ void __launch_bounds__(128) select_candidates_kernel(const float* __restrict__ mdist, int M, int n, int K,
+                                                                float band, int* __restrict__ cand_cnt,
+                                                                int* __restrict__ row_base, int* __restrict__ row_sample,
+                                                                int* __restrict__ row_obs, int* __restrict__ counters) {
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (w >= n) return;
   const float* md = mdist + (size_t)w * M;
-  // K-th smallest approximate value (with multiplicity)
-  float last_v = -FLT_MAX;
-  int last_j = -1;
-  bool first = true;
-  for (int kk = 0; kk < K; ++kk) {
-    float bv = FLT_MAX;
-    int bj = 0x7fffffff;
-    for (int t = lane; t < M; t += 32) {
-      const float v = md[t];
-      const bool after = first || v > last_v || (v == last_v && t > last_j);
-      if (after && (v < bv || (v == bv && t < bj))) { bv = v; bj = t; }
+  // K-th smallest approximate value (with multiplicity), one streaming pass: every lane keeps the K smallest of
+  // its own elements sorted in registers (ties: lower obstacle index first), then the warp merges the 32 lists
+  float lv[MAXK];
+  int lj[MAXK];
+#pragma unroll
+  for (int k = 0; k < MAXK; ++k) { lv[k] = FLT_MAX; lj[k] = 0x7fffffff; }
+#pragma unroll 4
+  for (int t = lane; t < M; t += 32) {
+    float v = md[t];
+    int j = t;
+    if (v < lv[MAXK - 1]) {
+#pragma unroll
+      for (int k = 0; k < MAXK; ++k) {
+        if (v < lv[k]) {                      // strict: an equal value seen later (higher index) stays behind
+          const float tv = lv[k]; lv[k] = v; v = tv;
+          const int tj = lj[k]; lj[k] = j; j = tj;
+        }
+      }
     }
+  }
+  float last_v = -FLT_MAX;
+  for (int kk = 0; kk < K; ++kk) {
+    float bv = lv[0];
+    int bj = lj[0];
+    int src = lane;
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
       const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
       const int oj = __shfl_xor_sync(0xffffffffu, bj, off);
-      if (ov < bv || (ov == bv && oj < bj)) { bv = ov; bj = oj; }
+      const int os = __shfl_xor_sync(0xffffffffu, src, off);
+      if (ov < bv || (ov == bv && oj < bj)) { bv = ov; bj = oj; src = os; }
     }
-    last_v = bv; last_j = bj; first = false;
+    last_v = bv;
+    if (lane == src) {                         // pop the winner's head
+#pragma unroll
+      for (int k = 0; k + 1 < MAXK; ++k) { lv[k] = lv[k + 1]; lj[k] = lj[k + 1]; }
+      lv[MAXK - 1] = FLT_MAX;
+      lj[MAXK - 1] = 0x7fffffff;
+    }
   }
   const float thr = last_v + band;
   // count, reserve a contiguous row range, then fill (ascending obstacle index within the sample)
   int mine = 0;
+#pragma unroll 4
   for (int t = lane; t < M; t += 32) mine += (md[t] <= thr) ? 1 : 0;
   int total = mine;
 #pragma unroll
@@ -693,7 +714,9 @@ int launch_step(dsmppi_ctx* c, const dsmppi_rollout_args* a, int t, cudaStream_t
   s.traj = a->all_traj_dev; s.closest = a->closest_dist_all_dev; s.kval = a->kernel_val_all_dev;
   s.dots = a->dot_products_dev; s.acts = a->kernel_activations_dev; s.qdot = a->qdot_dev;
   s.grads = a->nn_grad_all_dev;
-  step_kernel<<<(a->N + 127) / 128, 128, 0, st>>>(s);
+  // one thread per sample, a long dependent chain each: spread small batches over all SMs (one warp per CTA)
+  const int bs = a->N <= c->sm_count * 128 ? 32 : 128;
+  step_kernel<<<(a->N + bs - 1) / bs, bs, 0, st>>>(s);
   LAUNCH_CHECK(c);
   return 0;
 }
