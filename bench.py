@@ -37,6 +37,13 @@ WORKLOADS = {
                              alpha_s=3.0, sigma=1.0, ignored=[0, 1, 2]),
     "planar7": dict(net="planar7", n_pts=None, N=1000, H=30, K=1, nk=10, dt=0.3, dst_thr=0.25, ker_thr=1e-3,
                     alpha_s=0.75, sigma=0.5, ignored=[]),
+    # BASELINE.json configs[0]: planar 2-DoF, script defaults (standalonePlanar2d.py:76-77,109-129)
+    "planar2": dict(net="planar2", n_pts=None, N=100, H=10, K=2, nk=10, dt=0.3, dst_thr=0.25, ker_thr=1e-3,
+                    alpha_s=2.0, sigma=0.5, ignored=[]),
+    # BASELINE.json configs[3]: dense velocity-field evaluation over a 1000 x 1000 joint-space grid (policy-plot
+    # path, standalonePlanar2d_policyPlots.py:160,257-259): H = 1, per-sample start states
+    "field_1m": dict(net="planar2", n_pts=None, N=1_000_000, H=1, K=1, nk=10, dt=0.05, dst_thr=0.25, ker_thr=1e-3,
+                     alpha_s=2.0, sigma=0.5, ignored=[], grid=1000),
 }
 
 
@@ -73,6 +80,14 @@ def problem(name):
         qlim = (torch.tensor([-2.8973, -1.7628, -2.8973, -3.0718, -2.8973, -0.0175, -2.8973]),
                 torch.tensor([2.8973, 1.7628, 2.8973, -0.0698, 2.8973, 3.7525, 2.8973]))
         dof, out = 7, 9
+    elif w["net"] == "planar2":
+        dof, out = 2, 2
+        dh_a = torch.zeros(dof + 1); dh_a[1:] = 3
+        dh = torch.vstack((dh_a * 0, dh_a * 0, dh_a, dh_a * 0)).T.contiguous()
+        q0 = torch.tensor([-3.14, 0.0])
+        qf = torch.tensor([3.14, 0.0])
+        obs = torch.tensor([[6, 0, 0, .5], [0., 4.5, 0, .5]])
+        qlim = (-0.99 * 3.14 * torch.ones(dof), 0.99 * 3.14 * torch.ones(dof))
     else:
         dof, out = 7, 7
         dh_a = torch.zeros(dof + 1); dh_a[1:] = 1
@@ -98,7 +113,7 @@ def load_net_arrays(name):
         z = np.load(path)
         return [torch.from_numpy(z[f"W{i}"]) for i in range(5)], [torch.from_numpy(z[f"b{i}"]) for i in range(5)], "shipped"
     torch.manual_seed(0)
-    d, O = (7, 9) if name == "franka" else (7, 7)
+    d, O = {"franka": (7, 9), "planar7": (7, 7), "planar2": (2, 2)}[name]
     dims = [3 * (d + 3), 256, 256, 256, 256, O]
     lin = [torch.nn.Linear(dims[i], dims[i + 1]) for i in range(5)]
     return [l.weight.detach() for l in lin], [l.bias.detach() for l in lin], "random-init"
@@ -213,7 +228,8 @@ def main():
     N, H = p["N"], p["H"]
     M = p["obs"].shape[0]
     f_fwd, f_bwd, f_step = flops_per_state_step(p)
-    config = dict(workload=args.workload, robot="franka_panda_7dof" if p["net"] == "franka" else "planar_7dof",
+    robot = {"franka": "franka_panda_7dof", "planar7": "planar_7dof", "planar2": "planar_2dof"}[p["net"]]
+    config = dict(workload=args.workload, robot=robot,
                   n_obstacles=M, samples_per_gpu=N, horizon=H, n_closest_obs=p["K"], n_kernels=p["nk"],
                   weights="tests/golden/weights (shipped checkpoint)", sharding=f"samples x{world}",
                   l2="flushed between timed steps (256 MiB write, outside the per-step event pairs)")
@@ -252,6 +268,11 @@ def main():
     mppi.Cost.q_min, mppi.Cost.q_max = t(p["qlim"][0]), t(p["qlim"][1])
     if world > 1:
         mppi.enable_sample_sharding()
+    q_start = p["q0"]
+    if p.get("grid"):            # dense field: every sample starts at its own grid point (MPPI.py:99 broadcast)
+        g = torch.linspace(-math.pi, math.pi, p["grid"])
+        q_start = torch.stack(torch.meshgrid(g, g, indexing="ij"), -1).reshape(-1, p["dof"])[:N].contiguous()
+        mppi.q_cur = t(q_start)
     mu_c, sigma_c, alpha_c, mu_tmp, sigma_tmp, alpha_tmp = seeded_policy(p, N, 100 + rank)
     P = mppi.Policy
     P.n_kernels = p["nk"]
@@ -306,7 +327,7 @@ def main():
     # ---- e2e: the same iteration through the C ABI with pinned HOST buffers (H2D + D2H inside the timed region)
     pin = lambda x: x.contiguous().pin_memory()  # noqa: E731
     d = p["dof"]
-    host = dict(q_cur=pin(p["q0"]), mu_tmp=pin(mu_tmp), sigma_tmp=pin(sigma_tmp), alpha_tmp=pin(alpha_tmp),
+    host = dict(q_cur=pin(q_start), mu_tmp=pin(mu_tmp), sigma_tmp=pin(sigma_tmp), alpha_tmp=pin(alpha_tmp),
                 mu_c=pin(mu_c), sigma_c=pin(sigma_c), alpha_c=pin(alpha_c),
                 all_traj=pin(torch.empty(N, H, d)), closest_dist_all=pin(torch.empty(N, H)),
                 kernel_val_all=pin(torch.zeros(N, H, 50)), dot_products=pin(torch.empty(N, H)),
@@ -343,11 +364,24 @@ def main():
     if stats["mode"] == 0:
         peak_tf, peak_src = 74.0, "FFMA nominal 74 TFLOP/s (fp32 scoring kernel; no tensor cores in this mode)"
     kern_ms = kt_ms / max(kt_n, 1)
-    achieved = (N * M * f_fwd) / (kern_ms * 1e-3) / 1e12 if kern_ms > 0 else 0.0
-    roofline = dict(bound="tensor", kernel="tc_pass1_kernel" if stats["mode"] else "exact_mlp_kernel<fwd>",
-                    achieved=achieved, peak=peak_tf, unit="TFLOP/s", frac=achieved / peak_tf, traffic=None,
-                    peak_source=peak_src, flops_per_launch=N * M * f_fwd, ms_per_launch=kern_ms, launches_timed=kt_n,
-                    share_of_step=kern_ms * H / ms_per_step)
+    traffic = None
+    try:      # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed ncu capture
+        prof = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
+        ent = prof.get(f"{args.workload}:{'tc_pass1_kernel' if stats['mode'] else 'exact_mlp_kernel'}")
+        if ent and ent.get("samples") == N:
+            traffic = ent["dram_bytes_per_launch"]
+    except Exception:  # noqa: BLE001
+        pass
+    # algorithmic FLOPs of the dominant kernel: the all-pairs forward (tensor-core prefilter, or the fp32 forward when
+    # M > 16), or forward + input gradient on every pair when few obstacles make one fused fp32 launch cheaper
+    f_pair = f_fwd if (stats["mode"] or M > 16) else f_fwd + f_bwd
+    launches_per_step = max(1, round(kt_n / (args.steps * H)))       # > 1 when a huge batch is rolled out in blocks
+    flops_per_launch = N * M * f_pair / launches_per_step
+    achieved = flops_per_launch / (kern_ms * 1e-3) / 1e12 if kern_ms > 0 else 0.0
+    roofline = dict(bound="tensor", kernel="tc_pass1_kernel" if stats["mode"] else "exact_mlp_kernel",
+                    achieved=achieved, peak=peak_tf, unit="TFLOP/s", frac=achieved / peak_tf, traffic=traffic,
+                    peak_source=peak_src, flops_per_launch=flops_per_launch, ms_per_launch=kern_ms, launches_timed=kt_n,
+                    share_of_step=kt_ms / args.steps / ms_per_step)
     line = dict(metric="mppi_rollout_state_steps_per_sec", value=value, unit="state-steps/s", n_gpus=world,
                 steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=ms_per_step, higher_is_better=True,
                 scaling="weak", vs_baseline=None, dtype="f32 (obstacle-ranking prefilter: f16 tcgen05, f32 accumulate)",

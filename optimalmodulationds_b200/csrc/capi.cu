@@ -277,14 +277,35 @@ int dsmppi_rollout(dsmppi_ctx* c, const dsmppi_rollout_args* a, void* stream) {
   REQUIRE(a->n_kernels == 0 || (a->mu_tmp_dev && a->sigma_tmp_dev && a->alpha_tmp_dev), "null policy pointer");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   CUDA_TRY(cudaSetDevice(c->device));
+  REQUIRE(c->M >= 1, "obstacles not set");
   c->ev_used = 0;
   CUDA_TRY(cudaMemsetAsync(c->counters + 1, 0, 3 * sizeof(int), st));
-  if (launch_init_traj(c, a, st)) return 1;
   const int d = c->d;
-  for (int t = 1; t <= a->H; ++t) {
-    const float* q = a->all_traj_dev + (size_t)(t - 1) * d;          // q_prev = all_traj[:, t-1, :]
-    if (distance_pipeline(c, q, a->H * d, a->N, a->n_closest, a->ignored_link_mask, st)) return 1;
-    if (launch_step(c, a, t, st)) return 1;
+  // Samples never interact, so a very large batch is rolled out in blocks of samples: it bounds the workspace
+  // (the (n, M) prefilter matrix is the big one: <= 1 GiB) and keeps every row index inside 31 bits.
+  long long block = (1LL << 28) / c->M;
+  if (block > (1 << 18)) block = 1 << 18;
+  if (block < 1) block = 1;
+  for (long long off = 0; off < a->N; off += block) {
+    dsmppi_rollout_args b = *a;
+    b.N = (int)(a->N - off < block ? a->N - off : block);
+    if (a->q_cur_is_batch) b.q_cur_dev = a->q_cur_dev + off * d;
+    if (a->mu_tmp_dev) b.mu_tmp_dev = a->mu_tmp_dev + off * NKMAX * d;
+    if (a->sigma_tmp_dev) b.sigma_tmp_dev = a->sigma_tmp_dev + off * NKMAX;
+    if (a->alpha_tmp_dev) b.alpha_tmp_dev = a->alpha_tmp_dev + off * NKMAX * d;
+    b.all_traj_dev = a->all_traj_dev + off * a->H * d;
+    b.closest_dist_all_dev = a->closest_dist_all_dev + off * a->H;
+    b.kernel_val_all_dev = a->kernel_val_all_dev + off * a->H * NKMAX;
+    b.dot_products_dev = a->dot_products_dev + off * a->H;
+    b.kernel_activations_dev = a->kernel_activations_dev + off * a->H;
+    b.qdot_dev = a->qdot_dev + off * d;
+    b.nn_grad_all_dev = a->nn_grad_all_dev + off * a->H * d;
+    if (launch_init_traj(c, &b, st)) return 1;
+    for (int t = 1; t <= b.H; ++t) {
+      const float* q = b.all_traj_dev + (size_t)(t - 1) * d;          // q_prev = all_traj[:, t-1, :]
+      if (distance_pipeline(c, q, b.H * d, b.N, b.n_closest, b.ignored_link_mask, st)) return 1;
+      if (launch_step(c, &b, t, st)) return 1;
+    }
   }
   if (a->norm_basis_dev)
     if (launch_basis(c, a->nn_grad_all_dev, (int64_t)a->N * a->H, a->norm_basis_dev, st)) return 1;
@@ -297,8 +318,16 @@ int dsmppi_distance_grad(dsmppi_ctx* c, const float* q_dev, int32_t n, int32_t n
   REQUIRE(n >= 1, "n must be positive");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   CUDA_TRY(cudaSetDevice(c->device));
-  if (distance_pipeline(c, q_dev, c->d, n, n_closest, ignored_link_mask, st)) return 1;
-  return launch_blend(c, n, n_closest, distance_dev, nn_grad_dev, st);
+  REQUIRE(c->M >= 1, "obstacles not set");
+  long long block = (1LL << 28) / c->M;
+  if (block > (1 << 18)) block = 1 << 18;
+  if (block < 1) block = 1;
+  for (long long off = 0; off < n; off += block) {
+    const int nb = (int)(n - off < block ? n - off : block);
+    if (distance_pipeline(c, q_dev + off * c->d, c->d, nb, n_closest, ignored_link_mask, st)) return 1;
+    if (launch_blend(c, nb, n_closest, distance_dev + off, nn_grad_dev + off * c->d, st)) return 1;
+  }
+  return 0;
 }
 
 int dsmppi_debug_pass1(dsmppi_ctx* c, const float* q_dev, int32_t n, uint32_t ignored_link_mask, int32_t mode,

@@ -285,3 +285,62 @@ def test_constructor_rejects_missing_cuda_path(monkeypatch, factory):
     c = load_npz("case_planar2")
     with pytest.raises(RuntimeError):
         factory.make_mppi(c)
+
+
+def _subset_matches_big_run(c, factory, N, H, q_big, idx, pass1):
+    """Roll out a big batch, then only the samples `idx` of it in a fresh object: per-sample results must be
+    BITWISE equal (samples never interact; blocks, tiles and candidate-row order must not leak into results)."""
+    big = factory.make_mppi(c, device="cuda", N=N, H=H, q_cur=q_big, pass1=pass1, copy_policy=False)
+    torch.manual_seed(21)
+    big.Policy.sample_policy()
+    traj, dist, kv, dots, acts = big.propagate()
+    cost = big.get_cost()
+    assert torch.isfinite(traj).all() and torch.isfinite(dist).all()
+    small = factory.make_mppi(c, device="cuda", N=len(idx), H=H, q_cur=q_big[idx], pass1=pass1, copy_policy=False)
+    for name in ("mu_tmp", "sigma_tmp", "alpha_tmp"):
+        getattr(small.Policy, name).copy_(getattr(big.Policy, name)[idx.to(traj.device)])
+    traj_s, dist_s, kv_s, dots_s, acts_s = small.propagate()
+    cost_s = small.get_cost()
+    j = idx.to(traj.device)
+    for a, b2, name in ((traj[j], traj_s, "all_traj"), (dist[j], dist_s, "closest_dist_all"), (kv[j], kv_s, "kval"),
+                        (dots[j], dots_s, "dots"), (acts[j], acts_s, "acts"), (cost[j], cost_s, "cost"),
+                        (big.qdot[j], small.qdot, "qdot")):
+        assert torch.equal(a, b2), f"{name}: big-batch rows differ from the same samples rolled out alone"
+    return big, small
+
+
+def test_dense_field_1m_points_config4(factory):
+    """BASELINE config 4 at full size: 10^6 grid points x 1 step (policy-plot path).  Size-independent checks:
+    a sample subset spanning the internal block boundaries equals the same samples run alone bit for bit, and
+    that subset matches the CPU oracle."""
+    import math
+    c = load_npz("case_field2")
+    G = 1000
+    g = torch.linspace(-math.pi, math.pi, G)
+    q = torch.stack(torch.meshgrid(g, g, indexing="ij"), -1).reshape(-1, 2).contiguous()
+    N = q.shape[0]
+    gen = torch.Generator().manual_seed(3)
+    idx = torch.cat((torch.tensor([0, 1, 262143, 262144, 262145, 524287, 524288, N - 2, N - 1]),
+                     torch.randint(0, N, (1500,), generator=gen))).unique()
+    big, small = _subset_matches_big_run(c, factory, N, 1, q, idx, "exact")
+    W, b = load_weights(c["net"])
+    prm = orc.RolloutParams(dt=float(c["dt"]), dt_H=1, n_closest_obs=int(c["K"]), dst_thr=float(c["dst_thr"]),
+                            ignored_links=c["ignored_links"].tolist(), p=float(c["p"]), with_basis=False)
+    P = small.Policy
+    o = orc.rollout(orc.Net(W, b), q[idx], c["qf"], c["obs"], P.mu_tmp.cpu(), P.sigma_tmp.cpu(), P.alpha_tmp.cpu(),
+                    int(c["nk"]), prm, len(idx))
+    check(small.closest_dist_all, o.closest_dist_all, 1e-5, 2e-6, "closest_dist_all")
+    check(small.qdot, o.qdot, 1e-5, 1e-5, "qdot")
+    check(small.kernel_activations, o.kernel_activations, 1e-4, 1e-5, "kernel_activations")
+
+
+def test_franka_large_batch_is_blockwise_consistent(factory):
+    """A Franka-shelf batch larger than one internal sample block (2^18) through the tensor-core path."""
+    c = load_npz("case_franka_shelf")
+    N, H = 270_000, 2
+    gen = torch.Generator().manual_seed(4)
+    q = c["q0"] + 0.25 * torch.randn(N, 7, generator=gen)
+    idx = torch.cat((torch.tensor([0, 262143, 262144, N - 1]), torch.randint(0, N, (300,), generator=gen))).unique()
+    big, _ = _subset_matches_big_run(c, factory, N, H, q, idx, "tc_f16")
+    st = big.pass1_stats()
+    assert st["mode"] == 1 and st["band_overflows"] == 0, st
