@@ -70,6 +70,23 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// Packed fp32 FMA (Blackwell fma.rn.f32x2): two IEEE fused multiply-adds per issue slot, bit-identical to two
+// fmaf().  The inner loop is issue-bound with scalar FFMAs (ncu: issue 68 %, fma pipe 51 %), so halving the FFMA
+// issue count is what lets the pipe fill.
+__device__ __forceinline__ uint64_t pack2f(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2f(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+
 // The weight stream: GEMM g = 0..3 are the forward layers (Wf[g], K = nenc or 256), g = 4..6 the backward ones
 // (Wb[3], Wb[2], Wb[1]); stage indices run through all of them.
 struct WeightStream {
@@ -107,10 +124,11 @@ struct WeightStream {
 template <int RPT>
 __device__ __forceinline__ void gemm_tile(WeightStream& ws, int& stage, int K, const float (*act)[4 * RPT], const Tile& t,
                                           float (&acc)[RPT][8]) {
+  uint64_t acc2[RPT][4];                  // acc2[i][p] = (acc[i][2p], acc[i][2p+1])
 #pragma unroll
   for (int i = 0; i < RPT; ++i)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    for (int p = 0; p < 4; ++p) acc2[i][p] = 0ull;
   for (int k0 = 0; k0 < K; k0 += WS, ++stage) {
     cp_async_wait<NSTAGE - 2>();          // this thread's share of `stage` has landed ...
     __syncthreads();                      // ... and everybody's; the buffer of stage-1 is free again
@@ -124,11 +142,13 @@ __device__ __forceinline__ void gemm_tile(WeightStream& ws, int& stage, int K, c
         load_rows<RPT>(&act[k0 + kk][t.r0], a);
         const float4 w0 = *reinterpret_cast<const float4*>(wb + kk * HID);
         const float4 w1 = *reinterpret_cast<const float4*>(wb + kk * HID + 32);
-        const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+        const uint64_t wp[4] = {pack2f(w0.x, w0.y), pack2f(w0.z, w0.w), pack2f(w1.x, w1.y), pack2f(w1.z, w1.w)};
 #pragma unroll
-        for (int i = 0; i < RPT; ++i)
+        for (int i = 0; i < RPT; ++i) {
+          const uint64_t ad = pack2f(a[i], a[i]);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+          for (int p = 0; p < 4; ++p) acc2[i][p] = fma2(ad, wp[p], acc2[i][p]);
+        }
       }
     } else {
       for (int kk = 0; kk < rows; ++kk) {
@@ -136,14 +156,20 @@ __device__ __forceinline__ void gemm_tile(WeightStream& ws, int& stage, int K, c
         load_rows<RPT>(&act[k0 + kk][t.r0], a);
         const float4 w0 = *reinterpret_cast<const float4*>(wb + kk * HID);
         const float4 w1 = *reinterpret_cast<const float4*>(wb + kk * HID + 32);
-        const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+        const uint64_t wp[4] = {pack2f(w0.x, w0.y), pack2f(w0.z, w0.w), pack2f(w1.x, w1.y), pack2f(w1.z, w1.w)};
 #pragma unroll
-        for (int i = 0; i < RPT; ++i)
+        for (int i = 0; i < RPT; ++i) {
+          const uint64_t ad = pack2f(a[i], a[i]);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+          for (int p = 0; p < 4; ++p) acc2[i][p] = fma2(ad, wp[p], acc2[i][p]);
+        }
       }
     }
   }
+#pragma unroll
+  for (int i = 0; i < RPT; ++i)
+#pragma unroll
+    for (int p = 0; p < 4; ++p) unpack2f(acc2[i][p], acc[i][2 * p], acc[i][2 * p + 1]);
 }
 
 template <int RPT>
