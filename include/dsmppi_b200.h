@@ -157,6 +157,27 @@ int dsmppi_update_partial(dsmppi_ctx* ctx, const dsmppi_update_args* args, const
 int dsmppi_update_finalize(dsmppi_ctx* ctx, const dsmppi_update_args* args, const float* packed_dev,
                            int32_t* n_updated_dev, void* stream);
 
+/* TensorPolicyMPPI.check_traj_for_kernels (policy.py:153-175): state-steps that are close to an obstacle
+ * (closest_dist < thr_dist), moving into it (dot < thr_dot) and not covered by any policy kernel
+ * (max_k exp(-sigma_k ||q - mu_k||_p^2) < thr_kernel; always true with no kernels).  Appends the flat index
+ * i*H + h of every such state-step to out_index_dev (UNORDERED, at most `capacity` entries) and stores their
+ * total number in count_dev[0] (which may exceed capacity: the caller re-runs with a larger buffer). */
+typedef struct {
+  int32_t N, H;
+  int32_t n_kernels;
+  float rbf_p;                   /* Policy.p                                                            */
+  float thr_dist, thr_kernel, thr_dot;
+  const float* all_traj_dev;         /* (N, H, d) */
+  const float* closest_dist_all_dev; /* (N, H)    */
+  const float* dot_products_dev;     /* (N, H)    */
+  const float* mu_c_dev;             /* (50, d)   */
+  const float* sigma_c_dev;          /* (50,)     */
+  int32_t* out_index_dev;            /* (capacity,) */
+  int32_t* count_dev;                /* (1,) zeroed by the call */
+  int64_t capacity;
+} dsmppi_candidates_args;
+int dsmppi_kernel_candidates(dsmppi_ctx* ctx, const dsmppi_candidates_args* args, void* stream);
+
 /* One whole MPPI iteration with HOST buffers (what a CPU-tensor caller of the reference API pays):
  * H2D of q_cur / sampled policy, rollout, cost, policy update, D2H of every output.  Host pointers may be
  * pageable or pinned.  Synchronises `stream` before returning. */

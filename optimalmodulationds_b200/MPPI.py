@@ -60,6 +60,7 @@ class MPPI:
             self._dev = torch.device('cuda', int(os.environ.get('DSMPPI_DEVICE', os.environ.get('LOCAL_RANK', 0))))
         self.n_dof = q0.shape[0]
         self.Policy = TensorPolicyMPPI(N_traj, self.n_dof, self.tensor_args)
+        self.Policy._backend = self
         self.q0 = q0
         self.DS_idx = 0
         self.DS_ARRAY = DS_ARRAY
@@ -326,6 +327,32 @@ class MPPI:
         user = self._u(cost)
         self._remember(user, cost)
         return user
+
+    def kernel_candidates(self, policy, all_traj, closest_dist_all, dot_products, thr_dist, thr_kernel, thr_dot):
+        """Backend of TensorPolicyMPPI.check_traj_for_kernels (policy.py:153-175)."""
+        N, H, d = all_traj.shape
+        nk = int(policy.n_kernels)
+        a = _capi.CandidatesArgs()
+        a.N, a.H, a.n_kernels, a.rbf_p = N, H, nk, float(policy.p)
+        a.thr_dist, a.thr_kernel, a.thr_dot = float(thr_dist), float(thr_kernel), float(thr_dot)
+        with torch.cuda.device(self._dev):
+            tr, cd, dp = self._dev_of(all_traj), self._dev_of(closest_dist_all), self._dev_of(dot_products)
+            mu_c, sigma_c = self._d(policy.mu_c), self._d(policy.sigma_c)
+            count = torch.zeros(1, dtype=torch.int32, device=self._dev)
+            cap = min(N * H, 1 << 20)
+            while True:
+                idx = torch.empty(cap, dtype=torch.int32, device=self._dev)
+                a.all_traj_dev, a.closest_dist_all_dev, a.dot_products_dev = tr.data_ptr(), cd.data_ptr(), dp.data_ptr()
+                a.mu_c_dev, a.sigma_c_dev = mu_c.data_ptr(), sigma_c.data_ptr()
+                a.out_index_dev, a.count_dev, a.capacity = idx.data_ptr(), count.data_ptr(), cap
+                _capi.check(self._lib.dsmppi_kernel_candidates(self._ctx, _capi.C.byref(a), self._stream()))
+                n = int(count.item())
+                if n <= cap:
+                    break
+                cap = N * H                      # rare: more candidates than the first buffer holds
+            order = torch.sort(idx[:n].long())[0]          # the reference returns them in (i, h) order
+            cand = tr.reshape(-1, d)[order]
+        return self._u(cand)
 
     def get_cost(self):
         self.cur_cost = self.Cost.evaluate_costs(self.all_traj, self.closest_dist_all)

@@ -55,6 +55,16 @@ class UpdateArgs(C.Structure):
     ]
 
 
+class CandidatesArgs(C.Structure):
+    _fields_ = [
+        ("N", C.c_int32), ("H", C.c_int32), ("n_kernels", C.c_int32), ("rbf_p", C.c_float),
+        ("thr_dist", C.c_float), ("thr_kernel", C.c_float), ("thr_dot", C.c_float),
+        ("all_traj_dev", _fp), ("closest_dist_all_dev", _fp), ("dot_products_dev", _fp),
+        ("mu_c_dev", _fp), ("sigma_c_dev", _fp), ("out_index_dev", _fp), ("count_dev", _fp),
+        ("capacity", C.c_int64),
+    ]
+
+
 class IterationHostArgs(C.Structure):
     _fields_ = [
         ("rollout", RolloutArgs),
@@ -83,6 +93,7 @@ EXPORTS = {
     "dsmppi_debug_pass1": (C.c_int, [C.c_void_p, _fp, C.c_int32, C.c_uint32, C.c_int32, _fp, C.c_void_p]),
     "dsmppi_norm_basis": (C.c_int, [C.c_void_p, _fp, C.c_int64, _fp, C.c_void_p]),
     "dsmppi_cost": (C.c_int, [C.c_void_p, C.POINTER(CostArgs), C.c_void_p]),
+    "dsmppi_kernel_candidates": (C.c_int, [C.c_void_p, C.POINTER(CandidatesArgs), C.c_void_p]),
     "dsmppi_update_packed_len": (C.c_int32, [C.c_int32, C.c_int32]),
     "dsmppi_update_cost_stats": (C.c_int, [C.c_void_p, _fp, C.c_int32, _fp, C.c_void_p]),
     "dsmppi_update_partial": (C.c_int, [C.c_void_p, C.POINTER(UpdateArgs), _fp, _fp, C.c_void_p]),

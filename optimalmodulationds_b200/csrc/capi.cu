@@ -363,6 +363,18 @@ int dsmppi_norm_basis(dsmppi_ctx* c, const float* grad_dev, int64_t n, float* ba
   return launch_basis(c, grad_dev, n, basis_dev, static_cast<cudaStream_t>(stream));
 }
 
+int dsmppi_kernel_candidates(dsmppi_ctx* c, const dsmppi_candidates_args* a, void* stream) {
+  REQUIRE(c && a && a->all_traj_dev && a->closest_dist_all_dev && a->dot_products_dev && a->out_index_dev &&
+              a->count_dev,
+          "null argument");
+  REQUIRE(a->N >= 1 && a->H >= 1 && (long long)a->N * a->H < (1LL << 31), "N * H must fit 31 bits");
+  REQUIRE(a->n_kernels >= 0 && a->n_kernels <= NKMAX, "n_kernels out of range");
+  REQUIRE(a->n_kernels == 0 || (a->mu_c_dev && a->sigma_c_dev), "null policy pointer");
+  REQUIRE(a->capacity >= 1, "capacity must be positive");
+  CUDA_TRY(cudaSetDevice(c->device));
+  return launch_kernel_candidates(c, a, static_cast<cudaStream_t>(stream));
+}
+
 int dsmppi_cost(dsmppi_ctx* c, const dsmppi_cost_args* a, void* stream) {
   REQUIRE(c && a && a->all_traj_dev && a->closest_dist_all_dev && a->cost_dev, "null argument");
   CUDA_TRY(cudaSetDevice(c->device));

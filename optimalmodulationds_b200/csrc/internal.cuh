@@ -140,4 +140,5 @@ int launch_update_partial(dsmppi_ctx* c, const dsmppi_update_args* a, const floa
                           cudaStream_t st);
 int launch_update_finalize(dsmppi_ctx* c, const dsmppi_update_args* a, const float* packed, int* n_updated,
                            cudaStream_t st);
+int launch_kernel_candidates(dsmppi_ctx* c, const dsmppi_candidates_args* a, cudaStream_t st);
 int ensure_workspace(dsmppi_ctx* c, int n, int M);

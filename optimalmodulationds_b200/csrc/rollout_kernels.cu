@@ -342,6 +342,59 @@ __global__ void __launch_bounds__(128) step_kernel(StepArgs s) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Kernel-candidate detection (policy.py:153-175): one thread per state-step, unordered atomic append
+// ------------------------------------------------------------------------------------------------
+struct CandArgs {
+  long long total;            // N * H
+  int d, nk;
+  float p, thr_dist, thr_kernel, thr_dot;
+  const float* traj; const float* closest; const float* dots; const float* mu; const float* sigma;
+  int* out_index; int* count; long long capacity;
+};
+
+__global__ void __launch_bounds__(256) kernel_candidates_kernel(CandArgs c) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  bool keep = false;
+  if (idx < c.total && c.closest[idx] < c.thr_dist && c.dots[idx] < c.thr_dot) {
+    keep = true;
+    if (c.nk > 0) {
+      float q[MAXD];
+#pragma unroll
+      for (int a = 0; a < MAXD; ++a) q[a] = a < c.d ? c.traj[idx * c.d + a] : 0.f;
+      float cover = -FLT_MAX;
+      for (int k = 0; k < c.nk; ++k) {
+        float acc = 0.f;
+        if (c.p == 2.f) {
+#pragma unroll
+          for (int a = 0; a < MAXD; ++a)
+            if (a < c.d) { const float df = q[a] - c.mu[k * c.d + a]; acc += df * df; }
+          acc = sqrtf(acc);
+        } else {
+#pragma unroll
+          for (int a = 0; a < MAXD; ++a)
+            if (a < c.d) acc += powf(fabsf(q[a] - c.mu[k * c.d + a]), c.p);
+          acc = powf(acc, 1.f / c.p);
+        }
+        cover = fmaxf(cover, expf(-c.sigma[k] * (acc * acc)));          // eval_rbf_simple, policy.py:201-214
+      }
+      keep = cover < c.thr_kernel;
+    }
+  }
+  // warp-aggregated append
+  const unsigned bal = __ballot_sync(0xffffffffu, keep);
+  if (bal) {
+    const int lane = threadIdx.x & 31, leader = __ffs(bal) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(c.count, __popc(bal));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (keep) {
+      const long long pos = base + __popc(bal & ((1u << lane) - 1u));
+      if (pos < c.capacity) c.out_index[pos] = (int)idx;
+    }
+  }
+}
+
 __global__ void init_traj_kernel(const float* __restrict__ q_cur, int is_batch, int N, int H, int d,
                                  float* __restrict__ traj) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -692,6 +745,20 @@ int launch_rank_candidates(dsmppi_ctx* c, int n, int K, cudaStream_t st) {
 int launch_blend(dsmppi_ctx* c, int n, int K, float* dist_out, float* grad_out, cudaStream_t st) {
   blend_kernel<<<(n + 127) / 128, 128, 0, st>>>(c->row_dist, c->row_grad, c->sel_rows, n, K, c->d, dist_out,
                                                 grad_out);
+  LAUNCH_CHECK(c);
+  return 0;
+}
+
+int launch_kernel_candidates(dsmppi_ctx* c, const dsmppi_candidates_args* a, cudaStream_t st) {
+  CandArgs k;
+  k.total = (long long)a->N * a->H;
+  k.d = c->d; k.nk = a->n_kernels; k.p = a->rbf_p;
+  k.thr_dist = a->thr_dist; k.thr_kernel = a->thr_kernel; k.thr_dot = a->thr_dot;
+  k.traj = a->all_traj_dev; k.closest = a->closest_dist_all_dev; k.dots = a->dot_products_dev;
+  k.mu = a->mu_c_dev; k.sigma = a->sigma_c_dev;
+  k.out_index = a->out_index_dev; k.count = a->count_dev; k.capacity = a->capacity;
+  CUDA_TRY(cudaMemsetAsync(a->count_dev, 0, sizeof(int), st));
+  kernel_candidates_kernel<<<(unsigned)((k.total + 255) / 256), 256, 0, st>>>(k);
   LAUNCH_CHECK(c);
   return 0;
 }

@@ -36,6 +36,7 @@ class TensorPolicyMPPI:
         self.kernel_gammas = torch.zeros(K, **tensor_params)
         self.kernel_obstacle_bases = torch.zeros((K, n_dof, n_dof), **tensor_params)
         self.p = 2
+        self._backend = None          # set by the MPPI object that owns this policy
 
     def reset_policy(self):
         self.n_kernels = 0
@@ -97,15 +98,14 @@ class TensorPolicyMPPI:
         self.n_kernels = nk + 1
 
     def check_traj_for_kernels(self, all_traj, closests_dist_all, dotproducts_all, thr_dist, thr_kernel, thr_dot):
-        """States that are close to an obstacle, moving into it, and not yet covered by a kernel."""
-        near = (closests_dist_all < thr_dist) & (dotproducts_all < thr_dot)
-        cand = all_traj[near].view(-1, self.n_dof)
-        if self.n_kernels > 0:
-            nk = self.n_kernels
-            cover = eval_rbf_simple(cand, self.mu_c[:nk].to(cand.device), self.sigma_c[:nk].to(cand.device), self.p)
-            keep = cover.max(dim=-1)[0] < thr_kernel
-            return cand[keep]
-        return cand
+        """States that are close to an obstacle, moving into it, and not yet covered by a kernel
+        (policy.py:153-175), in trajectory-major order.  Runs as one CUDA pass over the (N, H) state-steps of
+        the MPPI object that owns this policy (dsmppi_kernel_candidates)."""
+        if self._backend is None:
+            raise RuntimeError("check_traj_for_kernels needs the CUDA backend of the MPPI object that owns this "
+                               "policy (there is no CPU path)")
+        return self._backend.kernel_candidates(self, all_traj, closests_dist_all, dotproducts_all, thr_dist,
+                                               thr_kernel, thr_dot)
 
 
 def eval_policy(rbf_val, alphas):

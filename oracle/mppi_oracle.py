@@ -302,6 +302,19 @@ def rollout(net: Net, q_cur: torch.Tensor, q_goal: torch.Tensor, obs: torch.Tens
 # ----------------------------------------------------------------------------------------------
 # Forward kinematics + cost  (ds_mppi/functions/fk_num.py:7-75, cost.py:13-46)
 # ----------------------------------------------------------------------------------------------
+def kernel_candidates(all_traj, closest_dist_all, dot_products, mu_c, sigma_c, n_kernels, thr_dist, thr_kernel,
+                      thr_dot, p=2):
+    """TensorPolicyMPPI.check_traj_for_kernels (ds_mppi/functions/policy.py:153-175): state-steps close to an
+    obstacle and moving into it, not covered by any kernel; returned in (sample, step) order."""
+    near = (closest_dist_all < thr_dist) & (dot_products < thr_dot)
+    cand = all_traj[near].reshape(-1, all_traj.shape[-1])
+    if n_kernels > 0:
+        dist2 = torch.norm(cand[:, None, :] - mu_c[:n_kernels], p, -1) ** 2            # policy.py:201-214
+        cover = torch.exp(-sigma_c[:n_kernels] * dist2).max(dim=-1)[0]
+        cand = cand[cover < thr_kernel]
+    return cand
+
+
 def dh_transform(q, d, theta, a, alpha):
     """Modified-DH transform, batched over q (n,) -> (n, 4, 4)   (fk_num.py:7-27)."""
     sa, ca = torch.sin(alpha), torch.cos(alpha)

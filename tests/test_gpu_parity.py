@@ -344,3 +344,18 @@ def test_franka_large_batch_is_blockwise_consistent(factory):
     big, _ = _subset_matches_big_run(c, factory, N, H, q, idx, "tc_f16")
     st = big.pass1_stats()
     assert st["mode"] == 1 and st["band_overflows"] == 0, st
+
+
+@pytest.mark.parametrize("tag", case_names())
+def test_kernel_candidates_vs_reference(tag, factory):
+    """Policy.check_traj_for_kernels through the CUDA pass (dsmppi_kernel_candidates) on the reference's own
+    trajectories: same candidate states, same (sample, step) order as the reference class returned."""
+    c = load_npz(f"case_{tag}")
+    g = load_npz(f"cand_{tag}")
+    m = factory.make_mppi(c, device="cpu")
+    for i in range(int(g["n_sets"])):
+        thr_dist, thr_kernel, thr_dot = (float(x) for x in g[f"thr{i}"])
+        cand = m.Policy.check_traj_for_kernels(c["all_traj"], c["closest_dist_all"], c["dot_products"], thr_dist,
+                                               thr_kernel, thr_dot)
+        assert cand.device.type == "cpu" and cand.shape == g[f"cand{i}"].shape, (cand.shape, g[f"cand{i}"].shape)
+        assert torch.equal(cand, g[f"cand{i}"])

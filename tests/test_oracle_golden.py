@@ -183,3 +183,17 @@ def test_policy_update_partials_sum_to_full_update():
     mu_sum = tot[1:1 + nk * d].reshape(nk, d) / wsum
     ref_mu_sum = torch.sum(w[:, None, None] * mu[:, :nk], 0)
     torch.testing.assert_close(mu_sum, ref_mu_sum, rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize("tag", case_names())
+def test_kernel_candidates_vs_reference(tag):
+    """check_traj_for_kernels (policy.py:153-175): goldens come from the reference class itself
+    (tests/golden/make_golden_candidates.py)."""
+    c = load_npz(f"case_{tag}")
+    g = load_npz(f"cand_{tag}")
+    for i in range(int(g["n_sets"])):
+        thr_dist, thr_kernel, thr_dot = (float(x) for x in g[f"thr{i}"])
+        cand = orc.kernel_candidates(c["all_traj"], c["closest_dist_all"], c["dot_products"], c["mu_c0"], c["sigma_c0"],
+                                     int(c["nk"]), thr_dist, thr_kernel, thr_dot, float(c["p"]))
+        assert cand.shape == g[f"cand{i}"].shape
+        assert torch.equal(cand, g[f"cand{i}"])
