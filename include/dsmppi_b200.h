@@ -40,9 +40,32 @@ typedef struct dsmppi_ctx dsmppi_ctx;
 typedef struct {
   int32_t n_dof;                 /* d  */
   int32_t n_out;                 /* O  */
+  int32_t n_point_dim;           /* P: obstacle coordinates fed to the network (in_channels = d + P); 3 for every
+                                  * robot net, 2 for the planar "toy" net (standaloneToy2d.py:30); 0 means 3      */
+  int32_t reserved;
   const float* W_host[5];
   const float* b_host[5];
 } dsmppi_net;
+
+/* Constants of the modulation law.  The reference compiles two sets into its sources: MPPI.py:132-155,194,216
+ * (every robot of the live scripts) and MPPI_toy.py:89,114-133,176-180,199 (the 2-D point "toy").
+ * dsmppi_modulation_default / dsmppi_modulation_toy fill them; sigmoid(x; y0, y1, x0, x1, k) of MPPI.py:352-353 is
+ * passed as its midpoint (x0 + x1) / 2 and slope k. */
+enum {
+  DSMPPI_DS_LINEAR_ATTRACTOR = 0,  /* LinDS.get_velocity (LinDS.py:11-21): unit speed outside lin_thr              */
+  DSMPPI_DS_MATRIX = 1             /* v = (q - q_goal) @ A (MPPI_toy.py:89), not normalised                         */
+};
+typedef struct {
+  int32_t ds_kind;               /* DSMPPI_DS_*                                                                  */
+  int32_t fold_activation;       /* 1: kernel_val_all[:, t, :nk] *= activation (MPPI_toy.py:178-179)             */
+  float lvel_mid, lvel_k;        /* l_vel = sigmoid(dot; 0, 1, ..): (-0.5, 10) | toy (-0.1, 100)                  */
+  float dist_mid, dist_k;        /* l_n, l_tau over the distance: (0.05, 100) | toy (0.25, 30)                    */
+  float ltau_max;                /* 5 | toy 3                                                                    */
+  float goal_act_thr;            /* goal activation below this is zeroed: 0.5 | toy 0.3                          */
+  float repulsion;               /* collision case: m = 0.1 m + repulsion |v| e0: 0.1 | toy 0.05                 */
+  float reserved;
+  float ds_A[DSMPPI_MAX_DOF * DSMPPI_MAX_DOF];   /* DSMPPI_DS_MATRIX: A[a][c] at a * DSMPPI_MAX_DOF + c           */
+} dsmppi_modulation;
 
 /* Pass-1 precision: how the all-pairs forward pass that ranks obstacles (MPPI.py:231-253) is evaluated. */
 enum {
@@ -65,6 +88,7 @@ typedef struct {
   float lin_thr;                 /* LinDS.lin_thr (LinDS.py:9)                                          */
   float rbf_p;                   /* Policy.p (policy.py:41,186-199)                                     */
   float q_goal[DSMPPI_MAX_DOF];  /* DS.q_goal == MPPI.qf                                                */
+  dsmppi_modulation mod;         /* constants of the modulation law (fill with dsmppi_modulation_default)      */
   /* inputs (device) */
   const float* q_cur_dev;
   const float* mu_tmp_dev;       /* (N, 50, d)  Policy.mu_tmp                                           */
@@ -81,8 +105,15 @@ typedef struct {
   float* norm_basis_dev;         /* (N, H, d, d) or NULL (lazy: see dsmppi_norm_basis)                  */
 } dsmppi_rollout_args;
 
+enum {
+  DSMPPI_COST_JOINT_LIMITS = 1,  /* cost.py:16,36-39                                                            */
+  DSMPPI_COST_TERMINAL_FK = 2,   /* cost.py:19,27-31                                                            */
+  DSMPPI_COST_ALL = 3            /* cost.py:13-21; cost_toy.py:13-19 keeps goal + collision + stagnation only: 0 */
+};
 typedef struct {
   int32_t N, H;
+  int32_t terms;                 /* DSMPPI_COST_* bit mask of the optional terms                                */
+  int32_t reserved;
   float q_goal[DSMPPI_MAX_DOF];
   float q_min[DSMPPI_MAX_DOF];   /* Cost.q_min / q_max (cost.py:10-11)                                  */
   float q_max[DSMPPI_MAX_DOF];
@@ -95,6 +126,9 @@ typedef struct {
   int32_t N, H;
   int32_t n_kernels;
   int32_t owns_sample0;          /* 1 when this shard holds global sample 0 (the noise-free rollout)    */
+  int32_t variant;               /* 0: MPPI.py:335-342 (max_t kernel_val * activation, and the sample-0 base
+                                  * mask); 1: MPPI_toy.py:318-321 (max_t kernel_val, no base mask)            */
+  int32_t reserved;
   int64_t N_global;              /* total samples over all shards (for the means)                       */
   float ker_thr;                 /* MPPI.ker_thr                                                        */
   float upd_rate;                /* MPPI.policy_upd_rate (MPPI.py:58,344)                               */
@@ -111,6 +145,8 @@ typedef struct {
 
 const char* dsmppi_last_error(void);
 int dsmppi_version(void);
+void dsmppi_modulation_default(dsmppi_modulation* out);   /* MPPI.py constants, LinDS nominal dynamics   */
+void dsmppi_modulation_toy(dsmppi_modulation* out);       /* MPPI_toy.py constants, matrix DS with A = -I */
 
 /* MPPI.__init__ (MPPI.py:22-73): packs the network (fp32 both orientations + fp16/bf16 UMMA smem images),
  * the DH table (dh_params (d+1, 4) = [d, theta, a, alpha], HOST) and sizes the workspace for
@@ -120,7 +156,8 @@ int dsmppi_ctx_create(dsmppi_ctx** out, const dsmppi_net* net, const float* dh_p
 int dsmppi_ctx_destroy(dsmppi_ctx* ctx);
 int dsmppi_set_pass1_mode(dsmppi_ctx* ctx, int32_t mode, float guard_band);
 
-/* MPPI.update_obstacles (MPPI.py:347-350) and the obs argument of __init__: (M, 4) = [x, y, z, r]. */
+/* MPPI.update_obstacles (MPPI.py:347-350) and the obs argument of __init__: (M, P + 1) = [x, y, z, r], or
+ * [x, y, r] for a network created with n_point_dim = 2. */
 int dsmppi_set_obstacles(dsmppi_ctx* ctx, const float* obs_dev, int32_t M, void* stream);
 int dsmppi_set_obstacles_host(dsmppi_ctx* ctx, const float* obs_host, int32_t M, void* stream);
 
@@ -186,6 +223,8 @@ typedef struct {
   float q_min[DSMPPI_MAX_DOF];
   float q_max[DSMPPI_MAX_DOF];
   float ker_thr, upd_rate;
+  int32_t cost_terms;            /* dsmppi_cost_args.terms                                              */
+  int32_t update_variant;        /* dsmppi_update_args.variant                                          */
   const float* q_cur_host;       /* (d,) or (N, d)                                                      */
   const float* mu_tmp_host;      /* (N, 50, d) */
   const float* sigma_tmp_host;   /* (N, 50)    */

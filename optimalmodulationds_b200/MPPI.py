@@ -38,14 +38,21 @@ def _network_arrays(nn_model):
         raise NotImplementedError(f"expected the 5-layer distance MLP (4 hidden + output), found {len(lin)} layers")
     W = [m.weight.detach().to('cpu', torch.float32).contiguous() for m in lin]
     b = [m.bias.detach().to('cpu', torch.float32).contiguous() for m in lin]
-    d = nn_model.in_channels - 3
     if W[0].shape != (256, 3 * nn_model.in_channels) or any(w.shape != (256, 256) for w in W[1:4]) \
             or W[4].shape != (nn_model.out_channels, 256):
-        raise NotImplementedError("only the shipped 3(d+3)-256-256-256-256-O layout (skips=[]) is supported")
-    return W, b, d
+        raise NotImplementedError("only the shipped 3(d+P)-256-256-256-256-O layout (skips=[]) is supported")
+    return W, b
 
 
 class MPPI:
+    # which of the two constant sets the reference compiles into its sources (MPPI.py vs MPPI_toy.py); the toy
+    # subclass (optimalmodulationds_b200/MPPI_toy.py) overrides these
+    _TOY = False
+    _COST_TERMS = _capi.COST_ALL
+    _UPDATE_VARIANT = 0
+    _DEFAULT_DST_THR = 0.5
+    _COST_CLASS = Cost
+
     def __init__(self, q0: torch.Tensor, qf: torch.Tensor, dh_params: torch.Tensor, obs: torch.Tensor, dt: float,
                  dt_H: int, N_traj: int, DS_ARRAY, dh_a, nn_model, n_closest_obs):
         self.tensor_args = {'device': q0.device, 'dtype': q0.dtype}
@@ -76,7 +83,7 @@ class MPPI:
         self.nn_model = nn_model
         self.q_cur = q0
         self.policy_upd_rate = 0.1
-        self.dst_thr = 0.5
+        self.dst_thr = self._DEFAULT_DST_THR
         self.ker_thr = 1e-3
         self.ignored_links = [0, 1, 2] if self.n_dof >= 7 else []
         self.n_closest_obs = n_closest_obs
@@ -88,7 +95,7 @@ class MPPI:
         self._norm_basis = None
         self._ctx = None
         self._make_context()
-        self.Cost = Cost(self.qf, self.dh_params, backend=self)
+        self.Cost = self._COST_CLASS(self.qf, self.dh_params, backend=self)
         self.reset_tensors()
         self.qdot = torch.zeros((self.N_traj, self.n_dof), **self.tensor_args)
         self.nn_grad = torch.zeros(N_traj, self.n_dof, **self.tensor_args)
@@ -100,17 +107,21 @@ class MPPI:
 
     # ------------------------------------------------------------------ backend plumbing
     def _make_context(self):
-        W, b, d = _network_arrays(self.nn_model)
-        if d != self.n_dof:
-            raise ValueError(f"network expects {d} joints, q0 has {self.n_dof}")
+        W, b = _network_arrays(self.nn_model)
+        # network input = [q, obstacle coordinates]: 3 coordinates for the robot nets, 2 for the planar toy net
+        self._point_dim = int(self.nn_model.in_channels) - self.n_dof
+        if self._point_dim not in (2, 3):
+            raise ValueError(f"network takes {self.nn_model.in_channels} inputs, q0 has {self.n_dof} joints: "
+                             "expected n_dof + 3 (or n_dof + 2 for the planar toy net)")
         net = _capi.Net()
-        net.n_dof, net.n_out = self.n_dof, self.nn_model.out_channels
+        net.n_dof, net.n_out, net.n_point_dim = self.n_dof, self.nn_model.out_channels, self._point_dim
         for i in range(5):
             net.W_host[i] = W[i].data_ptr()
             net.b_host[i] = b[i].data_ptr()
         dh = self.dh_params.detach().to('cpu', torch.float32).contiguous()
-        if dh.shape != (self.n_dof + 1, 4):
+        if dh.dim() != 2 or dh.shape[1] != 4 or dh.shape[0] < self.n_dof + 1:
             raise ValueError("dh_params must be (n_dof + 1, 4) = [d, theta, a, alpha]")
+        dh = dh[:self.n_dof + 1].contiguous()      # standaloneToy2d.py:55 passes a (4, 4) dummy for 2 joints
         handle = _capi.C.c_void_p()
         with torch.cuda.device(self._dev):
             _capi.check(self._lib.dsmppi_ctx_create(_capi.C.byref(handle), _capi.C.byref(net), dh.data_ptr(),
@@ -156,8 +167,9 @@ class MPPI:
 
     def _upload_obstacles(self):
         obs = self._d(self.obs)
-        if obs.dim() != 2 or obs.shape[1] != 4:
-            raise ValueError("obs must be (M, 4) = [x, y, z, r]")
+        if obs.dim() != 2 or obs.shape[1] != self._point_dim + 1:
+            raise ValueError("obs must be (M, 4) = [x, y, z, r]" if self._point_dim == 3 else
+                             "obs must be (M, 3) = [x, y, r] for a network with n_dof + 2 inputs")
         self.n_obs = obs.shape[0]
         _capi.check(self._lib.dsmppi_set_obstacles(self._ctx, obs.data_ptr(), int(obs.shape[0]), self._stream()))
         return obs
@@ -182,7 +194,7 @@ class MPPI:
 
     def _rebuild_cost(self):
         old = getattr(self, 'Cost', None)
-        self.Cost = Cost(self.qf, self.dh_params, backend=self)
+        self.Cost = self._COST_CLASS(self.qf, self.dh_params, backend=self)
         if old is not None:                      # keep limits the caller assigned after construction
             self.Cost.q_min, self.Cost.q_max = old.q_min, old.q_max
 
@@ -199,15 +211,34 @@ class MPPI:
         self.nn_input = torch.hstack((q_tens.tile(obs_tens.shape[0], 1), obs_tens.repeat_interleave(q_tens.shape[0], 0)))
         return self.nn_input
 
+    def _modulation(self, mod):
+        """Fills the constants of the modulation law and the nominal dynamics (read at call time)."""
+        if self._TOY:
+            self._lib.dsmppi_modulation_toy(_capi.C.byref(mod))
+        else:
+            self._lib.dsmppi_modulation_default(_capi.C.byref(mod))
+        if hasattr(self.DS, 'lin_thr'):
+            mod.ds_kind = _capi.DS_LINEAR_ATTRACTOR
+        elif hasattr(self.DS, 'A'):
+            mod.ds_kind = _capi.DS_MATRIX
+            A = torch.as_tensor(self.DS.A).detach().to('cpu', torch.float32)
+            if A.shape != (self.n_dof, self.n_dof):
+                raise ValueError("the matrix DS needs A of shape (n_dof, n_dof)")
+            for r in range(self.n_dof):
+                for c in range(self.n_dof):
+                    mod.ds_A[r * _capi.MAX_DOF + c] = float(A[r, c])
+        else:
+            raise NotImplementedError("the CUDA rollout implements the LinDS attractor (LinDS.py) and the matrix DS "
+                                      "v = (q - qf) @ A (MPPI_toy.py:89) as nominal dynamics")
+
     def _rollout_args(self, N, H, nk, q_cur, mu, sigma, alpha, out):
         a = _capi.RolloutArgs()
         a.N, a.H, a.n_kernels, a.n_closest = N, H, nk, int(self.n_closest_obs)
         a.q_cur_is_batch = 1 if q_cur.dim() == 2 else 0
         a.ignored_link_mask = self._ignore_mask()
         a.dt, a.dst_thr = float(self.dt), float(self.dst_thr)
-        if not hasattr(self.DS, 'lin_thr'):
-            raise NotImplementedError("only the LinDS nominal dynamics is implemented in the CUDA rollout")
-        a.lin_thr, a.rbf_p = float(self.DS.lin_thr), float(self.Policy.p)
+        self._modulation(a.mod)
+        a.lin_thr, a.rbf_p = float(getattr(self.DS, 'lin_thr', 0.0)), float(self.Policy.p)
         goal = torch.as_tensor(self.DS.q_goal).detach().reshape(-1).to('cpu', torch.float32)
         for i in range(self.n_dof):
             a.q_goal[i] = float(goal[i])
@@ -311,7 +342,7 @@ class MPPI:
         """Backend of Cost.evaluate_costs (cost.py:13-22)."""
         N, H, d = all_traj.shape
         a = _capi.CostArgs()
-        a.N, a.H = N, H
+        a.N, a.H, a.terms = N, H, self._COST_TERMS
         goal = torch.as_tensor(cost_obj.qf).detach().reshape(-1).to('cpu', torch.float32)
         qmin = torch.as_tensor(cost_obj.q_min).detach().reshape(-1).to('cpu', torch.float32)
         qmax = torch.as_tensor(cost_obj.q_max).detach().reshape(-1).to('cpu', torch.float32)
@@ -385,7 +416,7 @@ class MPPI:
         with torch.cuda.device(dev):
             a = _capi.UpdateArgs()
             a.N, a.H, a.n_kernels = N, H, nk
-            a.owns_sample0, a.N_global = 1, N
+            a.owns_sample0, a.N_global, a.variant = 1, N, self._UPDATE_VARIANT
             a.ker_thr, a.upd_rate = float(self.ker_thr), float(self.policy_upd_rate)
             cost = self._dev_of(self.cur_cost)
             kv, acts = self._dev_of(self.kernel_val_all), self._dev_of(self.kernel_activations)
@@ -433,6 +464,7 @@ class MPPI:
         for i in range(d):
             a.q_min[i], a.q_max[i] = float(qmin[i]), float(qmax[i])
         a.ker_thr, a.upd_rate = float(self.ker_thr), float(self.policy_upd_rate)
+        a.cost_terms, a.update_variant = self._COST_TERMS, self._UPDATE_VARIANT
         for name in ('q_cur', 'mu_tmp', 'sigma_tmp', 'alpha_tmp', 'mu_c', 'sigma_c', 'alpha_c', 'all_traj',
                      'closest_dist_all', 'kernel_val_all', 'dot_products', 'kernel_activations', 'qdot', 'cost',
                      'n_updated'):

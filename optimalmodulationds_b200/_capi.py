@@ -20,8 +20,22 @@ PASS1_EXACT_FP32, PASS1_TC_F16, PASS1_TC_BF16, PASS1_AUTO = 0, 1, 2, 3
 _fp = C.c_void_p   # device / host float pointers travel as integers from tensor.data_ptr()
 
 
+DS_LINEAR_ATTRACTOR, DS_MATRIX = 0, 1
+COST_JOINT_LIMITS, COST_TERMINAL_FK, COST_ALL = 1, 2, 3
+
+
 class Net(C.Structure):
-    _fields_ = [("n_dof", C.c_int32), ("n_out", C.c_int32), ("W_host", _fp * 5), ("b_host", _fp * 5)]
+    _fields_ = [("n_dof", C.c_int32), ("n_out", C.c_int32), ("n_point_dim", C.c_int32), ("reserved", C.c_int32),
+                ("W_host", _fp * 5), ("b_host", _fp * 5)]
+
+
+class Modulation(C.Structure):
+    _fields_ = [
+        ("ds_kind", C.c_int32), ("fold_activation", C.c_int32),
+        ("lvel_mid", C.c_float), ("lvel_k", C.c_float), ("dist_mid", C.c_float), ("dist_k", C.c_float),
+        ("ltau_max", C.c_float), ("goal_act_thr", C.c_float), ("repulsion", C.c_float), ("reserved", C.c_float),
+        ("ds_A", C.c_float * (MAX_DOF * MAX_DOF)),
+    ]
 
 
 class RolloutArgs(C.Structure):
@@ -29,7 +43,7 @@ class RolloutArgs(C.Structure):
         ("N", C.c_int32), ("H", C.c_int32), ("q_cur_is_batch", C.c_int32), ("n_kernels", C.c_int32),
         ("n_closest", C.c_int32), ("ignored_link_mask", C.c_uint32),
         ("dt", C.c_float), ("dst_thr", C.c_float), ("lin_thr", C.c_float), ("rbf_p", C.c_float),
-        ("q_goal", C.c_float * MAX_DOF),
+        ("q_goal", C.c_float * MAX_DOF), ("mod", Modulation),
         ("q_cur_dev", _fp), ("mu_tmp_dev", _fp), ("sigma_tmp_dev", _fp), ("alpha_tmp_dev", _fp),
         ("all_traj_dev", _fp), ("closest_dist_all_dev", _fp), ("kernel_val_all_dev", _fp),
         ("dot_products_dev", _fp), ("kernel_activations_dev", _fp), ("qdot_dev", _fp),
@@ -39,7 +53,7 @@ class RolloutArgs(C.Structure):
 
 class CostArgs(C.Structure):
     _fields_ = [
-        ("N", C.c_int32), ("H", C.c_int32),
+        ("N", C.c_int32), ("H", C.c_int32), ("terms", C.c_int32), ("reserved", C.c_int32),
         ("q_goal", C.c_float * MAX_DOF), ("q_min", C.c_float * MAX_DOF), ("q_max", C.c_float * MAX_DOF),
         ("all_traj_dev", _fp), ("closest_dist_all_dev", _fp), ("cost_dev", _fp),
     ]
@@ -48,7 +62,7 @@ class CostArgs(C.Structure):
 class UpdateArgs(C.Structure):
     _fields_ = [
         ("N", C.c_int32), ("H", C.c_int32), ("n_kernels", C.c_int32), ("owns_sample0", C.c_int32),
-        ("N_global", C.c_int64), ("ker_thr", C.c_float), ("upd_rate", C.c_float),
+        ("variant", C.c_int32), ("reserved", C.c_int32), ("N_global", C.c_int64), ("ker_thr", C.c_float), ("upd_rate", C.c_float),
         ("cost_dev", _fp), ("kernel_val_all_dev", _fp), ("kernel_activations_dev", _fp),
         ("mu_tmp_dev", _fp), ("sigma_tmp_dev", _fp), ("alpha_tmp_dev", _fp),
         ("mu_c_dev", _fp), ("sigma_c_dev", _fp), ("alpha_c_dev", _fp),
@@ -69,7 +83,7 @@ class IterationHostArgs(C.Structure):
     _fields_ = [
         ("rollout", RolloutArgs),
         ("q_min", C.c_float * MAX_DOF), ("q_max", C.c_float * MAX_DOF),
-        ("ker_thr", C.c_float), ("upd_rate", C.c_float),
+        ("ker_thr", C.c_float), ("upd_rate", C.c_float), ("cost_terms", C.c_int32), ("update_variant", C.c_int32),
         ("q_cur_host", _fp), ("mu_tmp_host", _fp), ("sigma_tmp_host", _fp), ("alpha_tmp_host", _fp),
         ("mu_c_host", _fp), ("sigma_c_host", _fp), ("alpha_c_host", _fp),
         ("all_traj_host", _fp), ("closest_dist_all_host", _fp), ("kernel_val_all_host", _fp),
@@ -83,6 +97,8 @@ EXPORTS = {
     # name: (restype, argtypes)
     "dsmppi_last_error": (C.c_char_p, []),
     "dsmppi_version": (C.c_int, []),
+    "dsmppi_modulation_default": (None, [C.POINTER(Modulation)]),
+    "dsmppi_modulation_toy": (None, [C.POINTER(Modulation)]),
     "dsmppi_ctx_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(Net), _fp, C.c_int32, C.c_int32]),
     "dsmppi_ctx_destroy": (C.c_int, [C.c_void_p]),
     "dsmppi_set_pass1_mode": (C.c_int, [C.c_void_p, C.c_int32, C.c_float]),

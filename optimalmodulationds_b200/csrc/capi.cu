@@ -92,7 +92,31 @@ int ensure_workspace(dsmppi_ctx* c, int n, int M) {
 extern "C" {
 
 const char* dsmppi_last_error(void) { return g_last_error.c_str(); }
-int dsmppi_version(void) { return 100; }
+int dsmppi_version(void) { return 101; }
+
+void dsmppi_modulation_default(dsmppi_modulation* m) {
+  if (!m) return;
+  std::memset(m, 0, sizeof(*m));
+  m->ds_kind = DSMPPI_DS_LINEAR_ATTRACTOR;
+  m->lvel_mid = (-1.f + 0.f) / 2.f; m->lvel_k = 10.f;       // MPPI.py:132
+  m->dist_mid = (0.0f + 0.1f) / 2.f; m->dist_k = 100.f;     // MPPI.py:148-151 (the "franka" set, used by all robots)
+  m->ltau_max = 5.f;                                        // MPPI.py:152
+  m->goal_act_thr = 0.5f;                                   // MPPI.py:194
+  m->repulsion = 0.1f;                                      // MPPI.py:216
+}
+
+void dsmppi_modulation_toy(dsmppi_modulation* m) {
+  if (!m) return;
+  std::memset(m, 0, sizeof(*m));
+  m->ds_kind = DSMPPI_DS_MATRIX;
+  for (int i = 0; i < MAXD; ++i) m->ds_A[i * MAXD + i] = -1.f;   // standaloneToy2d.py:70 (callers overwrite)
+  m->fold_activation = 1;                                   // MPPI_toy.py:178-179
+  m->lvel_mid = (float)((-0.2 + 0.0) / 2); m->lvel_k = 100.f;    // MPPI_toy.py:114
+  m->dist_mid = (0.0f + 0.5f) / 2.f; m->dist_k = 30.f;      // MPPI_toy.py:124-127
+  m->ltau_max = 3.f;                                        // MPPI_toy.py:133
+  m->goal_act_thr = 0.3f;                                   // MPPI_toy.py:176
+  m->repulsion = 0.05f;                                     // MPPI_toy.py:199
+}
 
 int dsmppi_ctx_create(dsmppi_ctx** out, const dsmppi_net* net, const float* dh_params_host, int32_t capacity,
                       int32_t device) {
@@ -100,6 +124,8 @@ int dsmppi_ctx_create(dsmppi_ctx** out, const dsmppi_net* net, const float* dh_p
   REQUIRE(net->n_dof >= 1 && net->n_dof <= MAXD, "n_dof out of range (1..8)");
   REQUIRE(net->n_out >= 1 && net->n_out <= MAXO, "n_out out of range (1..16)");
   REQUIRE(capacity >= 1, "capacity must be positive");
+  const int P = net->n_point_dim == 0 ? 3 : net->n_point_dim;
+  REQUIRE(P == 2 || P == 3, "n_point_dim must be 2 or 3");
   int ndev = 0;
   CUDA_TRY(cudaGetDeviceCount(&ndev));
   REQUIRE(ndev > 0 && device < ndev, "no such CUDA device (this library has no CPU fallback)");
@@ -112,7 +138,8 @@ int dsmppi_ctx_create(dsmppi_ctx** out, const dsmppi_net* net, const float* dh_p
   c->sm_count = prop.multiProcessorCount;
   c->d = net->n_dof;
   c->O = net->n_out;
-  c->nin = c->d + 3;
+  c->P = P;
+  c->nin = c->d + P;
   c->nenc = 3 * c->nin;
   c->capacity = capacity;
   for (int i = 0; i <= c->d; ++i)
@@ -167,7 +194,7 @@ int dsmppi_ctx_destroy(dsmppi_ctx* c) {
   if (!c) return 0;
   cudaSetDevice(c->device);
   tc_free_images(c);
-  void* ptrs[] = {c->weights_blob, c->obs, c->obs_enc, c->q_work, c->m_rows, c->mdist, c->enc_q,
+  void* ptrs[] = {c->weights_blob, c->obs, c->obs_raw, c->obs_enc, c->q_work, c->m_rows, c->mdist, c->enc_q,
                   c->cand_obs, c->cand_cnt, c->row_base, c->row_sample, c->row_obs, c->counters, c->sel,
                   c->sel_rows, c->row_dist, c->row_grad, c->dist_tmp, c->grad_tmp, c->upd_partials, c->stats_tmp,
                   c->packed_tmp, c->stage};
@@ -199,7 +226,19 @@ int dsmppi_set_obstacles(dsmppi_ctx* c, const float* obs_dev, int32_t M, void* s
     CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c->obs), (size_t)M * 4 * sizeof(float)));
     c->obs_cap = M;
   }
-  CUDA_TRY(cudaMemcpyAsync(c->obs, obs_dev, (size_t)M * 4 * sizeof(float), cudaMemcpyDefault, st));
+  if (c->P == 3) {
+    CUDA_TRY(cudaMemcpyAsync(c->obs, obs_dev, (size_t)M * 4 * sizeof(float), cudaMemcpyDefault, st));
+  } else {
+    // (M, P + 1) rows [x, y, r] -> the device layout [x, y, 0, r]; the staging copy also serves host sources
+    if (M > c->obs_raw_cap) {
+      if (c->obs_raw) CUDA_TRY(cudaFree(c->obs_raw));
+      c->obs_raw = nullptr;
+      CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c->obs_raw), (size_t)M * (c->P + 1) * sizeof(float)));
+      c->obs_raw_cap = M;
+    }
+    CUDA_TRY(cudaMemcpyAsync(c->obs_raw, obs_dev, (size_t)M * (c->P + 1) * sizeof(float), cudaMemcpyDefault, st));
+    if (launch_pack_obstacles(c, c->obs_raw, M, c->P, st)) return 1;
+  }
   c->M = M;
   if (c->tc_blob) return tc_set_obstacles(c, st);
   return 0;
@@ -275,6 +314,9 @@ int dsmppi_rollout(dsmppi_ctx* c, const dsmppi_rollout_args* a, void* stream) {
               a->dot_products_dev && a->kernel_activations_dev && a->qdot_dev && a->nn_grad_all_dev,
           "null device pointer");
   REQUIRE(a->n_kernels == 0 || (a->mu_tmp_dev && a->sigma_tmp_dev && a->alpha_tmp_dev), "null policy pointer");
+  REQUIRE(a->mod.ds_kind == DSMPPI_DS_LINEAR_ATTRACTOR || a->mod.ds_kind == DSMPPI_DS_MATRIX, "unknown mod.ds_kind");
+  REQUIRE(a->mod.lvel_k != 0.f && a->mod.dist_k != 0.f,
+          "rollout_args.mod is not initialised (dsmppi_modulation_default / _toy)");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   CUDA_TRY(cudaSetDevice(c->device));
   REQUIRE(c->M >= 1, "obstacles not set");
@@ -451,12 +493,12 @@ int dsmppi_iteration_host(dsmppi_ctx* c, dsmppi_iteration_host_args* h, void* st
   a.nn_grad_all_dev = S + o_gr; a.norm_basis_dev = nullptr;
   if (dsmppi_rollout(c, &a, stream)) return 1;
   dsmppi_cost_args ca{};
-  ca.N = r.N; ca.H = r.H;
+  ca.N = r.N; ca.H = r.H; ca.terms = h->cost_terms;
   for (int i = 0; i < MAXD; ++i) { ca.q_goal[i] = r.q_goal[i]; ca.q_min[i] = h->q_min[i]; ca.q_max[i] = h->q_max[i]; }
   ca.all_traj_dev = a.all_traj_dev; ca.closest_dist_all_dev = a.closest_dist_all_dev; ca.cost_dev = S + o_co;
   if (launch_cost(c, &ca, st)) return 1;
   dsmppi_update_args ua{};
-  ua.N = r.N; ua.H = r.H; ua.n_kernels = r.n_kernels; ua.owns_sample0 = 1; ua.N_global = r.N;
+  ua.N = r.N; ua.H = r.H; ua.n_kernels = r.n_kernels; ua.owns_sample0 = 1; ua.N_global = r.N; ua.variant = h->update_variant;
   ua.ker_thr = h->ker_thr; ua.upd_rate = h->upd_rate;
   ua.cost_dev = S + o_co; ua.kernel_val_all_dev = a.kernel_val_all_dev;
   ua.kernel_activations_dev = a.kernel_activations_dev;

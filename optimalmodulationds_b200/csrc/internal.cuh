@@ -65,6 +65,7 @@ struct DhTable { float v[MAXD + 1][4]; };   // rows [d, theta, a, alpha]
 struct dsmppi_ctx {
   int device = 0;
   int d = 0, O = 0, nin = 0, nenc = 0;
+  int P = 3;                          // obstacle coordinates fed to the network (nin = d + P)
   int capacity = 0;
   int M = 0;
   int pass1_mode = DSMPPI_PASS1_AUTO;
@@ -75,7 +76,8 @@ struct dsmppi_ctx {
   void* tc_blob = nullptr;            // tensor-core operand images (tc_pass1.cu)
   size_t tc_blob_bytes = 0;
   // obstacles
-  float* obs = nullptr; int obs_cap = 0;
+  float* obs = nullptr; int obs_cap = 0;   // always (M, 4) = [x, y, z, r] on the device (z = 0 when P == 2)
+  float* obs_raw = nullptr; int obs_raw_cap = 0;   // P == 2: the caller's (M, 3) rows before repacking
   void* obs_enc = nullptr; size_t obs_enc_cap = 0;   // tensor path: per-obstacle packed encodings
   // workspace (grown on demand)
   int ws_n = 0, ws_M = 0;
@@ -128,6 +130,7 @@ int tc_pass1(dsmppi_ctx* c, const float* q, int q_stride, int n, uint32_t ignore
 // rollout_kernels.cu
 int launch_rank_dense(dsmppi_ctx* c, int n, int K, bool rows_out, cudaStream_t st);
 int launch_identity_rows(dsmppi_ctx* c, int n, int K, cudaStream_t st);
+int launch_pack_obstacles(dsmppi_ctx* c, const float* raw, int M, int P, cudaStream_t st);
 int launch_select_candidates(dsmppi_ctx* c, int n, int K, float band, cudaStream_t st);
 int launch_rank_candidates(dsmppi_ctx* c, int n, int K, cudaStream_t st);
 int launch_blend(dsmppi_ctx* c, int n, int K, float* dist_out, float* grad_out, cudaStream_t st);

@@ -181,6 +181,15 @@ __device__ __forceinline__ void blend(const float* __restrict__ row_dist, const 
   dist = sd[0];
 }
 
+__global__ void pack_obstacles_kernel(const float* __restrict__ raw, int M, int P, float* __restrict__ obs) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= M) return;
+  float o[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int c = 0; c < P; ++c) o[c] = raw[j * (P + 1) + c];
+  o[3] = raw[j * (P + 1) + P];
+  for (int c = 0; c < 4; ++c) obs[j * 4 + c] = o[c];
+}
+
 __global__ void identity_rows_kernel(int total, int* __restrict__ rows) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < total) rows[i] = i;
@@ -205,6 +214,7 @@ struct StepArgs {
   int N, H, d, t, nk, K;
   float dt, dst_thr, lin_thr, p;
   float goal[MAXD];
+  dsmppi_modulation mod;
   const float* row_dist; const float* row_grad; const int* sel_rows;
   const float* mu; const float* sigma; const float* alpha;
   float* traj; float* closest; float* kval; float* dots; float* acts; float* qdot; float* grads;
@@ -227,18 +237,32 @@ __global__ void __launch_bounds__(128) step_kernel(StepArgs s) {
   const int d = s.d;
   const size_t st = (size_t)i * s.H + (s.t - 1);     // state-step index
   float q[MAXD], v[MAXD], vhat[MAXD], e0[MAXD], g[MAXD], u[MAXD], vt[MAXD], m[MAXD];
-  // S0 nominal DS (LinDS.py:11-21) and its norm (MPPI.py:106-108)
+  // S0 nominal DS and its norm (MPPI.py:106-108)
   float ss = 0.f;
 #pragma unroll
-  for (int a = 0; a < MAXD; ++a) {
-    q[a] = a < d ? s.traj[st * d + a] : 0.f;
-    v[a] = a < d ? -(q[a] - s.goal[a]) : 0.f;
-    ss += v[a] * v[a];
-  }
-  const float dst = sqrtf(ss);
-  if (dst > s.lin_thr) {
+  for (int a = 0; a < MAXD; ++a) q[a] = a < d ? s.traj[st * d + a] : 0.f;
+  if (s.mod.ds_kind == DSMPPI_DS_MATRIX) {
+    // v = (q - q_goal) @ A, not normalised (MPPI_toy.py:89)
 #pragma unroll
-    for (int a = 0; a < MAXD; ++a) v[a] = v[a] / dst;
+    for (int cc = 0; cc < MAXD; ++cc) {
+      float acc = 0.f;
+#pragma unroll
+      for (int a = 0; a < MAXD; ++a)
+        if (a < d && cc < d) acc += (q[a] - s.goal[a]) * s.mod.ds_A[a * MAXD + cc];
+      v[cc] = acc;
+    }
+  } else {
+    // unit-speed attractor, linear inside lin_thr (LinDS.py:11-21)
+#pragma unroll
+    for (int a = 0; a < MAXD; ++a) {
+      v[a] = a < d ? -(q[a] - s.goal[a]) : 0.f;
+      ss += v[a] * v[a];
+    }
+    const float dst = sqrtf(ss);
+    if (dst > s.lin_thr) {
+#pragma unroll
+      for (int a = 0; a < MAXD; ++a) v[a] = v[a] / dst;
+    }
   }
   ss = 0.f;
 #pragma unroll
@@ -267,11 +291,22 @@ __global__ void __launch_bounds__(128) step_kernel(StepArgs s) {
   }
   s.dots[st] = dot;
   // S3 modulation coefficients (MPPI.py:132,149-155)
-  const float l_vel = gsigmoid(dot, 0.f, 1.f, -0.5f, 10.f);
-  const float l_n = gsigmoid(dist, 0.f, 1.f, 0.05f, 100.f);
-  const float l_tau = gsigmoid(dist, 5.f, 1.f, 0.05f, 100.f);
+  const float l_vel = gsigmoid(dot, 0.f, 1.f, s.mod.lvel_mid, s.mod.lvel_k);
+  const float l_n = gsigmoid(dist, 0.f, 1.f, s.mod.dist_mid, s.mod.dist_k);
+  const float l_tau = gsigmoid(dist, s.mod.ltau_max, 1.f, s.mod.dist_mid, s.mod.dist_k);
   const float l_nv = l_vel * 1.f + (1.f - l_vel) * l_n;
 
+  // activations (MPPI.py:191-196)
+  float ga = 0.f;
+#pragma unroll
+  for (int a = 0; a < MAXD; ++a)
+    if (a < d) ga += sqrtf(fabsf(q[a] - s.goal[a]));
+  ga = ga * ga;                                        // (sum |x|^0.5)^(1/0.5)
+  ga = fminf(fmaxf(ga, 0.f), 1.f);
+  if (ga < s.mod.goal_act_thr) ga = 0.f;
+  const float act = (1.f - l_n) * (1.f - l_vel) * ga;
+  s.acts[st] = act;
+  const float kv_scale = s.mod.fold_activation ? act : 1.f;   // MPPI_toy.py:178-179
   // S4 RBF policy (policy.py:186-199, MPPI.py:165-186)
 #pragma unroll
   for (int a = 0; a < MAXD; ++a) u[a] = 0.f;
@@ -291,22 +326,12 @@ __global__ void __launch_bounds__(128) step_kernel(StepArgs s) {
     }
     const float num = acc * acc;                       // norm ** 2
     const float phi = expf(-s.sigma[(size_t)i * NKMAX + k] * num);
-    s.kval[st * NKMAX + k] = phi;                      // MPPI.py:184
+    s.kval[st * NKMAX + k] = s.mod.fold_activation ? phi * kv_scale : phi;   // MPPI.py:184
     const float* al = s.alpha + ((size_t)i * NKMAX + k) * d;
 #pragma unroll
     for (int a = 0; a < MAXD; ++a)
       if (a < d) u[a] += al[a] * phi;                  // MPPI.py:174-177
   }
-  // activations (MPPI.py:191-196)
-  float ga = 0.f;
-#pragma unroll
-  for (int a = 0; a < MAXD; ++a)
-    if (a < d) ga += sqrtf(fabsf(q[a] - s.goal[a]));
-  ga = ga * ga;                                        // (sum |x|^0.5)^(1/0.5)
-  ga = fminf(fmaxf(ga, 0.f), 1.f);
-  if (ga < 0.5f) ga = 0.f;
-  const float act = (1.f - l_n) * (1.f - l_vel) * ga;
-  s.acts[st] = act;
   // total velocity and modulation M = l_tau I + (l_nv - l_tau) e0 e0^T  (MPPI.py:158-161,197-209)
   float proj = 0.f;
 #pragma unroll
@@ -327,7 +352,7 @@ __global__ void __launch_bounds__(128) step_kernel(StepArgs s) {
 #pragma unroll
   for (int a = 0; a < MAXD; ++a) {
     float mv = nan_to_num(m[a] / mn);                  // MPPI.py:213
-    if (coll) mv = mv * 0.1f + e0[a] * vn * 0.1f;      // MPPI.py:215-217
+    if (coll) mv = mv * 0.1f + e0[a] * vn * s.mod.repulsion;   // MPPI.py:215-217
     m[a] = mv;
   }
   if (s.t < s.H) {
@@ -407,7 +432,7 @@ __global__ void init_traj_kernel(const float* __restrict__ q_cur, int is_batch, 
 // Cost (cost.py:13-46) with the terminal forward kinematics (fk_num.py:7-75)
 // ------------------------------------------------------------------------------------------------
 struct CostArgs {
-  int N, H, d;
+  int N, H, d, terms;
   float goal[MAXD], qmin[MAXD], qmax[MAXD];
   DhTable dh;
   const float* traj; const float* closest; float* cost;
@@ -471,22 +496,27 @@ __global__ void __launch_bounds__(128) cost_kernel(CostArgs c) {
     }
   }
   const float coll_cost = 100.f * (float)ncoll;
-  const float jl_cost = 100.f * (nviol > 0 ? 1.f : 0.f);
+  const float jl_cost = (c.terms & DSMPPI_COST_JOINT_LIMITS) ? 100.f * (nviol > 0 ? 1.f : 0.f) : 0.f;
   float inv = 1.f / sqrtf(s0);
   if (isnan(inv)) inv = 0.f;                                          // nan_to_num(0): nan -> 0,
   else if (isinf(inv)) inv = inv > 0.f ? FLT_MAX : -FLT_MAX;          // +-inf -> +-FLT_MAX
   const float stag_cost = 10.f * goal_cost * inv;                     // cost.py:17,41-43
-  float pT[MAXD][3], pG[MAXD][3];
-  fk_points(qT, d, c.dh, pT);
-  fk_points(c.goal, d, c.dh, pG);
   float fk = 0.f;
+  if (c.terms & DSMPPI_COST_TERMINAL_FK) {
+    float pT[MAXD][3], pG[MAXD][3];
+    fk_points(qT, d, c.dh, pT);
+    fk_points(c.goal, d, c.dh, pG);
 #pragma unroll
-  for (int l = 0; l < MAXD; ++l)
-    if (l < d) {
-      const float dx = pT[l][0] - pG[l][0], dy = pT[l][1] - pG[l][1], dz = pT[l][2] - pG[l][2];
-      fk += sqrtf(dx * dx + dy * dy + dz * dz);                        // cost.py:27-31
-    }
-  c.cost[i] = goal_cost + coll_cost + jl_cost + stag_cost + 10.f * fk; // cost.py:21
+    for (int l = 0; l < MAXD; ++l)
+      if (l < d) {
+        const float dx = pT[l][0] - pG[l][0], dy = pT[l][1] - pG[l][1], dz = pT[l][2] - pG[l][2];
+        fk += sqrtf(dx * dx + dy * dy + dz * dz);                      // cost.py:27-31
+      }
+    c.cost[i] = goal_cost + coll_cost + jl_cost + stag_cost + 10.f * fk;   // cost.py:21
+  } else {
+    c.cost[i] = (c.terms & DSMPPI_COST_JOINT_LIMITS) ? goal_cost + coll_cost + jl_cost + stag_cost
+                                                      : goal_cost + coll_cost + stag_cost;   // cost_toy.py:18
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -611,7 +641,7 @@ __global__ void __launch_bounds__(1024) cost_stats_kernel(const float* __restric
 }
 
 struct UpdArgs {
-  int N, H, d, nk, owns0, L;
+  int N, H, d, nk, owns0, L, variant;
   const float* cost; const float* kval; const float* acts; const float* mu; const float* sigma; const float* alpha;
   const float* stats;
   float* partials;
@@ -644,8 +674,12 @@ __global__ void __launch_bounds__(UPD_T) update_partial_kernel(UpdArgs u) {
       else if (idx < o_b0) {
         const int k = idx - o_mx;
         float mx = -FLT_MAX;
-        for (int t = 0; t < H; ++t)
-          mx = fmaxf(mx, u.kval[((size_t)i * H + t) * NKMAX + k] * u.acts[(size_t)i * H + t]);   // MPPI.py:336
+        if (u.variant == 0) {
+          for (int t = 0; t < H; ++t)
+            mx = fmaxf(mx, u.kval[((size_t)i * H + t) * NKMAX + k] * u.acts[(size_t)i * H + t]);   // MPPI.py:336
+        } else {
+          for (int t = 0; t < H; ++t) mx = fmaxf(mx, u.kval[((size_t)i * H + t) * NKMAX + k]);     // MPPI_toy.py:318
+        }
         val = mx;
       } else {
         val = 0.f;
@@ -675,7 +709,7 @@ __global__ void update_block_sum_kernel(const float* __restrict__ partials, int 
   packed[idx] = s;
 }
 
-__global__ void update_finalize_kernel(const float* __restrict__ packed, int nk, int d, float n_global,
+__global__ void update_finalize_kernel(const float* __restrict__ packed, int nk, int d, int variant, float n_global,
                                        float ker_thr, float rate, float* __restrict__ mu_c,
                                        float* __restrict__ sigma_c, float* __restrict__ alpha_c,
                                        int* __restrict__ n_updated) {
@@ -683,7 +717,8 @@ __global__ void update_finalize_kernel(const float* __restrict__ packed, int nk,
   const float wsum = packed[0];
   int cnt = 0;
   for (int k = threadIdx.x; k < nk; k += blockDim.x) {
-    const bool on = (packed[o_mx + k] / n_global > ker_thr) && (packed[o_b0 + k] > ker_thr);   // MPPI.py:338-342
+    // MPPI.py:338-342; MPPI_toy.py:319-320 has no sample-0 base mask
+    const bool on = (packed[o_mx + k] / n_global > ker_thr) && (variant != 0 || packed[o_b0 + k] > ker_thr);
     const float r = on ? rate : 0.f;                                   // policy.py:97-99
     for (int a = 0; a < d; ++a) {
       mu_c[k * d + a] = (1.f - r) * mu_c[k * d + a] + r * (packed[o_mu + k * d + a] / wsum);
@@ -721,6 +756,12 @@ int launch_rank_dense(dsmppi_ctx* c, int n, int K, bool rows_out, cudaStream_t s
 
 int launch_identity_rows(dsmppi_ctx* c, int n, int K, cudaStream_t st) {
   identity_rows_kernel<<<(n * K + 255) / 256, 256, 0, st>>>(n * K, c->sel_rows);
+  LAUNCH_CHECK(c);
+  return 0;
+}
+
+int launch_pack_obstacles(dsmppi_ctx* c, const float* raw, int M, int P, cudaStream_t st) {
+  pack_obstacles_kernel<<<(M + 127) / 128, 128, 0, st>>>(raw, M, P, c->obs);
   LAUNCH_CHECK(c);
   return 0;
 }
@@ -776,6 +817,7 @@ int launch_step(dsmppi_ctx* c, const dsmppi_rollout_args* a, int t, cudaStream_t
   s.N = a->N; s.H = a->H; s.d = c->d; s.t = t; s.nk = a->n_kernels; s.K = a->n_closest;
   s.dt = a->dt; s.dst_thr = a->dst_thr; s.lin_thr = a->lin_thr; s.p = a->rbf_p;
   for (int i = 0; i < MAXD; ++i) s.goal[i] = a->q_goal[i];
+  s.mod = a->mod;
   s.row_dist = c->row_dist; s.row_grad = c->row_grad; s.sel_rows = c->sel_rows;
   s.mu = a->mu_tmp_dev; s.sigma = a->sigma_tmp_dev; s.alpha = a->alpha_tmp_dev;
   s.traj = a->all_traj_dev; s.closest = a->closest_dist_all_dev; s.kval = a->kernel_val_all_dev;
@@ -790,7 +832,7 @@ int launch_step(dsmppi_ctx* c, const dsmppi_rollout_args* a, int t, cudaStream_t
 
 int launch_cost(dsmppi_ctx* c, const dsmppi_cost_args* a, cudaStream_t st) {
   CostArgs k;
-  k.N = a->N; k.H = a->H; k.d = c->d;
+  k.N = a->N; k.H = a->H; k.d = c->d; k.terms = a->terms;
   for (int i = 0; i < MAXD; ++i) { k.goal[i] = a->q_goal[i]; k.qmin[i] = a->q_min[i]; k.qmax[i] = a->q_max[i]; }
   k.dh = c->dh;
   k.traj = a->all_traj_dev; k.closest = a->closest_dist_all_dev; k.cost = a->cost_dev;
@@ -821,7 +863,7 @@ int launch_cost_stats(dsmppi_ctx* c, const float* cost, int N, float* stats, cud
 int launch_update_partial(dsmppi_ctx* c, const dsmppi_update_args* a, const float* stats, float* packed,
                           cudaStream_t st) {
   UpdArgs u;
-  u.N = a->N; u.H = a->H; u.d = c->d; u.nk = a->n_kernels; u.owns0 = a->owns_sample0;
+  u.N = a->N; u.H = a->H; u.d = c->d; u.nk = a->n_kernels; u.owns0 = a->owns_sample0; u.variant = a->variant;
   u.L = dsmppi_update_packed_len(a->n_kernels, c->d);
   u.cost = a->cost_dev; u.kval = a->kernel_val_all_dev; u.acts = a->kernel_activations_dev;
   u.mu = a->mu_tmp_dev; u.sigma = a->sigma_tmp_dev; u.alpha = a->alpha_tmp_dev; u.stats = stats;
@@ -838,7 +880,7 @@ int launch_update_partial(dsmppi_ctx* c, const dsmppi_update_args* a, const floa
 
 int launch_update_finalize(dsmppi_ctx* c, const dsmppi_update_args* a, const float* packed, int* n_updated,
                            cudaStream_t st) {
-  update_finalize_kernel<<<1, 64, 0, st>>>(packed, a->n_kernels, c->d, (float)a->N_global, a->ker_thr, a->upd_rate,
+  update_finalize_kernel<<<1, 64, 0, st>>>(packed, a->n_kernels, c->d, a->variant, (float)a->N_global, a->ker_thr, a->upd_rate,
                                           a->mu_c_dev, a->sigma_c_dev, a->alpha_c_dev, n_updated);
   LAUNCH_CHECK(c);
   return 0;

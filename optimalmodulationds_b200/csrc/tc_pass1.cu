@@ -695,8 +695,8 @@ int tc_set_obstacles(dsmppi_ctx* c, cudaStream_t st) {
   }
   uint16_t* out = static_cast<uint16_t*>(c->obs_enc);
   const int th = 128, bl = (c->M + th - 1) / th;
-  encode_kernel<false><<<bl, th, 0, st>>>(c->obs, 4, 0, c->M, 3, c->d, c->nin, out);
-  encode_kernel<true><<<bl, th, 0, st>>>(c->obs, 4, 0, c->M, 3, c->d, c->nin, out + (size_t)c->M * 64);
+  encode_kernel<false><<<bl, th, 0, st>>>(c->obs, 4, 0, c->M, c->P, c->d, c->nin, out);
+  encode_kernel<true><<<bl, th, 0, st>>>(c->obs, 4, 0, c->M, c->P, c->d, c->nin, out + (size_t)c->M * 64);
   CUDA_TRY(cudaGetLastError());
   c->launches += 2;
   return 0;

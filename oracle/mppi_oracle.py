@@ -213,6 +213,22 @@ class RolloutParams:
     with_basis: bool = True                  # materialise norm_basis (Householder E)
     explicit_M: bool = True                  # M = E D E^T like MPPI.py:158-161 (needs with_basis);
                                              # False: rank-1 closed form, what the GPU uses
+    # constants the reference compiles into MPPI.py; toy_params() returns the MPPI_toy.py set
+    lvel: Sequence[float] = (-1, 0, 10)      # (x0, x1, k) of l_vel                        MPPI.py:132
+    dist_sig: Sequence[float] = (0.0, 0.1, 100)   # (dist_low, dist_high, k_sigmoid)       MPPI.py:148-151
+    ltau_max: float = 5                      # MPPI.py:152
+    goal_act_thr: float = 0.5                # MPPI.py:194
+    repulsion: float = 0.1                   # MPPI.py:216
+    fold_activation: bool = False            # kernel_val_all *= activation                MPPI_toy.py:178-179
+    A: Optional[torch.Tensor] = None         # matrix DS v = (q - qf) @ A                  MPPI_toy.py:89
+
+
+def toy_params(dt, dt_H, n_closest_obs, A, **kw):
+    """The constant set of ds_mppi/functions/MPPI_toy.py (:56,89,114,124-133,176-179,199)."""
+    base = dict(dst_thr=0.1, ignored_links=(), lvel=(-0.2, 0.0, 100), dist_sig=(0.0, 0.5, 30), ltau_max=3,
+                goal_act_thr=0.3, repulsion=0.05, fold_activation=True, A=A)
+    base.update(kw)
+    return RolloutParams(dt=dt, dt_H=dt_H, n_closest_obs=n_closest_obs, **base)
 
 
 @dataclass
@@ -247,7 +263,10 @@ def rollout(net: Net, q_cur: torch.Tensor, q_goal: torch.Tensor, obs: torch.Tens
     aux = []
     for i in range(1, H + 1):
         q = all_traj[:, i - 1, :]
-        v = lin_ds_velocity(q, q_goal, prm.lin_thr)                       # MPPI.py:106
+        if prm.A is not None:
+            v = (q - q_goal) @ prm.A                                      # MPPI_toy.py:89
+        else:
+            v = lin_ds_velocity(q, q_goal, prm.lin_thr)                   # MPPI.py:106
         vn = v.norm(dim=1).reshape(-1, 1)                                 # :107
         vhat = v / vn                                                     # :108
         if keep_aux:
@@ -263,10 +282,11 @@ def rollout(net: Net, q_cur: torch.Tensor, q_goal: torch.Tensor, obs: torch.Tens
             basis[:, i - 1] = householder_basis(g)                        # :122-127
         dot = (e0 * vhat).sum(dim=-1)                                     # :129
         dots[:, i - 1] = dot
-        l_vel = generalized_sigmoid(dot, 0, 1, -1, 0, 10)                 # :132
-        l_n = generalized_sigmoid(dist, 0, 1, 0.0, 0.1, 100)              # :153
+        d_lo, d_hi, d_k = prm.dist_sig
+        l_vel = generalized_sigmoid(dot, 0, 1, *prm.lvel)                 # :132
+        l_n = generalized_sigmoid(dist, 0, 1, d_lo, d_hi, d_k)            # :153
         l_n_vel = l_vel + (1 - l_vel) * l_n                               # :154
-        l_tau = generalized_sigmoid(dist, 5, 1, 0.0, 0.1, 100)            # :155
+        l_tau = generalized_sigmoid(dist, prm.ltau_max, 1, d_lo, d_hi, d_k)   # :155
         if nk > 0:
             kv = eval_rbf(q, mu_tmp[:, :nk], sigma_tmp[:, :nk], prm.p)    # :165  (N, nk, 1)
             policy_value = torch.sum(alpha_tmp[:, :nk] * kv, 1)           # :174-177
@@ -274,9 +294,11 @@ def rollout(net: Net, q_cur: torch.Tensor, q_goal: torch.Tensor, obs: torch.Tens
         else:
             policy_value = v * 0                                          # :186
         goal_act = (q - q_goal).norm(p=0.5, dim=1).clamp(0, 1).unsqueeze(1)   # :193
-        goal_act = torch.where(goal_act < 0.5, torch.zeros_like(goal_act), goal_act)  # :194
+        goal_act = torch.where(goal_act < prm.goal_act_thr, torch.zeros_like(goal_act), goal_act)  # :194
         act = (1 - l_n[:, None]) * (1 - l_vel[:, None]) * goal_act        # :191-195
         acts[:, i - 1] = act.squeeze(1)
+        if prm.fold_activation and nk > 0:
+            kval[:, i - 1, :nk] *= act                                    # MPPI_toy.py:178-179
         vt = v + act * policy_value * vn                                  # :197-206
         if prm.with_basis and prm.explicit_M:
             E = basis[:, i - 1]
@@ -291,7 +313,7 @@ def rollout(net: Net, q_cur: torch.Tensor, q_goal: torch.Tensor, obs: torch.Tens
         mnorm = torch.where(mnorm <= 0.5, torch.ones_like(mnorm), mnorm)  # :212
         m = torch.nan_to_num(m / mnorm)                                   # :213
         coll = (dist < 0).unsqueeze(1)
-        m = torch.where(coll, 0.1 * m + e0 * vn * 0.1, m)                 # :215-217
+        m = torch.where(coll, 0.1 * m + e0 * vn * prm.repulsion, m)       # :215-217
         if i < H:
             all_traj[:, i, :] = q + prm.dt * m                            # :220-221
         if i == 1:
@@ -353,12 +375,23 @@ def evaluate_costs(all_traj, closest_dist_all, q_goal, dh_params, q_min, q_max):
     return goal + coll + jl + stag + fk
 
 
+def evaluate_costs_toy(all_traj, closest_dist_all, q_goal):
+    """cost_toy.py:13-19: goal + collision + stagnation only."""
+    q_T = all_traj[:, -1, :]
+    goal = 10 * (q_T - q_goal).norm(p=2, dim=1)                           # :14
+    coll = 100 * (closest_dist_all < 0).sum(dim=1)                        # :15
+    dist = (all_traj[:, 0, :] - q_T).norm(2, dim=1)
+    stag = 10 * goal * (1 / dist).nan_to_num(0)                           # :16
+    return goal + coll + stag
+
+
 # ----------------------------------------------------------------------------------------------
 # Policy update  (ds_mppi/functions/MPPI.py:331-345, policy.py:88-113)
 # ----------------------------------------------------------------------------------------------
 def policy_update(cost, kernel_val_all, kernel_activations, mu_tmp, sigma_tmp, alpha_tmp,
-                  mu_c, sigma_c, alpha_c, n_kernels, ker_thr, upd_rate=0.1):
-    """Returns (mu_c', sigma_c', alpha_c', n_updated, w)."""
+                  mu_c, sigma_c, alpha_c, n_kernels, ker_thr, upd_rate=0.1, toy=False):
+    """Returns (mu_c', sigma_c', alpha_c', n_updated, w).  toy=True: MPPI_toy.py:314-324 (max_t of the already
+    activation-folded kernel values, no sample-0 base mask)."""
     nk = n_kernels
     beta = cost.mean() / 50
     w = torch.exp(-1 / beta * cost)
@@ -366,9 +399,12 @@ def policy_update(cost, kernel_val_all, kernel_activations, mu_tmp, sigma_tmp, a
     mu_c, sigma_c, alpha_c = mu_c.clone(), sigma_c.clone(), alpha_c.clone()
     if nk == 0:
         return mu_c, sigma_c, alpha_c, 0, w
-    max_act = (kernel_val_all[:, :, :nk] * kernel_activations.unsqueeze(-1)).max(dim=1)[0]
-    mask = max_act.mean(dim=0) > ker_thr
-    mask = (kernel_val_all[0, :, :nk].mean(dim=0) > ker_thr) * mask
+    if toy:
+        mask = kernel_val_all[:, :, :nk].max(dim=1)[0].mean(dim=0) > ker_thr          # MPPI_toy.py:318-320
+    else:
+        max_act = (kernel_val_all[:, :, :nk] * kernel_activations.unsqueeze(-1)).max(dim=1)[0]
+        mask = max_act.mean(dim=0) > ker_thr
+        mask = (kernel_val_all[0, :, :nk].mean(dim=0) > ker_thr) * mask
     mu_sum = torch.sum(w[:, None, None] * mu_tmp[:, :nk], 0)
     sigma_sum = torch.sum(w[:, None] * sigma_tmp[:, :nk], 0)
     alpha_sum = torch.sum(w[:, None, None] * alpha_tmp[:, :nk], 0)

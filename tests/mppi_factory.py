@@ -42,3 +42,40 @@ def make_mppi(c, device="cpu", H=None, N=None, q_cur=None, pass1="exact", copy_p
         P.alpha_tmp.copy_(t(full_policy(c, "alpha_tmp", N)))
     m.q_cur = t(c["q_cur"]) if q_cur is None else t(q_cur)
     return m
+
+
+def make_toy_net():
+    net = RobotSdfCollisionNet(in_channels=4, out_channels=1, layers=[256] * 4, skips=[])
+    W, b = load_weights("toy2")
+    net.load_arrays(W, b)
+    return net
+
+
+def make_toy_mppi(c, device="cpu", H=None, N=None, pass1="exact"):
+    """The toy variant (optimalmodulationds_b200.MPPI_toy.MPPI) from a toycase_* golden dictionary, driven like
+    standaloneToy2d.py:83-91."""
+    from optimalmodulationds_b200.MPPI_toy import MPPI as ToyMPPI
+    dev = torch.device(device)
+    t = lambda x: x.to(dev)  # noqa: E731
+    N = int(c["N"]) if N is None else N
+    H = int(c["H"]) if H is None else H
+    m = ToyMPPI(t(c["q0"]), t(c["qf"]), torch.zeros(4, 4), t(c["obs"]), float(c["dt"]), H, N, t(c["A"]), 0,
+                make_toy_net(), int(c["K"]))
+    m.set_pass1_mode(pass1)
+    m.Policy.p = float(c["p"])
+    m.dst_thr = float(c["dst_thr"])
+    m.ker_thr = float(c["ker_thr"])
+    m.policy_upd_rate = float(c["upd_rate"])
+    m.ignored_links = []
+    d = c["q0"].shape[0]
+    m.Cost.q_min, m.Cost.q_max = -10 * torch.ones(d, device=dev), 10 * torch.ones(d, device=dev)
+    nk = int(c["nk"])
+    P = m.Policy
+    P.n_kernels = nk
+    P.mu_c.copy_(t(c["mu_c0"])); P.sigma_c.copy_(t(c["sigma_c0"])); P.alpha_c.copy_(t(c["alpha_c0"]))
+    if N == int(c["N"]):
+        P.mu_tmp.copy_(t(full_policy(c, "mu_tmp", N)))
+        P.sigma_tmp.copy_(t(full_policy(c, "sigma_tmp", N)))
+        P.alpha_tmp.copy_(t(full_policy(c, "alpha_tmp", N)))
+    m.q_cur = t(c["q_cur"])
+    return m

@@ -38,10 +38,12 @@ def test_library_exports_every_declared_symbol(capi):
 
 def test_struct_layout_matches_the_c_compiler(capi, tmp_path):
     structs = {"dsmppi_net": capi.Net, "dsmppi_rollout_args": capi.RolloutArgs, "dsmppi_cost_args": capi.CostArgs,
-               "dsmppi_update_args": capi.UpdateArgs, "dsmppi_iteration_host_args": capi.IterationHostArgs}
-    probes = {"dsmppi_rollout_args": ["q_goal", "q_cur_dev", "norm_basis_dev"],
-              "dsmppi_cost_args": ["q_max", "cost_dev"], "dsmppi_update_args": ["N_global", "ker_thr", "alpha_c_dev"],
-              "dsmppi_iteration_host_args": ["q_min", "q_cur_host", "n_updated_host", "d2h_bytes"],
+               "dsmppi_update_args": capi.UpdateArgs, "dsmppi_iteration_host_args": capi.IterationHostArgs, "dsmppi_modulation": capi.Modulation}
+    probes = {"dsmppi_rollout_args": ["q_goal", "mod", "q_cur_dev", "norm_basis_dev"],
+              "dsmppi_modulation": ["lvel_mid", "repulsion", "ds_A"],
+              "dsmppi_cost_args": ["terms", "q_max", "cost_dev"],
+              "dsmppi_update_args": ["variant", "N_global", "ker_thr", "alpha_c_dev"],
+              "dsmppi_iteration_host_args": ["q_min", "cost_terms", "q_cur_host", "n_updated_host", "d2h_bytes"],
               "dsmppi_net": ["W_host", "b_host"]}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "dsmppi_b200.h"', 'int main(void){']
     for s, fields in probes.items():
@@ -74,7 +76,7 @@ def test_constants_and_pure_helpers(capi):
 def test_no_gpu_means_loud_failure_not_fallback(capi):
     lib = capi.load()
     net = capi.Net()
-    net.n_dof, net.n_out = 2, 2
+    net.n_dof, net.n_out, net.n_point_dim = 2, 2, 3
     W = [torch.zeros(256, 15)] + [torch.zeros(256, 256)] * 3 + [torch.zeros(2, 256)]
     b = [torch.zeros(256)] * 4 + [torch.zeros(2)]
     for i in range(5):
