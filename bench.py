@@ -299,7 +299,7 @@ def main():
     sampler.start()
     launches0 = mppi.launch_count()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    kt_ms, kt_n = 0.0, 0
+    kt_ms, kt_n, kern_name = 0.0, 0, "exact_mlp_kernel"
     sync_all()
     for a, bq in evs:
         flush.fill_(1.0)
@@ -307,10 +307,10 @@ def main():
         step()
         bq.record()
         bq.synchronize()
-        kt = mppi.kernel_timing()
-        key = "pass1" if kt["pass1_launches"] else "exact"
-        kt_ms += kt[key + "_ms"] * kt[key + "_launches"]
-        kt_n += kt[key + "_launches"]
+        kt = mppi.kernel_timing_ex()
+        kern_name = kt["kernel"]
+        kt_ms += kt["ms"] * kt["launches"]
+        kt_n += kt["launches"]
     sync_all()
     total_ms = sum(a.elapsed_time(bq) for a, bq in evs)
     launches = mppi.launch_count() - launches0
@@ -367,18 +367,24 @@ def main():
     traffic = None
     try:      # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed ncu capture
         prof = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
-        ent = prof.get(f"{args.workload}:{'tc_pass1_kernel' if stats['mode'] else 'exact_mlp_kernel'}")
+        ent = prof.get(f"{args.workload}:{kern_name}")
         if ent and ent.get("samples") == N:
             traffic = ent["dram_bytes_per_launch"]
     except Exception:  # noqa: BLE001
         pass
     # algorithmic FLOPs of the dominant kernel: the all-pairs forward (tensor-core prefilter, or the fp32 forward when
-    # M > 16), or forward + input gradient on every pair when few obstacles make one fused fp32 launch cheaper
-    f_pair = f_fwd if (stats["mode"] or M > 16) else f_fwd + f_bwd
-    launches_per_step = max(1, round(kt_n / (args.steps * H)))       # > 1 when a huge batch is rolled out in blocks
-    flops_per_launch = N * M * f_pair / launches_per_step
+    # M > 16), or forward + input gradient on every pair when few obstacles make one fused fp32 launch cheaper; the
+    # whole-horizon kernel does that for all H steps in one launch
+    if kern_name == "rollout_fused_kernel":
+        launches_per_iter = max(1, round(kt_n / args.steps))         # > 1 when a huge batch is rolled out in blocks
+        flops_per_launch = N * M * (f_fwd + f_bwd) * H / launches_per_iter
+    else:
+        f_pair = f_fwd if (stats["mode"] or M > 16) else f_fwd + f_bwd
+        launches_per_step = max(1, round(kt_n / (args.steps * H)))
+        flops_per_launch = N * M * f_pair / launches_per_step
     achieved = flops_per_launch / (kern_ms * 1e-3) / 1e12 if kern_ms > 0 else 0.0
-    roofline = dict(bound="tensor", kernel="tc_pass1_kernel" if stats["mode"] else "exact_mlp_kernel",
+    roofline = dict(bound="tensor", pipe="tcgen05 f16" if stats["mode"] else "fp32 FFMA (compute-bound; no tensor cores)",
+                    kernel=kern_name,
                     achieved=achieved, peak=peak_tf, unit="TFLOP/s", frac=achieved / peak_tf, traffic=traffic,
                     peak_source=peak_src, flops_per_launch=flops_per_launch, ms_per_launch=kern_ms, launches_timed=kt_n,
                     share_of_step=kt_ms / args.steps / ms_per_step)

@@ -155,6 +155,9 @@ int dsmppi_ctx_create(dsmppi_ctx** out, const dsmppi_net* net, const float* dh_p
                       int32_t capacity, int32_t device);
 int dsmppi_ctx_destroy(dsmppi_ctx* ctx);
 int dsmppi_set_pass1_mode(dsmppi_ctx* ctx, int32_t mode, float guard_band);
+/* Small obstacle sets scored in fp32 (M <= 16, or M <= 32 with a latency-bound batch) are rolled out over the whole
+ * horizon by ONE launch (rollout_fused_kernel); on = 0 forces the per-step launch sequence (tests compare both). */
+int dsmppi_set_whole_horizon(dsmppi_ctx* ctx, int32_t on);
 
 /* MPPI.update_obstacles (MPPI.py:347-350) and the obs argument of __init__: (M, P + 1) = [x, y, z, r], or
  * [x, y, r] for a network created with n_point_dim = 2. */
@@ -254,6 +257,9 @@ int dsmppi_pass1_stats(dsmppi_ctx* ctx, int64_t* rescored_pairs, int64_t* band_o
 int dsmppi_enable_kernel_timing(dsmppi_ctx* ctx, int32_t on);
 int dsmppi_kernel_timing(dsmppi_ctx* ctx, double* pass1_ms_per_launch, int32_t* pass1_launches,
                          double* exact_ms_per_launch, int32_t* exact_launches);
+/* Same, naming the kernel: kind 0 = exact_mlp_kernel (fp32 scoring, one launch per step), 1 = tc_pass1_kernel,
+ * 2 = rollout_fused_kernel (one launch per rollout block: all H steps). */
+int dsmppi_kernel_timing_ex(dsmppi_ctx* ctx, int32_t* kind, double* ms_per_launch, int32_t* launches);
 
 #ifdef __cplusplus
 }

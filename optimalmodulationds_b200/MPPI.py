@@ -165,6 +165,10 @@ class MPPI:
                 'auto': _capi.PASS1_AUTO}[mode]
         _capi.check(self._lib.dsmppi_set_pass1_mode(self._ctx, code, float(guard_band)))
 
+    def set_whole_horizon(self, on=True):
+        """Small obstacle sets are rolled out by one launch over the whole horizon; False forces per-step launches."""
+        _capi.check(self._lib.dsmppi_set_whole_horizon(self._ctx, 1 if on else 0))
+
     def _upload_obstacles(self):
         obs = self._d(self.obs)
         if obs.dim() != 2 or obs.shape[1] != self._point_dim + 1:
@@ -504,6 +508,13 @@ class MPPI:
 
     def enable_kernel_timing(self, on=True):
         _capi.check(self._lib.dsmppi_enable_kernel_timing(self._ctx, 1 if on else 0))
+
+    def kernel_timing_ex(self):
+        """(kernel name, ms per launch, launches) of the dominant kernel in the last rollout."""
+        k, ms, n = _capi.C.c_int32(), _capi.C.c_double(), _capi.C.c_int32()
+        _capi.check(self._lib.dsmppi_kernel_timing_ex(self._ctx, _capi.C.byref(k), _capi.C.byref(ms), _capi.C.byref(n)))
+        name = {0: 'exact_mlp_kernel', 1: 'tc_pass1_kernel', 2: 'rollout_fused_kernel'}[k.value]
+        return dict(kernel=name, ms=ms.value, launches=n.value)
 
     def kernel_timing(self):
         p, pn, e, en = _capi.C.c_double(), _capi.C.c_int32(), _capi.C.c_double(), _capi.C.c_int32()

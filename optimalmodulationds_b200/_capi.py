@@ -102,6 +102,7 @@ EXPORTS = {
     "dsmppi_ctx_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(Net), _fp, C.c_int32, C.c_int32]),
     "dsmppi_ctx_destroy": (C.c_int, [C.c_void_p]),
     "dsmppi_set_pass1_mode": (C.c_int, [C.c_void_p, C.c_int32, C.c_float]),
+    "dsmppi_set_whole_horizon": (C.c_int, [C.c_void_p, C.c_int32]),
     "dsmppi_set_obstacles": (C.c_int, [C.c_void_p, _fp, C.c_int32, C.c_void_p]),
     "dsmppi_set_obstacles_host": (C.c_int, [C.c_void_p, _fp, C.c_int32, C.c_void_p]),
     "dsmppi_rollout": (C.c_int, [C.c_void_p, C.POINTER(RolloutArgs), C.c_void_p]),
@@ -121,6 +122,8 @@ EXPORTS = {
     "dsmppi_enable_kernel_timing": (C.c_int, [C.c_void_p, C.c_int32]),
     "dsmppi_kernel_timing": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int32),
                                        C.POINTER(C.c_double), C.POINTER(C.c_int32)]),
+    "dsmppi_kernel_timing_ex": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_double),
+                                          C.POINTER(C.c_int32)]),
 }
 
 _lib = None

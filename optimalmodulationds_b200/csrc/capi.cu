@@ -32,12 +32,22 @@ int alloc(T*& p, size_t n) {
 }
 
 constexpr int FUSE_M_MAX = 16;   // up to this many obstacles the fp32 path differentiates every pair in one launch
-
 int resolved_mode(const dsmppi_ctx* c) {
   int m = c->pass1_mode;
   if (m == DSMPPI_PASS1_AUTO) m = (c->M >= 64 && c->tc_blob) ? DSMPPI_PASS1_TC_F16 : DSMPPI_PASS1_EXACT_FP32;
   if (m != DSMPPI_PASS1_EXACT_FP32 && !c->tc_blob) m = DSMPPI_PASS1_EXACT_FP32;
   return m;
+}
+
+constexpr int WHOLE_M_MAX = 32;  // largest obstacle set a row tile of the whole-horizon kernel can hold
+
+// Whole-horizon single launch: fp32 scoring with every (sample, obstacle) pair differentiated.  Always for
+// M <= 16 (same FLOPs as the per-step launches); for 17..32 obstacles only while the batch is latency-bound,
+// because differentiating all M pairs instead of the K closest costs up to 1.5x the FLOPs.
+bool use_whole_horizon(const dsmppi_ctx* c, int n) {
+  if (!c->fused_rollout || resolved_mode(c) != DSMPPI_PASS1_EXACT_FP32) return false;
+  if (c->M <= FUSE_M_MAX) return true;
+  return c->M <= WHOLE_M_MAX && n <= 2 * c->sm_count;
 }
 
 // records one event of a start/stop pair on the launching stream (no host synchronisation)
@@ -75,7 +85,7 @@ int ensure_workspace(dsmppi_ctx* c, int n, int M) {
   if (grow(c->m_rows, c->m_rows_cap, rows)) return 1;
   // rows that get a distance + gradient: all candidates (fused single launch) or the K selected
   size_t drows = (size_t)nn * CAND_MAX;
-  if (mm <= FUSE_M_MAX && (size_t)nn * mm > drows) drows = (size_t)nn * mm;
+  if (mm <= WHOLE_M_MAX && (size_t)nn * mm > drows) drows = (size_t)nn * mm;
   if (grow(c->row_dist, c->row_dist_cap, drows)) return 1;
   if (grow(c->row_grad, c->row_grad_cap, drows * d)) return 1;
   cap = c->rowlist_cap;
@@ -215,6 +225,12 @@ int dsmppi_set_pass1_mode(dsmppi_ctx* c, int32_t mode, float guard_band) {
   return 0;
 }
 
+int dsmppi_set_whole_horizon(dsmppi_ctx* c, int32_t on) {
+  REQUIRE(c, "null ctx");
+  c->fused_rollout = on ? 1 : 0;
+  return 0;
+}
+
 int dsmppi_set_obstacles(dsmppi_ctx* c, const float* obs_dev, int32_t M, void* stream) {
   REQUIRE(c && obs_dev, "null argument");
   REQUIRE(M >= 1, "need at least one obstacle");
@@ -343,6 +359,15 @@ int dsmppi_rollout(dsmppi_ctx* c, const dsmppi_rollout_args* a, void* stream) {
     b.qdot_dev = a->qdot_dev + off * d;
     b.nn_grad_all_dev = a->nn_grad_all_dev + off * a->H * d;
     if (launch_init_traj(c, &b, st)) return 1;
+    if (use_whole_horizon(c, b.N)) {
+      REQUIRE(b.n_closest >= 1 && b.n_closest <= MAXK, "n_closest_obs out of range (1..8)");
+      REQUIRE(b.n_closest <= c->M, "n_closest_obs exceeds the number of obstacles");
+      if (ensure_workspace(c, b.N, c->M)) return 1;
+      if (timing_mark(c, 2, st)) return 1;
+      if (launch_rollout_fused(c, &b, st)) return 1;
+      if (timing_mark(c, 2, st)) return 1;
+      continue;
+    }
     for (int t = 1; t <= b.H; ++t) {
       const float* q = b.all_traj_dev + (size_t)(t - 1) * d;          // q_prev = all_traj[:, t-1, :]
       if (distance_pipeline(c, q, b.H * d, b.N, b.n_closest, b.ignored_link_mask, st)) return 1;
@@ -550,6 +575,23 @@ int dsmppi_pass1_stats(dsmppi_ctx* c, int64_t* rescored_pairs, int64_t* band_ove
 int dsmppi_enable_kernel_timing(dsmppi_ctx* c, int32_t on) {
   REQUIRE(c, "null ctx");
   c->timing = on;
+  return 0;
+}
+
+int dsmppi_kernel_timing_ex(dsmppi_ctx* c, int32_t* kind, double* ms_per_launch, int32_t* launches) {
+  REQUIRE(c, "null ctx");
+  double tot = 0.0;
+  int n = 0;
+  for (int i = 0; i + 1 < c->ev_used; i += 2) {
+    CUDA_TRY(cudaEventSynchronize(c->ev[i + 1]));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, c->ev[i], c->ev[i + 1]));
+    tot += ms;
+    ++n;
+  }
+  if (kind) *kind = c->ev_kind;
+  if (ms_per_launch) *ms_per_launch = n ? tot / n : 0.0;
+  if (launches) *launches = n;
   return 0;
 }
 

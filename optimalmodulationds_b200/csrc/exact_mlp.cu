@@ -3,10 +3,14 @@
 //   exact_mlp_kernel<false, RPT>: forward only  -> masked minimum link distance per row  (MPPI.py:235-242)
 //   exact_mlp_kernel<true,  RPT>: forward + analytic VJP at argmin_l of the raw output   (robot_sdf.py:153-158)
 //
-// One CTA of 4 warps owns R = 4*RPT rows (RPT = 8, 4 or 2).  Activations live in shared memory feature-major
-// (act[k][row]) and are updated in place layer by layer.  A warp owns an R-row x 64-feature block of the layer
-// output, its lanes form a 4 x 8 grid and each thread keeps an RPT-row x 8-feature register tile, so one k-step of a
-// warp is 8*RPT FFMAs fed by single-wavefront shared-memory loads (broadcast over the row / feature groups).
+// One CTA owns R = 4*RPT rows (RPT = 8, 4 or 2).  Activations live in shared memory feature-major
+// (act[k][row]) and are updated in place layer by layer.  A warp owns an R-row x (8*FT)-feature block of the layer
+// output, its lanes form a 4 x 8 grid and each thread keeps an RPT-row x FT-feature register tile (FT = 8, 4 or 2
+// => 4, 8 or 16 warps per CTA), so one k-step of a warp is FT*RPT FFMAs fed by single-wavefront shared-memory
+// loads (broadcast over the row / feature groups).  FT = 8 amortises the loads best and is used whenever there are
+// enough row tiles to fill the SMs; the 8- and 16-warp shapes put 2 or 4 warps on every scheduler of an SM that
+// holds a single tile, which is what the latency of a small batch (and of the whole-horizon kernel) is made of
+// (pick_shape below has the measurements; only 8x8, 8x4 and 4x4 are instantiated).
 // The weights of all seven GEMMs (4 forward, 3 backward) are one stream of 8-row stages that the CTA pulls from L2
 // through a 4-deep cp.async ring, three stages (24 k-steps) ahead of the FFMAs and straight across layer
 // boundaries: a lone CTA on an SM is then FFMA-bound instead of waiting ~500 cycles for L2 every four k-steps,
@@ -19,10 +23,11 @@
 #include <cstdlib>
 
 #include "internal.cuh"
+#include "step_device.cuh"
 
 namespace {
 
-constexpr int NT = 128;   // threads per CTA: 4 warps, one per 64-feature quarter
+__host__ __device__ constexpr int nthreads(int FT) { return 32 * (HID / (8 * FT)); }   // 128 / 256 / 512 threads for FT = 8 / 4 / 2
 constexpr int XS = 12;    // padded row stride of the raw-input scratch (nin <= 11)
 constexpr int WS = 8;     // k-rows of weights per pipeline stage (8 KB)
 constexpr int NSTAGE = 4; // ring depth
@@ -42,11 +47,32 @@ __device__ __forceinline__ bool row_lookup(const RowSrc& s, int r, int n_rows, i
   return true;
 }
 
-// Thread tile: rows r0 .. r0+RPT-1, features {fa .. fa+3} (j = 0..3) and {fa+32 .. fa+35} (j = 4..7).
+// Thread tile: rows r0 .. r0+RPT-1 and FT features: FT = 8: {fa .. fa+3} (j = 0..3) and {fa+32 .. fa+35} (j = 4..7);
+// FT = 4 / 2: {fa .. fa+FT-1}.
+template <int FT>
 struct Tile {
   int r0, fa;
-  __device__ __forceinline__ int feat(int j) const { return fa + (j & 3) + ((j >> 2) << 5); }
+  __device__ __forceinline__ void init(int tid, int RPT) {
+    r0 = ((tid & 31) >> 3) * RPT;                                  // lane / 8: one of four RPT-row groups
+    fa = (tid >> 5) * (8 * FT) + (tid & 7) * (FT == 8 ? 4 : FT);   // warp: feature block; lane % 8: feature group
+  }
+  __device__ __forceinline__ int feat(int j) const { return FT == 8 ? fa + (j & 3) + ((j >> 2) << 5) : fa + j; }
 };
+
+// FT consecutive-group values of a 256-wide row (weights of one k, or a bias vector) for this thread's tile
+template <int FT>
+__device__ __forceinline__ void load_feats(const float* p, float (&w)[FT]) {
+  if constexpr (FT == 8) {
+    const float4 w0 = *reinterpret_cast<const float4*>(p), w1 = *reinterpret_cast<const float4*>(p + 32);
+    w[0] = w0.x; w[1] = w0.y; w[2] = w0.z; w[3] = w0.w; w[4] = w1.x; w[5] = w1.y; w[6] = w1.z; w[7] = w1.w;
+  } else if constexpr (FT == 4) {
+    const float4 w0 = *reinterpret_cast<const float4*>(p);
+    w[0] = w0.x; w[1] = w0.y; w[2] = w0.z; w[3] = w0.w;
+  } else {
+    const float2 w0 = *reinterpret_cast<const float2*>(p);
+    w[0] = w0.x; w[1] = w0.y;
+  }
+}
 
 template <int RPT>
 __device__ __forceinline__ void load_rows(const float* p, float (&a)[RPT]) {
@@ -93,11 +119,13 @@ struct WeightStream {
   const NetDev* net;
   float* ring;            // [NSTAGE][WS][HID]
   int n0;                 // stages of GEMM 0 = ceil(nenc / WS)
-  int total;              // stages in the whole stream
+  int per_pass;           // stages of one pass over a row tile (forward, or forward + backward)
+  int total;              // stages in the whole stream: per_pass x number of passes this CTA makes
   int issued;             // next stage to request
 
   __device__ __forceinline__ void locate(int stage, const float*& src, int& rows) const {
     int g, st;
+    stage %= per_pass;
     if (stage < n0) { g = 0; st = stage; }
     else { g = 1 + (stage - n0) / (HID / WS); st = (stage - n0) % (HID / WS); }
     const int K = g == 0 ? net->nenc : HID;
@@ -106,6 +134,7 @@ struct WeightStream {
     rows = min(WS, K - st * WS);
   }
   // every thread requests its share of the next stage (or nothing past the end) and closes one group
+  template <int NT>
   __device__ __forceinline__ void request_next() {
     if (issued < total) {
       const float* src;
@@ -121,47 +150,50 @@ struct WeightStream {
 
 // acc[i][j] = sum_k act[k][r0+i] * W[k*256 + feat(j)], W arriving through the ring; `stage` is the stream position
 // of this GEMM's first stage and is advanced past its last one
-template <int RPT>
-__device__ __forceinline__ void gemm_tile(WeightStream& ws, int& stage, int K, const float (*act)[4 * RPT], const Tile& t,
-                                          float (&acc)[RPT][8]) {
-  uint64_t acc2[RPT][4];                  // acc2[i][p] = (acc[i][2p], acc[i][2p+1])
+template <int RPT, int FT>
+__device__ __forceinline__ void gemm_tile(WeightStream& ws, int& stage, int K, const float (*act)[4 * RPT],
+                                          const Tile<FT>& t, float (&acc)[RPT][FT]) {
+  constexpr int NT = nthreads(FT);
+  uint64_t acc2[RPT][FT / 2];             // acc2[i][p] = (acc[i][2p], acc[i][2p+1])
 #pragma unroll
   for (int i = 0; i < RPT; ++i)
 #pragma unroll
-    for (int p = 0; p < 4; ++p) acc2[i][p] = 0ull;
+    for (int p = 0; p < FT / 2; ++p) acc2[i][p] = 0ull;
   for (int k0 = 0; k0 < K; k0 += WS, ++stage) {
     cp_async_wait<NSTAGE - 2>();          // this thread's share of `stage` has landed ...
     __syncthreads();                      // ... and everybody's; the buffer of stage-1 is free again
-    ws.request_next();                    // refill it with stage + NSTAGE - 1
+    ws.template request_next<NT>();       // refill it with stage + NSTAGE - 1
     const float* wb = ws.ring + (size_t)(stage % NSTAGE) * WS * HID + t.fa;
     const int rows = min(WS, K - k0);
     if (rows == WS) {
 #pragma unroll
       for (int kk = 0; kk < WS; ++kk) {
-        float a[RPT];
+        float a[RPT], w[FT];
         load_rows<RPT>(&act[k0 + kk][t.r0], a);
-        const float4 w0 = *reinterpret_cast<const float4*>(wb + kk * HID);
-        const float4 w1 = *reinterpret_cast<const float4*>(wb + kk * HID + 32);
-        const uint64_t wp[4] = {pack2f(w0.x, w0.y), pack2f(w0.z, w0.w), pack2f(w1.x, w1.y), pack2f(w1.z, w1.w)};
+        load_feats<FT>(wb + kk * HID, w);
+        uint64_t wp[FT / 2];
+#pragma unroll
+        for (int p = 0; p < FT / 2; ++p) wp[p] = pack2f(w[2 * p], w[2 * p + 1]);
 #pragma unroll
         for (int i = 0; i < RPT; ++i) {
           const uint64_t ad = pack2f(a[i], a[i]);
 #pragma unroll
-          for (int p = 0; p < 4; ++p) acc2[i][p] = fma2(ad, wp[p], acc2[i][p]);
+          for (int p = 0; p < FT / 2; ++p) acc2[i][p] = fma2(ad, wp[p], acc2[i][p]);
         }
       }
     } else {
       for (int kk = 0; kk < rows; ++kk) {
-        float a[RPT];
+        float a[RPT], w[FT];
         load_rows<RPT>(&act[k0 + kk][t.r0], a);
-        const float4 w0 = *reinterpret_cast<const float4*>(wb + kk * HID);
-        const float4 w1 = *reinterpret_cast<const float4*>(wb + kk * HID + 32);
-        const uint64_t wp[4] = {pack2f(w0.x, w0.y), pack2f(w0.z, w0.w), pack2f(w1.x, w1.y), pack2f(w1.z, w1.w)};
+        load_feats<FT>(wb + kk * HID, w);
+        uint64_t wp[FT / 2];
+#pragma unroll
+        for (int p = 0; p < FT / 2; ++p) wp[p] = pack2f(w[2 * p], w[2 * p + 1]);
 #pragma unroll
         for (int i = 0; i < RPT; ++i) {
           const uint64_t ad = pack2f(a[i], a[i]);
 #pragma unroll
-          for (int p = 0; p < 4; ++p) acc2[i][p] = fma2(ad, wp[p], acc2[i][p]);
+          for (int p = 0; p < FT / 2; ++p) acc2[i][p] = fma2(ad, wp[p], acc2[i][p]);
         }
       }
     }
@@ -169,13 +201,13 @@ __device__ __forceinline__ void gemm_tile(WeightStream& ws, int& stage, int K, c
 #pragma unroll
   for (int i = 0; i < RPT; ++i)
 #pragma unroll
-    for (int p = 0; p < 4; ++p) unpack2f(acc2[i][p], acc[i][2 * p], acc[i][2 * p + 1]);
+    for (int p = 0; p < FT / 2; ++p) unpack2f(acc2[i][p], acc[i][2 * p], acc[i][2 * p + 1]);
 }
 
-template <int RPT>
-__device__ __forceinline__ void store_tile(float (*act)[4 * RPT], const Tile& t, const float (&v)[RPT][8]) {
+template <int RPT, int FT>
+__device__ __forceinline__ void store_tile(float (*act)[4 * RPT], const Tile<FT>& t, const float (&v)[RPT][FT]) {
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
+  for (int j = 0; j < FT; ++j) {
     float* p = &act[t.feat(j)][t.r0];
     if constexpr (RPT == 8) {
       *reinterpret_cast<float4*>(p) = make_float4(v[0][j], v[1][j], v[2][j], v[3][j]);
@@ -188,39 +220,57 @@ __device__ __forceinline__ void store_tile(float (*act)[4 * RPT], const Tile& t,
   }
 }
 
-template <bool BWD, int RPT>
-__global__ void __launch_bounds__(NT, RPT == 8 ? 4 : (RPT == 4 ? 6 : 8))
-exact_mlp_kernel(NetDev net, RowSrc src, const float* __restrict__ q, int q_stride, const float* __restrict__ obs,
-                 uint32_t ignore_mask, float* __restrict__ out_m, float* __restrict__ out_dist,
-                 float* __restrict__ out_grad) {
-  constexpr int R = 4 * RPT;
-  extern __shared__ __align__(16) float smem[];
-  float (*act)[R] = reinterpret_cast<float (*)[R]>(smem);   // [256][R]
-  float* ring = smem + HID * R;                             // [NSTAGE][WS][256] weight stages
-  float* xs = ring + NSTAGE * WS * HID;                     // [R][XS]  raw inputs x = [q, p]
-  float* zs = xs + R * XS;                                  // [R][MAXO] raw outputs
-  float* rad = zs + R * MAXO;                               // [R]
-  int* lst = reinterpret_cast<int*>(rad + R);               // [R] argmin link
+template <int RPT>
+struct TileSmem {
+  static constexpr int R = 4 * RPT;
+  float (*act)[R];   // [256][R]
+  float* ring;       // [NSTAGE][WS][256] weight stages
+  float* xs;         // [R][XS]  raw inputs x = [q, p]
+  float* zs;         // [R][MAXO] raw outputs
+  float* rad;        // [R]
+  int* lst;          // [R] argmin link
+  __device__ __forceinline__ explicit TileSmem(float* smem) {
+    act = reinterpret_cast<float (*)[R]>(smem);
+    ring = smem + HID * R;
+    xs = ring + NSTAGE * WS * HID;
+    zs = xs + R * XS;
+    rad = zs + R * MAXO;
+    lst = reinterpret_cast<int*>(rad + R);
+  }
+};
 
-  const int n_rows = src.n_rows_dev ? min(*src.n_rows_dev, src.n_rows) : src.n_rows;
-  const int row0 = blockIdx.x * R;
-  if (row0 >= n_rows) return;
-  const int tid = threadIdx.x;
-  Tile t;
-  t.r0 = ((tid & 31) >> 3) * RPT;                     // lane / 8: one of four RPT-row groups
-  t.fa = (tid >> 5) * 64 + (tid & 7) * 4;             // warp: 64-feature quarter; lane % 8: 4-feature group
-  const int d = net.d, nin = net.nin, nenc = net.nenc, O = net.O;
-
-  // start the weight stream before anything else: the first three stages fly while the inputs are encoded
-  WeightStream ws;
-  ws.net = &net;
+// starts the weight stream of a CTA that will make `passes` passes over row tiles: the first three stages fly
+// while the inputs are encoded
+template <bool BWD, int NT>
+__device__ __forceinline__ void stream_begin(WeightStream& ws, const NetDev* net, float* ring, int passes) {
+  ws.net = net;
   ws.ring = ring;
-  ws.n0 = (nenc + WS - 1) / WS;
-  ws.total = ws.n0 + (BWD ? 6 : 3) * (HID / WS);
+  ws.n0 = (net->nenc + WS - 1) / WS;
+  ws.per_pass = ws.n0 + (BWD ? 6 : 3) * (HID / WS);
+  ws.total = ws.per_pass * passes;
   ws.issued = 0;
 #pragma unroll
-  for (int i = 0; i < NSTAGE - 1; ++i) ws.request_next();
-  int stage = 0;
+  for (int i = 0; i < NSTAGE - 1; ++i) ws.template request_next<NT>();
+}
+
+// One pass of the network over the R rows [row0, row0 + R) of `src` (rows >= n_rows are padding): forward, and with
+// BWD the analytic VJP.  Called by all NT threads of the CTA; `ws` / `stage` carry the weight stream across calls.
+template <bool BWD, int RPT, int FT>
+__device__ __forceinline__ void mlp_tile(const NetDev& net, const RowSrc& src, int row0, int n_rows,
+                                         const float* q, int q_stride, const float* __restrict__ obs,
+                                         uint32_t ignore_mask, float* out_m, float* out_dist, float* out_grad,
+                                         const TileSmem<RPT>& sm, WeightStream& ws, int& stage) {
+  constexpr int R = 4 * RPT;
+  constexpr int NT = nthreads(FT);
+  float (*act)[R] = sm.act;
+  float* xs = sm.xs;
+  float* zs = sm.zs;
+  float* rad = sm.rad;
+  int* lst = sm.lst;
+  const int tid = threadIdx.x;
+  Tile<FT> t;
+  t.init(tid, RPT);
+  const int d = net.d, nin = net.nin, nenc = net.nenc, O = net.O;
 
   // ---- rows -> encoded inputs [x, sin x, cos x]  (network_macros_mod.py:139-140)
   for (int idx = tid; idx < R * nin; idx += NT) {
@@ -237,28 +287,27 @@ exact_mlp_kernel(NetDev net, RowSrc src, const float* __restrict__ q, int q_stri
   }
   __syncthreads();
 
-  uint64_t mk[4];          // ReLU masks of this thread's tile, bit i*8+j
-  float acc[RPT][8];
+  uint64_t mk[4];          // ReLU masks of this thread's tile, bit i*FT+j
+  float acc[RPT][FT];
   // ---- hidden layers: h = relu(W h + b)
 #pragma unroll 1
   for (int l = 0; l < 4; ++l) {
-    gemm_tile<RPT>(ws, stage, l == 0 ? nenc : HID, act, t, acc);
+    gemm_tile<RPT, FT>(ws, stage, l == 0 ? nenc : HID, act, t, acc);
     __syncthreads();
-    const float4 b0 = __ldg(reinterpret_cast<const float4*>(net.b[l] + t.fa));
-    const float4 b1 = __ldg(reinterpret_cast<const float4*>(net.b[l] + t.fa + 32));
-    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    float bb[FT];
+    load_feats<FT>(net.b[l] + t.fa, bb);
     uint64_t m = 0;
 #pragma unroll
     for (int i = 0; i < RPT; ++i)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
+      for (int j = 0; j < FT; ++j) {
         const float v = acc[i][j] + bb[j];
         const bool on = v > 0.f;
-        if (BWD) m |= (uint64_t)(on ? 1u : 0u) << (i * 8 + j);
+        if (BWD) m |= (uint64_t)(on ? 1u : 0u) << (i * FT + j);
         acc[i][j] = on ? v : 0.f;
       }
     mk[l] = m;
-    store_tile<RPT>(act, t, acc);
+    store_tile<RPT, FT>(act, t, acc);
     __syncthreads();
   }
 
@@ -273,7 +322,7 @@ exact_mlp_kernel(NetDev net, RowSrc src, const float* __restrict__ q, int q_stri
   }
   __syncthreads();
 
-  if (!BWD) {
+  if constexpr (!BWD) {
     // MPPI.py:236-242: /100 for the 9-link Franka net, minus radius, ignored links := 1e6, min over links
     if (tid < R && row0 + tid < n_rows) {
       float m = 3.0e38f;
@@ -286,9 +335,7 @@ exact_mlp_kernel(NetDev net, RowSrc src, const float* __restrict__ q, int q_stri
       }
       out_m[row0 + tid] = m;
     }
-    return;
-  }
-
+  } else {
   // ---- pass 2: l* = argmin of the RAW output (robot_sdf.py:155), distance of that link (MPPI.py:265-274);
   //      optionally also the pass-1 ranking key (masked minimum) so one launch serves both passes
   if (tid < R) {
@@ -318,26 +365,26 @@ exact_mlp_kernel(NetDev net, RowSrc src, const float* __restrict__ q, int q_stri
 #pragma unroll
   for (int i = 0; i < RPT; ++i) {
     const float* w = net.W4 + lst[t.r0 + i] * HID;
-    const uint32_t bits = (uint32_t)(mk[3] >> (i * 8)) & 0xffu;
+    const uint32_t bits = (uint32_t)(mk[3] >> (i * FT)) & 0xffu;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j] = ((bits >> j) & 1u) ? __ldg(w + t.feat(j)) : 0.f;
+    for (int j = 0; j < FT; ++j) acc[i][j] = ((bits >> j) & 1u) ? __ldg(w + t.feat(j)) : 0.f;
   }
-  store_tile<RPT>(act, t, acc);
+  store_tile<RPT, FT>(act, t, acc);
   __syncthreads();
 
   // g_{l-1} = (W_l^T g_l) * s_{l-1},  l = 3, 2, 1   (Wb[l] is torch's [out][in]: out = k, in = n)
 #pragma unroll 1
   for (int l = 3; l >= 1; --l) {
-    gemm_tile<RPT>(ws, stage, HID, act, t, acc);
+    gemm_tile<RPT, FT>(ws, stage, HID, act, t, acc);
     __syncthreads();
     const uint64_t m = mk[l - 1];
 #pragma unroll
     for (int i = 0; i < RPT; ++i) {
-      const uint32_t bits = (uint32_t)(m >> (i * 8)) & 0xffu;
+      const uint32_t bits = (uint32_t)(m >> (i * FT)) & 0xffu;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[i][j] = ((bits >> j) & 1u) ? acc[i][j] : 0.f;
+      for (int j = 0; j < FT; ++j) acc[i][j] = ((bits >> j) & 1u) ? acc[i][j] : 0.f;
     }
-    store_tile<RPT>(act, t, acc);
+    store_tile<RPT, FT>(act, t, acc);
     __syncthreads();
   }
 
@@ -357,53 +404,188 @@ exact_mlp_kernel(NetDev net, RowSrc src, const float* __restrict__ q, int q_stri
     const float x = xs[r * XS + c];
     if (row0 + r < n_rows) out_grad[(size_t)(row0 + r) * d + c] = a0 + cosf(x) * a1 - sinf(x) * a2;
   }
+  }  // BWD
+}
+
+// resident CTAs per SM the register budget is sized for: the 4-warp shape packs 4 (32-row) or 6 (16-row) tiles on
+// an SM, the 8-warp shape 2, the 16-warp shape 1
+__host__ __device__ constexpr int min_ctas(int RPT, int FT) { return FT == 8 ? (RPT == 8 ? 4 : 6) : (FT == 4 ? (RPT == 8 ? 2 : 3) : 1); }
+
+template <bool BWD, int RPT, int FT>
+__global__ void __launch_bounds__(nthreads(FT), min_ctas(RPT, FT))
+exact_mlp_kernel(NetDev net, RowSrc src, const float* __restrict__ q, int q_stride, const float* __restrict__ obs,
+                 uint32_t ignore_mask, float* __restrict__ out_m, float* __restrict__ out_dist,
+                 float* __restrict__ out_grad) {
+  constexpr int R = 4 * RPT;
+  extern __shared__ __align__(16) float smem[];
+  const int n_rows = src.n_rows_dev ? min(*src.n_rows_dev, src.n_rows) : src.n_rows;
+  const int row0 = blockIdx.x * R;
+  if (row0 >= n_rows) return;
+  TileSmem<RPT> sm(smem);
+  WeightStream ws;
+  stream_begin<BWD, nthreads(FT)>(ws, &net, sm.ring, 1);
+  int stage = 0;
+  mlp_tile<BWD, RPT, FT>(net, src, row0, n_rows, q, q_stride, obs, ignore_mask, out_m, out_dist, out_grad, sm, ws,
+                         stage);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Whole-horizon rollout in ONE launch for small obstacle sets (M <= R): a CTA owns S = R / M samples and all of
+// their (sample, obstacle) rows, and samples never interact, so it can run all H steps by itself -- network
+// forward + VJP on its tile, then one thread per sample ranks its M rows, blends the K closest gradients and takes
+// the modulation / policy / Euler step (step_device.cuh) -- with no grid-wide dependency and no launch per step.
+// The weight stream simply keeps running across steps.  This is the path of the reference's own CPU-sized
+// problems (planar scripts: M = 2..4; Franka integrator tick: N = 1, H = 2) where launch latency, not FLOPs,
+// set the pace of the per-step launch sequence.
+// ------------------------------------------------------------------------------------------------
+template <int RPT, int FT>
+__global__ void __launch_bounds__(nthreads(FT), FT == 8 ? 3 : 2)
+rollout_fused_kernel(NetDev net, StepArgs sa, const float* __restrict__ obs, int M, uint32_t ignore_mask,
+                     float* m_rows, float* row_dist, float* row_grad, int* sel_rows) {
+  constexpr int R = 4 * RPT;
+  extern __shared__ __align__(16) float smem[];
+  const int S = R / M;                                  // samples per CTA
+  const int i0 = blockIdx.x * S;
+  if (i0 >= sa.N) return;
+  const int ns = min(S, sa.N - i0);
+  const int row0 = i0 * M;                              // dense rows: row = i * M + j
+  const int n_rows = row0 + ns * M;
+  TileSmem<RPT> sm(smem);
+  WeightStream ws;
+  stream_begin<true, nthreads(FT)>(ws, &net, sm.ring, sa.H);
+  int stage = 0;
+  RowSrc src{};
+  src.mode = ROWS_DENSE;
+  src.M = M;
+  const int d = net.d, K = sa.K;
+  const int tid = threadIdx.x;
+  for (int t = 1; t <= sa.H; ++t) {
+    const float* q = sa.traj + (size_t)(t - 1) * d;     // q_prev = all_traj[:, t-1, :]
+    mlp_tile<true, RPT, FT>(net, src, row0, n_rows, q, sa.H * d, obs, ignore_mask, m_rows, row_dist, row_grad, sm,
+                            ws, stage);
+    __syncthreads();                                    // the tile's rows are visible to the whole CTA
+    if (tid < ns) {
+      const int i = i0 + tid;
+      // the K closest obstacles, ascending by (masked distance, obstacle index)  (MPPI.py:243-247)
+      const float* mr = m_rows + (size_t)i * M;
+      float last_v = -3.4e38f;
+      int last_j = -1;
+      for (int kk = 0; kk < K; ++kk) {
+        float bv = 3.4e38f;
+        int bj = -1;
+        for (int j = 0; j < M; ++j) {
+          const float v = mr[j];
+          const bool after = kk == 0 || v > last_v || (v == last_v && j > last_j);
+          if (after && (bj < 0 || v < bv)) { bv = v; bj = j; }
+        }
+        if (bj < 0) bj = last_j < 0 ? 0 : last_j;
+        sel_rows[(size_t)i * K + kk] = i * M + bj;
+        last_v = bv; last_j = bj;
+      }
+      StepArgs s = sa;
+      s.t = t;
+      step_sample(s, i);
+    }
+    __syncthreads();                                    // next state written before the next tile reads it
+  }
 }
 
 constexpr size_t smem_bytes(int R) {
   return (size_t)(HID * R + NSTAGE * WS * HID + R * XS + R * MAXO + R + R) * sizeof(float);
 }
 
-// Rows-per-thread for a launch over about `rows` rows.  Measured on B200 (Franka shelf, ~24.6k candidate rows per
-// step: 171.8 / 177.0 / 187.1 ms per iteration for RPT = 8 / 4 / 2; planar-7, 4000 rows: 6.32 / 6.02 / 6.81 ms):
-// 32-row tiles win as soon as they give every SM two CTAs to overlap, 16-row tiles when rows are scarce; 8-row
-// tiles re-read the weights from shared memory too often (LSU-bound) and are only kept for experiments.
-int pick_rpt(const dsmppi_ctx* c, long long rows) {
-  const char* force = std::getenv("DSMPPI_EXACT_RPT");
-  if (force) { const int f = std::atoi(force); if (f == 8 || f == 4 || f == 2) return f; }
-  return (rows + 31) / 32 >= 2LL * c->sm_count ? 8 : 4;
+// Tile shape (rows per thread, features per thread).  Measured on B200 (tools/exact_shape_sweep.py, ms per
+// propagate, planar-7 net, M = 4, H = 30; shapes as RPTxFT):
+//     rows per step   8x8     4x8     8x4     4x4     8x2     4x2
+//        1 000        5.52    4.20    4.79    3.77    5.61    4.13
+//        4 000        5.54    5.06    4.86    5.80    5.68    8.19
+//        8 000        7.63    7.91    7.84   10.64   11.17   16.19
+//       16 000       13.84   13.73   15.29   18.57   22.13   28.28
+// While the batch gives an SM at most one 32-row tile, the 8-warp shapes win: two warps per scheduler hide part of
+// the shared-memory / FMA latency a lone 4-warp CTA exposes (ncu: 27 % -> 39 % issue-active), 16-row tiles while even
+// those leave SMs idle.  16 warps (FT = 2) lose again: 2-feature register tiles need a load per two FFMA2.  From two
+// tiles per SM on, the 4-warp 8 x 8 register tile is best (fewest shared-memory loads per FMA; 87 % of the FMA
+// peak in steady state with 4 CTAs per SM).
+struct Shape { int rpt, ft; };
+Shape pick_shape(const dsmppi_ctx* c, long long rows, int min_rows_per_tile) {
+  const long long sms = c->sm_count;
+  const long long tiles32 = (rows + 31) / 32, tiles16 = (rows + 15) / 16;
+  Shape s = {8, 8};
+  if (tiles32 <= sms) s = {(min_rows_per_tile <= 16 && tiles16 <= sms) ? 4 : 8, 4};
+  const char* fr = std::getenv("DSMPPI_EXACT_RPT");
+  const char* ff = std::getenv("DSMPPI_EXACT_FT");
+  if (ff) { const int f = std::atoi(ff); if (f == 8 || f == 4) s.ft = f; }
+  if (fr) { const int f = std::atoi(fr); if (f == 8 || (f == 4 && min_rows_per_tile <= 16)) s.rpt = f; }
+  if (s.ft == 8) s.rpt = 8;
+  return s;
 }
 
-template <bool BWD, int RPT>
+template <bool BWD, int RPT, int FT>
 int launch_variant(dsmppi_ctx* c, const float* q, int q_stride, const RowSrc& src, uint32_t ignore_mask, float* out_m,
                    float* out_dist, float* out_grad, cudaStream_t st) {
   constexpr int R = 4 * RPT;
+  static bool init = false;
+  if (!init) {
+    CUDA_TRY(cudaFuncSetAttribute(exact_mlp_kernel<BWD, RPT, FT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem_bytes(R)));
+    init = true;
+  }
   const long long grid = ((long long)src.n_rows + R - 1) / R;
-  exact_mlp_kernel<BWD, RPT><<<(unsigned)grid, NT, smem_bytes(R), st>>>(c->net, src, q, q_stride, c->obs, ignore_mask,
-                                                                       out_m, out_dist, out_grad);
+  exact_mlp_kernel<BWD, RPT, FT><<<(unsigned)grid, nthreads(FT), smem_bytes(R), st>>>(
+      c->net, src, q, q_stride, c->obs, ignore_mask, out_m, out_dist, out_grad);
   CUDA_TRY(cudaGetLastError());
   c->launches++;
   return 0;
 }
 
+#define SHAPE_DISPATCH(sh, CALL)                                  \
+  do {                                                            \
+    if (sh.ft == 8) return CALL(8, 8);                            \
+    if (sh.rpt == 8) return CALL(8, 4);                           \
+    return CALL(4, 4);                                            \
+  } while (0)
+
 template <bool BWD>
 int launch(dsmppi_ctx* c, const float* q, int q_stride, const RowSrc& src, uint32_t ignore_mask, float* out_m,
            float* out_dist, float* out_grad, long long rows_estimate, cudaStream_t st) {
-  static bool init[2] = {false, false};
-  if (!init[BWD]) {
-    CUDA_TRY(cudaFuncSetAttribute(exact_mlp_kernel<BWD, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(32)));
-    CUDA_TRY(cudaFuncSetAttribute(exact_mlp_kernel<BWD, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(16)));
-    init[BWD] = true;
-  }
   if (src.n_rows <= 0) return 0;
   if (rows_estimate <= 0 || rows_estimate > src.n_rows) rows_estimate = src.n_rows;
-  switch (pick_rpt(c, rows_estimate)) {
-    case 8: return launch_variant<BWD, 8>(c, q, q_stride, src, ignore_mask, out_m, out_dist, out_grad, st);
-    case 4: return launch_variant<BWD, 4>(c, q, q_stride, src, ignore_mask, out_m, out_dist, out_grad, st);
-    default: return launch_variant<BWD, 2>(c, q, q_stride, src, ignore_mask, out_m, out_dist, out_grad, st);
+  const Shape sh = pick_shape(c, rows_estimate, 1);
+#define CALL(RPT, FT) launch_variant<BWD, RPT, FT>(c, q, q_stride, src, ignore_mask, out_m, out_dist, out_grad, st)
+  SHAPE_DISPATCH(sh, CALL);
+#undef CALL
+}
+
+template <int RPT, int FT>
+int launch_fused_variant(dsmppi_ctx* c, const dsmppi_rollout_args* a, cudaStream_t st) {
+  constexpr int R = 4 * RPT;
+  static bool init = false;
+  if (!init) {
+    CUDA_TRY(cudaFuncSetAttribute(rollout_fused_kernel<RPT, FT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem_bytes(R)));
+    init = true;
   }
+  const int S = R / c->M;
+  const long long grid = ((long long)a->N + S - 1) / S;
+  const StepArgs sa = make_step_args(c, a, 0);
+  rollout_fused_kernel<RPT, FT><<<(unsigned)grid, nthreads(FT), smem_bytes(R), st>>>(
+      c->net, sa, c->obs, c->M, a->ignored_link_mask, c->m_rows, c->row_dist, c->row_grad, c->sel_rows);
+  CUDA_TRY(cudaGetLastError());
+  c->launches++;
+  return 0;
 }
 
 }  // namespace
+
+// whole-horizon single launch; the caller has checked M <= 32 and initialised all_traj[:, 0]
+int launch_rollout_fused(dsmppi_ctx* c, const dsmppi_rollout_args* a, cudaStream_t st) {
+  const int M = c->M;
+  // a CTA holds whole samples: S = R / M of them, so the row count that matters is N * (R / S) ~ N * M
+  const Shape sh = pick_shape(c, (long long)a->N * M, M);
+#define CALL(RPT, FT) launch_fused_variant<RPT, FT>(c, a, st)
+  SHAPE_DISPATCH(sh, CALL);
+#undef CALL
+}
 
 int launch_exact_forward(dsmppi_ctx* c, const float* q, int q_stride, const RowSrc& src, uint32_t ignore_mask,
                          float* m_rows, cudaStream_t st) {

@@ -111,7 +111,8 @@ struct dsmppi_ctx {
   int timing = 0;
   std::vector<cudaEvent_t> ev;        // start/stop pairs around the scoring kernel of each step
   int ev_used = 0;                    // events recorded by the last rollout
-  int ev_kind = 0;                    // 1: tensor-core pass 1, 0: fp32 dense scoring
+  int ev_kind = 0;                    // 1: tensor-core pass 1, 0: fp32 dense scoring, 2: whole-horizon fused kernel
+  int fused_rollout = 1;              // 0 disables the single-launch path (tests compare the two)
 };
 
 // exact_mlp.cu
@@ -122,6 +123,8 @@ int launch_exact_forward(dsmppi_ctx* c, const float* q, int q_stride, const RowS
 // rows_estimate: expected row count when src.n_rows is only an upper bound (device-side counter), else 0
 int launch_exact_fwdbwd(dsmppi_ctx* c, const float* q, int q_stride, const RowSrc& src, uint32_t ignore_mask,
                         float* m_rows, float* row_dist, float* row_grad, long long rows_estimate, cudaStream_t st);
+// whole-horizon rollout in one launch (M <= 32, fp32 scoring); all_traj[:, 0] must be initialised
+int launch_rollout_fused(dsmppi_ctx* c, const dsmppi_rollout_args* a, cudaStream_t st);
 // tc_pass1.cu
 int tc_build_images(dsmppi_ctx* c, const dsmppi_net* net);
 void tc_free_images(dsmppi_ctx* c);

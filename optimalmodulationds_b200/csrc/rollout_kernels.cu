@@ -4,6 +4,7 @@
 #include <cfloat>
 
 #include "internal.cuh"
+#include "step_device.cuh"
 
 namespace {
 
@@ -150,37 +151,6 @@ __global__ void __launch_bounds__(128) select_candidates_kernel(const float* __r
   }
 }
 
-// ------------------------------------------------------------------------------------------------
-// Gradient blend (MPPI.py:270-280): w = softmax(-10 * dist_k), grad = sum_k w_k grad_k, distance = dist_0
-// ------------------------------------------------------------------------------------------------
-// rows[k] = row of row_dist / row_grad holding the k-th closest obstacle of this sample
-__device__ __forceinline__ void blend(const float* __restrict__ row_dist, const float* __restrict__ row_grad,
-                                      const int* __restrict__ rows, int K, int d, float& dist, float (&g)[MAXD]) {
-  float sd[MAXK];
-  int rr[MAXK];
-  float mx = -FLT_MAX;
-#pragma unroll
-  for (int k = 0; k < MAXK; ++k)
-    if (k < K) { rr[k] = rows[k]; sd[k] = row_dist[rr[k]]; mx = fmaxf(mx, -10.f * sd[k]); }
-  float wk[MAXK];
-  float den = 0.f;
-#pragma unroll
-  for (int k = 0; k < MAXK; ++k)
-    if (k < K) { wk[k] = expf(-10.f * sd[k] - mx); den += wk[k]; }
-#pragma unroll
-  for (int a = 0; a < MAXD; ++a) g[a] = 0.f;
-#pragma unroll
-  for (int k = 0; k < MAXK; ++k)
-    if (k < K) {
-      const float w = wk[k] / den;
-      const float* sg = row_grad + (size_t)rr[k] * d;
-#pragma unroll
-      for (int a = 0; a < MAXD; ++a)
-        if (a < d) g[a] += sg[a] * w;
-    }
-  dist = sd[0];
-}
-
 __global__ void pack_obstacles_kernel(const float* __restrict__ raw, int M, int P, float* __restrict__ obs) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= M) return;
@@ -206,165 +176,9 @@ __global__ void blend_kernel(const float* __restrict__ row_dist, const float* __
   for (int a = 0; a < d; ++a) grad_out[(size_t)i * d + a] = g[a];
 }
 
-// ------------------------------------------------------------------------------------------------
-// One rollout step for all samples: nominal DS, modulation, RBF policy blend, integration
-// (MPPI.py:101-223, LinDS.py:11-21, policy.py:186-199).
-// ------------------------------------------------------------------------------------------------
-struct StepArgs {
-  int N, H, d, t, nk, K;
-  float dt, dst_thr, lin_thr, p;
-  float goal[MAXD];
-  dsmppi_modulation mod;
-  const float* row_dist; const float* row_grad; const int* sel_rows;
-  const float* mu; const float* sigma; const float* alpha;
-  float* traj; float* closest; float* kval; float* dots; float* acts; float* qdot; float* grads;
-};
-
-__device__ __forceinline__ float gsigmoid(float x, float y_min, float y_max, float mid, float k) {
-  // MPPI.py:352-353 with mid = (x0 + x1) / 2 folded on the host side of the expression
-  return y_min + (y_max - y_min) / (1.f + expf(k * (-x + mid)));
-}
-
-__device__ __forceinline__ float nan_to_num(float v) {
-  if (isnan(v)) return 0.f;
-  if (isinf(v)) return v > 0.f ? FLT_MAX : -FLT_MAX;
-  return v;
-}
-
 __global__ void __launch_bounds__(128) step_kernel(StepArgs s) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= s.N) return;
-  const int d = s.d;
-  const size_t st = (size_t)i * s.H + (s.t - 1);     // state-step index
-  float q[MAXD], v[MAXD], vhat[MAXD], e0[MAXD], g[MAXD], u[MAXD], vt[MAXD], m[MAXD];
-  // S0 nominal DS and its norm (MPPI.py:106-108)
-  float ss = 0.f;
-#pragma unroll
-  for (int a = 0; a < MAXD; ++a) q[a] = a < d ? s.traj[st * d + a] : 0.f;
-  if (s.mod.ds_kind == DSMPPI_DS_MATRIX) {
-    // v = (q - q_goal) @ A, not normalised (MPPI_toy.py:89)
-#pragma unroll
-    for (int cc = 0; cc < MAXD; ++cc) {
-      float acc = 0.f;
-#pragma unroll
-      for (int a = 0; a < MAXD; ++a)
-        if (a < d && cc < d) acc += (q[a] - s.goal[a]) * s.mod.ds_A[a * MAXD + cc];
-      v[cc] = acc;
-    }
-  } else {
-    // unit-speed attractor, linear inside lin_thr (LinDS.py:11-21)
-#pragma unroll
-    for (int a = 0; a < MAXD; ++a) {
-      v[a] = a < d ? -(q[a] - s.goal[a]) : 0.f;
-      ss += v[a] * v[a];
-    }
-    const float dst = sqrtf(ss);
-    if (dst > s.lin_thr) {
-#pragma unroll
-      for (int a = 0; a < MAXD; ++a) v[a] = v[a] / dst;
-    }
-  }
-  ss = 0.f;
-#pragma unroll
-  for (int a = 0; a < MAXD; ++a) ss += v[a] * v[a];
-  const float vn = sqrtf(ss);
-#pragma unroll
-  for (int a = 0; a < MAXD; ++a) vhat[a] = a < d ? v[a] / vn : 0.f;
-
-  // S2e blended distance / gradient
-  float dist;
-  blend(s.row_dist, s.row_grad, s.sel_rows + (size_t)i * s.K, s.K, d, dist, g);
-  dist -= s.dst_thr;                                  // MPPI.py:117
-  s.closest[st] = dist;
-  ss = 0.f;
-#pragma unroll
-  for (int a = 0; a < MAXD; ++a) {
-    if (a < d) s.grads[st * d + a] = g[a];
-    ss += g[a] * g[a];
-  }
-  const float gn = sqrtf(ss);
-  float dot = 0.f;
-#pragma unroll
-  for (int a = 0; a < MAXD; ++a) {
-    e0[a] = a < d ? g[a] / gn : 0.f;                  // MPPI.py:126
-    dot += e0[a] * vhat[a];                           // MPPI.py:129
-  }
-  s.dots[st] = dot;
-  // S3 modulation coefficients (MPPI.py:132,149-155)
-  const float l_vel = gsigmoid(dot, 0.f, 1.f, s.mod.lvel_mid, s.mod.lvel_k);
-  const float l_n = gsigmoid(dist, 0.f, 1.f, s.mod.dist_mid, s.mod.dist_k);
-  const float l_tau = gsigmoid(dist, s.mod.ltau_max, 1.f, s.mod.dist_mid, s.mod.dist_k);
-  const float l_nv = l_vel * 1.f + (1.f - l_vel) * l_n;
-
-  // activations (MPPI.py:191-196)
-  float ga = 0.f;
-#pragma unroll
-  for (int a = 0; a < MAXD; ++a)
-    if (a < d) ga += sqrtf(fabsf(q[a] - s.goal[a]));
-  ga = ga * ga;                                        // (sum |x|^0.5)^(1/0.5)
-  ga = fminf(fmaxf(ga, 0.f), 1.f);
-  if (ga < s.mod.goal_act_thr) ga = 0.f;
-  const float act = (1.f - l_n) * (1.f - l_vel) * ga;
-  s.acts[st] = act;
-  const float kv_scale = s.mod.fold_activation ? act : 1.f;   // MPPI_toy.py:178-179
-  // S4 RBF policy (policy.py:186-199, MPPI.py:165-186)
-#pragma unroll
-  for (int a = 0; a < MAXD; ++a) u[a] = 0.f;
-  for (int k = 0; k < s.nk; ++k) {
-    const float* mu = s.mu + ((size_t)i * NKMAX + k) * d;
-    float acc = 0.f;
-    if (s.p == 2.f) {
-#pragma unroll
-      for (int a = 0; a < MAXD; ++a)
-        if (a < d) { const float df = q[a] - mu[a]; acc += df * df; }
-      acc = sqrtf(acc);
-    } else {
-#pragma unroll
-      for (int a = 0; a < MAXD; ++a)
-        if (a < d) acc += powf(fabsf(q[a] - mu[a]), s.p);
-      acc = powf(acc, 1.f / s.p);
-    }
-    const float num = acc * acc;                       // norm ** 2
-    const float phi = expf(-s.sigma[(size_t)i * NKMAX + k] * num);
-    s.kval[st * NKMAX + k] = s.mod.fold_activation ? phi * kv_scale : phi;   // MPPI.py:184
-    const float* al = s.alpha + ((size_t)i * NKMAX + k) * d;
-#pragma unroll
-    for (int a = 0; a < MAXD; ++a)
-      if (a < d) u[a] += al[a] * phi;                  // MPPI.py:174-177
-  }
-  // total velocity and modulation M = l_tau I + (l_nv - l_tau) e0 e0^T  (MPPI.py:158-161,197-209)
-  float proj = 0.f;
-#pragma unroll
-  for (int a = 0; a < MAXD; ++a) {
-    vt[a] = v[a] + act * u[a] * vn;
-    proj += e0[a] * vt[a];
-  }
-  ss = 0.f;
-#pragma unroll
-  for (int a = 0; a < MAXD; ++a) {
-    m[a] = l_tau * vt[a] + (l_nv - l_tau) * e0[a] * proj;
-    if (a >= d) m[a] = 0.f;
-    ss += m[a] * m[a];
-  }
-  float mn = sqrtf(ss);
-  if (mn <= 0.5f) mn = 1.f;                            // MPPI.py:211-212
-  const bool coll = dist < 0.f;
-#pragma unroll
-  for (int a = 0; a < MAXD; ++a) {
-    float mv = nan_to_num(m[a] / mn);                  // MPPI.py:213
-    if (coll) mv = mv * 0.1f + e0[a] * vn * s.mod.repulsion;   // MPPI.py:215-217
-    m[a] = mv;
-  }
-  if (s.t < s.H) {
-#pragma unroll
-    for (int a = 0; a < MAXD; ++a)
-      if (a < d) s.traj[(st + 1) * d + a] = q[a] + s.dt * m[a];   // MPPI.py:220-221
-  }
-  if (s.t == 1) {
-#pragma unroll
-    for (int a = 0; a < MAXD; ++a)
-      if (a < d) s.qdot[(size_t)i * d + a] = m[a];                // MPPI.py:222-223
-  }
+  if (i < s.N) step_sample(s, i);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -813,16 +627,7 @@ int launch_init_traj(dsmppi_ctx* c, const dsmppi_rollout_args* a, cudaStream_t s
 }
 
 int launch_step(dsmppi_ctx* c, const dsmppi_rollout_args* a, int t, cudaStream_t st) {
-  StepArgs s;
-  s.N = a->N; s.H = a->H; s.d = c->d; s.t = t; s.nk = a->n_kernels; s.K = a->n_closest;
-  s.dt = a->dt; s.dst_thr = a->dst_thr; s.lin_thr = a->lin_thr; s.p = a->rbf_p;
-  for (int i = 0; i < MAXD; ++i) s.goal[i] = a->q_goal[i];
-  s.mod = a->mod;
-  s.row_dist = c->row_dist; s.row_grad = c->row_grad; s.sel_rows = c->sel_rows;
-  s.mu = a->mu_tmp_dev; s.sigma = a->sigma_tmp_dev; s.alpha = a->alpha_tmp_dev;
-  s.traj = a->all_traj_dev; s.closest = a->closest_dist_all_dev; s.kval = a->kernel_val_all_dev;
-  s.dots = a->dot_products_dev; s.acts = a->kernel_activations_dev; s.qdot = a->qdot_dev;
-  s.grads = a->nn_grad_all_dev;
+  const StepArgs s = make_step_args(c, a, t);
   // one thread per sample, a long dependent chain each: spread small batches over all SMs (one warp per CTA)
   const int bs = a->N <= c->sm_count * 128 ? 32 : 128;
   step_kernel<<<(a->N + bs - 1) / bs, bs, 0, st>>>(s);

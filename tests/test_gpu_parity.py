@@ -359,3 +359,23 @@ def test_kernel_candidates_vs_reference(tag, factory):
                                                thr_kernel, thr_dot)
         assert cand.device.type == "cpu" and cand.shape == g[f"cand{i}"].shape, (cand.shape, g[f"cand{i}"].shape)
         assert torch.equal(cand, g[f"cand{i}"])
+
+
+@pytest.mark.parametrize("tag", ["planar2", "planar2_near", "planar2_nk0", "field2", "planar7", "planar7_near"])
+def test_whole_horizon_kernel_is_bitwise_identical_to_per_step_launches(tag, factory):
+    """Small obstacle sets are rolled out by ONE launch (rollout_fused_kernel: network tile + ranking + step inside
+    the kernel's own horizon loop); it must reproduce the per-step launch sequence bit for bit."""
+    c = load_npz(f"case_{tag}")
+    outs = []
+    for whole in (True, False):
+        m = factory.make_mppi(c, device="cuda")
+        m.set_whole_horizon(whole)
+        n0 = m.launch_count()
+        res = [x.clone() for x in m.propagate()]
+        launches = m.launch_count() - n0
+        outs.append((res + [m.qdot.clone(), m.norm_basis.clone()], launches))
+    (a, la), (b, lb) = outs
+    H = int(c["H"])
+    assert la <= 4 and lb >= 3 * H, (la, lb)      # obstacle encodings (2) + init + fused vs 3 launches per step
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
