@@ -75,6 +75,13 @@ enum {
   DSMPPI_PASS1_AUTO = 3          /* TC_F16 when M >= 64, else EXACT                                     */
 };
 
+/* Where the per-step distance and its joint gradient come from (MPPI.py:113-115). */
+enum {
+  DSMPPI_DISTANCE_NN = 0,        /* learned network, distance_repulsion_nn (MPPI.py:227-282) -- the live path     */
+  DSMPPI_DISTANCE_FK = 1         /* forward kinematics + sphere distances, distance_repulsion_fk (MPPI.py:306-313) */
+};
+#define DSMPPI_FK_MAX_PTS 32     /* sample points per link (the reference uses 10, MPPI.py:307) */
+
 typedef struct {
   /* state / problem */
   int32_t N;                     /* samples in this call (<= capacity)                                  */
@@ -89,6 +96,9 @@ typedef struct {
   float rbf_p;                   /* Policy.p (policy.py:41,186-199)                                     */
   float q_goal[DSMPPI_MAX_DOF];  /* DS.q_goal == MPPI.qf                                                */
   dsmppi_modulation mod;         /* constants of the modulation law (fill with dsmppi_modulation_default)      */
+  int32_t distance_provider;     /* DSMPPI_DISTANCE_*                                                           */
+  int32_t fk_n_pts;              /* DSMPPI_DISTANCE_FK: points per link (1..32)                                 */
+  float fk_span[DSMPPI_FK_MAX_PTS];  /* fractions along a link, torch.linspace(0.01, 1, fk_n_pts) (fk_num.py:79)   */
   /* inputs (device) */
   const float* q_cur_dev;
   const float* mu_tmp_dev;       /* (N, 50, d)  Policy.mu_tmp                                           */
@@ -170,6 +180,14 @@ int dsmppi_rollout(dsmppi_ctx* ctx, const dsmppi_rollout_args* args, void* strea
 /* MPPI.distance_repulsion_nn (MPPI.py:227-282): q (n, d) -> distance (n,), nn_grad (n, d). */
 int dsmppi_distance_grad(dsmppi_ctx* ctx, const float* q_dev, int32_t n, int32_t n_closest,
                          uint32_t ignored_link_mask, float* distance_dev, float* nn_grad_dev, void* stream);
+
+/* MPPI.distance_repulsion_fk (MPPI.py:306-313): true distance between the robot's links (fk_n_pts sample points per
+ * link of the modified-DH chain, fk_num.py:78-89) and the obstacle spheres, minimised over (link, obstacle, point)
+ * (fk_num.py:142-160), and its analytic gradient w.r.t. the joints: q (n, d) -> distance (n,), grad (n, d).
+ * span_host: the fk_n_pts fractions along a link (torch.linspace(0.01, 1, n_pts)) or NULL for the same ramp computed
+ * internally; closest_idx_dev: optional (n, 3) = [obstacle, link, point] of the minimum. */
+int dsmppi_distance_grad_fk(dsmppi_ctx* ctx, const float* q_dev, int32_t n, int32_t fk_n_pts, const float* span_host,
+                            float* distance_dev, float* grad_dev, int32_t* closest_idx_dev, void* stream);
 
 /* Test hook: the per-pair masked minimum link distance of pass 1 (MPPI.py:235-243), (n, M) row-major, from
  * the fp32 path (mode = DSMPPI_PASS1_EXACT_FP32) or the tensor-core prefilter (TC_F16 / TC_BF16). */

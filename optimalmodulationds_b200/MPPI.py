@@ -87,6 +87,10 @@ class MPPI:
         self.ker_thr = 1e-3
         self.ignored_links = [0, 1, 2] if self.n_dof >= 7 else []
         self.n_closest_obs = n_closest_obs
+        # 'nn': learned distance network (MPPI.py:113, the live path); 'fk': forward kinematics + sphere distances
+        # (the alternative the reference keeps one comment away, MPPI.py:115,306-313)
+        self.distance_provider = 'nn'
+        self.fk_n_pts = 10
         self.traj_range = torch.arange(self.N_traj, device=q0.device)
         self.kernel_obstacle_bases_tmp = torch.zeros((self.Policy.N_KERNEL_MAX, self.n_dof, self.n_dof),
                                                      **self.tensor_args)
@@ -242,6 +246,12 @@ class MPPI:
         a.ignored_link_mask = self._ignore_mask()
         a.dt, a.dst_thr = float(self.dt), float(self.dst_thr)
         self._modulation(a.mod)
+        if self.distance_provider == 'fk':
+            a.distance_provider, a.fk_n_pts = _capi.DISTANCE_FK, int(self.fk_n_pts)
+            for i, v in enumerate(torch.linspace(0.01, 1, int(self.fk_n_pts)).tolist()):
+                a.fk_span[i] = v
+        elif self.distance_provider != 'nn':
+            raise ValueError("distance_provider must be 'nn' or 'fk'")
         a.lin_thr, a.rbf_p = float(getattr(self.DS, 'lin_thr', 0.0)), float(self.Policy.p)
         goal = torch.as_tensor(self.DS.q_goal).detach().reshape(-1).to('cpu', torch.float32)
         for i in range(self.n_dof):
@@ -329,6 +339,29 @@ class MPPI:
                                                        self._stream()))
         self.nn_grad = self._u(grad)
         return self._u(dist), self.nn_grad
+
+    def distance_repulsion_fk(self, q_prev, return_indices=False):
+        """MPPI.py:306-313: true link-to-sphere distance (10 points per link) and its joint gradient, padded to 7
+        columns like the reference's `lambda_rep_vec` (fk_sym_gen.py:265-269)."""
+        q = self._d(q_prev)
+        n = q.shape[0]
+        n_pts = int(self.fk_n_pts)
+        span = torch.linspace(0.01, 1, n_pts).contiguous()
+        with torch.cuda.device(self._dev):
+            self._upload_obstacles()
+            dist = torch.empty(n, device=self._dev)
+            grad = torch.empty(n, self.n_dof, device=self._dev)
+            idx = torch.empty(n, 3, dtype=torch.int32, device=self._dev)
+            _capi.check(self._lib.dsmppi_distance_grad_fk(self._ctx, q.data_ptr(), n, n_pts, span.data_ptr(),
+                                                          dist.data_ptr(), grad.data_ptr(), idx.data_ptr(),
+                                                          self._stream()))
+        rep = torch.zeros(n, max(7, self.n_dof), device=self._dev)
+        rep[:, :self.n_dof] = grad
+        rep = self._u(rep)
+        self.nn_grad = rep[:, 0:self.n_dof]
+        if return_indices:
+            return self._u(dist), rep, self._u(idx)
+        return self._u(dist), rep
 
     def update_kernel_normal_bases(self):
         nk = int(self.Policy.n_kernels)

@@ -21,6 +21,8 @@ _fp = C.c_void_p   # device / host float pointers travel as integers from tensor
 
 
 DS_LINEAR_ATTRACTOR, DS_MATRIX = 0, 1
+DISTANCE_NN, DISTANCE_FK = 0, 1
+FK_MAX_PTS = 32
 COST_JOINT_LIMITS, COST_TERMINAL_FK, COST_ALL = 1, 2, 3
 
 
@@ -44,6 +46,7 @@ class RolloutArgs(C.Structure):
         ("n_closest", C.c_int32), ("ignored_link_mask", C.c_uint32),
         ("dt", C.c_float), ("dst_thr", C.c_float), ("lin_thr", C.c_float), ("rbf_p", C.c_float),
         ("q_goal", C.c_float * MAX_DOF), ("mod", Modulation),
+        ("distance_provider", C.c_int32), ("fk_n_pts", C.c_int32), ("fk_span", C.c_float * FK_MAX_PTS),
         ("q_cur_dev", _fp), ("mu_tmp_dev", _fp), ("sigma_tmp_dev", _fp), ("alpha_tmp_dev", _fp),
         ("all_traj_dev", _fp), ("closest_dist_all_dev", _fp), ("kernel_val_all_dev", _fp),
         ("dot_products_dev", _fp), ("kernel_activations_dev", _fp), ("qdot_dev", _fp),
@@ -107,6 +110,7 @@ EXPORTS = {
     "dsmppi_set_obstacles_host": (C.c_int, [C.c_void_p, _fp, C.c_int32, C.c_void_p]),
     "dsmppi_rollout": (C.c_int, [C.c_void_p, C.POINTER(RolloutArgs), C.c_void_p]),
     "dsmppi_distance_grad": (C.c_int, [C.c_void_p, _fp, C.c_int32, C.c_int32, C.c_uint32, _fp, _fp, C.c_void_p]),
+    "dsmppi_distance_grad_fk": (C.c_int, [C.c_void_p, _fp, C.c_int32, C.c_int32, _fp, _fp, _fp, _fp, C.c_void_p]),
     "dsmppi_debug_pass1": (C.c_int, [C.c_void_p, _fp, C.c_int32, C.c_uint32, C.c_int32, _fp, C.c_void_p]),
     "dsmppi_norm_basis": (C.c_int, [C.c_void_p, _fp, C.c_int64, _fp, C.c_void_p]),
     "dsmppi_cost": (C.c_int, [C.c_void_p, C.POINTER(CostArgs), C.c_void_p]),

@@ -330,6 +330,10 @@ int dsmppi_rollout(dsmppi_ctx* c, const dsmppi_rollout_args* a, void* stream) {
               a->dot_products_dev && a->kernel_activations_dev && a->qdot_dev && a->nn_grad_all_dev,
           "null device pointer");
   REQUIRE(a->n_kernels == 0 || (a->mu_tmp_dev && a->sigma_tmp_dev && a->alpha_tmp_dev), "null policy pointer");
+  REQUIRE(a->distance_provider == DSMPPI_DISTANCE_NN || a->distance_provider == DSMPPI_DISTANCE_FK,
+          "unknown distance_provider");
+  REQUIRE(a->distance_provider != DSMPPI_DISTANCE_FK || (c->P == 3 && a->fk_n_pts >= 1 && a->fk_n_pts <= DSMPPI_FK_MAX_PTS),
+          "the FK distance provider needs 3-D obstacles and 1..32 points per link");
   REQUIRE(a->mod.ds_kind == DSMPPI_DS_LINEAR_ATTRACTOR || a->mod.ds_kind == DSMPPI_DS_MATRIX, "unknown mod.ds_kind");
   REQUIRE(a->mod.lvel_k != 0.f && a->mod.dist_k != 0.f,
           "rollout_args.mod is not initialised (dsmppi_modulation_default / _toy)");
@@ -359,6 +363,19 @@ int dsmppi_rollout(dsmppi_ctx* c, const dsmppi_rollout_args* a, void* stream) {
     b.qdot_dev = a->qdot_dev + off * d;
     b.nn_grad_all_dev = a->nn_grad_all_dev + off * a->H * d;
     if (launch_init_traj(c, &b, st)) return 1;
+    if (a->distance_provider == DSMPPI_DISTANCE_FK) {
+      // true-distance provider: FK + sphere distances write one (distance, gradient) row per sample, K = 1
+      if (ensure_workspace(c, b.N, c->M)) return 1;
+      if (launch_identity_rows(c, b.N, 1, st)) return 1;
+      b.n_closest = 1;
+      for (int t = 1; t <= b.H; ++t) {
+        const float* q = b.all_traj_dev + (size_t)(t - 1) * d;
+        if (launch_fk_distance(c, q, b.H * d, b.N, b.fk_n_pts, b.fk_span, c->row_dist, c->row_grad, d, nullptr, st))
+          return 1;
+        if (launch_step(c, &b, t, st)) return 1;
+      }
+      continue;
+    }
     if (use_whole_horizon(c, b.N)) {
       REQUIRE(b.n_closest >= 1 && b.n_closest <= MAXK, "n_closest_obs out of range (1..8)");
       REQUIRE(b.n_closest <= c->M, "n_closest_obs exceeds the number of obstacles");
@@ -395,6 +412,17 @@ int dsmppi_distance_grad(dsmppi_ctx* c, const float* q_dev, int32_t n, int32_t n
     if (launch_blend(c, nb, n_closest, distance_dev + off, nn_grad_dev + off * c->d, st)) return 1;
   }
   return 0;
+}
+
+int dsmppi_distance_grad_fk(dsmppi_ctx* c, const float* q_dev, int32_t n, int32_t fk_n_pts, const float* span_host,
+                            float* distance_dev, float* grad_dev, int32_t* closest_idx_dev, void* stream) {
+  REQUIRE(c && q_dev && distance_dev && grad_dev, "null argument");
+  REQUIRE(n >= 1, "n must be positive");
+  REQUIRE(c->M >= 1, "obstacles not set");
+  REQUIRE(c->P == 3, "the FK distance provider needs 3-D obstacles");
+  CUDA_TRY(cudaSetDevice(c->device));
+  return launch_fk_distance(c, q_dev, c->d, n, fk_n_pts, span_host, distance_dev, grad_dev, c->d, closest_idx_dev,
+                            static_cast<cudaStream_t>(stream));
 }
 
 int dsmppi_debug_pass1(dsmppi_ctx* c, const float* q_dev, int32_t n, uint32_t ignored_link_mask, int32_t mode,

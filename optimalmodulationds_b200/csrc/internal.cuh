@@ -141,6 +141,8 @@ int launch_step(dsmppi_ctx* c, const dsmppi_rollout_args* a, int t, cudaStream_t
 int launch_init_traj(dsmppi_ctx* c, const dsmppi_rollout_args* a, cudaStream_t st);
 int launch_cost(dsmppi_ctx* c, const dsmppi_cost_args* a, cudaStream_t st);
 int launch_basis(dsmppi_ctx* c, const float* grad, int64_t n, float* basis, cudaStream_t st);
+int launch_fk_distance(dsmppi_ctx* c, const float* q, int q_stride, int n, int n_pts, const float* span_host,
+                       float* dist, float* grad, int grad_stride, int* idx, cudaStream_t st);
 int launch_cost_stats(dsmppi_ctx* c, const float* cost, int N, float* stats, cudaStream_t st);
 int launch_update_partial(dsmppi_ctx* c, const dsmppi_update_args* a, const float* stats, float* packed,
                           cudaStream_t st);

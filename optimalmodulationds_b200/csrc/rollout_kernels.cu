@@ -334,6 +334,113 @@ __global__ void __launch_bounds__(128) cost_kernel(CostArgs c) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// True-distance provider (MPPI.distance_repulsion_fk, MPPI.py:306-313): batched modified-DH forward kinematics
+// (fk_num.py:78-89: n_pts sample points on every link, at fractions linspace(0.01, 1, n_pts) of the next link's `a`),
+// minimum sphere distance over (link, obstacle, point) (dist_tens, fk_num.py:142-160) and the analytic gradient of
+// that distance w.r.t. the joints.  The reference differentiates sympy-generated planar closed forms
+// (fk_sym_gen.py:r1..r7); here the same derivative comes from the geometric Jacobian of the DH chain,
+// d|P - y|/dq_j = (P - y)/|P - y| . (z_j x (P - o_j)) for every joint j at or before the point's link, which is valid
+// for any modified-DH arm (the reference marks this path "not implemented for Franka").
+// LANES = 1: one thread per sample; LANES = 32: one warp per sample, lanes stride over the obstacles.
+// ------------------------------------------------------------------------------------------------
+constexpr int FK_MAX_PTS = 32;
+struct FkDistArgs {
+  int n, d, M, n_pts;
+  float span[FK_MAX_PTS];    // torch.linspace(0.01, 1, n_pts), computed on the host with torch's own formula
+  DhTable dh;
+  const float* q; int q_stride;
+  const float* obs;          // (M, 4)
+  float* dist;               // (n)
+  float* grad; int grad_stride;   // (n, grad_stride): first d entries written
+  int* idx;                  // (n, 3) = [obstacle, link, point] or nullptr
+};
+
+template <int LANES>
+__global__ void __launch_bounds__(128) fk_distance_kernel(FkDistArgs a) {
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = gid / LANES, lane = gid % LANES;
+  if (i >= a.n) return;
+  const int d = a.d;
+  // frames of every joint: R[k], o[k] = rotation / origin of frame k+1 (its z axis is the axis of joint k)
+  float R[MAXD][3][3], o[MAXD][3], q[MAXD];
+  {
+    float Rm[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    float tv[3] = {0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < MAXD; ++k) {
+      if (k < d) {
+        q[k] = a.q[(size_t)i * a.q_stride + k];
+        const float dd = a.dh.v[k][0], th = a.dh.v[k][1], aa = a.dh.v[k][2], al = a.dh.v[k][3];
+        const float sa = sinf(al), ca = cosf(al), sq = sinf(q[k] + th), cq = cosf(q[k] + th);
+        const float A[3][4] = {{cq, -sq, 0.f, aa}, {sq * ca, cq * ca, -sa, -dd * sa}, {sq * sa, cq * sa, ca, dd * ca}};
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) R[k][r][c] = Rm[r][0] * A[0][c] + Rm[r][1] * A[1][c] + Rm[r][2] * A[2][c];
+          o[k][r] = Rm[r][0] * A[0][3] + Rm[r][1] * A[1][3] + Rm[r][2] * A[2][3] + tv[r];
+        }
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) Rm[r][c] = R[k][r][c];
+          tv[r] = o[k][r];
+        }
+      }
+    }
+  }
+  // minimum over (link, obstacle, point); ties: first in that order, like the nested torch.min of dist_tens
+  float best = FLT_MAX;
+  int bl = 0, bj = 0, bp = 0;
+  for (int l = 0; l < d; ++l) {
+    const float an = a.dh.v[l + 1][2];
+    for (int j = lane; j < a.M; j += LANES) {
+      const float ox = a.obs[j * 4], oy = a.obs[j * 4 + 1], oz = a.obs[j * 4 + 2], orad = a.obs[j * 4 + 3];
+      for (int p = 0; p < a.n_pts; ++p) {
+        const float x = an * a.span[p];
+        const float dx = R[l][0][0] * x + o[l][0] - ox, dy = R[l][1][0] * x + o[l][1] - oy,
+                    dz = R[l][2][0] * x + o[l][2] - oz;
+        const float dist = sqrtf(dx * dx + dy * dy + dz * dz) - orad;
+        if (dist < best) { best = dist; bl = l; bj = j; bp = p; }
+      }
+    }
+  }
+  if (LANES > 1) {
+    // warp argmin with the (link, obstacle, point) order as tie-break
+#pragma unroll
+    for (int off = LANES / 2; off > 0; off >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, best, off);
+      const int ol = __shfl_xor_sync(0xffffffffu, bl, off), oj = __shfl_xor_sync(0xffffffffu, bj, off),
+                op = __shfl_xor_sync(0xffffffffu, bp, off);
+      const bool earlier = ol < bl || (ol == bl && (oj < bj || (oj == bj && op < bp)));
+      if (ov < best || (ov == best && earlier)) { best = ov; bl = ol; bj = oj; bp = op; }
+    }
+    if (lane != 0) return;
+  }
+  // gradient at the closest (link, obstacle, point)
+  const float x = a.dh.v[bl + 1][2] * a.span[bp];
+  float P[3], u[3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) P[r] = R[bl][r][0] * x + o[bl][r];
+  u[0] = P[0] - a.obs[bj * 4]; u[1] = P[1] - a.obs[bj * 4 + 1]; u[2] = P[2] - a.obs[bj * 4 + 2];
+  const float un = sqrtf(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
+  a.dist[i] = best;
+#pragma unroll
+  for (int k = 0; k < MAXD; ++k) {
+    if (k < d) {
+      float g = 0.f;
+      if (k <= bl) {
+        const float zx = R[k][0][2], zy = R[k][1][2], zz = R[k][2][2];
+        const float rx = P[0] - o[k][0], ry = P[1] - o[k][1], rz = P[2] - o[k][2];
+        const float cx = zy * rz - zz * ry, cy = zz * rx - zx * rz, cz = zx * ry - zy * rx;
+        g = (u[0] * cx + u[1] * cy + u[2] * cz) / un;
+      }
+      a.grad[(size_t)i * a.grad_stride + k] = g;
+    }
+  }
+  if (a.idx) { a.idx[i * 3] = bj; a.idx[i * 3 + 1] = bl; a.idx[i * 3 + 2] = bp; }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Householder basis: Q of the unblocked QR (geqr2 + org2r) of [g | e_2 .. e_d], column 0 := g/|g|
 // (MPPI.py:122-127).  One thread per state-step, D compile-time so the d x d tiles stay in registers.
 // ------------------------------------------------------------------------------------------------
@@ -642,6 +749,31 @@ int launch_cost(dsmppi_ctx* c, const dsmppi_cost_args* a, cudaStream_t st) {
   k.dh = c->dh;
   k.traj = a->all_traj_dev; k.closest = a->closest_dist_all_dev; k.cost = a->cost_dev;
   cost_kernel<<<(a->N + 127) / 128, 128, 0, st>>>(k);
+  LAUNCH_CHECK(c);
+  return 0;
+}
+
+int launch_fk_distance(dsmppi_ctx* c, const float* q, int q_stride, int n, int n_pts, const float* span_host,
+                       float* dist, float* grad, int grad_stride, int* idx, cudaStream_t st) {
+  FkDistArgs a;
+  if (n_pts < 1 || n_pts > FK_MAX_PTS) { dsmppi_set_error("n_pts out of range (1..32)"); return 2; }
+  a.n = n; a.d = c->d; a.M = c->M; a.n_pts = n_pts;
+  // fractions along a link: the caller's torch.linspace(0.01, 1, n_pts) (fk_num.py:79), or the same ramp computed
+  // here (start + i * step in the lower half, end - (n - 1 - i) * step above; may differ from torch by one ulp)
+  const float start = 0.01f, end = 1.f;
+  const float step = n_pts > 1 ? (end - start) / (float)(n_pts - 1) : 0.f;
+  for (int p = 0; p < n_pts; ++p)
+    a.span[p] = span_host ? span_host[p]
+                          : (p < n_pts / 2 ? start + step * (float)p : end - step * (float)(n_pts - 1 - p));
+  a.dh = c->dh;
+  a.q = q; a.q_stride = q_stride; a.obs = c->obs;
+  a.dist = dist; a.grad = grad; a.grad_stride = grad_stride; a.idx = idx;
+  if (c->M >= 32) {
+    const long long threads = (long long)n * 32;
+    fk_distance_kernel<32><<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(a);
+  } else {
+    fk_distance_kernel<1><<<(n + 127) / 128, 128, 0, st>>>(a);
+  }
   LAUNCH_CHECK(c);
   return 0;
 }

@@ -145,6 +145,46 @@ def distance_repulsion(net: Net, q: torch.Tensor, obs: torch.Tensor, n_closest: 
     return distance, nn_grad
 
 
+def distance_repulsion_fk(q: torch.Tensor, obs: torch.Tensor, dh_params: torch.Tensor, n_pts: int = 10,
+                          return_idx: bool = False):
+    """MPPI.distance_repulsion_fk (MPPI.py:306-313): n_pts points on every link of the modified-DH chain
+    (numeric_fk_model_vec, fk_num.py:78-89), sphere distances minimised over points, obstacles, links in that
+    nesting (dist_tens, fk_num.py:142-160), and the gradient of the minimal distance w.r.t. the joints.  The
+    reference evaluates sympy closed forms of that gradient for the planar chain (fk_sym_gen.py:r1..r7,
+    lambda_rep_vec :265-269); this restatement uses the geometric Jacobian dP/dq_j = z_j x (P - o_j), the same
+    derivative.  q: (n, d), obs: (M, 4) -> distance (n,), gradient (n, d)."""
+    n, d = q.shape
+    span = torch.linspace(0.01, 1, n_pts)
+    T = torch.eye(4).repeat(n, 1, 1)
+    frames = []
+    pts = torch.zeros(n, d, n_pts, 3)
+    for i in range(d):
+        T = T @ dh_transform(q[:, i], dh_params[i, 0], dh_params[i, 1], dh_params[i, 2], dh_params[i, 3])
+        frames.append(T)
+        local = torch.zeros(n_pts, 3)
+        local[:, 0] = dh_params[i + 1, 2] * span
+        pts[:, i] = torch.einsum('nrc,pc->npr', T[:, :3, :3], local) + T[:, None, :3, 3]
+    dst = torch.norm(pts.unsqueeze(2) - obs[:, :3].reshape(1, 1, -1, 1, 3), 2, 4) - obs[:, 3].reshape(1, 1, -1, 1)
+    mind_pts, idx_pts = torch.min(dst, 3)                     # (n, d, M)
+    mind_obs, idx_obs = torch.min(mind_pts, 2)                # (n, d)
+    mind, idx_link = torch.min(mind_obs, 1)                   # (n,)
+    ar = torch.arange(n)
+    j = idx_obs[ar, idx_link]
+    p = idx_pts[ar, idx_link, j]
+    P = pts[ar, idx_link, p]                                  # (n, 3)
+    u = P - obs[j, :3]
+    u = u / u.norm(dim=1, keepdim=True)
+    grad = torch.zeros(n, d)
+    for k in range(d):
+        z = frames[k][:, :3, 2]
+        o = frames[k][:, :3, 3]
+        dP = torch.cross(z, P - o, dim=1)
+        grad[:, k] = torch.where(idx_link >= k, (u * dP).sum(1), torch.zeros(n))
+    if return_idx:
+        return mind, grad, torch.stack((j, idx_link, p), 1)
+    return mind, grad
+
+
 # ----------------------------------------------------------------------------------------------
 # Householder basis  (torch.linalg.qr on [g | e_2 .. e_d], MPPI.py:122-127)
 # ----------------------------------------------------------------------------------------------
@@ -221,6 +261,7 @@ class RolloutParams:
     repulsion: float = 0.1                   # MPPI.py:216
     fold_activation: bool = False            # kernel_val_all *= activation                MPPI_toy.py:178-179
     A: Optional[torch.Tensor] = None         # matrix DS v = (q - qf) @ A                  MPPI_toy.py:89
+    fk_dh_params: Optional[torch.Tensor] = None   # set: distances from distance_repulsion_fk (MPPI.py:115)
 
 
 def toy_params(dt, dt_H, n_closest_obs, A, **kw):
@@ -269,7 +310,9 @@ def rollout(net: Net, q_cur: torch.Tensor, q_goal: torch.Tensor, obs: torch.Tens
             v = lin_ds_velocity(q, q_goal, prm.lin_thr)                   # MPPI.py:106
         vn = v.norm(dim=1).reshape(-1, 1)                                 # :107
         vhat = v / vn                                                     # :108
-        if keep_aux:
+        if prm.fk_dh_params is not None:
+            dist, g = distance_repulsion_fk(q, obs, prm.fk_dh_params)
+        elif keep_aux:
             dist, g, a = distance_repulsion(net, q, obs, prm.n_closest_obs, prm.ignored_links, True)
             aux.append(a)
         else:
