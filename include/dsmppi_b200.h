@@ -53,7 +53,9 @@ typedef struct {
  * passed as its midpoint (x0 + x1) / 2 and slope k. */
 enum {
   DSMPPI_DS_LINEAR_ATTRACTOR = 0,  /* LinDS.get_velocity (LinDS.py:11-21): unit speed outside lin_thr              */
-  DSMPPI_DS_MATRIX = 1             /* v = (q - q_goal) @ A (MPPI_toy.py:89), not normalised                         */
+  DSMPPI_DS_MATRIX = 1,            /* v = (q - q_goal) @ A (MPPI_toy.py:89), not normalised                         */
+  DSMPPI_DS_SEDS = 2               /* Gaussian-mixture regression, SEDS.get_velocity (SEDS.py:61-76); parameters
+                                    * uploaded beforehand with dsmppi_set_seds                                    */
 };
 typedef struct {
   int32_t ds_kind;               /* DSMPPI_DS_*                                                                  */
@@ -173,6 +175,23 @@ int dsmppi_set_whole_horizon(dsmppi_ctx* ctx, int32_t on);
  * [x, y, r] for a network created with n_point_dim = 2. */
 int dsmppi_set_obstacles(dsmppi_ctx* ctx, const float* obs_dev, int32_t M, void* stream);
 int dsmppi_set_obstacles_host(dsmppi_ctx* ctx, const float* obs_host, int32_t M, void* stream);
+
+/* Parameters of a SEDS nominal DS (ds_mppi/functions/SEDS.py:9-27), already in the form its GMR uses (:36-59):
+ * for Gaussian j: prior, pdf_den = sqrt(2 pi^d det_j + 1e-100) (the denominator of gaussPDF, :28-34), the input and
+ * output means Mu[:d, j] / Mu[d:, j], Sigma_xx^-1 (d, d) and A_j = Sigma_yx Sigma_xx^-1 (d, d), all row-major HOST
+ * arrays with the Gaussian index leading.  dsmppi_rollout with mod.ds_kind = DSMPPI_DS_SEDS uses the last upload;
+ * lin_thr travels in dsmppi_rollout_args.lin_thr. */
+typedef struct {
+  int32_t n_gaussians;           /* G <= 32                                                              */
+  float seds_thr;                /* SEDS.seds_thr: weaker GMR outputs fall back to the linear DS (:72-75)  */
+  const float* priors_host;      /* (G,)      */
+  const float* pdf_den_host;     /* (G,)      */
+  const float* mu_x_host;        /* (G, d)    */
+  const float* mu_y_host;        /* (G, d)    */
+  const float* sigma_inv_host;   /* (G, d, d) */
+  const float* A_host;           /* (G, d, d) */
+} dsmppi_seds;
+int dsmppi_set_seds(dsmppi_ctx* ctx, const dsmppi_seds* seds, void* stream);
 
 /* MPPI.propagate (MPPI.py:97-224): the H-step rollout of all N samples. */
 int dsmppi_rollout(dsmppi_ctx* ctx, const dsmppi_rollout_args* args, void* stream);

@@ -225,7 +225,10 @@ class MPPI:
             self._lib.dsmppi_modulation_toy(_capi.C.byref(mod))
         else:
             self._lib.dsmppi_modulation_default(_capi.C.byref(mod))
-        if hasattr(self.DS, 'lin_thr'):
+        if hasattr(self.DS, 'Mu') and hasattr(self.DS, 'Sigma'):
+            mod.ds_kind = _capi.DS_SEDS
+            self._upload_seds(self.DS)
+        elif hasattr(self.DS, 'lin_thr'):
             mod.ds_kind = _capi.DS_LINEAR_ATTRACTOR
         elif hasattr(self.DS, 'A'):
             mod.ds_kind = _capi.DS_MATRIX
@@ -236,8 +239,27 @@ class MPPI:
                 for c in range(self.n_dof):
                     mod.ds_A[r * _capi.MAX_DOF + c] = float(A[r, c])
         else:
-            raise NotImplementedError("the CUDA rollout implements the LinDS attractor (LinDS.py) and the matrix DS "
-                                      "v = (q - qf) @ A (MPPI_toy.py:89) as nominal dynamics")
+            raise NotImplementedError("the CUDA rollout implements the LinDS attractor (LinDS.py), the SEDS mixture "
+                                      "(SEDS.py) and the matrix DS v = (q - qf) @ A (MPPI_toy.py:89) as nominal "
+                                      "dynamics")
+
+    def _upload_seds(self, ds):
+        """Packs a SEDS object (reference class or optimalmodulationds_b200.SEDS) for the step kernel; re-uploaded
+        only when another DS object becomes current."""
+        if getattr(self, '_seds_uploaded', None) is ds:
+            return
+        from .SEDS import SEDS as _SEDS
+        src = ds if isinstance(ds, _SEDS) else _SEDS.from_arrays(ds.Mu, ds.Sigma, ds.Priors, ds.q_goal)
+        if src.dof != self.n_dof:
+            raise ValueError(f"SEDS has {src.dof} joints, the robot {self.n_dof}")
+        arrs = [t.detach().to('cpu', torch.float32).contiguous() for t in src.kernel_arrays()]
+        sd = _capi.Seds()
+        sd.n_gaussians, sd.seds_thr = int(src.n_gaussians), float(getattr(ds, 'seds_thr', 1e-2))
+        (sd.priors_host, sd.pdf_den_host, sd.mu_x_host, sd.mu_y_host, sd.sigma_inv_host,
+         sd.A_host) = (t.data_ptr() for t in arrs)
+        with torch.cuda.device(self._dev):
+            _capi.check(self._lib.dsmppi_set_seds(self._ctx, _capi.C.byref(sd), self._stream()))
+        self._seds_uploaded = ds
 
     def _rollout_args(self, N, H, nk, q_cur, mu, sigma, alpha, out):
         a = _capi.RolloutArgs()

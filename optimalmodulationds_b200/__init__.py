@@ -9,5 +9,6 @@ from .MPPI import MPPI, generalized_sigmoid  # noqa: F401
 from .policy import TensorPolicyMPPI, eval_rbf, eval_rbf_simple  # noqa: F401
 from .cost import Cost  # noqa: F401
 from .LinDS import LinDS  # noqa: F401
+from .SEDS import SEDS  # noqa: F401
 
-__all__ = ["MPPI", "TensorPolicyMPPI", "Cost", "LinDS", "eval_rbf", "eval_rbf_simple", "generalized_sigmoid"]
+__all__ = ["MPPI", "TensorPolicyMPPI", "Cost", "LinDS", "SEDS", "eval_rbf", "eval_rbf_simple", "generalized_sigmoid"]

@@ -20,7 +20,7 @@ PASS1_EXACT_FP32, PASS1_TC_F16, PASS1_TC_BF16, PASS1_AUTO = 0, 1, 2, 3
 _fp = C.c_void_p   # device / host float pointers travel as integers from tensor.data_ptr()
 
 
-DS_LINEAR_ATTRACTOR, DS_MATRIX = 0, 1
+DS_LINEAR_ATTRACTOR, DS_MATRIX, DS_SEDS = 0, 1, 2
 DISTANCE_NN, DISTANCE_FK = 0, 1
 FK_MAX_PTS = 32
 COST_JOINT_LIMITS, COST_TERMINAL_FK, COST_ALL = 1, 2, 3
@@ -38,6 +38,11 @@ class Modulation(C.Structure):
         ("ltau_max", C.c_float), ("goal_act_thr", C.c_float), ("repulsion", C.c_float), ("reserved", C.c_float),
         ("ds_A", C.c_float * (MAX_DOF * MAX_DOF)),
     ]
+
+
+class Seds(C.Structure):
+    _fields_ = [("n_gaussians", C.c_int32), ("seds_thr", C.c_float), ("priors_host", _fp), ("pdf_den_host", _fp),
+                ("mu_x_host", _fp), ("mu_y_host", _fp), ("sigma_inv_host", _fp), ("A_host", _fp)]
 
 
 class RolloutArgs(C.Structure):
@@ -106,6 +111,7 @@ EXPORTS = {
     "dsmppi_ctx_destroy": (C.c_int, [C.c_void_p]),
     "dsmppi_set_pass1_mode": (C.c_int, [C.c_void_p, C.c_int32, C.c_float]),
     "dsmppi_set_whole_horizon": (C.c_int, [C.c_void_p, C.c_int32]),
+    "dsmppi_set_seds": (C.c_int, [C.c_void_p, C.POINTER(Seds), C.c_void_p]),
     "dsmppi_set_obstacles": (C.c_int, [C.c_void_p, _fp, C.c_int32, C.c_void_p]),
     "dsmppi_set_obstacles_host": (C.c_int, [C.c_void_p, _fp, C.c_int32, C.c_void_p]),
     "dsmppi_rollout": (C.c_int, [C.c_void_p, C.POINTER(RolloutArgs), C.c_void_p]),

@@ -204,7 +204,7 @@ int dsmppi_ctx_destroy(dsmppi_ctx* c) {
   if (!c) return 0;
   cudaSetDevice(c->device);
   tc_free_images(c);
-  void* ptrs[] = {c->weights_blob, c->obs, c->obs_raw, c->obs_enc, c->q_work, c->m_rows, c->mdist, c->enc_q,
+  void* ptrs[] = {c->weights_blob, c->seds, c->obs, c->obs_raw, c->obs_enc, c->q_work, c->m_rows, c->mdist, c->enc_q,
                   c->cand_obs, c->cand_cnt, c->row_base, c->row_sample, c->row_obs, c->counters, c->sel,
                   c->sel_rows, c->row_dist, c->row_grad, c->dist_tmp, c->grad_tmp, c->upd_partials, c->stats_tmp,
                   c->packed_tmp, c->stage};
@@ -228,6 +228,34 @@ int dsmppi_set_pass1_mode(dsmppi_ctx* c, int32_t mode, float guard_band) {
 int dsmppi_set_whole_horizon(dsmppi_ctx* c, int32_t on) {
   REQUIRE(c, "null ctx");
   c->fused_rollout = on ? 1 : 0;
+  return 0;
+}
+
+int dsmppi_set_seds(dsmppi_ctx* c, const dsmppi_seds* sd, void* stream) {
+  REQUIRE(c && sd, "null argument");
+  REQUIRE(sd->n_gaussians >= 1 && sd->n_gaussians <= 32, "n_gaussians out of range (1..32)");
+  REQUIRE(sd->priors_host && sd->pdf_den_host && sd->mu_x_host && sd->mu_y_host && sd->sigma_inv_host && sd->A_host,
+          "null SEDS array");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CUDA_TRY(cudaSetDevice(c->device));
+  const int G = sd->n_gaussians, d = c->d;
+  std::vector<float> blob;
+  blob.insert(blob.end(), sd->priors_host, sd->priors_host + G);
+  blob.insert(blob.end(), sd->pdf_den_host, sd->pdf_den_host + G);
+  blob.insert(blob.end(), sd->mu_x_host, sd->mu_x_host + G * d);
+  blob.insert(blob.end(), sd->mu_y_host, sd->mu_y_host + G * d);
+  blob.insert(blob.end(), sd->sigma_inv_host, sd->sigma_inv_host + G * d * d);
+  blob.insert(blob.end(), sd->A_host, sd->A_host + G * d * d);
+  if (G > c->seds_G || !c->seds) {
+    if (c->seds) CUDA_TRY(cudaFree(c->seds));
+    c->seds = nullptr;
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c->seds), blob.size() * sizeof(float)));
+  }
+  // the host vector dies with this call: a synchronous copy ordered after earlier work on the stream
+  CUDA_TRY(cudaStreamSynchronize(st));
+  CUDA_TRY(cudaMemcpy(c->seds, blob.data(), blob.size() * sizeof(float), cudaMemcpyHostToDevice));
+  c->seds_G = G;
+  c->seds_thr = sd->seds_thr;
   return 0;
 }
 
@@ -334,7 +362,9 @@ int dsmppi_rollout(dsmppi_ctx* c, const dsmppi_rollout_args* a, void* stream) {
           "unknown distance_provider");
   REQUIRE(a->distance_provider != DSMPPI_DISTANCE_FK || (c->P == 3 && a->fk_n_pts >= 1 && a->fk_n_pts <= DSMPPI_FK_MAX_PTS),
           "the FK distance provider needs 3-D obstacles and 1..32 points per link");
-  REQUIRE(a->mod.ds_kind == DSMPPI_DS_LINEAR_ATTRACTOR || a->mod.ds_kind == DSMPPI_DS_MATRIX, "unknown mod.ds_kind");
+  REQUIRE(a->mod.ds_kind == DSMPPI_DS_LINEAR_ATTRACTOR || a->mod.ds_kind == DSMPPI_DS_MATRIX ||
+              a->mod.ds_kind == DSMPPI_DS_SEDS, "unknown mod.ds_kind");
+  REQUIRE(a->mod.ds_kind != DSMPPI_DS_SEDS || (c->seds && c->seds_G > 0), "SEDS parameters not set (dsmppi_set_seds)");
   REQUIRE(a->mod.lvel_k != 0.f && a->mod.dist_k != 0.f,
           "rollout_args.mod is not initialised (dsmppi_modulation_default / _toy)");
   cudaStream_t st = static_cast<cudaStream_t>(stream);

@@ -79,6 +79,8 @@ struct dsmppi_ctx {
   float* obs = nullptr; int obs_cap = 0;   // always (M, 4) = [x, y, z, r] on the device (z = 0 when P == 2)
   float* obs_raw = nullptr; int obs_raw_cap = 0;   // P == 2: the caller's (M, 3) rows before repacking
   void* obs_enc = nullptr; size_t obs_enc_cap = 0;   // tensor path: per-obstacle packed encodings
+  // SEDS nominal DS: [priors G | pdf_den G | mu_x G*d | mu_y G*d | sigma_inv G*d*d | A G*d*d]
+  float* seds = nullptr; int seds_G = 0; float seds_thr = 0.f;
   // workspace (grown on demand)
   int ws_n = 0, ws_M = 0;
   float* q_work = nullptr;            // (n, d) states of the current step

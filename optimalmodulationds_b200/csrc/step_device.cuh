@@ -47,6 +47,7 @@ struct StepArgs {
   float dt, dst_thr, lin_thr, p;
   float goal[MAXD];
   dsmppi_modulation mod;
+  const float* seds; int seds_G; float seds_thr;     // DSMPPI_DS_SEDS parameters (dsmppi_ctx::seds)
   const float* row_dist; const float* row_grad; const int* sel_rows;
   const float* mu; const float* sigma; const float* alpha;
   float* traj; float* closest; float* kval; float* dots; float* acts; float* qdot; float* grads;
@@ -81,6 +82,75 @@ __device__ __forceinline__ void step_sample(const StepArgs& s, int i) {
       for (int a = 0; a < MAXD; ++a)
         if (a < d && cc < d) acc += (q[a] - s.goal[a]) * s.mod.ds_A[a * MAXD + cc];
       v[cc] = acc;
+    }
+  } else if (s.mod.ds_kind == DSMPPI_DS_SEDS) {
+    // Gaussian-mixture regression on x = q - q_goal (SEDS.py:36-76)
+    const int G = s.seds_G;
+    const float* pri = s.seds;
+    const float* den = pri + G;
+    const float* mux = den + G;
+    const float* muy = mux + G * d;
+    const float* sinv = muy + G * d;
+    const float* Am = sinv + G * d * d;
+    float x[MAXD], y[MAXD];
+    float dst2 = 0.f;
+#pragma unroll
+    for (int a = 0; a < MAXD; ++a) {
+      x[a] = a < d ? q[a] - s.goal[a] : 0.f;
+      y[a] = 0.f;
+      dst2 += x[a] * x[a];
+    }
+    float psum = 0.f;
+    for (int j = 0; j < G; ++j) {                      // responsibilities Priors_j N(x; Mu_j, Sigma_j)  (:28-34,48-49)
+      float quad = 0.f;
+#pragma unroll
+      for (int r = 0; r < MAXD; ++r) {
+        if (r < d) {
+          float row = 0.f;
+#pragma unroll
+          for (int cc = 0; cc < MAXD; ++cc)
+            if (cc < d) row += (x[cc] - mux[j * d + cc]) * sinv[(j * d + cc) * d + r];
+          quad += row * (x[r] - mux[j * d + r]);
+        }
+      }
+      psum += pri[j] * (expf(-0.5f * quad) / den[j]);
+    }
+    for (int j = 0; j < G; ++j) {
+      float quad = 0.f;
+#pragma unroll
+      for (int r = 0; r < MAXD; ++r) {
+        if (r < d) {
+          float row = 0.f;
+#pragma unroll
+          for (int cc = 0; cc < MAXD; ++cc)
+            if (cc < d) row += (x[cc] - mux[j * d + cc]) * sinv[(j * d + cc) * d + r];
+          quad += row * (x[r] - mux[j * d + r]);
+        }
+      }
+      float beta = nan_to_num(pri[j] * (expf(-0.5f * quad) / den[j]) / psum);     // :50-51
+      beta = fmaxf(beta, 1e-8f);                                                  // :52
+#pragma unroll
+      for (int r = 0; r < MAXD; ++r) {
+        if (r < d) {
+          float yr = 0.f;
+#pragma unroll
+          for (int cc = 0; cc < MAXD; ++cc)
+            if (cc < d) yr += Am[(j * d + r) * d + cc] * (x[cc] - mux[j * d + cc]);
+          y[r] += beta * (muy[j * d + r] + yr);                                   // :53-59
+        }
+      }
+    }
+    float yn2 = 0.f;
+#pragma unroll
+    for (int a = 0; a < MAXD; ++a) yn2 += y[a] * y[a];
+    const float ynorm = sqrtf(yn2), dst = sqrtf(dst2);
+    const bool far = dst > s.lin_thr;                                             // :63
+    const bool weak = ynorm < s.seds_thr;                                         // :72
+#pragma unroll
+    for (int a = 0; a < MAXD; ++a) {
+      float va = y[a];
+      if (far) va = weak ? -x[a] / dst : y[a] / ynorm;                            // :68-75 (|-x| == dst)
+      v[a] = a < d ? va : 0.f;
     }
   } else {
     // unit-speed attractor, linear inside lin_thr (LinDS.py:11-21)
@@ -206,6 +276,7 @@ static inline StepArgs make_step_args(const dsmppi_ctx* c, const dsmppi_rollout_
   s.dt = a->dt; s.dst_thr = a->dst_thr; s.lin_thr = a->lin_thr; s.p = a->rbf_p;
   for (int i = 0; i < MAXD; ++i) s.goal[i] = a->q_goal[i];
   s.mod = a->mod;
+  s.seds = c->seds; s.seds_G = c->seds_G; s.seds_thr = c->seds_thr;
   s.row_dist = c->row_dist; s.row_grad = c->row_grad; s.sel_rows = c->sel_rows;
   s.mu = a->mu_tmp_dev; s.sigma = a->sigma_tmp_dev; s.alpha = a->alpha_tmp_dev;
   s.traj = a->all_traj_dev; s.closest = a->closest_dist_all_dev; s.kval = a->kernel_val_all_dev;

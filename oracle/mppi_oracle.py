@@ -95,6 +95,44 @@ def lin_ds_velocity(q: torch.Tensor, q_goal: torch.Tensor, lin_thr: float = 0.01
     return v
 
 
+@dataclass
+class SedsParams:
+    """Arrays of a SEDS model as the MATLAB files store them (ds_mppi/functions/SEDS.py:12-18)."""
+    Mu: torch.Tensor        # (2d, G)
+    Sigma: torch.Tensor     # (2d, 2d, G)
+    Priors: torch.Tensor    # (G,) or (G, 1)
+    seds_thr: float = 1e-2  # SEDS.py:26
+    lin_thr: float = 1e-2   # SEDS.py:27
+
+
+def seds_velocity(x: torch.Tensor, q_goal: torch.Tensor, sp: SedsParams) -> torch.Tensor:
+    """SEDS.get_velocity (SEDS.py:61-76) with gaussPDF (:28-34) and GMR (:36-59), restated per state (the
+    reference's own batched indexing at :70-71 only broadcasts for a single state).  x: (n, d) -> (n, d)."""
+    d = sp.Mu.shape[0] // 2
+    G = sp.Sigma.shape[2]
+    pri = sp.Priors.reshape(-1)
+    out = torch.zeros_like(x)
+    inv = [torch.inverse(sp.Sigma[:d, :d, j]) for j in range(G)]
+    det = [torch.abs(torch.det(sp.Sigma[:d, :d, j])) for j in range(G)]
+    for i in range(x.shape[0]):
+        xd = x[i] - q_goal.reshape(-1)                                              # :62
+        pxi = torch.zeros(G)
+        for j in range(G):
+            D = (xd - sp.Mu[:d, j]).reshape(1, d)
+            quad = torch.sum((D @ inv[j]) * D, dim=1)
+            pxi[j] = pri[j] * (torch.exp(-0.5 * quad) /
+                               torch.sqrt((2 * torch.tensor(torch.pi) ** d) * det[j] + torch.tensor(1e-100)))[0]
+        beta = torch.clamp((pxi / pxi.sum()).nan_to_num(), min=1e-8)                # :50-52
+        y = torch.zeros(d)
+        for j in range(G):
+            y = y + beta[j] * (sp.Mu[d:, j] + sp.Sigma[d:, :d, j] @ inv[j] @ (xd - sp.Mu[:d, j]))   # :53-59
+        dst, y_norm = xd.norm(), y.norm()
+        if dst > sp.lin_thr:                                                        # :63,68-71
+            y = (-xd / dst) if y_norm < sp.seds_thr else y / y_norm                 # :72-75
+        out[i] = y
+    return out
+
+
 def generalized_sigmoid(x, y_min, y_max, x0, x1, k):
     """ds_mppi/functions/MPPI.py:352-353."""
     return y_min + (y_max - y_min) / (1 + torch.exp(k * (-x + (x0 + x1) / 2)))
@@ -262,6 +300,7 @@ class RolloutParams:
     fold_activation: bool = False            # kernel_val_all *= activation                MPPI_toy.py:178-179
     A: Optional[torch.Tensor] = None         # matrix DS v = (q - qf) @ A                  MPPI_toy.py:89
     fk_dh_params: Optional[torch.Tensor] = None   # set: distances from distance_repulsion_fk (MPPI.py:115)
+    seds: Optional["SedsParams"] = None      # set: nominal DS = SEDS.get_velocity (MPPI.py:106 with a SEDS object)
 
 
 def toy_params(dt, dt_H, n_closest_obs, A, **kw):
@@ -304,7 +343,9 @@ def rollout(net: Net, q_cur: torch.Tensor, q_goal: torch.Tensor, obs: torch.Tens
     aux = []
     for i in range(1, H + 1):
         q = all_traj[:, i - 1, :]
-        if prm.A is not None:
+        if prm.seds is not None:
+            v = seds_velocity(q, q_goal, prm.seds)                        # MPPI.py:106, SEDS.py:61-76
+        elif prm.A is not None:
             v = (q - q_goal) @ prm.A                                      # MPPI_toy.py:89
         else:
             v = lin_ds_velocity(q, q_goal, prm.lin_thr)                   # MPPI.py:106

@@ -38,9 +38,10 @@ def test_library_exports_every_declared_symbol(capi):
 
 def test_struct_layout_matches_the_c_compiler(capi, tmp_path):
     structs = {"dsmppi_net": capi.Net, "dsmppi_rollout_args": capi.RolloutArgs, "dsmppi_cost_args": capi.CostArgs,
-               "dsmppi_update_args": capi.UpdateArgs, "dsmppi_iteration_host_args": capi.IterationHostArgs, "dsmppi_modulation": capi.Modulation}
-    probes = {"dsmppi_rollout_args": ["q_goal", "mod", "q_cur_dev", "norm_basis_dev"],
+               "dsmppi_update_args": capi.UpdateArgs, "dsmppi_iteration_host_args": capi.IterationHostArgs, "dsmppi_modulation": capi.Modulation, "dsmppi_seds": capi.Seds}
+    probes = {"dsmppi_rollout_args": ["q_goal", "mod", "distance_provider", "fk_span", "q_cur_dev", "norm_basis_dev"],
               "dsmppi_modulation": ["lvel_mid", "repulsion", "ds_A"],
+              "dsmppi_seds": ["seds_thr", "priors_host", "A_host"],
               "dsmppi_cost_args": ["terms", "q_max", "cost_dev"],
               "dsmppi_update_args": ["variant", "N_global", "ker_thr", "alpha_c_dev"],
               "dsmppi_iteration_host_args": ["q_min", "cost_terms", "q_cur_host", "n_updated_host", "d2h_bytes"],
