@@ -217,6 +217,9 @@ def main():
     ap.add_argument("--workload", default="franka_shelf_2064", choices=sorted(WORKLOADS))
     ap.add_argument("--samples", type=int, default=0, help="samples per GPU (default: the workload's)")
     ap.add_argument("--pass1", default="auto", choices=["auto", "exact", "tc_f16", "tc_bf16"])
+    ap.add_argument("--score", default="auto", choices=["auto", "ffma", "tc_split"],
+                    help="arithmetic of the scoring rows: split-fp16 tcgen05 (default) or strict IEEE FFMA")
+    ap.add_argument("--per-step", action="store_true", help="disable the whole-horizon single-launch path")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
@@ -264,6 +267,9 @@ def main():
     DS = [LinDS(t(p["qf"])), LinDS(t(p["q0"]))]
     mppi = MPPI(t(p["q0"]), t(p["qf"]), t(p["dh"]), t(p["obs"]), p["dt"], H, N, DS, t(p["dh_a"]), net, p["K"])
     mppi.set_pass1_mode(args.pass1)
+    mppi.set_score_mode(args.score)
+    if args.per_step:
+        mppi.set_whole_horizon(False)
     mppi.dst_thr, mppi.ker_thr, mppi.ignored_links = p["dst_thr"], p["ker_thr"], list(p["ignored"])
     mppi.Cost.q_min, mppi.Cost.q_max = t(p["qlim"][0]), t(p["qlim"][1])
     if world > 1:

@@ -77,6 +77,16 @@ enum {
   DSMPPI_PASS1_AUTO = 3          /* TC_F16 when M >= 64, else EXACT                                     */
 };
 
+/* Scoring arithmetic: how the rows that produce OUTPUTS (ranking keys, distances, gradients) are evaluated. */
+enum {
+  DSMPPI_SCORE_FFMA = 0,         /* IEEE fp32 FFMA on the CUDA cores (exact_mlp.cu): the strict mode              */
+  DSMPPI_SCORE_TC_SPLIT = 1,     /* tcgen05: operands split into two fp16 halves (22 bits), three MMAs per
+                                  * product sum, fp32 accumulation with truncation compensation (tc_exact.cu):
+                                  * rms error 2-3e-7 of the rms distance like FFMA; rows whose activations leave
+                                  * the fp16 range are re-scored by the FFMA kernel                              */
+  DSMPPI_SCORE_AUTO = 2          /* TC_SPLIT whenever the network fits its tiles (3(d+P) <= 32, O <= 16)           */
+};
+
 /* Where the per-step distance and its joint gradient come from (MPPI.py:113-115). */
 enum {
   DSMPPI_DISTANCE_NN = 0,        /* learned network, distance_repulsion_nn (MPPI.py:227-282) -- the live path     */
@@ -167,6 +177,7 @@ int dsmppi_ctx_create(dsmppi_ctx** out, const dsmppi_net* net, const float* dh_p
                       int32_t capacity, int32_t device);
 int dsmppi_ctx_destroy(dsmppi_ctx* ctx);
 int dsmppi_set_pass1_mode(dsmppi_ctx* ctx, int32_t mode, float guard_band);
+int dsmppi_set_score_mode(dsmppi_ctx* ctx, int32_t mode);     /* DSMPPI_SCORE_*; default AUTO */
 /* Small obstacle sets scored in fp32 (M <= 16, or M <= 32 with a latency-bound batch) are rolled out over the whole
  * horizon by ONE launch (rollout_fused_kernel); on = 0 forces the per-step launch sequence (tests compare both). */
 int dsmppi_set_whole_horizon(dsmppi_ctx* ctx, int32_t on);
@@ -289,6 +300,10 @@ int dsmppi_iteration_host(dsmppi_ctx* ctx, dsmppi_iteration_host_args* args, voi
 int64_t dsmppi_launch_count(const dsmppi_ctx* ctx);
 int dsmppi_pass1_stats(dsmppi_ctx* ctx, int64_t* rescored_pairs, int64_t* band_overflows, int32_t* mode,
                        void* stream);
+/* Scoring arithmetic in effect (DSMPPI_SCORE_FFMA / _TC_SPLIT) and, for the tensor-core path, how many rows left the
+ * fp16 range of its split operands and were re-scored by the FFMA kernel since the context was created
+ * (`dropped_rows` > 0 means the re-scoring list overflowed: results of those rows are saturated, not exact). */
+int dsmppi_score_stats(dsmppi_ctx* ctx, int32_t* mode, int64_t* range_fixup_rows, int64_t* dropped_rows, void* stream);
 /* Average device time (ms) of the dominant kernel over its launches in the last rollout; requires
  * dsmppi_enable_kernel_timing(ctx, 1) beforehand (CUDA events on the launching stream). */
 int dsmppi_enable_kernel_timing(dsmppi_ctx* ctx, int32_t on);

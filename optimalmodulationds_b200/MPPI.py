@@ -169,6 +169,20 @@ class MPPI:
                 'auto': _capi.PASS1_AUTO}[mode]
         _capi.check(self._lib.dsmppi_set_pass1_mode(self._ctx, code, float(guard_band)))
 
+    def set_score_mode(self, mode='auto'):
+        """Arithmetic of the rows that produce outputs: 'ffma' (IEEE fp32 on the CUDA cores, the strict mode),
+        'tc_split' (tcgen05 with split-fp16 operands, fp32-accurate) or 'auto' (tc_split when the network fits)."""
+        code = {'ffma': _capi.SCORE_FFMA, 'tc_split': _capi.SCORE_TC_SPLIT, 'auto': _capi.SCORE_AUTO}[mode]
+        _capi.check(self._lib.dsmppi_set_score_mode(self._ctx, code))
+
+    def score_stats(self):
+        """Scoring arithmetic in effect and the rows the tensor-core path handed to the FFMA kernel (fp16 range)."""
+        mode, fix, drop = _capi.C.c_int32(), _capi.C.c_int64(), _capi.C.c_int64()
+        _capi.check(self._lib.dsmppi_score_stats(self._ctx, _capi.C.byref(mode), _capi.C.byref(fix),
+                                                 _capi.C.byref(drop), self._stream()))
+        return dict(mode={_capi.SCORE_FFMA: 'ffma', _capi.SCORE_TC_SPLIT: 'tc_split'}[mode.value],
+                    range_fixup_rows=fix.value, dropped_rows=drop.value)
+
     def set_whole_horizon(self, on=True):
         """Small obstacle sets are rolled out by one launch over the whole horizon; False forces per-step launches."""
         _capi.check(self._lib.dsmppi_set_whole_horizon(self._ctx, 1 if on else 0))

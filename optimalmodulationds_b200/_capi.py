@@ -16,6 +16,7 @@ MAX_LINKS = 16
 MAX_CLOSEST = 8
 
 PASS1_EXACT_FP32, PASS1_TC_F16, PASS1_TC_BF16, PASS1_AUTO = 0, 1, 2, 3
+SCORE_FFMA, SCORE_TC_SPLIT, SCORE_AUTO = 0, 1, 2
 
 _fp = C.c_void_p   # device / host float pointers travel as integers from tensor.data_ptr()
 
@@ -110,6 +111,7 @@ EXPORTS = {
     "dsmppi_ctx_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(Net), _fp, C.c_int32, C.c_int32]),
     "dsmppi_ctx_destroy": (C.c_int, [C.c_void_p]),
     "dsmppi_set_pass1_mode": (C.c_int, [C.c_void_p, C.c_int32, C.c_float]),
+    "dsmppi_set_score_mode": (C.c_int, [C.c_void_p, C.c_int32]),
     "dsmppi_set_whole_horizon": (C.c_int, [C.c_void_p, C.c_int32]),
     "dsmppi_set_seds": (C.c_int, [C.c_void_p, C.POINTER(Seds), C.c_void_p]),
     "dsmppi_set_obstacles": (C.c_int, [C.c_void_p, _fp, C.c_int32, C.c_void_p]),
@@ -128,6 +130,8 @@ EXPORTS = {
     "dsmppi_iteration_host": (C.c_int, [C.c_void_p, C.POINTER(IterationHostArgs), C.c_void_p]),
     "dsmppi_launch_count": (C.c_int64, [C.c_void_p]),
     "dsmppi_pass1_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int32),
+                                     C.c_void_p]),
+    "dsmppi_score_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_int64),
                                      C.c_void_p]),
     "dsmppi_enable_kernel_timing": (C.c_int, [C.c_void_p, C.c_int32]),
     "dsmppi_kernel_timing": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int32),

@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdsmppi_b200.so")
-SOURCES = ["capi.cu", "exact_mlp.cu", "rollout_kernels.cu", "tc_pass1.cu"]
+SOURCES = ["capi.cu", "exact_mlp.cu", "rollout_kernels.cu", "tc_pass1.cu", "tc_exact.cu"]
 # -fmad=false: no implicit mul+add contraction -- every FMA in the library is an explicit fmaf / fma.rn.f32x2, so the
 # per-sample arithmetic (blend, modulation, cost) rounds like the reference's separate torch ops and does not depend
 # on which kernel a device function was inlined into (the whole-horizon kernel equals the per-step launches bitwise)

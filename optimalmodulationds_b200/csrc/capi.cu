@@ -46,6 +46,7 @@ constexpr int WHOLE_M_MAX = 32;  // largest obstacle set a row tile of the whole
 // because differentiating all M pairs instead of the K closest costs up to 1.5x the FLOPs.
 bool use_whole_horizon(const dsmppi_ctx* c, int n) {
   if (!c->fused_rollout || resolved_mode(c) != DSMPPI_PASS1_EXACT_FP32) return false;
+  if (use_tc_scoring(c)) return false;   // the per-step tensor-core launches beat the fused FFMA kernel
   if (c->M <= FUSE_M_MAX) return true;
   return c->M <= WHOLE_M_MAX && n <= 2 * c->sm_count;
 }
@@ -189,6 +190,7 @@ int dsmppi_ctx_create(dsmppi_ctx** out, const dsmppi_net* net, const float* dh_p
   c->net.W4 = c->weights_blob + off_w4;
   for (int l = 0; l < 5; ++l) c->net.b[l] = c->weights_blob + off_bias[l];
   if (tc_build_images(c, net)) { delete c; return 1; }
+  if (tcx_build_images(c, net)) { delete c; return 1; }
   c->upd_blocks = c->sm_count * 2;
   CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c->upd_partials),
                       (size_t)c->upd_blocks * dsmppi_update_packed_len(NKMAX, MAXD) * sizeof(float)));
@@ -204,8 +206,9 @@ int dsmppi_ctx_destroy(dsmppi_ctx* c) {
   if (!c) return 0;
   cudaSetDevice(c->device);
   tc_free_images(c);
+  tcx_free_images(c);
   void* ptrs[] = {c->weights_blob, c->seds, c->obs, c->obs_raw, c->obs_enc, c->q_work, c->m_rows, c->mdist, c->enc_q,
-                  c->cand_obs, c->cand_cnt, c->row_base, c->row_sample, c->row_obs, c->counters, c->sel,
+                  c->cand_obs, c->cand_cnt, c->row_base, c->row_sample, c->row_obs, c->counters, c->sel, c->fix_list,
                   c->sel_rows, c->row_dist, c->row_grad, c->dist_tmp, c->grad_tmp, c->upd_partials, c->stats_tmp,
                   c->packed_tmp, c->stage};
   for (void* p : ptrs)
@@ -222,6 +225,14 @@ int dsmppi_set_pass1_mode(dsmppi_ctx* c, int32_t mode, float guard_band) {
   if (guard_band > 0.f) c->guard_band = guard_band;
   c->ws_n = 0;   // force re-sizing of the workspace for the new mode
   c->ws_M = 0;
+  return 0;
+}
+
+int dsmppi_set_score_mode(dsmppi_ctx* c, int32_t mode) {
+  REQUIRE(c, "null ctx");
+  REQUIRE(mode >= 0 && mode <= 2, "bad score mode");
+  REQUIRE(mode != DSMPPI_SCORE_TC_SPLIT || c->tcx_blob, "this network does not fit the tensor-core scoring tiles");
+  c->score_mode = mode;
   return 0;
 }
 
@@ -627,6 +638,18 @@ int dsmppi_pass1_stats(dsmppi_ctx* c, int64_t* rescored_pairs, int64_t* band_ove
     *rescored_pairs = (int64_t)v;
   }
   if (mode) *mode = resolved_mode(c);
+  return 0;
+}
+
+int dsmppi_score_stats(dsmppi_ctx* c, int32_t* mode, int64_t* range_fixup_rows, int64_t* dropped_rows, void* stream) {
+  REQUIRE(c, "null ctx");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int host[2] = {0, 0};
+  CUDA_TRY(cudaMemcpyAsync(host, c->counters + 6, sizeof(host), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  if (mode) *mode = use_tc_scoring(c) ? DSMPPI_SCORE_TC_SPLIT : DSMPPI_SCORE_FFMA;
+  if (range_fixup_rows) *range_fixup_rows = host[0];
+  if (dropped_rows) *dropped_rows = host[1];
   return 0;
 }
 

@@ -333,7 +333,7 @@ __device__ __forceinline__ void mlp_tile(const NetDev& net, const RowSrc& src, i
         if ((ignore_mask >> o) & 1u) y = 1e6f;
         m = fminf(m, y);
       }
-      out_m[row0 + tid] = m;
+      out_m[src.out_row ? src.out_row[row0 + tid] : row0 + tid] = m;
     }
   } else {
   // ---- pass 2: l* = argmin of the RAW output (robot_sdf.py:155), distance of that link (MPPI.py:265-274);
@@ -355,8 +355,9 @@ __device__ __forceinline__ void mlp_tile(const NetDev& net, const RowSrc& src, i
     if (row0 + tid < n_rows) {
       float y = bv;
       if (net.scale != 1.f) y = y / 100.f;
-      out_dist[row0 + tid] = y - rad[tid];
-      if (out_m) out_m[row0 + tid] = m;
+      const int orow = src.out_row ? src.out_row[row0 + tid] : row0 + tid;
+      out_dist[orow] = y - rad[tid];
+      if (out_m) out_m[orow] = m;
     }
   }
   __syncthreads();
@@ -402,7 +403,10 @@ __device__ __forceinline__ void mlp_tile(const NetDev& net, const RowSrc& src, i
       a2 = fmaf(g, __ldg(w + k * nenc + 2 * nin + c), a2);
     }
     const float x = xs[r * XS + c];
-    if (row0 + r < n_rows) out_grad[(size_t)(row0 + r) * d + c] = a0 + cosf(x) * a1 - sinf(x) * a2;
+    if (row0 + r < n_rows) {
+      const int orow = src.out_row ? src.out_row[row0 + r] : row0 + r;
+      out_grad[(size_t)orow * d + c] = a0 + cosf(x) * a1 - sinf(x) * a2;
+    }
   }
   }  // BWD
 }
@@ -419,14 +423,18 @@ exact_mlp_kernel(NetDev net, RowSrc src, const float* __restrict__ q, int q_stri
   constexpr int R = 4 * RPT;
   extern __shared__ __align__(16) float smem[];
   const int n_rows = src.n_rows_dev ? min(*src.n_rows_dev, src.n_rows) : src.n_rows;
-  const int row0 = blockIdx.x * R;
-  if (row0 >= n_rows) return;
+  const int tiles = (n_rows + R - 1) / R;
+  if ((int)blockIdx.x >= tiles) return;
   TileSmem<RPT> sm(smem);
   WeightStream ws;
-  stream_begin<BWD, nthreads(FT)>(ws, &net, sm.ring, 1);
+  // one tile per CTA in the regular launches; the re-scoring launch (launch_exact_fixup) strides a bounded grid
+  stream_begin<BWD, nthreads(FT)>(ws, &net, sm.ring, (tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x);
   int stage = 0;
-  mlp_tile<BWD, RPT, FT>(net, src, row0, n_rows, q, q_stride, obs, ignore_mask, out_m, out_dist, out_grad, sm, ws,
-                         stage);
+  for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    mlp_tile<BWD, RPT, FT>(net, src, tile * R, n_rows, q, q_stride, obs, ignore_mask, out_m, out_dist, out_grad, sm, ws,
+                           stage);
+    __syncthreads();
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -587,12 +595,38 @@ int launch_rollout_fused(dsmppi_ctx* c, const dsmppi_rollout_args* a, cudaStream
 #undef CALL
 }
 
+int launch_exact_fixup(dsmppi_ctx* c, const float* q, int q_stride, const RowSrc& src, uint32_t ignore_mask,
+                       float* m_rows, float* row_dist, float* row_grad, bool bwd, cudaStream_t st) {
+  constexpr int RPT = 8, FT = 8, R = 4 * RPT;
+  static bool init = false;
+  if (!init) {
+    CUDA_TRY(cudaFuncSetAttribute(exact_mlp_kernel<true, RPT, FT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem_bytes(R)));
+    CUDA_TRY(cudaFuncSetAttribute(exact_mlp_kernel<false, RPT, FT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem_bytes(R)));
+    init = true;
+  }
+  long long grid = ((long long)src.n_rows + R - 1) / R;
+  if (grid > 4LL * c->sm_count) grid = 4LL * c->sm_count;       // usually no row is flagged: keep the launch tiny
+  if (bwd)
+    exact_mlp_kernel<true, RPT, FT><<<(unsigned)grid, nthreads(FT), smem_bytes(R), st>>>(
+        c->net, src, q, q_stride, c->obs, ignore_mask, m_rows, row_dist, row_grad);
+  else
+    exact_mlp_kernel<false, RPT, FT><<<(unsigned)grid, nthreads(FT), smem_bytes(R), st>>>(
+        c->net, src, q, q_stride, c->obs, ignore_mask, m_rows, nullptr, nullptr);
+  CUDA_TRY(cudaGetLastError());
+  c->launches++;
+  return 0;
+}
+
 int launch_exact_forward(dsmppi_ctx* c, const float* q, int q_stride, const RowSrc& src, uint32_t ignore_mask,
                          float* m_rows, cudaStream_t st) {
+  if (use_tc_scoring(c)) return launch_tc_exact(c, q, q_stride, src, ignore_mask, m_rows, nullptr, nullptr, false, st);
   return launch<false>(c, q, q_stride, src, ignore_mask, m_rows, nullptr, nullptr, 0, st);
 }
 
 int launch_exact_fwdbwd(dsmppi_ctx* c, const float* q, int q_stride, const RowSrc& src, uint32_t ignore_mask,
                         float* m_rows, float* row_dist, float* row_grad, long long rows_estimate, cudaStream_t st) {
+  if (use_tc_scoring(c)) return launch_tc_exact(c, q, q_stride, src, ignore_mask, m_rows, row_dist, row_grad, true, st);
   return launch<true>(c, q, q_stride, src, ignore_mask, m_rows, row_dist, row_grad, rows_estimate, st);
 }

@@ -58,6 +58,7 @@ struct RowSrc {
   const int* sel;         // ROWS_SELECTED: (n, K) obstacle index
   const int* row_sample;  // ROWS_LIST
   const int* row_obs;     // ROWS_LIST
+  const int* out_row;     // optional: row r writes its outputs at index out_row[r] (re-scoring of flagged rows)
 };
 
 struct DhTable { float v[MAXD + 1][4]; };   // rows [d, theta, a, alpha]
@@ -75,6 +76,10 @@ struct dsmppi_ctx {
   float* weights_blob = nullptr;      // all fp32 weights
   void* tc_blob = nullptr;            // tensor-core operand images (tc_pass1.cu)
   size_t tc_blob_bytes = 0;
+  void* tcx_blob = nullptr;           // split-fp16 weight images of the tensor-core scoring kernel (tc_exact.cu)
+  int* fix_list = nullptr; size_t fix_cap = 0;   // rows whose activations left the fp16 range: (sample, obs, out row)
+  int fix_parity = 0;                 // which of counters[4..5] the next tc_exact launch appends to
+  int score_mode = DSMPPI_SCORE_AUTO; // which kernel scores / differentiates rows in fp32 accuracy
   // obstacles
   float* obs = nullptr; int obs_cap = 0;   // always (M, 4) = [x, y, z, r] on the device (z = 0 when P == 2)
   float* obs_raw = nullptr; int obs_raw_cap = 0;   // P == 2: the caller's (M, 3) rows before repacking
@@ -93,7 +98,8 @@ struct dsmppi_ctx {
   int* cand_cnt = nullptr;            // (n)
   int* row_base = nullptr;            // (n)
   int* row_sample = nullptr; int* row_obs = nullptr; size_t rowlist_cap = 0;
-  int* counters = nullptr;            // [0] n_rows, [1] band overflows, [2..3] rescored pairs (u64)
+  int* counters = nullptr;            // [0] n_rows, [1] band overflows, [2..3] rescored pairs (u64), [4..5] range-fixup
+                                      // row counts (ping-pong), [6] rows re-scored in FFMA so far, [7] rows dropped
   int* sel = nullptr;                 // (n, K) selected obstacle indices (two-launch fp32 path)
   int* sel_rows = nullptr;            // (n, K) rows of row_dist / row_grad holding the K closest, ranked
   float* row_dist = nullptr;          // pass-2 distance of every differentiated row
@@ -127,6 +133,16 @@ int launch_exact_fwdbwd(dsmppi_ctx* c, const float* q, int q_stride, const RowSr
                         float* m_rows, float* row_dist, float* row_grad, long long rows_estimate, cudaStream_t st);
 // whole-horizon rollout in one launch (M <= 32, fp32 scoring); all_traj[:, 0] must be initialised
 int launch_rollout_fused(dsmppi_ctx* c, const dsmppi_rollout_args* a, cudaStream_t st);
+// the FFMA kernels over a device-counted row list with remapped outputs (grid-stride; used to re-score the rows the
+// tensor-core kernel flags as out of fp16 range)
+int launch_exact_fixup(dsmppi_ctx* c, const float* q, int q_stride, const RowSrc& src, uint32_t ignore_mask,
+                       float* m_rows, float* row_dist, float* row_grad, bool bwd, cudaStream_t st);
+// tc_exact.cu: the same rows / outputs as the two launches above, on the tensor cores (split-fp16 operands)
+int tcx_build_images(dsmppi_ctx* c, const dsmppi_net* net);
+void tcx_free_images(dsmppi_ctx* c);
+int launch_tc_exact(dsmppi_ctx* c, const float* q, int q_stride, const RowSrc& src, uint32_t ignore_mask, float* m_rows,
+                    float* row_dist, float* row_grad, bool bwd, cudaStream_t st);
+inline bool use_tc_scoring(const dsmppi_ctx* c) { return c->tcx_blob && c->score_mode != DSMPPI_SCORE_FFMA; }
 // tc_pass1.cu
 int tc_build_images(dsmppi_ctx* c, const dsmppi_net* net);
 void tc_free_images(dsmppi_ctx* c);

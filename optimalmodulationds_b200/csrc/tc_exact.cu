@@ -1,0 +1,672 @@
+// fp32-accurate evaluation of the distance network AND its analytic input gradient on the tensor cores.
+//
+//   tc_exact_kernel<false>: forward only  -> masked minimum link distance per row  (MPPI.py:235-242)
+//   tc_exact_kernel<true>:  forward + VJP at argmin_l of the raw output            (robot_sdf.py:153-158)
+//
+// Same rows, same outputs as exact_mlp.cu (which stays as the strict IEEE-FFMA mode); this is the scoring path of
+// every workload by default.  Arithmetic: every operand is split a = hi + lo * 2^-11 with hi = fp16(a),
+// lo = fp16((a - hi) * 2^11) -- 22 significant bits, the lo half scaled up so it cannot underflow -- and a product
+// sum is three fp16 tcgen05 MMAs with fp32 accumulation in TMEM:
+//       D1 += A_hi * B_hi          D2 += A_hi * B_lo + A_lo * B_hi          result = D1 + D2 * 2^-11
+// (the lo * lo term is below 2^-24 of the product).  The tensor core truncates its fp32 accumulator toward zero at
+// every MMA (K = 16) step, which shrinks a D1 chain of n steps by (1.65e-8 n + 2.1e-8) of its value on average
+// (tools/split_precision_probe.py measures both the bias and this fit); uncorrected that bias adds up coherently over
+// the layers (rms error 1.4e-6 of the rms distance), so the epilogue multiplies it back: result += D1 * c(n).
+// Measured on the shipped nets against an fp64 evaluation: rms error 1.9e-7 .. 3.1e-7 of the rms distance and
+// 2.1e-7 .. 3.8e-7 of the rms gradient -- the same as IEEE FFMA (1.5e-7 .. 2.5e-7 / 1.9e-7 .. 2.6e-7); DESIGN.md
+// section 3 has the table.
+//
+// Design (B200, one CTA pair per TPC, persistent over 256-row tiles):
+//   * cta_group::2 MMAs, M = 256 (128 rows per CTA = the 128 TMEM lanes), N = 256: D1 and D2 fill the 512 TMEM
+//     columns.  The A operand (activations, then back-propagated gradients) lives in shared memory as two K-major
+//     fp16 images (hi, lo; 2 x 64 KB) that the epilogue warps rewrite in place once a layer's MMAs have retired.
+//   * weights never fit on chip in split form (7 GEMMs x 256 KB), so they stream: each CTA pulls ITS N-half of
+//     every stage (K = 64: 32 KB) from L2 with one bulk TMA copy into a 3-slot ring, running ahead across layer and
+//     tile boundaries (the ring refills while the epilogue runs).  The pair shares every stage, so a tile of 256
+//     rows costs 816 KB of L2 reads per SM for 41 k cycles of MMAs (20 B/cycle/SM, half the L2 limit).
+//   * warp roles: warps 0-7 epilogue (TMEM lane quarter = warp % 4, column half = warp / 4): D1/D2 -> bias, ReLU
+//     (bit masks kept in registers for the backward pass), hi/lo split, st.shared of the next A operand;
+//     warp 8 = TMEM allocator + MMA issuer (leader CTA) / "stage landed" relay (peer CTA); warp 9 = weight loader.
+//   * the output layer (N = 32), the one-hot seed g4 = W5[l*, :] * mask and the final W1^T contraction (N = 32)
+//     plus the encoding Jacobian run in the same pipeline: 9 GEMMs per tile with BWD.
+#include <cuda_fp16.h>
+
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "internal.cuh"
+#include "tc_ptx.cuh"
+
+namespace {
+using namespace tcx;
+
+constexpr int TROWS = 128;                 // rows per CTA per tile
+constexpr int W_MMA = 8, W_LOAD = 9;
+// three warpgroups: two of epilogue warps and one holding the two control warps (warps 10-11 only complete it), so
+// that setmaxnreg can hand the control group's registers to the epilogue: double-buffered TMEM loads need ~200
+constexpr int NTHREADS = 12 * 32;
+constexpr int EPI_REGS = 224, CTRL_REGS = 40;   // 8*32*224 + 4*32*40 = 62464 <= 65536
+constexpr int NSLOT = 3;
+constexpr int SLOT_BYTES = 32768;
+constexpr uint32_t A_LBO = TROWS * 16;     // bytes between consecutive 8-element K chunks of the A images
+constexpr float SPLIT = 2048.f, INV_SPLIT = 1.f / 2048.f;
+// accumulator-truncation compensation of a D1 chain of n MMA steps: 1.65e-8 n + 2.1e-8 (see the header)
+constexpr float COMP_K256 = 1.65e-8f * 16 + 2.1e-8f, COMP_K32 = 1.65e-8f * 2 + 2.1e-8f;
+__device__ __forceinline__ float combine(uint32_t d1, uint32_t d2, float comp) {
+  const float a = __uint_as_float(d1);
+  return fmaf(a, comp, fmaf(__uint_as_float(d2), INV_SPLIT, a));
+}
+
+// ---- shared-memory map (bytes)
+constexpr int OFF_AHI = 0;                 // 128 rows x 256 K fp16, canonical K-major (32 chunks x 2 KB)
+constexpr int OFF_ALO = 65536;
+constexpr int OFF_RING = 131072;           // NSLOT x 32 KB weight stages
+constexpr int OFF_BAR = OFF_RING + NSLOT * SLOT_BYTES;
+enum { BAR_FULL = 0, BAR_PEER = NSLOT, BAR_EMPTY = 2 * NSLOT, BAR_AREADY = 3 * NSLOT, BAR_DFULL = 3 * NSLOT + 1,
+       NBAR = 3 * NSLOT + 2 };
+constexpr int OFF_TMEMPTR = OFF_BAR + 96;  // NBAR * 8 = 88, padded
+constexpr int OFF_LST = OFF_TMEMPTR + 16;  // argmin link per row (128 ints)
+constexpr int OFF_OVF = OFF_LST + TROWS * 4;   // "left the fp16 range" flag per row (128 ints)
+constexpr int SMEM_BYTES = OFF_OVF + TROWS * 4;
+constexpr int OFF_SCRATCH = OFF_ALO + 32768;   // final epilogue: a[e][row] fp32 (16 KB) inside the idle A_lo image
+static_assert(NBAR * 8 <= 96, "barrier block");
+static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB shared-memory budget");
+
+// ---- weight image of one CTA rank: the stages of one pass in issue order
+//   s = 0        GEMM 0  forward layer 1      K = 32   N = 256   16 KB  [hi 8 KB | lo 8 KB]
+//   s = 1..12    GEMM 1-3 forward layers 2-4  K = 64   N = 256   32 KB  [hi 16 KB | lo 16 KB], 4 stages per GEMM
+//   s = 13       GEMM 4  output layer         K = 256  N = 32    16 KB  (16 rows per CTA)
+//   s = 14..25   GEMM 5-7 backward W4^T..W2^T K = 64   N = 256   32 KB
+//   s = 26       GEMM 8  backward W1^T        K = 256  N = 32    16 KB
+constexpr int STAGES_FWD = 14, STAGES_BWD = 27;
+constexpr size_t IMG_BYTES = 16384 + 12 * 32768 + 16384 + 12 * 32768 + 16384;   // 835584
+constexpr size_t W4_TABLE_BYTES = 2 * 16 * HID * 2;                              // [hi | lo] x 16 links x 256 fp16
+__host__ __device__ __forceinline__ void stage_info(int s, uint32_t& off, uint32_t& bytes) {
+  if (s == 0) { off = 0; bytes = 16384; }
+  else if (s <= 12) { off = 16384 + (uint32_t)(s - 1) * 32768; bytes = 32768; }
+  else if (s == 13) { off = 16384 + 12 * 32768; bytes = 16384; }
+  else if (s <= 25) { off = 2 * 16384 + 12 * 32768 + (uint32_t)(s - 14) * 32768; bytes = 32768; }
+  else { off = 2 * 16384 + 24 * 32768; bytes = 16384; }
+}
+
+struct TxImages {
+  uint8_t* dev = nullptr;      // [rank 0 image | rank 1 image | W4 hi/lo table]
+};
+
+struct TxArgs {
+  const uint8_t* img0; const uint8_t* img1;
+  const uint4* w4hi; const uint4* w4lo;      // (16, 32) uint4 each: fp16 halves of the output layer's rows
+  NetDev net;
+  RowSrc src;
+  const float* q; int q_stride;
+  const float* obs;
+  uint32_t ignore_mask;
+  float* out_m; float* out_dist; float* out_grad;
+  int* fix_count;                            // rows appended to fix_list by this launch
+  int* fix_next;                             // the counter of the NEXT launch: zeroed here
+  int* fix_total;                            // rows handed to the FFMA kernel since the context was created
+  int* fix_dropped;                          // rows that did not fit fix_list (both reported by dsmppi_score_stats)
+  int* fix_list;                             // (3, fix_cap) = [samples | obstacles | output rows]
+  int fix_cap;
+  int dbg;                                   // DSMPPI_TCX_DEBUG bits: 1 cluster-scope release arrivals, 2 no load prefetch
+};
+
+__device__ __forceinline__ bool row_lookup(const RowSrc& s, int r, int n_rows, int& i, int& j) {
+  if (r >= n_rows) return false;
+  if (s.mode == ROWS_DENSE) {
+    i = r / s.M;
+    j = r - i * s.M;
+  } else if (s.mode == ROWS_SELECTED) {
+    i = r / s.K;
+    j = s.sel[r];
+  } else {
+    i = s.row_sample[r];
+    j = s.row_obs[r];
+  }
+  return true;
+}
+
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ float2 unpack_h2(uint32_t p) {
+  return __half22float2(*reinterpret_cast<const __half2*>(&p));
+}
+// v[0..8) -> fp16 hi halves and scaled fp16 lo halves, 16 bytes each; `range` keeps the largest |hi| bit pattern
+// seen (per 16-bit lane): a saturated conversion (0x7bff = 65504) marks the row as out of fp16 range
+__device__ __forceinline__ void split8(const float (&v)[8], uint4& hi, uint4& lo, uint32_t& range) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    h[p] = pack_h2(v[2 * p], v[2 * p + 1]);
+    range = __vmaxu2(range, h[p] & 0x7fff7fffu);
+    const float2 f = unpack_h2(h[p]);
+    l[p] = pack_h2((v[2 * p] - f.x) * SPLIT, (v[2 * p + 1] - f.y) * SPLIT);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+template <bool BWD>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_exact_kernel(TxArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int n_rows = a.src.n_rows_dev ? min(*a.src.n_rows_dev, a.src.n_rows) : a.src.n_rows;
+  const int n_tiles = (n_rows + 2 * TROWS - 1) / (2 * TROWS);
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  if (pair >= n_tiles) return;               // both CTAs of the pair leave together, before any allocation
+
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bar0 = sbase + OFF_BAR;
+  auto BAR = [&](int i) { return bar0 + (uint32_t)i * 8u; };
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + OFF_TMEMPTR);
+  int* lst = reinterpret_cast<int*>(smem + OFF_LST);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();
+  constexpr int NG = BWD ? 9 : 5;            // GEMMs per tile
+  constexpr int NST = BWD ? STAGES_BWD : STAGES_FWD;
+
+  if (blockIdx.x == 0 && tid == 0) *a.fix_next = 0;
+  if (warp == W_MMA) {
+    if (lane == 0) {
+      for (int s = 0; s < NSLOT; ++s) {
+        mbar_init(BAR(BAR_FULL + s), 1);     // the loader's expect_tx arrival (+ the bytes)
+        mbar_init(BAR(BAR_PEER + s), 1);     // leader only: the peer's relay
+        mbar_init(BAR(BAR_EMPTY + s), 1);    // tcgen05.commit
+      }
+      mbar_init(BAR(BAR_AREADY), 16);        // leader only: 8 epilogue warps x 2 CTAs
+      mbar_init(BAR(BAR_DFULL), 1);          // tcgen05.commit
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    tmem_alloc_512_2cta(smem_u32((const void*)tmem_ptr_smem));
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  cluster_sync_all();                        // barrier inits visible cluster-wide before any remote arrival
+
+  if (warp < W_MMA) {
+    // =================================== epilogue warps ===================================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(EPI_REGS));
+    const int q4 = warp & 3, h = warp >> 2;
+    const int row = q4 * 32 + lane;                         // row within the CTA's 128 == TMEM lane
+    const uint32_t tD = tmem_base + ((uint32_t)(q4 * 32) << 16);
+    uint8_t* a_hi = smem + OFF_AHI + row * 16;
+    uint8_t* a_lo = smem + OFF_ALO + row * 16;
+    const NetDev& net = a.net;
+    const int d = net.d, nin = net.nin, nenc = net.nenc, O = net.O;
+    uint32_t gcount = 0;                                    // GEMMs whose accumulators this thread has consumed
+
+    auto signal_a = [&]() {                                 // the next A operand (or nothing) is in place
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (a.dbg & 1) mbar_arrive_remote_release(BAR(BAR_AREADY), 0);
+        else mbar_arrive_remote(BAR(BAR_AREADY), 0);
+      }
+    };
+    auto wait_d = [&]() {
+      mbar_wait(BAR(BAR_DFULL), gcount & 1);
+      ++gcount;
+      tc_fence_after();
+    };
+
+    for (int tile = pair; tile < n_tiles; tile += npairs) {
+      const int grow = tile * (2 * TROWS) + (int)rank * TROWS + row;     // global row of this thread
+      float xs[MAXD], sn[MAXD], cs[MAXD];
+      float rad = 0.f;
+      uint32_t mk[4][4];                                    // ReLU masks: layer x 32-column chunk of this thread's half
+      uint32_t range = 0;                                   // largest fp16 magnitude written to the A operand
+      int row_i = 0, row_j = 0;
+      int* ovf = reinterpret_cast<int*>(smem + OFF_OVF);
+      // ---- rows -> encoded inputs [x, sin x, cos x], split, K = 32 (network_macros_mod.py:139-140)
+      if (h == 0) {
+        int i = 0, j = 0;
+        const bool valid = row_lookup(a.src, grow, n_rows, i, j);
+        row_i = i; row_j = j;
+        ovf[row] = 0;
+        const uint4 z4 = make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          *reinterpret_cast<uint4*>(a_hi + ch * A_LBO) = z4;
+          *reinterpret_cast<uint4*>(a_lo + ch * A_LBO) = z4;
+        }
+        auto put = [&](int e, float v) {                  // saturating like split8, and range-checked
+          const uint32_t hh = pack_h2(v, 0.f);
+          const uint32_t ll = pack_h2((v - unpack_h2(hh).x) * SPLIT, 0.f);
+          range = __vmaxu2(range, hh & 0x7fff7fffu);
+          const int off = (e >> 3) * A_LBO + (e & 7) * 2;
+          *reinterpret_cast<uint16_t*>(a_hi + off) = (uint16_t)hh;
+          *reinterpret_cast<uint16_t*>(a_lo + off) = (uint16_t)ll;
+        };
+#pragma unroll
+        for (int c = 0; c < MAXD; ++c) {
+          xs[c] = 0.f; sn[c] = 0.f; cs[c] = 1.f;
+          if (c < d) {
+            const float x = valid ? a.q[(size_t)i * a.q_stride + c] : 0.f;
+            xs[c] = x; sn[c] = sinf(x); cs[c] = cosf(x);
+            put(c, x); put(nin + c, sn[c]); put(2 * nin + c, cs[c]);
+          }
+        }
+        for (int c = d; c < nin; ++c) {
+          const float x = valid ? a.obs[j * 4 + (c - d)] : 0.f;
+          put(c, x); put(nin + c, sinf(x)); put(2 * nin + c, cosf(x));
+        }
+        rad = valid ? a.obs[j * 4 + 3] : 0.f;
+      }
+      signal_a();
+
+      // ---- hidden layers: h = relu(W h + b), masks kept for the backward pass
+#pragma unroll 1
+      for (int l = 0; l < 4; ++l) {
+        wait_d();
+        const float* bl = net.b[l] + 128 * h;
+        const float comp = (a.dbg & 4) ? 0.f : (l == 0 ? COMP_K32 : COMP_K256);
+        uint32_t r1[2][32], r2[2][32];                       // double-buffered: chunk c+1 loads under chunk c's math
+        tmem_ld32(tD + 128 * h, r1[0]);
+        tmem_ld32(tD + 256 + 128 * h, r2[0]);
+        tc_wait_ld();
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (c < 3) {
+            tmem_ld32(tD + 128 * h + 32 * (c + 1), r1[(c + 1) & 1]);
+            tmem_ld32(tD + 256 + 128 * h + 32 * (c + 1), r2[(c + 1) & 1]);
+            if (a.dbg & 2) tc_wait_ld();
+          }
+          uint32_t m = 0;
+#pragma unroll
+          for (int j8 = 0; j8 < 4; ++j8) {
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(bl + 32 * c + 8 * j8));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(bl + 32 * c + 8 * j8 + 4));
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int idx = 8 * j8 + j;
+              const float x = combine(r1[c & 1][idx], r2[c & 1][idx], comp) + bb[j];
+              const bool on = x > 0.f;
+              m |= (on ? 1u : 0u) << idx;
+              v[j] = on ? x : 0.f;
+            }
+            uint4 hi, lo;
+            split8(v, hi, lo, range);
+            const int ch = 16 * h + 4 * c + j8;             // 8-column chunk of the next A operand
+            *reinterpret_cast<uint4*>(a_hi + ch * A_LBO) = hi;
+            *reinterpret_cast<uint4*>(a_lo + ch * A_LBO) = lo;
+          }
+          mk[l][c] = m;
+          if (c < 3) tc_wait_ld();
+        }
+        signal_a();
+      }
+
+      // ---- output layer (no activation): links 0..15 sit in D columns 0..15
+      wait_d();
+      if (h == 0) {
+        uint32_t r1[16], r2[16];
+        tmem_ld16(tD, r1);
+        tmem_ld16(tD + 256, r2);
+        tc_wait_ld();
+        int best = 0;
+        float bv = 0.f, m = 3.0e38f;
+#pragma unroll
+        for (int o = 0; o < 16; ++o) {
+          if (o < O) {
+            const float v = combine(r1[o], r2[o], (a.dbg & 4) ? 0.f : COMP_K256) + __ldg(net.b[4] + o);
+            if (o == 0 || v < bv) { bv = v; best = o; }     // argmin of the RAW output (robot_sdf.py:155)
+            float y = v;                                      // MPPI.py:236-242: /100, minus radius, ignored := 1e6
+            if (net.scale != 1.f) y = y / 100.f;
+            y -= rad;
+            if ((a.ignore_mask >> o) & 1u) y = 1e6f;
+            m = fminf(m, y);
+          }
+        }
+        if (grow < n_rows) {
+          if (a.out_m) a.out_m[grow] = m;
+          if (BWD) {
+            float y = bv;                                     // pass-2 distance of the argmin link (MPPI.py:265-274)
+            if (net.scale != 1.f) y = y / 100.f;
+            a.out_dist[grow] = y - rad;
+          }
+        }
+        if (BWD) lst[row] = best;
+      }
+      if constexpr (BWD) {
+        asm volatile("bar.sync 1, 256;" ::: "memory");      // lst visible to the column-half-1 warps
+        // ---- g4 = W5[l*, :] * s4 from the pre-split table
+        {
+          const int ls = lst[row];
+          const uint4* th = a.w4hi + ls * 32 + 16 * h;
+          const uint4* tl = a.w4lo + ls * 32 + 16 * h;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const uint32_t bits = mk[3][c];
+#pragma unroll
+            for (int j8 = 0; j8 < 4; ++j8) {
+              uint4 hi = __ldg(th + 4 * c + j8), lo = __ldg(tl + 4 * c + j8);
+              const uint32_t b8 = bits >> (8 * j8);
+              const uint32_t m0 = (b8 & 1u) * 0xffffu + ((b8 >> 1) & 1u) * 0xffff0000u;
+              const uint32_t m1 = ((b8 >> 2) & 1u) * 0xffffu + ((b8 >> 3) & 1u) * 0xffff0000u;
+              const uint32_t m2 = ((b8 >> 4) & 1u) * 0xffffu + ((b8 >> 5) & 1u) * 0xffff0000u;
+              const uint32_t m3 = ((b8 >> 6) & 1u) * 0xffffu + ((b8 >> 7) & 1u) * 0xffff0000u;
+              hi.x &= m0; hi.y &= m1; hi.z &= m2; hi.w &= m3;
+              lo.x &= m0; lo.y &= m1; lo.z &= m2; lo.w &= m3;
+              const int ch = 16 * h + 4 * c + j8;
+              *reinterpret_cast<uint4*>(a_hi + ch * A_LBO) = hi;
+              *reinterpret_cast<uint4*>(a_lo + ch * A_LBO) = lo;
+            }
+          }
+        }
+        signal_a();
+
+        // ---- g_{l-1} = (W_l^T g_l) * s_{l-1},  l = 3, 2, 1
+#pragma unroll 1
+        for (int l = 3; l >= 1; --l) {
+          wait_d();
+          uint32_t r1[2][32], r2[2][32];
+          tmem_ld32(tD + 128 * h, r1[0]);
+          tmem_ld32(tD + 256 + 128 * h, r2[0]);
+          tc_wait_ld();
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            if (c < 3) {
+              tmem_ld32(tD + 128 * h + 32 * (c + 1), r1[(c + 1) & 1]);
+              tmem_ld32(tD + 256 + 128 * h + 32 * (c + 1), r2[(c + 1) & 1]);
+              if (a.dbg & 2) tc_wait_ld();
+            }
+            const uint32_t bits = mk[l - 1][c];
+#pragma unroll
+            for (int j8 = 0; j8 < 4; ++j8) {
+              float v[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const int idx = 8 * j8 + j;
+                const float x = combine(r1[c & 1][idx], r2[c & 1][idx], (a.dbg & 4) ? 0.f : COMP_K256);
+                v[j] = ((bits >> idx) & 1u) ? x : 0.f;
+              }
+              uint4 hi, lo;
+              split8(v, hi, lo, range);
+              const int ch = 16 * h + 4 * c + j8;
+              *reinterpret_cast<uint4*>(a_hi + ch * A_LBO) = hi;
+              *reinterpret_cast<uint4*>(a_lo + ch * A_LBO) = lo;
+            }
+            if (c < 3) tc_wait_ld();
+          }
+          signal_a();
+        }
+
+        // ---- a = W_1^T g_1 (N = 32), then the encoding Jacobian dz/dx_c = a[c] + cos(x_c) a[nin+c] - sin(x_c) a[2nin+c]
+        wait_d();
+        if (h == 0) {
+          uint32_t r1[32], r2[32];
+          tmem_ld32(tD, r1);
+          tmem_ld32(tD + 256, r2);
+          tc_wait_ld();
+          float* scr = reinterpret_cast<float*>(smem + OFF_SCRATCH) + row;     // a[e] at scr[e * 128]
+#pragma unroll
+          for (int e = 0; e < 32; ++e) scr[e * TROWS] = combine(r1[e], r2[e], (a.dbg & 4) ? 0.f : COMP_K256);
+          if (grow < n_rows) {
+#pragma unroll
+            for (int c = 0; c < MAXD; ++c)
+              if (c < d)
+                a.out_grad[(size_t)grow * d + c] =
+                    scr[c * TROWS] + cs[c] * scr[(nin + c) * TROWS] - sn[c] * scr[(2 * nin + c) * TROWS];
+          }
+        }
+      }
+      (void)nenc;
+      // ---- rows whose activations or gradients saturated fp16 are handed to the FFMA kernel (launch_exact_fixup)
+      if (((range & 0xffffu) >= 0x7bffu) || ((range >> 16) >= 0x7bffu)) ovf[row] = 1;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (h == 0 && grow < n_rows && ovf[row]) {
+        const int k = atomicAdd(a.fix_count, 1);
+        atomicAdd(a.fix_total, 1);
+        if (k < a.fix_cap) {
+          a.fix_list[k] = row_i;
+          a.fix_list[a.fix_cap + k] = row_j;
+          a.fix_list[2 * a.fix_cap + k] = grow;
+        } else {
+          atomicAdd(a.fix_dropped, 1);
+        }
+      }
+    }
+  } else {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(CTRL_REGS));
+  }
+  if (warp == W_LOAD) {
+    // =================================== weight loader (both CTAs) ===================================
+    const uint8_t* img = rank == 0 ? a.img0 : a.img1;
+    uint32_t n = 0;
+    for (int tile = pair; tile < n_tiles; tile += npairs)
+      for (int s = 0; s < NST; ++s, ++n) {
+        const uint32_t slot = n % NSLOT, use = n / NSLOT;
+        if (lane == 0) {
+          if (use > 0) mbar_wait(BAR(BAR_EMPTY + slot), (use - 1) & 1);
+          uint32_t off, bytes;
+          stage_info(s, off, bytes);
+          mbar_expect_tx(BAR(BAR_FULL + slot), bytes);
+          bulk_g2s(sbase + OFF_RING + slot * SLOT_BYTES, img + off, bytes, BAR(BAR_FULL + slot));
+        }
+        __syncwarp();
+      }
+  } else if (warp == W_MMA && rank == 1) {
+    // =================================== relay (peer CTA): "my half of the stage has landed" ===================
+    uint32_t n = 0;
+    for (int tile = pair; tile < n_tiles; tile += npairs)
+      for (int s = 0; s < NST; ++s, ++n) {
+        const uint32_t slot = n % NSLOT, use = n / NSLOT;
+        if (lane == 0) {
+          mbar_wait(BAR(BAR_FULL + slot), use & 1);
+          mbar_arrive_remote_release(BAR(BAR_PEER + slot), 0);
+        }
+        __syncwarp();
+      }
+  } else if (warp == W_MMA) {
+    // =================================== MMA issuer (leader CTA) ===================================
+    constexpr uint32_t idesc256 = make_idesc_f16(256, 256), idesc32 = make_idesc_f16(256, 32);
+    const uint32_t a_hi = sbase + OFF_AHI, a_lo = sbase + OFF_ALO;
+    uint32_t n = 0, gcount = 0;
+    for (int tile = pair; tile < n_tiles; tile += npairs) {
+#pragma unroll 1
+      for (int g = 0; g < NG; ++g, ++gcount) {
+        const bool small = (g == 4 || g == 8);
+        const int nst = (g == 0 || small) ? 1 : 4;
+        const int ksteps = g == 0 ? 2 : (small ? 16 : 4);
+        const uint32_t b_lbo = small ? 16 * 16 : TROWS * 16;
+        const uint32_t lo_off = (g == 0 || small) ? 8192 : 16384;
+        const uint32_t idesc = small ? idesc32 : idesc256;
+        mbar_wait_cluster(BAR(BAR_AREADY), gcount & 1);
+        tc_fence_after();
+        for (int st = 0; st < nst; ++st, ++n) {
+          const uint32_t slot = n % NSLOT, par = (n / NSLOT) & 1;
+          mbar_wait(BAR(BAR_FULL + slot), par);
+          mbar_wait_cluster(BAR(BAR_PEER + slot), par);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t b_hi = sbase + OFF_RING + slot * SLOT_BYTES, b_lo = b_hi + lo_off;
+            for (int ks = 0; ks < ksteps; ++ks) {
+              const uint32_t ka = (uint32_t)(st * 4 + ks) * 2 * A_LBO, kb = (uint32_t)ks * 2 * b_lbo;
+              const uint64_t adh = make_desc(a_hi + ka, A_LBO), adl = make_desc(a_lo + ka, A_LBO);
+              const uint64_t bdh = make_desc(b_hi + kb, b_lbo), bdl = make_desc(b_lo + kb, b_lbo);
+              const uint32_t acc = (st == 0 && ks == 0) ? 0u : 1u;
+              mma_ss_2cta(tmem_base, adh, bdh, idesc, acc);            // D1 += A_hi B_hi
+              mma_ss_2cta(tmem_base + 256, adh, bdl, idesc, acc);      // D2 += A_hi B_lo
+              mma_ss_2cta(tmem_base + 256, adl, bdh, idesc, 1u);       // D2 += A_lo B_hi
+            }
+            mma_commit_2cta(BAR(BAR_EMPTY + slot));                    // the slot may be refilled (both CTAs)
+            if (st == nst - 1) mma_commit_2cta(BAR(BAR_DFULL));        // the layer's accumulators are complete
+          }
+          __syncwarp();
+        }
+      }
+    }
+  }
+  // ---- teardown
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == W_MMA) {
+    __syncwarp();
+    tmem_free_512_2cta(tmem_base);
+  }
+}
+
+uint16_t f2h(float f) {
+  __half h = __float2half_rn(f);
+  uint16_t u;
+  std::memcpy(&u, &h, 2);
+  return u;
+}
+float h2f(uint16_t u) {
+  __half h;
+  std::memcpy(&h, &u, 2);
+  return __half2float(h);
+}
+// canonical K-major no-swizzle placement of element (n, k) inside a slab of `rows` rows (see tc_ptx.cuh make_desc)
+inline size_t canon(int n, int k, int rows) {
+  return (size_t)(k / 8) * rows * 16 + (size_t)n * 16 + (size_t)(k % 8) * 2;
+}
+
+}  // namespace
+
+int tcx_build_images(dsmppi_ctx* c, const dsmppi_net* net) {
+  c->tcx_blob = nullptr;
+  if (c->nenc > 32 || c->O > 16) return 0;          // layer-1 K and the output N are fixed at 32 / 16: FFMA path only
+  const char* dis = std::getenv("DSMPPI_DISABLE_TC");
+  if (dis && dis[0] == '1') return 0;
+  const size_t total = 2 * IMG_BYTES + W4_TABLE_BYTES;
+  std::vector<uint8_t> host(total, 0);
+  const int nenc = c->nenc, O = c->O;
+  auto put = [&](uint8_t* part_hi, uint8_t* part_lo, size_t off, float w) {
+    const uint16_t hi = f2h(w);
+    const uint16_t lo = f2h((w - h2f(hi)) * 2048.f);
+    std::memcpy(part_hi + off, &hi, 2);
+    std::memcpy(part_lo + off, &lo, 2);
+  };
+  for (int rank = 0; rank < 2; ++rank) {
+    uint8_t* img = host.data() + (size_t)rank * IMG_BYTES;
+    uint32_t off, bytes;
+    // GEMM 0: B[n][k] = W0[n][k], k < nenc
+    stage_info(0, off, bytes);
+    for (int n = 0; n < 128; ++n)
+      for (int k = 0; k < 32; ++k)
+        put(img + off, img + off + 8192, canon(n, k, 128),
+            k < nenc ? net->W_host[0][(size_t)(128 * rank + n) * nenc + k] : 0.f);
+    // GEMMs 1-3 (forward): B[n][k] = W_l[n][k];  GEMMs 5-7 (backward, l = 3, 2, 1): B[n][k] = W_l[k][n]
+    for (int g = 0; g < 3; ++g)
+      for (int j = 0; j < 4; ++j) {
+        stage_info(1 + 4 * g + j, off, bytes);
+        const float* W = net->W_host[1 + g];
+        for (int n = 0; n < 128; ++n)
+          for (int k = 0; k < 64; ++k)
+            put(img + off, img + off + 16384, canon(n, k, 128), W[(size_t)(128 * rank + n) * HID + 64 * j + k]);
+        stage_info(14 + 4 * g + j, off, bytes);
+        const float* Wt = net->W_host[3 - g];
+        for (int n = 0; n < 128; ++n)
+          for (int k = 0; k < 64; ++k)
+            put(img + off, img + off + 16384, canon(n, k, 128), Wt[(size_t)(64 * j + k) * HID + 128 * rank + n]);
+      }
+    // GEMM 4: N = 32 over the pair, links 0..15 on rank 0, padding on rank 1
+    stage_info(13, off, bytes);
+    for (int n = 0; n < 16; ++n)
+      for (int k = 0; k < HID; ++k) {
+        const int o = 16 * rank + n;
+        put(img + off, img + off + 8192, canon(n, k, 16), o < O ? net->W_host[4][(size_t)o * HID + k] : 0.f);
+      }
+    // GEMM 8: a[e] = sum_k g1[k] W0[k][e], e = 16 * rank + n
+    stage_info(26, off, bytes);
+    for (int n = 0; n < 16; ++n)
+      for (int k = 0; k < HID; ++k) {
+        const int e = 16 * rank + n;
+        put(img + off, img + off + 8192, canon(n, k, 16), e < nenc ? net->W_host[0][(size_t)k * nenc + e] : 0.f);
+      }
+  }
+  uint8_t* t_hi = host.data() + 2 * IMG_BYTES;
+  uint8_t* t_lo = t_hi + 16 * HID * 2;
+  for (int o = 0; o < 16; ++o)
+    for (int k = 0; k < HID; ++k)
+      put(t_hi, t_lo, ((size_t)o * HID + k) * 2, o < O ? net->W_host[4][(size_t)o * HID + k] : 0.f);
+  TxImages* t = new TxImages();
+  if (cudaMalloc(reinterpret_cast<void**>(&t->dev), total) != cudaSuccess) {
+    dsmppi_set_error("cudaMalloc(split weight images) failed");
+    delete t;
+    return 1;
+  }
+  CUDA_TRY(cudaMemcpy(t->dev, host.data(), total, cudaMemcpyHostToDevice));
+  c->tcx_blob = t;
+  CUDA_TRY(cudaFuncSetAttribute(tc_exact_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  CUDA_TRY(cudaFuncSetAttribute(tc_exact_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  return 0;
+}
+
+void tcx_free_images(dsmppi_ctx* c) {
+  if (!c->tcx_blob) return;
+  TxImages* t = static_cast<TxImages*>(c->tcx_blob);
+  if (t->dev) cudaFree(t->dev);
+  delete t;
+  c->tcx_blob = nullptr;
+}
+
+int launch_tc_exact(dsmppi_ctx* c, const float* q, int q_stride, const RowSrc& src, uint32_t ignore_mask, float* m_rows,
+                    float* row_dist, float* row_grad, bool bwd, cudaStream_t st) {
+  REQUIRE(c->tcx_blob, "split weight images not built");
+  if (src.n_rows <= 0) return 0;
+  TxImages* t = static_cast<TxImages*>(c->tcx_blob);
+  TxArgs a;
+  a.img0 = t->dev;
+  a.img1 = t->dev + IMG_BYTES;
+  a.w4hi = reinterpret_cast<const uint4*>(t->dev + 2 * IMG_BYTES);
+  a.w4lo = reinterpret_cast<const uint4*>(t->dev + 2 * IMG_BYTES + 16 * HID * 2);
+  a.net = c->net;
+  a.src = src;
+  a.q = q;
+  a.q_stride = q_stride;
+  a.obs = c->obs;
+  a.ignore_mask = ignore_mask;
+  a.out_m = m_rows;
+  a.out_dist = row_dist;
+  a.out_grad = row_grad;
+  // re-scoring list of the rows that leave the fp16 range (normally none): counters[4 + parity] counts this launch's
+  // rows, the kernel zeroes the other one for the next launch
+  size_t need = (size_t)(src.n_rows < (1 << 24) ? src.n_rows : (1 << 24));
+  if (need > c->fix_cap) {
+    if (c->fix_list) CUDA_TRY(cudaFree(c->fix_list));
+    c->fix_list = nullptr;
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c->fix_list), need * 3 * sizeof(int)));
+    c->fix_cap = need;
+  }
+  a.fix_count = c->counters + 4 + c->fix_parity;
+  a.fix_next = c->counters + 4 + (c->fix_parity ^ 1);
+  a.fix_total = c->counters + 6;
+  a.fix_dropped = c->counters + 7;
+  a.fix_list = c->fix_list;
+  a.fix_cap = (int)c->fix_cap;
+  c->fix_parity ^= 1;
+  const char* dbg = std::getenv("DSMPPI_TCX_DEBUG");
+  a.dbg = dbg ? std::atoi(dbg) : 0;
+  const long long tiles = ((long long)src.n_rows + 2 * TROWS - 1) / (2 * TROWS);
+  long long pairs = c->sm_count / 2;
+  if (pairs > tiles) pairs = tiles;
+  if (pairs < 1) pairs = 1;
+  const dim3 grid((unsigned)(2 * pairs));
+  if (bwd) tc_exact_kernel<true><<<grid, NTHREADS, SMEM_BYTES, st>>>(a);
+  else tc_exact_kernel<false><<<grid, NTHREADS, SMEM_BYTES, st>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  c->launches++;
+  // the flagged rows again, in IEEE fp32, written over the tensor-core results
+  RowSrc fix{};
+  fix.mode = ROWS_LIST;
+  fix.M = src.M;
+  fix.K = src.K;
+  fix.n_rows = (int)(src.n_rows < a.fix_cap ? src.n_rows : a.fix_cap);
+  fix.n_rows_dev = a.fix_count;
+  fix.row_sample = c->fix_list;
+  fix.row_obs = c->fix_list + c->fix_cap;
+  fix.out_row = c->fix_list + 2 * c->fix_cap;
+  return launch_exact_fixup(c, q, q_stride, fix, ignore_mask, m_rows, row_dist, row_grad, bwd, st);
+}

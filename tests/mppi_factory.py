@@ -6,6 +6,9 @@ from optimalmodulationds_b200.sdf.robot_sdf import RobotSdfCollisionNet
 from tests.golden_util import full_policy, load_weights
 
 NET_SHAPES = {"planar2": (2, 2), "planar7": (7, 7), "franka": (7, 9)}
+# scoring arithmetic of the objects built below: None = the library default (tensor-core split-fp16 when the network
+# fits), "ffma" = strict IEEE fp32 on the CUDA cores; test modules parametrise it through the `score_mode` fixture
+DEFAULT_SCORE = None
 
 
 def make_net(name):
@@ -27,6 +30,8 @@ def make_mppi(c, device="cpu", H=None, N=None, q_cur=None, pass1="exact", copy_p
     m = MPPI(t(c["q0"]), t(c["qf"]), t(c["dh_params"]), t(c["obs"]), float(c["dt"]), H, N, DS, t(c["dh_a"]), net,
              int(c["K"]))
     m.set_pass1_mode(pass1)
+    if DEFAULT_SCORE is not None:
+        m.set_score_mode(DEFAULT_SCORE)
     m.Policy.p = float(c["p"])
     m.dst_thr = float(c["dst_thr"])
     m.ker_thr = float(c["ker_thr"])
@@ -62,6 +67,8 @@ def make_toy_mppi(c, device="cpu", H=None, N=None, pass1="exact"):
     m = ToyMPPI(t(c["q0"]), t(c["qf"]), torch.zeros(4, 4), t(c["obs"]), float(c["dt"]), H, N, t(c["A"]), 0,
                 make_toy_net(), int(c["K"]))
     m.set_pass1_mode(pass1)
+    if DEFAULT_SCORE is not None:
+        m.set_score_mode(DEFAULT_SCORE)
     m.Policy.p = float(c["p"])
     m.dst_thr = float(c["dst_thr"])
     m.ker_thr = float(c["ker_thr"])

@@ -1,4 +1,6 @@
-"""Aggregates an `ncu --metrics gpu__time_duration.sum --csv` launch list per kernel (share of the captured window)."""
+"""Aggregates an `ncu --metrics gpu__time_duration.sum[,dram__bytes_read.sum,dram__bytes_write.sum] --csv` launch list
+per kernel: launches, average duration, share of the captured window and -- when the DRAM counters were collected --
+average DRAM bytes per launch and the resulting GB/s."""
 import collections
 import csv
 import sys
@@ -6,11 +8,20 @@ import sys
 rows = list(csv.reader(open(sys.argv[1])))
 hdr = [r for r in rows if r and r[0] == "ID"][0]
 data = [r for r in rows if r and r[0].isdigit()]
-ik, iv, ig = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Grid Size")
+ik, iv, ig, im, iu = (hdr.index(k) for k in ("Kernel Name", "Metric Value", "Grid Size", "Metric Name", "Metric Unit"))
+SCALE = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6, "byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 agg = collections.OrderedDict()
 for r in data:
-    agg.setdefault(r[ik][:86], []).append((float(r[iv].replace(",", "")), r[ig]))
-tot = sum(sum(v for v, _ in x) for x in agg.values())
-for k, v in agg.items():
-    s = sum(x for x, _ in v)
-    print(f"{k:88s} n={len(v):3d} avg={s / len(v) / 1e3:9.1f} us share={100 * s / tot:5.1f}% grid={v[0][1]}")
+    e = agg.setdefault(r[ik][:70], {"grid": r[ig], "t": [], "rd": [], "wr": []})
+    v = float(r[iv].replace(",", "")) * SCALE.get(r[iu], 1.0)
+    key = {"gpu__time_duration.sum": "t", "dram__bytes_read.sum": "rd", "dram__bytes_write.sum": "wr"}.get(r[im])
+    if key:
+        e[key].append(v)
+tot = sum(sum(e["t"]) for e in agg.values())
+for k, e in agg.items():
+    n, s = len(e["t"]), sum(e["t"])
+    line = f"{k:72s} n={n:4d} avg={s / n:10.1f} us share={100 * s / tot:5.1f}% grid={e['grid']}"
+    if e["rd"]:
+        b = (sum(e["rd"]) + sum(e["wr"])) / n
+        line += f" dram={b / 1e6:9.2f} MB/launch -> {b / (s / n) / 1e3:7.1f} GB/s"
+    print(line)
