@@ -309,8 +309,9 @@ int dsmppi_score_stats(dsmppi_ctx* ctx, int32_t* mode, int64_t* range_fixup_rows
 int dsmppi_enable_kernel_timing(dsmppi_ctx* ctx, int32_t on);
 int dsmppi_kernel_timing(dsmppi_ctx* ctx, double* pass1_ms_per_launch, int32_t* pass1_launches,
                          double* exact_ms_per_launch, int32_t* exact_launches);
-/* Same, naming the kernel: kind 0 = exact_mlp_kernel (fp32 scoring, one launch per step), 1 = tc_pass1_kernel,
- * 2 = rollout_fused_kernel (one launch per rollout block: all H steps). */
+/* Same, naming the kernel: kind 0 = exact_mlp_kernel (FFMA scoring, one launch per step), 1 = tc_pass1_kernel,
+ * 2 = rollout_fused_kernel (FFMA, one launch per rollout block: all H steps), 3 = tc_exact_kernel (tensor-core
+ * scoring, one launch per step), 4 = tc_exact_kernel in whole-horizon mode (one launch per rollout block). */
 int dsmppi_kernel_timing_ex(dsmppi_ctx* ctx, int32_t* kind, double* ms_per_launch, int32_t* launches);
 
 #ifdef __cplusplus

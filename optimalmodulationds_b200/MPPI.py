@@ -582,7 +582,8 @@ class MPPI:
         """(kernel name, ms per launch, launches) of the dominant kernel in the last rollout."""
         k, ms, n = _capi.C.c_int32(), _capi.C.c_double(), _capi.C.c_int32()
         _capi.check(self._lib.dsmppi_kernel_timing_ex(self._ctx, _capi.C.byref(k), _capi.C.byref(ms), _capi.C.byref(n)))
-        name = {0: 'exact_mlp_kernel', 1: 'tc_pass1_kernel', 2: 'rollout_fused_kernel'}[k.value]
+        name = {0: 'exact_mlp_kernel', 1: 'tc_pass1_kernel', 2: 'rollout_fused_kernel', 3: 'tc_exact_kernel',
+                4: 'tc_exact_kernel<whole horizon>'}[k.value]
         return dict(kernel=name, ms=ms.value, launches=n.value)
 
     def kernel_timing(self):

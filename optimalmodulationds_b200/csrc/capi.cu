@@ -46,7 +46,14 @@ constexpr int WHOLE_M_MAX = 32;  // largest obstacle set a row tile of the whole
 // because differentiating all M pairs instead of the K closest costs up to 1.5x the FLOPs.
 bool use_whole_horizon(const dsmppi_ctx* c, int n) {
   if (!c->fused_rollout || resolved_mode(c) != DSMPPI_PASS1_EXACT_FP32) return false;
-  if (use_tc_scoring(c)) return false;   // the per-step tensor-core launches beat the fused FFMA kernel
+  if (use_tc_scoring(c)) {
+    // tensor-core scoring: a CTA pair holds 2 * (128 / M) samples for the whole horizon.  Worth it while one wave of
+    // pairs covers the batch (the step then costs no launch); with more tiles per pair the per-step launches win,
+    // because their step kernel runs on all SMs instead of 128 / M threads per CTA
+    if (c->M > WHOLE_M_MAX) return false;
+    const long long per_pair = 2LL * (128 / c->M);
+    return (n + per_pair - 1) / per_pair <= c->sm_count / 2;
+  }
   if (c->M <= FUSE_M_MAX) return true;
   return c->M <= WHOLE_M_MAX && n <= 2 * c->sm_count;
 }
@@ -319,18 +326,18 @@ static int distance_pipeline(dsmppi_ctx* c, const float* q, int q_stride, int n,
     // few obstacles: one launch scores AND differentiates every (sample, obstacle) pair
     src.mode = ROWS_DENSE;
     src.n_rows = n * c->M;
-    if (timing_mark(c, 0, st)) return 1;
+    if (timing_mark(c, use_tc_scoring(c) ? 3 : 0, st)) return 1;
     if (launch_exact_fwdbwd(c, q, q_stride, src, ignore_mask, c->m_rows, c->row_dist, c->row_grad, 0, st)) return 1;
-    if (timing_mark(c, 0, st)) return 1;
+    if (timing_mark(c, use_tc_scoring(c) ? 3 : 0, st)) return 1;
     return launch_rank_dense(c, n, K, true, st);
   }
   if (mode == DSMPPI_PASS1_EXACT_FP32) {
     // many obstacles, no tensor-core prefilter: fp32 forward on every pair, then forward + VJP on the K closest
     src.mode = ROWS_DENSE;
     src.n_rows = n * c->M;
-    if (timing_mark(c, 0, st)) return 1;
+    if (timing_mark(c, use_tc_scoring(c) ? 3 : 0, st)) return 1;
     if (launch_exact_forward(c, q, q_stride, src, ignore_mask, c->m_rows, st)) return 1;
-    if (timing_mark(c, 0, st)) return 1;
+    if (timing_mark(c, use_tc_scoring(c) ? 3 : 0, st)) return 1;
     if (launch_rank_dense(c, n, K, false, st)) return 1;
     RowSrc s2{};
     s2.mode = ROWS_SELECTED;
@@ -421,9 +428,10 @@ int dsmppi_rollout(dsmppi_ctx* c, const dsmppi_rollout_args* a, void* stream) {
       REQUIRE(b.n_closest >= 1 && b.n_closest <= MAXK, "n_closest_obs out of range (1..8)");
       REQUIRE(b.n_closest <= c->M, "n_closest_obs exceeds the number of obstacles");
       if (ensure_workspace(c, b.N, c->M)) return 1;
-      if (timing_mark(c, 2, st)) return 1;
-      if (launch_rollout_fused(c, &b, st)) return 1;
-      if (timing_mark(c, 2, st)) return 1;
+      const bool tcx = use_tc_scoring(c);
+      if (timing_mark(c, tcx ? 4 : 2, st)) return 1;
+      if (tcx ? launch_tc_rollout(c, &b, st) : launch_rollout_fused(c, &b, st)) return 1;
+      if (timing_mark(c, tcx ? 4 : 2, st)) return 1;
       continue;
     }
     for (int t = 1; t <= b.H; ++t) {

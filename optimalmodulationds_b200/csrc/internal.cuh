@@ -119,7 +119,8 @@ struct dsmppi_ctx {
   int timing = 0;
   std::vector<cudaEvent_t> ev;        // start/stop pairs around the scoring kernel of each step
   int ev_used = 0;                    // events recorded by the last rollout
-  int ev_kind = 0;                    // 1: tensor-core pass 1, 0: fp32 dense scoring, 2: whole-horizon fused kernel
+  int ev_kind = 0;                    // 0: FFMA dense scoring, 1: tensor-core pass 1, 2: whole-horizon FFMA kernel,
+                                      // 3: tensor-core dense scoring, 4: whole-horizon tensor-core kernel
   int fused_rollout = 1;              // 0 disables the single-launch path (tests compare the two)
 };
 
@@ -142,6 +143,7 @@ int tcx_build_images(dsmppi_ctx* c, const dsmppi_net* net);
 void tcx_free_images(dsmppi_ctx* c);
 int launch_tc_exact(dsmppi_ctx* c, const float* q, int q_stride, const RowSrc& src, uint32_t ignore_mask, float* m_rows,
                     float* row_dist, float* row_grad, bool bwd, cudaStream_t st);
+int launch_tc_rollout(dsmppi_ctx* c, const dsmppi_rollout_args* a, cudaStream_t st);
 inline bool use_tc_scoring(const dsmppi_ctx* c) { return c->tcx_blob && c->score_mode != DSMPPI_SCORE_FFMA; }
 // tc_pass1.cu
 int tc_build_images(dsmppi_ctx* c, const dsmppi_net* net);

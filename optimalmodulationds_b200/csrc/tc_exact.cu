@@ -36,6 +36,8 @@
 #include <vector>
 
 #include "internal.cuh"
+#include "step_device.cuh"
+#include "exact_tile.cuh"
 #include "tc_ptx.cuh"
 
 namespace {
@@ -58,6 +60,52 @@ __device__ __forceinline__ float combine(uint32_t d1, uint32_t d2, float comp) {
   return fmaf(a, comp, fmaf(__uint_as_float(d2), INV_SPLIT, a));
 }
 
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi);
+__device__ __forceinline__ float2 unpack_h2(uint32_t p);
+// packed fp32 pairs (Blackwell fma.rn.f32x2 / add / mul .f32x2): two IEEE operations per issue slot, bit-identical to
+// the scalar forms -- the epilogue is issue-bound, so halving its fp32 instruction count is what shortens it
+__device__ __forceinline__ uint64_t pk2(uint32_t lo, uint32_t hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+__device__ __forceinline__ uint64_t pk2f(float lo, float hi) { return pk2(__float_as_uint(lo), __float_as_uint(hi)); }
+__device__ __forceinline__ void unpk2(uint64_t v, float& lo, float& hi) {
+  uint32_t a, b;
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(a), "=r"(b) : "l"(v));
+  lo = __uint_as_float(a);
+  hi = __uint_as_float(b);
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// D1 + D2 * 2^-11 + D1 * comp for two adjacent columns
+__device__ __forceinline__ uint64_t combine2(uint32_t d1a, uint32_t d1b, uint32_t d2a, uint32_t d2b, float comp) {
+  const uint64_t a = pk2(d1a, d1b);
+  return fma2(a, pk2f(comp, comp), fma2(pk2(d2a, d2b), pk2f(INV_SPLIT, INV_SPLIT), a));
+}
+// two fp32 values -> their fp16 hi pair and scaled fp16 lo pair (the caller tracks the largest |hi| bit pattern: a
+// saturated conversion, 0x7bff = 65504, marks the row as out of fp16 range)
+__device__ __forceinline__ void split2(float v0, float v1, uint32_t& h, uint32_t& l) {
+  h = pack_h2(v0, v1);
+  const float2 f = unpack_h2(h);
+  float l0, l1;
+  unpk2(mul2(add2(pk2f(v0, v1), pk2f(-f.x, -f.y)), pk2f(SPLIT, SPLIT)), l0, l1);
+  l = pack_h2(l0, l1);
+}
+
 // ---- shared-memory map (bytes)
 constexpr int OFF_AHI = 0;                 // 128 rows x 256 K fp16, canonical K-major (32 chunks x 2 KB)
 constexpr int OFF_ALO = 65536;
@@ -68,7 +116,10 @@ enum { BAR_FULL = 0, BAR_PEER = NSLOT, BAR_EMPTY = 2 * NSLOT, BAR_AREADY = 3 * N
 constexpr int OFF_TMEMPTR = OFF_BAR + 96;  // NBAR * 8 = 88, padded
 constexpr int OFF_LST = OFF_TMEMPTR + 16;  // argmin link per row (128 ints)
 constexpr int OFF_OVF = OFF_LST + TROWS * 4;   // "left the fp16 range" flag per row (128 ints)
-constexpr int SMEM_BYTES = OFF_OVF + TROWS * 4;
+constexpr int OFF_FIXN = OFF_OVF + TROWS * 4;   // whole-horizon kernel: flagged rows of this CTA's tile (count + list)
+constexpr int OFF_FIXL = OFF_FIXN + 16;         // (3, 128) ints: samples | obstacles | output rows
+constexpr int SMEM_BYTES = OFF_FIXL + 3 * TROWS * 4;
+static_assert(exact_tile::smem_bytes(32) <= OFF_RING, "the FFMA fallback tile lives in the A operand images");
 constexpr int OFF_SCRATCH = OFF_ALO + 32768;   // final epilogue: a[e][row] fp32 (16 KB) inside the idle A_lo image
 static_assert(NBAR * 8 <= 96, "barrier block");
 static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB shared-memory budget");
@@ -109,6 +160,8 @@ struct TxArgs {
   int* fix_dropped;                          // rows that did not fit fix_list (both reported by dsmppi_score_stats)
   int* fix_list;                             // (3, fix_cap) = [samples | obstacles | output rows]
   int fix_cap;
+  // whole-horizon mode (MODE 2): a CTA owns S = 128 / M samples and all of their (sample, obstacle) rows for all H steps
+  StepArgs sa; int M; int S; float* m_rows; float* row_dist; float* row_grad; int* sel_rows;
   int dbg;                                   // DSMPPI_TCX_DEBUG bits: 1 cluster-scope release arrivals, 2 no load prefetch
 };
 
@@ -135,26 +188,14 @@ __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
 __device__ __forceinline__ float2 unpack_h2(uint32_t p) {
   return __half22float2(*reinterpret_cast<const __half2*>(&p));
 }
-// v[0..8) -> fp16 hi halves and scaled fp16 lo halves, 16 bytes each; `range` keeps the largest |hi| bit pattern
-// seen (per 16-bit lane): a saturated conversion (0x7bff = 65504) marks the row as out of fp16 range
-__device__ __forceinline__ void split8(const float (&v)[8], uint4& hi, uint4& lo, uint32_t& range) {
-  uint32_t h[4], l[4];
-#pragma unroll
-  for (int p = 0; p < 4; ++p) {
-    h[p] = pack_h2(v[2 * p], v[2 * p + 1]);
-    range = __vmaxu2(range, h[p] & 0x7fff7fffu);
-    const float2 f = unpack_h2(h[p]);
-    l[p] = pack_h2((v[2 * p] - f.x) * SPLIT, (v[2 * p + 1] - f.y) * SPLIT);
-  }
-  hi = make_uint4(h[0], h[1], h[2], h[3]);
-  lo = make_uint4(l[0], l[1], l[2], l[3]);
-}
-
-template <bool BWD>
+// MODE 0: forward only, 1: forward + VJP on a list of rows, 2: whole-horizon rollout (forward + VJP + ranking + step, H times)
+template <int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_exact_kernel(TxArgs a) {
+  constexpr bool BWD = MODE >= 1;
   extern __shared__ __align__(1024) uint8_t smem[];
-  const int n_rows = a.src.n_rows_dev ? min(*a.src.n_rows_dev, a.src.n_rows) : a.src.n_rows;
-  const int n_tiles = (n_rows + 2 * TROWS - 1) / (2 * TROWS);
+  const int n_rows = MODE == 2 ? a.sa.N * a.M : (a.src.n_rows_dev ? min(*a.src.n_rows_dev, a.src.n_rows) : a.src.n_rows);
+  const int n_tiles = MODE == 2 ? (a.sa.N + 2 * a.S - 1) / (2 * a.S) : (n_rows + 2 * TROWS - 1) / (2 * TROWS);
+  const int n_steps = MODE == 2 ? a.sa.H : 1;
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
   if (pair >= n_tiles) return;               // both CTAs of the pair leave together, before any allocation
 
@@ -168,7 +209,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_exac
   constexpr int NG = BWD ? 9 : 5;            // GEMMs per tile
   constexpr int NST = BWD ? STAGES_BWD : STAGES_FWD;
 
-  if (blockIdx.x == 0 && tid == 0) *a.fix_next = 0;
+  if (MODE != 2 && blockIdx.x == 0 && tid == 0) *a.fix_next = 0;
   if (warp == W_MMA) {
     if (lane == 0) {
       for (int s = 0; s < NSLOT; ++s) {
@@ -216,18 +257,34 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_exac
       tc_fence_after();
     };
 
-    for (int tile = pair; tile < n_tiles; tile += npairs) {
-      const int grow = tile * (2 * TROWS) + (int)rank * TROWS + row;     // global row of this thread
+    for (int tile = pair; tile < n_tiles; tile += npairs)
+    for (int t = 1; t <= n_steps; ++t) {
+      // global row of this thread: consecutive rows of the list, or (whole-horizon) row j of sample i = dense row i * M + j
+      int grow = tile * (2 * TROWS) + (int)rank * TROWS + row;
+      int til_i = 0, til_j = 0;
+      bool til_valid = false;
+      if (MODE == 2) {
+        const int sl = row / a.M;
+        til_j = row - sl * a.M;
+        til_i = (tile * 2 + (int)rank) * a.S + sl;
+        til_valid = sl < a.S && til_i < a.sa.N;
+        grow = til_valid ? til_i * a.M + til_j : n_rows;
+      }
+      const float* qsrc = MODE == 2 ? a.sa.traj + (size_t)(t - 1) * d : a.q;     // q_prev = all_traj[:, t-1, :]
+      const int qstride = MODE == 2 ? a.sa.H * d : a.q_stride;
+      float* out_m = MODE == 2 ? a.m_rows : a.out_m;
+      float* out_dist = MODE == 2 ? a.row_dist : a.out_dist;
+      float* out_grad = MODE == 2 ? a.row_grad : a.out_grad;
       float xs[MAXD], sn[MAXD], cs[MAXD];
       float rad = 0.f;
-      uint32_t mk[4][4];                                    // ReLU masks: layer x 32-column chunk of this thread's half
+      uint32_t mk[4][4];    // sign bits of the pre-activations (set = ReLU off): layer x 32-column chunk, column 0 in bit 31
       uint32_t range = 0;                                   // largest fp16 magnitude written to the A operand
       int row_i = 0, row_j = 0;
       int* ovf = reinterpret_cast<int*>(smem + OFF_OVF);
       // ---- rows -> encoded inputs [x, sin x, cos x], split, K = 32 (network_macros_mod.py:139-140)
       if (h == 0) {
-        int i = 0, j = 0;
-        const bool valid = row_lookup(a.src, grow, n_rows, i, j);
+        int i = til_i, j = til_j;
+        const bool valid = MODE == 2 ? til_valid : row_lookup(a.src, grow, n_rows, i, j);
         row_i = i; row_j = j;
         ovf[row] = 0;
         const uint4 z4 = make_uint4(0, 0, 0, 0);
@@ -248,7 +305,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_exac
         for (int c = 0; c < MAXD; ++c) {
           xs[c] = 0.f; sn[c] = 0.f; cs[c] = 1.f;
           if (c < d) {
-            const float x = valid ? a.q[(size_t)i * a.q_stride + c] : 0.f;
+            const float x = valid ? qsrc[(size_t)i * qstride + c] : 0.f;
             xs[c] = x; sn[c] = sinf(x); cs[c] = cosf(x);
             put(c, x); put(nin + c, sn[c]); put(2 * nin + c, cs[c]);
           }
@@ -278,26 +335,27 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_exac
             tmem_ld32(tD + 256 + 128 * h + 32 * (c + 1), r2[(c + 1) & 1]);
             if (a.dbg & 2) tc_wait_ld();
           }
-          uint32_t m = 0;
+          uint32_t m = 0;                                   // SIGN bits of the pre-activations, column 0 in bit 31
 #pragma unroll
           for (int j8 = 0; j8 < 4; ++j8) {
             const float4 b0 = __ldg(reinterpret_cast<const float4*>(bl + 32 * c + 8 * j8));
             const float4 b1 = __ldg(reinterpret_cast<const float4*>(bl + 32 * c + 8 * j8 + 4));
             const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-            float v[8];
+            uint32_t hw[4], lw[4];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const int idx = 8 * j8 + j;
-              const float x = combine(r1[c & 1][idx], r2[c & 1][idx], comp) + bb[j];
-              const bool on = x > 0.f;
-              m |= (on ? 1u : 0u) << idx;
-              v[j] = on ? x : 0.f;
+            for (int p = 0; p < 4; ++p) {
+              const int idx = 8 * j8 + 2 * p;
+              float x0, x1;
+              unpk2(add2(combine2(r1[c & 1][idx], r1[c & 1][idx + 1], r2[c & 1][idx], r2[c & 1][idx + 1], comp),
+                         pk2f(bb[2 * p], bb[2 * p + 1])), x0, x1);
+              m = __funnelshift_l(__float_as_uint(x0), m, 1);
+              m = __funnelshift_l(__float_as_uint(x1), m, 1);
+              split2(fmaxf(x0, 0.f), fmaxf(x1, 0.f), hw[p], lw[p]);
+              range = __vmaxu2(range, hw[p]);
             }
-            uint4 hi, lo;
-            split8(v, hi, lo, range);
             const int ch = 16 * h + 4 * c + j8;             // 8-column chunk of the next A operand
-            *reinterpret_cast<uint4*>(a_hi + ch * A_LBO) = hi;
-            *reinterpret_cast<uint4*>(a_lo + ch * A_LBO) = lo;
+            *reinterpret_cast<uint4*>(a_hi + ch * A_LBO) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+            *reinterpret_cast<uint4*>(a_lo + ch * A_LBO) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
           }
           mk[l][c] = m;
           if (c < 3) tc_wait_ld();
@@ -327,11 +385,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_exac
           }
         }
         if (grow < n_rows) {
-          if (a.out_m) a.out_m[grow] = m;
+          if (out_m) out_m[grow] = m;
           if (BWD) {
             float y = bv;                                     // pass-2 distance of the argmin link (MPPI.py:265-274)
             if (net.scale != 1.f) y = y / 100.f;
-            a.out_dist[grow] = y - rad;
+            out_dist[grow] = y - rad;
           }
         }
         if (BWD) lst[row] = best;
@@ -349,11 +407,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_exac
 #pragma unroll
             for (int j8 = 0; j8 < 4; ++j8) {
               uint4 hi = __ldg(th + 4 * c + j8), lo = __ldg(tl + 4 * c + j8);
-              const uint32_t b8 = bits >> (8 * j8);
-              const uint32_t m0 = (b8 & 1u) * 0xffffu + ((b8 >> 1) & 1u) * 0xffff0000u;
-              const uint32_t m1 = ((b8 >> 2) & 1u) * 0xffffu + ((b8 >> 3) & 1u) * 0xffff0000u;
-              const uint32_t m2 = ((b8 >> 4) & 1u) * 0xffffu + ((b8 >> 5) & 1u) * 0xffff0000u;
-              const uint32_t m3 = ((b8 >> 6) & 1u) * 0xffffu + ((b8 >> 7) & 1u) * 0xffff0000u;
+              const uint32_t on = ~(bits >> (24 - 8 * j8));     // column 8 j8 + j of this chunk sits in bit 7 - j
+              const uint32_t m0 = ((on >> 7) & 1u) * 0xffffu + ((on >> 6) & 1u) * 0xffff0000u;
+              const uint32_t m1 = ((on >> 5) & 1u) * 0xffffu + ((on >> 4) & 1u) * 0xffff0000u;
+              const uint32_t m2 = ((on >> 3) & 1u) * 0xffffu + ((on >> 2) & 1u) * 0xffff0000u;
+              const uint32_t m3 = ((on >> 1) & 1u) * 0xffffu + (on & 1u) * 0xffff0000u;
               hi.x &= m0; hi.y &= m1; hi.z &= m2; hi.w &= m3;
               lo.x &= m0; lo.y &= m1; lo.z &= m2; lo.w &= m3;
               const int ch = 16 * h + 4 * c + j8;
@@ -380,20 +438,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_exac
               if (a.dbg & 2) tc_wait_ld();
             }
             const uint32_t bits = mk[l - 1][c];
+            const float comp = (a.dbg & 4) ? 0.f : COMP_K256;
 #pragma unroll
             for (int j8 = 0; j8 < 4; ++j8) {
-              float v[8];
+              uint32_t hw[4], lw[4];
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const int idx = 8 * j8 + j;
-                const float x = combine(r1[c & 1][idx], r2[c & 1][idx], (a.dbg & 4) ? 0.f : COMP_K256);
-                v[j] = ((bits >> idx) & 1u) ? x : 0.f;
+              for (int p = 0; p < 4; ++p) {
+                const int idx = 8 * j8 + 2 * p;
+                float x0, x1;
+                unpk2(combine2(r1[c & 1][idx], r1[c & 1][idx + 1], r2[c & 1][idx], r2[c & 1][idx + 1], comp), x0, x1);
+                x0 = (bits & (0x80000000u >> idx)) ? 0.f : x0;          // ReLU of the forward pass was off
+                x1 = (bits & (0x40000000u >> idx)) ? 0.f : x1;
+                split2(x0, x1, hw[p], lw[p]);
+                range = __vmaxu2(range, hw[p] & 0x7fff7fffu);
               }
-              uint4 hi, lo;
-              split8(v, hi, lo, range);
               const int ch = 16 * h + 4 * c + j8;
-              *reinterpret_cast<uint4*>(a_hi + ch * A_LBO) = hi;
-              *reinterpret_cast<uint4*>(a_lo + ch * A_LBO) = lo;
+              *reinterpret_cast<uint4*>(a_hi + ch * A_LBO) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+              *reinterpret_cast<uint4*>(a_lo + ch * A_LBO) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
             }
             if (c < 3) tc_wait_ld();
           }
@@ -414,25 +475,88 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_exac
 #pragma unroll
             for (int c = 0; c < MAXD; ++c)
               if (c < d)
-                a.out_grad[(size_t)grow * d + c] =
+                out_grad[(size_t)grow * d + c] =
                     scr[c * TROWS] + cs[c] * scr[(nin + c) * TROWS] - sn[c] * scr[(2 * nin + c) * TROWS];
           }
         }
       }
       (void)nenc;
-      // ---- rows whose activations or gradients saturated fp16 are handed to the FFMA kernel (launch_exact_fixup)
+      // ---- rows whose activations or gradients saturated fp16 are handed to the FFMA arithmetic
       if (((range & 0xffffu) >= 0x7bffu) || ((range >> 16) >= 0x7bffu)) ovf[row] = 1;
+      int* fixn = reinterpret_cast<int*>(smem + OFF_FIXN);
+      int* fixl = reinterpret_cast<int*>(smem + OFF_FIXL);
+      if (MODE == 2 && tid == 0) *fixn = 0;
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (h == 0 && grow < n_rows && ovf[row]) {
-        const int k = atomicAdd(a.fix_count, 1);
-        atomicAdd(a.fix_total, 1);
-        if (k < a.fix_cap) {
-          a.fix_list[k] = row_i;
-          a.fix_list[a.fix_cap + k] = row_j;
-          a.fix_list[2 * a.fix_cap + k] = grow;
-        } else {
-          atomicAdd(a.fix_dropped, 1);
+        if (MODE != 2) {                       // device-wide list, re-scored by launch_exact_fixup after this kernel
+          const int k = atomicAdd(a.fix_count, 1);
+          atomicAdd(a.fix_total, 1);
+          if (k < a.fix_cap) {
+            a.fix_list[k] = row_i;
+            a.fix_list[a.fix_cap + k] = row_j;
+            a.fix_list[2 * a.fix_cap + k] = grow;
+          } else {
+            atomicAdd(a.fix_dropped, 1);
+          }
+        } else {                               // this CTA's list, re-scored right here before the step needs the rows
+          const int k = atomicAdd(fixn, 1);
+          atomicAdd(a.fix_total, 1);
+          fixl[k] = row_i;
+          fixl[TROWS + k] = row_j;
+          fixl[2 * TROWS + k] = grow;
         }
+      }
+      if constexpr (MODE == 2) {
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const int nfix = *fixn;
+        if (nfix > 0 && tid < exact_tile::nthreads(8)) {
+          // the FFMA tile of exact_mlp.cu on warps 0-3, its shared memory carved out of the (idle) A operand images
+          exact_tile::TileSmem<8> ts(reinterpret_cast<float*>(smem + OFF_AHI));
+          exact_tile::WeightStream ws;
+          const int passes = (nfix + 31) / 32;
+          exact_tile::stream_begin<true, exact_tile::nthreads(8)>(ws, &a.net, ts.ring, passes);
+          RowSrc fs{};
+          fs.mode = ROWS_LIST;
+          fs.M = a.M;
+          fs.n_rows = nfix;
+          fs.row_sample = fixl;
+          fs.row_obs = fixl + TROWS;
+          fs.out_row = fixl + 2 * TROWS;
+          int stage = 0;
+          for (int r0 = 0; r0 < nfix; r0 += 32) {
+            exact_tile::mlp_tile<true, 8, 8>(a.net, fs, r0, nfix, qsrc, qstride, a.obs, a.ignore_mask, out_m, out_dist,
+                                            out_grad, ts, ws, stage);
+            exact_tile::tile_sync<exact_tile::nthreads(8)>();
+          }
+        }
+        if (nfix > 0) asm volatile("bar.sync 1, 256;" ::: "memory");
+        // ---- one thread per sample: the K closest obstacles, ascending by (masked distance, obstacle index)
+        //      (MPPI.py:243-247), then the modulation / policy / Euler step of step_device.cuh
+        if (tid < a.S) {
+          const int i = (tile * 2 + (int)rank) * a.S + tid;
+          if (i < a.sa.N) {
+            const int K = a.sa.K, M = a.M;
+            const float* mr = a.m_rows + (size_t)i * M;
+            float last_v = -3.4e38f;
+            int last_j = -1;
+            for (int kk = 0; kk < K; ++kk) {
+              float bv = 3.4e38f;
+              int bj = -1;
+              for (int j = 0; j < M; ++j) {
+                const float v = mr[j];
+                const bool after = kk == 0 || v > last_v || (v == last_v && j > last_j);
+                if (after && (bj < 0 || v < bv)) { bv = v; bj = j; }
+              }
+              if (bj < 0) bj = last_j < 0 ? 0 : last_j;
+              a.sel_rows[(size_t)i * K + kk] = i * M + bj;
+              last_v = bv; last_j = bj;
+            }
+            StepArgs st = a.sa;
+            st.t = t;
+            step_sample(st, i);
+          }
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");      // the next state is written before the next encoding reads it
       }
     }
   } else {
@@ -443,6 +567,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_exac
     const uint8_t* img = rank == 0 ? a.img0 : a.img1;
     uint32_t n = 0;
     for (int tile = pair; tile < n_tiles; tile += npairs)
+     for (int t = 1; t <= n_steps; ++t)
       for (int s = 0; s < NST; ++s, ++n) {
         const uint32_t slot = n % NSLOT, use = n / NSLOT;
         if (lane == 0) {
@@ -458,6 +583,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_exac
     // =================================== relay (peer CTA): "my half of the stage has landed" ===================
     uint32_t n = 0;
     for (int tile = pair; tile < n_tiles; tile += npairs)
+     for (int t = 1; t <= n_steps; ++t)
       for (int s = 0; s < NST; ++s, ++n) {
         const uint32_t slot = n % NSLOT, use = n / NSLOT;
         if (lane == 0) {
@@ -471,7 +597,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_exac
     constexpr uint32_t idesc256 = make_idesc_f16(256, 256), idesc32 = make_idesc_f16(256, 32);
     const uint32_t a_hi = sbase + OFF_AHI, a_lo = sbase + OFF_ALO;
     uint32_t n = 0, gcount = 0;
-    for (int tile = pair; tile < n_tiles; tile += npairs) {
+    for (int tile = pair; tile < n_tiles; tile += npairs)
+    for (int t = 1; t <= n_steps; ++t) {
 #pragma unroll 1
       for (int g = 0; g < NG; ++g, ++gcount) {
         const bool small = (g == 4 || g == 8);
@@ -599,8 +726,9 @@ int tcx_build_images(dsmppi_ctx* c, const dsmppi_net* net) {
   }
   CUDA_TRY(cudaMemcpy(t->dev, host.data(), total, cudaMemcpyHostToDevice));
   c->tcx_blob = t;
-  CUDA_TRY(cudaFuncSetAttribute(tc_exact_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-  CUDA_TRY(cudaFuncSetAttribute(tc_exact_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  CUDA_TRY(cudaFuncSetAttribute(tc_exact_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  CUDA_TRY(cudaFuncSetAttribute(tc_exact_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  CUDA_TRY(cudaFuncSetAttribute(tc_exact_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   return 0;
 }
 
@@ -654,8 +782,8 @@ int launch_tc_exact(dsmppi_ctx* c, const float* q, int q_stride, const RowSrc& s
   if (pairs > tiles) pairs = tiles;
   if (pairs < 1) pairs = 1;
   const dim3 grid((unsigned)(2 * pairs));
-  if (bwd) tc_exact_kernel<true><<<grid, NTHREADS, SMEM_BYTES, st>>>(a);
-  else tc_exact_kernel<false><<<grid, NTHREADS, SMEM_BYTES, st>>>(a);
+  if (bwd) tc_exact_kernel<1><<<grid, NTHREADS, SMEM_BYTES, st>>>(a);
+  else tc_exact_kernel<0><<<grid, NTHREADS, SMEM_BYTES, st>>>(a);
   CUDA_TRY(cudaGetLastError());
   c->launches++;
   // the flagged rows again, in IEEE fp32, written over the tensor-core results
@@ -669,4 +797,43 @@ int launch_tc_exact(dsmppi_ctx* c, const float* q, int q_stride, const RowSrc& s
   fix.row_obs = c->fix_list + c->fix_cap;
   fix.out_row = c->fix_list + 2 * c->fix_cap;
   return launch_exact_fixup(c, q, q_stride, fix, ignore_mask, m_rows, row_dist, row_grad, bwd, st);
+}
+
+// whole-horizon rollout in one launch on the tensor cores; the caller has checked M <= 128 / 1 and initialised
+// all_traj[:, 0] (same contract as launch_rollout_fused)
+int launch_tc_rollout(dsmppi_ctx* c, const dsmppi_rollout_args* ra, cudaStream_t st) {
+  REQUIRE(c->tcx_blob, "split weight images not built");
+  REQUIRE(c->M >= 1 && c->M <= TROWS, "whole-horizon tensor-core rollout needs M <= 128");
+  TxImages* t = static_cast<TxImages*>(c->tcx_blob);
+  TxArgs a{};
+  a.img0 = t->dev;
+  a.img1 = t->dev + IMG_BYTES;
+  a.w4hi = reinterpret_cast<const uint4*>(t->dev + 2 * IMG_BYTES);
+  a.w4lo = reinterpret_cast<const uint4*>(t->dev + 2 * IMG_BYTES + 16 * HID * 2);
+  a.net = c->net;
+  a.obs = c->obs;
+  a.ignore_mask = ra->ignored_link_mask;
+  a.sa = make_step_args(c, ra, 0);
+  a.M = c->M;
+  a.S = TROWS / c->M;
+  a.m_rows = c->m_rows;
+  a.row_dist = c->row_dist;
+  a.row_grad = c->row_grad;
+  a.sel_rows = c->sel_rows;
+  a.fix_count = c->counters + 4;
+  a.fix_next = c->counters + 5;
+  a.fix_total = c->counters + 6;
+  a.fix_dropped = c->counters + 7;
+  a.fix_list = nullptr;
+  a.fix_cap = 0;
+  const char* dbg = std::getenv("DSMPPI_TCX_DEBUG");
+  a.dbg = dbg ? std::atoi(dbg) : 0;
+  const long long tiles = ((long long)ra->N + 2 * a.S - 1) / (2 * a.S);
+  long long pairs = c->sm_count / 2;
+  if (pairs > tiles) pairs = tiles;
+  if (pairs < 1) pairs = 1;
+  tc_exact_kernel<2><<<dim3((unsigned)(2 * pairs)), NTHREADS, SMEM_BYTES, st>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  c->launches++;
+  return 0;
 }

@@ -408,10 +408,9 @@ def test_kernel_candidates_vs_reference(tag, factory):
 
 @pytest.mark.parametrize("tag", ["planar2", "planar2_near", "planar2_nk0", "field2", "planar7", "planar7_near"])
 def test_whole_horizon_kernel_is_bitwise_identical_to_per_step_launches(tag, factory, score_mode):
-    """Small obstacle sets are rolled out by ONE launch (rollout_fused_kernel: network tile + ranking + step inside
-    the kernel's own horizon loop); it must reproduce the per-step launch sequence bit for bit."""
-    if score_mode != "ffma":
-        pytest.skip("the whole-horizon kernel is the FFMA path's")
+    """Small obstacle sets are rolled out by ONE launch (rollout_fused_kernel, or tc_exact_kernel in whole-horizon
+    mode: network tile + ranking + step inside the kernel's own horizon loop); it must reproduce the per-step launch
+    sequence of the same scoring arithmetic bit for bit."""
     c = load_npz(f"case_{tag}")
     outs = []
     for whole in (True, False):
