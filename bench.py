@@ -367,8 +367,10 @@ def main():
     peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
     peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (measured)" if peaks else "fallback 1.4 PFLOP/s sustained"
     mode = {0: "exact_fp32", 1: "tc_f16", 2: "tc_bf16"}.get(stats["mode"], str(stats["mode"]))
-    if stats["mode"] == 0:
-        peak_tf, peak_src = 74.0, "FFMA nominal 74 TFLOP/s (fp32 scoring kernel; no tensor cores in this mode)"
+    sstats = mppi.score_stats()
+    tensor_kernel = kern_name.startswith("tc_")
+    if not tensor_kernel:
+        peak_tf, peak_src = 74.0, "FFMA nominal 74 TFLOP/s (IEEE fp32 scoring kernel; no tensor cores in this mode)"
     kern_ms = kt_ms / max(kt_n, 1)
     traffic = None
     try:      # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed ncu capture
@@ -378,10 +380,11 @@ def main():
             traffic = ent["dram_bytes_per_launch"]
     except Exception:  # noqa: BLE001
         pass
-    # algorithmic FLOPs of the dominant kernel: the all-pairs forward (tensor-core prefilter, or the fp32 forward when
-    # M > 16), or forward + input gradient on every pair when few obstacles make one fused fp32 launch cheaper; the
-    # whole-horizon kernel does that for all H steps in one launch
-    if kern_name == "rollout_fused_kernel":
+    # algorithmic FLOPs of the dominant kernel: the all-pairs forward (tensor-core prefilter, or the scoring kernel's
+    # forward when M > 16), or forward + input gradient on every pair when few obstacles make one launch cheaper; the
+    # whole-horizon kernels do that for all H steps in one launch
+    whole = kern_name in ("rollout_fused_kernel", "tc_exact_kernel<whole horizon>")
+    if whole:
         launches_per_iter = max(1, round(kt_n / args.steps))         # > 1 when a huge batch is rolled out in blocks
         flops_per_launch = N * M * (f_fwd + f_bwd) * H / launches_per_iter
     else:
@@ -389,17 +392,28 @@ def main():
         launches_per_step = max(1, round(kt_n / (args.steps * H)))
         flops_per_launch = N * M * f_pair / launches_per_step
     achieved = flops_per_launch / (kern_ms * 1e-3) / 1e12 if kern_ms > 0 else 0.0
-    roofline = dict(bound="tensor", pipe="tcgen05 f16" if stats["mode"] else "fp32 FFMA (compute-bound; no tensor cores)",
-                    kernel=kern_name,
+    pipe = {"tc_pass1_kernel": "tcgen05 f16 (obstacle-ranking prefilter)",
+            "tc_exact_kernel": "tcgen05 f16, split operands: 3 MMAs per algorithmic product sum",
+            "tc_exact_kernel<whole horizon>": "tcgen05 f16, split operands: 3 MMAs per algorithmic product sum"}.get(
+                kern_name, "fp32 FFMA (compute-bound; no tensor cores)")
+    roofline = dict(bound="tensor", pipe=pipe, kernel=kern_name,
                     achieved=achieved, peak=peak_tf, unit="TFLOP/s", frac=achieved / peak_tf, traffic=traffic,
                     peak_source=peak_src, flops_per_launch=flops_per_launch, ms_per_launch=kern_ms, launches_timed=kt_n,
                     share_of_step=kt_ms / args.steps / ms_per_step)
+    if kern_name.startswith("tc_exact"):
+        # fp32-accurate scoring issues three fp16 MMAs per algorithmic multiply-add: its ceiling is a third of the peak
+        roofline["mma_flops_per_algorithmic_flop"] = 3
+        roofline["frac_of_split_ceiling"] = 3 * achieved / peak_tf
     line = dict(metric="mppi_rollout_state_steps_per_sec", value=value, unit="state-steps/s", n_gpus=world,
                 steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=ms_per_step, higher_is_better=True,
-                scaling="weak", vs_baseline=None, dtype="f32 (obstacle-ranking prefilter: f16 tcgen05, f32 accumulate)",
-                data="synthetic", config=dict(config, pass1=mode, rescored_pairs_per_state_step=stats[
-                    "rescored_pairs"] / (N * H), band_overflows=stats["band_overflows"],
-                    flops_per_state_step=f_step),
+                scaling="weak", vs_baseline=None,
+                dtype=("f32 (scoring: split-fp16 tcgen05, fp32 accumulate, fp32-accurate; obstacle-ranking prefilter: "
+                       "f16 tcgen05)" if sstats["mode"] == "tc_split" else
+                       "f32 (IEEE FFMA scoring; obstacle-ranking prefilter: f16 tcgen05, f32 accumulate)"),
+                data="synthetic", config=dict(config, pass1=mode, score=sstats["mode"],
+                                              range_fixup_rows=sstats["range_fixup_rows"],
+                                              rescored_pairs_per_state_step=stats["rescored_pairs"] / (N * H),
+                                              band_overflows=stats["band_overflows"], flops_per_state_step=f_step),
                 clocks=sampler.summary(),
                 e2e=dict(value=e2e_value, unit="state-steps/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                          ms_per_step=float(e_ms), api="dsmppi_iteration_host (C ABI, pinned host buffers)"),

@@ -202,6 +202,9 @@ int dsmppi_ctx_create(dsmppi_ctx** out, const dsmppi_net* net, const float* dh_p
   CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c->upd_partials),
                       (size_t)c->upd_blocks * dsmppi_update_packed_len(NKMAX, MAXD) * sizeof(float)));
   CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c->stats_tmp), 4 * sizeof(float)));
+  CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c->stats_part), 3 * 1024 * sizeof(float)));
+  CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c->stats_ticket), sizeof(unsigned int)));
+  CUDA_TRY(cudaMemset(c->stats_ticket, 0, sizeof(unsigned int)));
   CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c->packed_tmp), dsmppi_update_packed_len(NKMAX, MAXD) * sizeof(float)));
   CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c->counters), 8 * sizeof(int)));
   CUDA_TRY(cudaMemset(c->counters, 0, 8 * sizeof(int)));
@@ -216,7 +219,8 @@ int dsmppi_ctx_destroy(dsmppi_ctx* c) {
   tcx_free_images(c);
   void* ptrs[] = {c->weights_blob, c->seds, c->obs, c->obs_raw, c->obs_enc, c->q_work, c->m_rows, c->mdist, c->enc_q,
                   c->cand_obs, c->cand_cnt, c->row_base, c->row_sample, c->row_obs, c->counters, c->sel, c->fix_list,
-                  c->sel_rows, c->row_dist, c->row_grad, c->dist_tmp, c->grad_tmp, c->upd_partials, c->stats_tmp,
+                  c->sel_rows, c->row_dist, c->row_grad, c->dist_tmp, c->grad_tmp, c->upd_partials, c->stats_tmp, c->stats_part,
+                  c->stats_ticket,
                   c->packed_tmp, c->stage};
   for (void* p : ptrs)
     if (p) cudaFree(p);

@@ -110,6 +110,8 @@ struct dsmppi_ctx {
   // policy-update scratch
   float* upd_partials = nullptr; int upd_blocks = 0;
   float* stats_tmp = nullptr;         // 4 floats
+  float* stats_part = nullptr;        // cost_stats_kernel: (sum, min, argmin) per CTA
+  unsigned int* stats_ticket = nullptr;
   float* packed_tmp = nullptr;
   // host-buffer iteration staging
   float* stage = nullptr; size_t stage_cap = 0;

@@ -523,41 +523,78 @@ __global__ void __launch_bounds__(128) basis_kernel(const float* __restrict__ gr
 // ------------------------------------------------------------------------------------------------
 // Policy update (MPPI.py:331-345, policy.py:88-113) as three reductions
 // ------------------------------------------------------------------------------------------------
-// stats = { sum cost, min cost, argmin, N }.  Single CTA, fixed order => deterministic.
+// stats = { sum cost, min cost, argmin, N }.  Fixed order => deterministic: every CTA reduces a contiguous chunk of
+// samples to (sum, min, argmin) and the last CTA to finish (ticket counter) combines the chunks in index order.
+// HBM-bound: 4 B per sample, read once, coalesced.
+constexpr int STATS_MAX_BLOCKS = 1024;
 __global__ void __launch_bounds__(1024) cost_stats_kernel(const float* __restrict__ cost, int N,
-                                                          float* __restrict__ stats) {
+                                                          float* __restrict__ stats, float* __restrict__ part,
+                                                          unsigned int* __restrict__ ticket) {
   __shared__ float ssum[32], smin[32];
   __shared__ int sidx[32];
+  __shared__ bool last;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nb = gridDim.x;
+  const long long chunk = ((long long)N + nb - 1) / nb;
+  const long long i0 = blockIdx.x * chunk, i1 = min((long long)N, i0 + chunk);
   float s = 0.f, mn = FLT_MAX;
   int mi = 0x7fffffff;
-  for (int i = threadIdx.x; i < N; i += blockDim.x) {
-    const float c = cost[i];
-    s += c;
-    if (c < mn || (c == mn && i < mi)) { mn = c; mi = i; }
-  }
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) {
-    s += __shfl_xor_sync(0xffffffffu, s, off);
-    const float om = __shfl_xor_sync(0xffffffffu, mn, off);
-    const int oi = __shfl_xor_sync(0xffffffffu, mi, off);
-    if (om < mn || (om == mn && oi < mi)) { mn = om; mi = oi; }
-  }
-  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (lane == 0) { ssum[w] = s; smin[w] = mn; sidx[w] = mi; }
-  __syncthreads();
-  if (w == 0) {
-    const int nw = blockDim.x >> 5;
-    s = lane < nw ? ssum[lane] : 0.f;
-    mn = lane < nw ? smin[lane] : FLT_MAX;
-    mi = lane < nw ? sidx[lane] : 0x7fffffff;
+  auto fold = [&](float om, int oi) { if (om < mn || (om == mn && oi < mi)) { mn = om; mi = oi; } };
+  auto block_reduce = [&]() {          // result valid in warp 0
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
       s += __shfl_xor_sync(0xffffffffu, s, off);
       const float om = __shfl_xor_sync(0xffffffffu, mn, off);
       const int oi = __shfl_xor_sync(0xffffffffu, mi, off);
-      if (om < mn || (om == mn && oi < mi)) { mn = om; mi = oi; }
+      fold(om, oi);
     }
-    if (lane == 0) { stats[0] = s; stats[1] = mn; stats[2] = (float)mi; stats[3] = (float)N; }
+    if (lane == 0) { ssum[w] = s; smin[w] = mn; sidx[w] = mi; }
+    __syncthreads();
+    if (w == 0) {
+      const int nw = blockDim.x >> 5;
+      s = lane < nw ? ssum[lane] : 0.f;
+      mn = lane < nw ? smin[lane] : FLT_MAX;
+      mi = lane < nw ? sidx[lane] : 0x7fffffff;
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, off);
+        const float om = __shfl_xor_sync(0xffffffffu, mn, off);
+        const int oi = __shfl_xor_sync(0xffffffffu, mi, off);
+        fold(om, oi);
+      }
+    }
+  };
+  for (long long i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
+    const float c = cost[i];
+    s += c;
+    fold(c, (int)i);
+  }
+  block_reduce();
+  if (nb == 1) {
+    if (threadIdx.x == 0) { stats[0] = s; stats[1] = mn; stats[2] = (float)mi; stats[3] = (float)N; }
+    return;
+  }
+  if (threadIdx.x == 0) {
+    part[3 * blockIdx.x + 0] = s;
+    part[3 * blockIdx.x + 1] = mn;
+    part[3 * blockIdx.x + 2] = __int_as_float(mi);
+    __threadfence();
+    last = atomicAdd(ticket, 1u) == (unsigned)nb - 1;
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  s = 0.f; mn = FLT_MAX; mi = 0x7fffffff;
+  if ((int)threadIdx.x < nb) {                 // nb <= 1024 == blockDim.x: one chunk per thread, combined in index order
+    s = part[3 * threadIdx.x + 0];
+    mn = part[3 * threadIdx.x + 1];
+    mi = __float_as_int(part[3 * threadIdx.x + 2]);
+  }
+  __syncthreads();
+  block_reduce();
+  if (threadIdx.x == 0) {
+    stats[0] = s; stats[1] = mn; stats[2] = (float)mi; stats[3] = (float)N;
+    *ticket = 0;                               // ready for the next launch
   }
 }
 
@@ -568,25 +605,36 @@ struct UpdArgs {
   float* partials;
 };
 
-constexpr int UPD_T = 256;
-constexpr int UPD_E = (1 + NKMAX * (2 * MAXD + 3) + UPD_T - 1) / UPD_T;   // packed elements per thread
+constexpr int UPD_T = 256, UPD_W = UPD_T / 32;
+constexpr int UPD_LMAX = 1 + NKMAX * (2 * MAXD + 3);
+constexpr int UPD_E = (UPD_LMAX + 31) / 32;                                // packed elements per lane
 
 // packed = [ sum w | sum w mu (nk*d) | sum w sigma (nk) | sum w alpha (nk*d) | sum_i max_t kv*act (nk) |
 //            mean_t kv[sample 0] (nk) ],  w = exp(-cost / beta),  beta = mean(cost) / 50
+// A CTA owns a contiguous chunk of samples, a warp takes every 8th sample of it, and the lanes run over the packed
+// elements: the live columns of a sample's (50, d) policy rows are contiguous, so every load is a coalesced segment
+// (the old one-CTA-per-sample walk reached 150 GB/s at 10^6 samples; this one is bandwidth-bound).  Fixed order:
+// per-warp sums over its samples, warps combined in index order, CTAs combined by update_block_sum_kernel.
 __global__ void __launch_bounds__(UPD_T) update_partial_kernel(UpdArgs u) {
-  const int nk = u.nk, d = u.d, H = u.H;
+  __shared__ float red[UPD_W][32 * UPD_E];
+  const int nk = u.nk, d = u.d, H = u.H, L = u.L;
   const int o_mu = 1, o_sg = o_mu + nk * d, o_al = o_sg + nk, o_mx = o_al + nk * d, o_b0 = o_mx + nk;
   const float beta = (u.stats[0] / u.stats[3]) / 50.f;               // MPPI.py:332
   const float nib = -1.f / beta;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long chunk = ((long long)u.N + gridDim.x - 1) / gridDim.x;
+  const long long i0 = blockIdx.x * chunk, i1 = min((long long)u.N, i0 + chunk);
   float acc[UPD_E];
 #pragma unroll
   for (int e = 0; e < UPD_E; ++e) acc[e] = 0.f;
-  for (int i = blockIdx.x; i < u.N; i += gridDim.x) {
+  for (long long i = i0 + warp; i < i1; i += UPD_W) {
     const float w = expf(nib * u.cost[i]);                            // MPPI.py:333
+    const float* kv = u.kval + (size_t)i * H * NKMAX;
+    const float* ac = u.acts + (size_t)i * H;
 #pragma unroll
     for (int e = 0; e < UPD_E; ++e) {
-      const int idx = threadIdx.x + e * UPD_T;
-      if (idx >= u.L) break;
+      const int idx = lane + 32 * e;
+      if (idx >= L) break;
       float val;
       if (idx == 0) val = w;
       else if (idx < o_sg) val = w * u.mu[(size_t)i * NKMAX * d + (idx - o_mu)];
@@ -596,10 +644,11 @@ __global__ void __launch_bounds__(UPD_T) update_partial_kernel(UpdArgs u) {
         const int k = idx - o_mx;
         float mx = -FLT_MAX;
         if (u.variant == 0) {
-          for (int t = 0; t < H; ++t)
-            mx = fmaxf(mx, u.kval[((size_t)i * H + t) * NKMAX + k] * u.acts[(size_t)i * H + t]);   // MPPI.py:336
+#pragma unroll 4
+          for (int t = 0; t < H; ++t) mx = fmaxf(mx, kv[t * NKMAX + k] * ac[t]);                    // MPPI.py:336
         } else {
-          for (int t = 0; t < H; ++t) mx = fmaxf(mx, u.kval[((size_t)i * H + t) * NKMAX + k]);     // MPPI_toy.py:318
+#pragma unroll 4
+          for (int t = 0; t < H; ++t) mx = fmaxf(mx, kv[t * NKMAX + k]);                            // MPPI_toy.py:318
         }
         val = mx;
       } else {
@@ -615,9 +664,13 @@ __global__ void __launch_bounds__(UPD_T) update_partial_kernel(UpdArgs u) {
     }
   }
 #pragma unroll
-  for (int e = 0; e < UPD_E; ++e) {
-    const int idx = threadIdx.x + e * UPD_T;
-    if (idx < u.L) u.partials[(size_t)blockIdx.x * u.L + idx] = acc[e];
+  for (int e = 0; e < UPD_E; ++e) red[warp][lane + 32 * e] = acc[e];
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < L; idx += UPD_T) {
+    float sum = 0.f;
+#pragma unroll
+    for (int w2 = 0; w2 < UPD_W; ++w2) sum += red[w2][idx];
+    u.partials[(size_t)blockIdx.x * L + idx] = sum;
   }
 }
 
@@ -792,7 +845,11 @@ int launch_basis(dsmppi_ctx* c, const float* grad, int64_t n, float* basis, cuda
 }
 
 int launch_cost_stats(dsmppi_ctx* c, const float* cost, int N, float* stats, cudaStream_t st) {
-  cost_stats_kernel<<<1, 1024, 0, st>>>(cost, N, stats);
+  // one CTA per 16 K samples, at most STATS_MAX_BLOCKS; small batches keep the single-CTA latency
+  int blocks = (N + 16383) / 16384;
+  if (blocks > STATS_MAX_BLOCKS) blocks = STATS_MAX_BLOCKS;
+  if (blocks < 1) blocks = 1;
+  cost_stats_kernel<<<blocks, 1024, 0, st>>>(cost, N, stats, c->stats_part, c->stats_ticket);
   LAUNCH_CHECK(c);
   return 0;
 }
@@ -806,7 +863,7 @@ int launch_update_partial(dsmppi_ctx* c, const dsmppi_update_args* a, const floa
   u.mu = a->mu_tmp_dev; u.sigma = a->sigma_tmp_dev; u.alpha = a->alpha_tmp_dev; u.stats = stats;
   u.partials = c->upd_partials;
   int blocks = c->upd_blocks;
-  if (blocks > a->N) blocks = a->N;
+  if (blocks > (a->N + UPD_W - 1) / UPD_W) blocks = (a->N + UPD_W - 1) / UPD_W;     // at least one sample per warp
   if (blocks < 1) blocks = 1;
   update_partial_kernel<<<blocks, UPD_T, 0, st>>>(u);
   LAUNCH_CHECK(c);
