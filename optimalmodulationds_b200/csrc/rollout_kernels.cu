@@ -607,16 +607,19 @@ struct UpdArgs {
 
 constexpr int UPD_T = 256, UPD_W = UPD_T / 32;
 constexpr int UPD_LMAX = 1 + NKMAX * (2 * MAXD + 3);
-constexpr int UPD_E = (UPD_LMAX + 31) / 32;                                // packed elements per lane
+constexpr int UPD_EMAX = (UPD_LMAX + 31) / 32;                             // packed elements per lane, worst case
 
 // packed = [ sum w | sum w mu (nk*d) | sum w sigma (nk) | sum w alpha (nk*d) | sum_i max_t kv*act (nk) |
 //            mean_t kv[sample 0] (nk) ],  w = exp(-cost / beta),  beta = mean(cost) / 50
-// A CTA owns a contiguous chunk of samples, a warp takes every 8th sample of it, and the lanes run over the packed
-// elements: the live columns of a sample's (50, d) policy rows are contiguous, so every load is a coalesced segment
-// (the old one-CTA-per-sample walk reached 150 GB/s at 10^6 samples; this one is bandwidth-bound).  Fixed order:
-// per-warp sums over its samples, warps combined in index order, CTAs combined by update_block_sum_kernel.
+// A CTA owns a contiguous chunk of samples, a warp takes every 8th sample of it (two at a time, so twice the loads
+// are in flight), and the lanes run over the packed elements: the live columns of a sample's (50, d) policy rows are
+// contiguous, so every load is a coalesced segment (the old one-CTA-per-sample walk reached 150 GB/s at 10^6
+// samples).  E = elements per lane is a template parameter so the common small policies (nk = 10) keep the register
+// count, and with it the number of resident warps, where a latency-bound kernel needs them.  Fixed order: per-warp
+// sums over its samples, warps combined in index order, CTAs combined by update_block_sum_kernel.
+template <int E>
 __global__ void __launch_bounds__(UPD_T) update_partial_kernel(UpdArgs u) {
-  __shared__ float red[UPD_W][32 * UPD_E];
+  __shared__ float red[UPD_W][32 * E];
   const int nk = u.nk, d = u.d, H = u.H, L = u.L;
   const int o_mu = 1, o_sg = o_mu + nk * d, o_al = o_sg + nk, o_mx = o_al + nk * d, o_b0 = o_mx + nk;
   const float beta = (u.stats[0] / u.stats[3]) / 50.f;               // MPPI.py:332
@@ -624,47 +627,75 @@ __global__ void __launch_bounds__(UPD_T) update_partial_kernel(UpdArgs u) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long chunk = ((long long)u.N + gridDim.x - 1) / gridDim.x;
   const long long i0 = blockIdx.x * chunk, i1 = min((long long)u.N, i0 + chunk);
-  float acc[UPD_E];
-#pragma unroll
-  for (int e = 0; e < UPD_E; ++e) acc[e] = 0.f;
-  for (long long i = i0 + warp; i < i1; i += UPD_W) {
-    const float w = expf(nib * u.cost[i]);                            // MPPI.py:333
-    const float* kv = u.kval + (size_t)i * H * NKMAX;
+  // Branch-free address selection: the lanes of a warp fall into different segments of the packed vector, and a
+  // divergent if-chain would serialise one DRAM latency per segment (that, not bandwidth, set the pace of the first
+  // version: 5 us per sample pair).  Every lane issues ONE load from its own segment (lane 0 and the max_t / base
+  // lanes re-read the sample's cost as a dummy), all of them before the first use.
+  auto seg_ptr = [&](long long i, int idx) -> const float* {
+    const float* p = u.cost + i;
+    p = (idx >= o_mu && idx < o_sg) ? u.mu + (size_t)i * NKMAX * d + (idx - o_mu) : p;
+    p = (idx >= o_sg && idx < o_al) ? u.sigma + (size_t)i * NKMAX + (idx - o_sg) : p;
+    p = (idx >= o_al && idx < o_mx) ? u.alpha + (size_t)i * NKMAX * d + (idx - o_al) : p;
+    return p;
+  };
+  auto max_t = [&](long long i, int k) -> float {          // max_t kernel_val * activation  (MPPI.py:336)
+    const float* kv = u.kval + (size_t)i * H * NKMAX + k;
     const float* ac = u.acts + (size_t)i * H;
+    float mx = -FLT_MAX;
+    if (u.variant == 0) {
+#pragma unroll 4
+      for (int t = 0; t < H; ++t) mx = fmaxf(mx, kv[t * NKMAX] * ac[t]);
+    } else {
+#pragma unroll 4
+      for (int t = 0; t < H; ++t) mx = fmaxf(mx, kv[t * NKMAX]);                                    // MPPI_toy.py:318
+    }
+    return mx;
+  };
+  auto base_mean = [&](long long i, int k) -> float {      // mean_t kernel_val of the noise-free sample 0  (MPPI.py:341)
+    if (i != 0 || !u.owns0) return 0.f;
+    float sm = 0.f;
+    for (int t = 0; t < H; ++t) sm += u.kval[(size_t)t * NKMAX + k];
+    return sm / (float)H;
+  };
+  auto finish = [&](long long i, int idx, float w, float x) -> float {
+    if (idx == 0) return w;
+    if (idx < o_mx) return w * x;
+    if (idx < o_b0) return max_t(i, idx - o_mx);
+    return base_mean(i, idx - o_b0);
+  };
+  float acc[E];
 #pragma unroll
-    for (int e = 0; e < UPD_E; ++e) {
+  for (int e = 0; e < E; ++e) acc[e] = 0.f;
+  long long i = i0 + warp;
+  for (; i + UPD_W < i1; i += 2 * UPD_W) {
+    const float w0 = expf(nib * u.cost[i]), w1 = expf(nib * u.cost[i + UPD_W]);                      // MPPI.py:333
+    float x0[E], x1[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const int idx = min(lane + 32 * e, L - 1);
+      x0[e] = *seg_ptr(i, idx);
+      x1[e] = *seg_ptr(i + UPD_W, idx);
+    }
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
       const int idx = lane + 32 * e;
-      if (idx >= L) break;
-      float val;
-      if (idx == 0) val = w;
-      else if (idx < o_sg) val = w * u.mu[(size_t)i * NKMAX * d + (idx - o_mu)];
-      else if (idx < o_al) val = w * u.sigma[(size_t)i * NKMAX + (idx - o_sg)];
-      else if (idx < o_mx) val = w * u.alpha[(size_t)i * NKMAX * d + (idx - o_al)];
-      else if (idx < o_b0) {
-        const int k = idx - o_mx;
-        float mx = -FLT_MAX;
-        if (u.variant == 0) {
-#pragma unroll 4
-          for (int t = 0; t < H; ++t) mx = fmaxf(mx, kv[t * NKMAX + k] * ac[t]);                    // MPPI.py:336
-        } else {
-#pragma unroll 4
-          for (int t = 0; t < H; ++t) mx = fmaxf(mx, kv[t * NKMAX + k]);                            // MPPI_toy.py:318
-        }
-        val = mx;
-      } else {
-        val = 0.f;
-        if (i == 0 && u.owns0) {
-          const int k = idx - o_b0;
-          float sm = 0.f;
-          for (int t = 0; t < H; ++t) sm += u.kval[(size_t)t * NKMAX + k];
-          val = sm / (float)H;                                        // MPPI.py:341
-        }
+      if (idx < L) {
+        const float v0 = finish(i, idx, w0, x0[e]), v1 = finish(i + UPD_W, idx, w1, x1[e]);
+        acc[e] += v0;
+        acc[e] += v1;
       }
-      acc[e] += val;
+    }
+  }
+  if (i < i1) {
+    const float w0 = expf(nib * u.cost[i]);
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const int idx = lane + 32 * e;
+      if (idx < L) acc[e] += finish(i, idx, w0, *seg_ptr(i, idx));
     }
   }
 #pragma unroll
-  for (int e = 0; e < UPD_E; ++e) red[warp][lane + 32 * e] = acc[e];
+  for (int e = 0; e < E; ++e) red[warp][lane + 32 * e] = acc[e];
   __syncthreads();
   for (int idx = threadIdx.x; idx < L; idx += UPD_T) {
     float sum = 0.f;
@@ -865,7 +896,9 @@ int launch_update_partial(dsmppi_ctx* c, const dsmppi_update_args* a, const floa
   int blocks = c->upd_blocks;
   if (blocks > (a->N + UPD_W - 1) / UPD_W) blocks = (a->N + UPD_W - 1) / UPD_W;     // at least one sample per warp
   if (blocks < 1) blocks = 1;
-  update_partial_kernel<<<blocks, UPD_T, 0, st>>>(u);
+  if (u.L <= 32 * 3) update_partial_kernel<3><<<blocks, UPD_T, 0, st>>>(u);
+  else if (u.L <= 32 * 6) update_partial_kernel<6><<<blocks, UPD_T, 0, st>>>(u);
+  else update_partial_kernel<UPD_EMAX><<<blocks, UPD_T, 0, st>>>(u);
   LAUNCH_CHECK(c);
   update_block_sum_kernel<<<(u.L + 127) / 128, 128, 0, st>>>(c->upd_partials, blocks, u.L, packed);
   LAUNCH_CHECK(c);

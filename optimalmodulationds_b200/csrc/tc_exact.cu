@@ -162,7 +162,7 @@ struct TxArgs {
   int fix_cap;
   // whole-horizon mode (MODE 2): a CTA owns S = 128 / M samples and all of their (sample, obstacle) rows for all H steps
   StepArgs sa; int M; int S; float* m_rows; float* row_dist; float* row_grad; int* sel_rows;
-  int dbg;                                   // DSMPPI_TCX_DEBUG bits: 1 cluster-scope release arrivals, 2 no load prefetch
+  int dbg;                                   // DSMPPI_TCX_DEBUG=4: no accumulator-truncation compensation (precision tools)
 };
 
 __device__ __forceinline__ bool row_lookup(const RowSrc& s, int r, int n_rows, int& i, int& j) {
@@ -246,10 +246,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_exac
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) {
-        if (a.dbg & 1) mbar_arrive_remote_release(BAR(BAR_AREADY), 0);
-        else mbar_arrive_remote(BAR(BAR_AREADY), 0);
-      }
+      if (lane == 0) mbar_arrive_remote(BAR(BAR_AREADY), 0);
     };
     auto wait_d = [&]() {
       mbar_wait(BAR(BAR_DFULL), gcount & 1);
@@ -333,7 +330,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_exac
           if (c < 3) {
             tmem_ld32(tD + 128 * h + 32 * (c + 1), r1[(c + 1) & 1]);
             tmem_ld32(tD + 256 + 128 * h + 32 * (c + 1), r2[(c + 1) & 1]);
-            if (a.dbg & 2) tc_wait_ld();
           }
           uint32_t m = 0;                                   // SIGN bits of the pre-activations, column 0 in bit 31
 #pragma unroll
@@ -435,8 +431,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_exac
             if (c < 3) {
               tmem_ld32(tD + 128 * h + 32 * (c + 1), r1[(c + 1) & 1]);
               tmem_ld32(tD + 256 + 128 * h + 32 * (c + 1), r2[(c + 1) & 1]);
-              if (a.dbg & 2) tc_wait_ld();
-            }
+              }
             const uint32_t bits = mk[l - 1][c];
             const float comp = (a.dbg & 4) ? 0.f : COMP_K256;
 #pragma unroll

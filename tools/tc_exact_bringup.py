@@ -47,7 +47,7 @@ def main():
         q = ((torch.rand(n, d) * 2 - 1) * 2.5).cuda()
         print(f"{case}: n={n} M={m.obs.shape[0]} K={m.n_closest_obs} pass1={pass1}")
         out = {}
-        for mode in ("ffma", "tc_split", "tc_split:1", "tc_split:2", "tc_split:3"):
+        for mode in ("ffma", "tc_split", "tc_split:4"):       # :4 = DSMPPI_TCX_DEBUG=4, no truncation compensation
             os.environ["DSMPPI_TCX_DEBUG"] = mode.split(":")[1] if ":" in mode else "0"
             m.set_score_mode(mode.split(":")[0])
             dist, grad = m.distance_repulsion_nn(q)
