@@ -29,8 +29,15 @@
 //     warp 8 = TMEM allocator + MMA issuer (leader CTA) / "stage landed" relay (peer CTA); warp 9 = weight loader.
 //   * the output layer (N = 32), the one-hot seed g4 = W5[l*, :] * mask and the final W1^T contraction (N = 32)
 //     plus the encoding Jacobian run in the same pipeline: 9 GEMMs per tile with BWD.
+//   * N-half pipelining: D1 and D2 fill TMEM, so a layer has no second accumulator to drain under the next GEMM.
+//     Every hidden GEMM is therefore issued as two N = 128 halves (same MMA rate: tools/tcx_ss_microbench.cu), each
+//     with its own "accumulator complete" barrier.  The epilogue of half 0 runs under the MMAs of half 1 and keeps its
+//     converted operand in 64 registers until those MMAs (which still read the old A operand) have retired; the
+//     epilogue of half 1 runs under the first K half of the NEXT layer's MMAs, which only need the columns half 0
+//     produced.  Per-element arithmetic (k-order, the three MMAs per step) is unchanged, hence bitwise equal results.
 #include <cuda_fp16.h>
 
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -111,9 +118,14 @@ constexpr int OFF_AHI = 0;                 // 128 rows x 256 K fp16, canonical K
 constexpr int OFF_ALO = 65536;
 constexpr int OFF_RING = 131072;           // NSLOT x 32 KB weight stages
 constexpr int OFF_BAR = OFF_RING + NSLOT * SLOT_BYTES;
-enum { BAR_FULL = 0, BAR_PEER = NSLOT, BAR_EMPTY = 2 * NSLOT, BAR_AREADY = 3 * NSLOT, BAR_DFULL = 3 * NSLOT + 1,
-       NBAR = 3 * NSLOT + 2 };
-constexpr int OFF_TMEMPTR = OFF_BAR + 96;  // NBAR * 8 = 88, padded
+// AREADY0..3: K quarter q (64 columns) of the next A operand is in place (epilogue -> issuer, leader CTA);
+// DFULL0 / DFULL1: accumulator columns of N half 0 / 1 are complete (tcgen05.commit -> epilogue, both CTAs).  One
+// barrier per quarter / half, so that no barrier can run two phases ahead of a waiter.
+// AFREE: the MMAs that read K half 0 of the CURRENT A operand have retired (the first K stage of N half 1 is the last
+// of them), so the parked half-0 columns of the next operand may be stored while N half 1 is still running.
+enum { BAR_FULL = 0, BAR_PEER = NSLOT, BAR_EMPTY = 2 * NSLOT, BAR_AREADY0 = 3 * NSLOT, BAR_DFULL0 = 3 * NSLOT + 4,
+       BAR_DFULL1 = 3 * NSLOT + 5, BAR_AFREE = 3 * NSLOT + 6, NBAR = 3 * NSLOT + 7 };
+constexpr int OFF_TMEMPTR = OFF_BAR + 128;  // NBAR * 8 = 128
 constexpr int OFF_LST = OFF_TMEMPTR + 16;  // argmin link per row (128 ints)
 constexpr int OFF_OVF = OFF_LST + TROWS * 4;   // "left the fp16 range" flag per row (128 ints)
 constexpr int OFF_FIXN = OFF_OVF + TROWS * 4;   // whole-horizon kernel: flagged rows of this CTA's tile (count + list)
@@ -121,23 +133,24 @@ constexpr int OFF_FIXL = OFF_FIXN + 16;         // (3, 128) ints: samples | obst
 constexpr int SMEM_BYTES = OFF_FIXL + 3 * TROWS * 4;
 static_assert(exact_tile::smem_bytes(32) <= OFF_RING, "the FFMA fallback tile lives in the A operand images");
 constexpr int OFF_SCRATCH = OFF_ALO + 32768;   // final epilogue: a[e][row] fp32 (16 KB) inside the idle A_lo image
-static_assert(NBAR * 8 <= 96, "barrier block");
+static_assert(NBAR * 8 <= 128, "barrier block");
 static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB shared-memory budget");
 
-// ---- weight image of one CTA rank: the stages of one pass in issue order
-//   s = 0        GEMM 0  forward layer 1      K = 32   N = 256   16 KB  [hi 8 KB | lo 8 KB]
-//   s = 1..12    GEMM 1-3 forward layers 2-4  K = 64   N = 256   32 KB  [hi 16 KB | lo 16 KB], 4 stages per GEMM
-//   s = 13       GEMM 4  output layer         K = 256  N = 32    16 KB  (16 rows per CTA)
-//   s = 14..25   GEMM 5-7 backward W4^T..W2^T K = 64   N = 256   32 KB
-//   s = 26       GEMM 8  backward W1^T        K = 256  N = 32    16 KB
-constexpr int STAGES_FWD = 14, STAGES_BWD = 27;
+// ---- weight image of one CTA rank: the stages of one pass in issue order.  A hidden GEMM (N = 256 over the pair) is
+// issued as two N = 128 halves x; of half x this CTA holds the 64 output features 128 x + 64 rank + [0, 64).
+//   s = 0, 1     GEMM 0  forward layer 1      K = 32   half x = s             8 KB  [hi 4 KB | lo 4 KB]
+//   s = 2..13    GEMM 1-3 forward layers 2-4  K = 128  (x, K half) = 4 stages 32 KB [hi 16 KB | lo 16 KB] per GEMM
+//   s = 14       GEMM 4  output layer         K = 256  N = 32                 16 KB (16 rows per CTA)
+//   s = 15..26   GEMM 5-7 backward W4^T..W2^T K = 128  (x, K half)            32 KB
+//   s = 27       GEMM 8  backward W1^T        K = 256  N = 32                 16 KB
+constexpr int STAGES_FWD = 15, STAGES_BWD = 28;
 constexpr size_t IMG_BYTES = 16384 + 12 * 32768 + 16384 + 12 * 32768 + 16384;   // 835584
 constexpr size_t W4_TABLE_BYTES = 2 * 16 * HID * 2;                              // [hi | lo] x 16 links x 256 fp16
 __host__ __device__ __forceinline__ void stage_info(int s, uint32_t& off, uint32_t& bytes) {
-  if (s == 0) { off = 0; bytes = 16384; }
-  else if (s <= 12) { off = 16384 + (uint32_t)(s - 1) * 32768; bytes = 32768; }
-  else if (s == 13) { off = 16384 + 12 * 32768; bytes = 16384; }
-  else if (s <= 25) { off = 2 * 16384 + 12 * 32768 + (uint32_t)(s - 14) * 32768; bytes = 32768; }
+  if (s <= 1) { off = (uint32_t)s * 8192; bytes = 8192; }
+  else if (s <= 13) { off = 16384 + (uint32_t)(s - 2) * 32768; bytes = 32768; }
+  else if (s == 14) { off = 16384 + 12 * 32768; bytes = 16384; }
+  else if (s <= 26) { off = 2 * 16384 + 12 * 32768 + (uint32_t)(s - 15) * 32768; bytes = 32768; }
   else { off = 2 * 16384 + 24 * 32768; bytes = 16384; }
 }
 
@@ -163,7 +176,23 @@ struct TxArgs {
   // whole-horizon mode (MODE 2): a CTA owns S = 128 / M samples and all of their (sample, obstacle) rows for all H steps
   StepArgs sa; int M; int S; float* m_rows; float* row_dist; float* row_grad; int* sel_rows;
   int dbg;                                   // DSMPPI_TCX_DEBUG=4: no accumulator-truncation compensation (precision tools)
+  long long* prof;                           // -DDSMPPI_TCX_PROF builds: (event id, clock64) pairs of CTA 0's warps
 };
+
+// Phase accounting (tools/tcx_prof.py): CTA 0's epilogue warps 0 / 4, its MMA issuer and its weight loader stamp
+// (event, clock64) pairs into a.prof -- only in builds with -DDSMPPI_TCX_PROF, the product kernel carries none of it.
+#ifdef DSMPPI_TCX_PROF
+#define TCX_PROF(region, id)                                                         \
+  do {                                                                               \
+    if (a.prof && blockIdx.x == 0 && lane == 0 && pcount < 1000) {                   \
+      a.prof[(region) * 2048 + 2 * pcount] = (id);                                   \
+      a.prof[(region) * 2048 + 2 * pcount + 1] = clock64();                          \
+      ++pcount;                                                                      \
+    }                                                                                \
+  } while (0)
+#else
+#define TCX_PROF(region, id) do { } while (0)
+#endif
 
 __device__ __forceinline__ bool row_lookup(const RowSrc& s, int r, int n_rows, int& i, int& j) {
   if (r >= n_rows) return false;
@@ -188,6 +217,56 @@ __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
 __device__ __forceinline__ float2 unpack_h2(uint32_t p) {
   return __half22float2(*reinterpret_cast<const __half2*>(&p));
 }
+// ---- epilogue building blocks: 32 accumulator columns of one row -> 16 packed hi and 16 packed lo operand words
+// forward: + bias, ReLU, split; returns the SIGN bits of the pre-activations (set = ReLU off), column 0 in bit 31
+__device__ __forceinline__ uint32_t fwd_chunk32(const uint32_t (&r1)[32], const uint32_t (&r2)[32], const float* bias,
+                                                float comp, uint32_t (&hw)[16], uint32_t (&lw)[16], uint32_t& range) {
+  uint32_t m = 0;
+#pragma unroll
+  for (int j8 = 0; j8 < 4; ++j8) {
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + 8 * j8));
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + 8 * j8 + 4));
+    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      const int idx = 8 * j8 + 2 * p;
+      float x0, x1;
+      unpk2(add2(combine2(r1[idx], r1[idx + 1], r2[idx], r2[idx + 1], comp), pk2f(bb[2 * p], bb[2 * p + 1])), x0, x1);
+      m = __funnelshift_l(__float_as_uint(x0), m, 1);
+      m = __funnelshift_l(__float_as_uint(x1), m, 1);
+      split2(fmaxf(x0, 0.f), fmaxf(x1, 0.f), hw[4 * j8 + p], lw[4 * j8 + p]);
+      range = __vmaxu2(range, hw[4 * j8 + p]);
+    }
+  }
+  return m;
+}
+// backward: columns whose forward ReLU was off (bit set in `bits`, column 0 in bit 31) are zeroed, then split
+__device__ __forceinline__ void bwd_chunk32(const uint32_t (&r1)[32], const uint32_t (&r2)[32], uint32_t bits, float comp,
+                                            uint32_t (&hw)[16], uint32_t (&lw)[16], uint32_t& range) {
+#pragma unroll
+  for (int j8 = 0; j8 < 4; ++j8) {
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      const int idx = 8 * j8 + 2 * p;
+      float x0, x1;
+      unpk2(combine2(r1[idx], r1[idx + 1], r2[idx], r2[idx + 1], comp), x0, x1);
+      x0 = (bits & (0x80000000u >> idx)) ? 0.f : x0;
+      x1 = (bits & (0x40000000u >> idx)) ? 0.f : x1;
+      split2(x0, x1, hw[4 * j8 + p], lw[4 * j8 + p]);
+      range = __vmaxu2(range, hw[4 * j8 + p] & 0x7fff7fffu);
+    }
+  }
+}
+// 32 converted columns -> four 8-column chunks (ch0 ..) of this thread's row in the two A images
+__device__ __forceinline__ void store_chunk32(uint8_t* a_hi, uint8_t* a_lo, int ch0, const uint32_t (&hw)[16],
+                                              const uint32_t (&lw)[16]) {
+#pragma unroll
+  for (int j8 = 0; j8 < 4; ++j8) {
+    *reinterpret_cast<uint4*>(a_hi + (ch0 + j8) * A_LBO) = make_uint4(hw[4 * j8], hw[4 * j8 + 1], hw[4 * j8 + 2], hw[4 * j8 + 3]);
+    *reinterpret_cast<uint4*>(a_lo + (ch0 + j8) * A_LBO) = make_uint4(lw[4 * j8], lw[4 * j8 + 1], lw[4 * j8 + 2], lw[4 * j8 + 3]);
+  }
+}
+
 // MODE 0: forward only, 1: forward + VJP on a list of rows, 2: whole-horizon rollout (forward + VJP + ranking + step, H times)
 template <int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_exact_kernel(TxArgs a) {
@@ -206,6 +285,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_exac
   int* lst = reinterpret_cast<int*>(smem + OFF_LST);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = cluster_ctarank();
+  int pcount = 0;
+  (void)pcount;
   constexpr int NG = BWD ? 9 : 5;            // GEMMs per tile
   constexpr int NST = BWD ? STAGES_BWD : STAGES_FWD;
 
@@ -217,8 +298,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_exac
         mbar_init(BAR(BAR_PEER + s), 1);     // leader only: the peer's relay
         mbar_init(BAR(BAR_EMPTY + s), 1);    // tcgen05.commit
       }
-      mbar_init(BAR(BAR_AREADY), 16);        // leader only: 8 epilogue warps x 2 CTAs
-      mbar_init(BAR(BAR_DFULL), 1);          // tcgen05.commit
+      for (int q = 0; q < 4; ++q) mbar_init(BAR(BAR_AREADY0 + q), 16);   // leader only: 8 epilogue warps x 2 CTAs
+      mbar_init(BAR(BAR_DFULL0), 1);         // tcgen05.commit
+      mbar_init(BAR(BAR_DFULL1), 1);
+      mbar_init(BAR(BAR_AFREE), 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
@@ -240,17 +323,30 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_exac
     uint8_t* a_lo = smem + OFF_ALO + row * 16;
     const NetDev& net = a.net;
     const int d = net.d, nin = net.nin, nenc = net.nenc, O = net.O;
-    uint32_t gcount = 0;                                    // GEMMs whose accumulators this thread has consumed
+    uint32_t d0count = 0, d1count = 0, afcount = 0;         // accumulator halves / operand releases this thread has consumed
+    // this thread's columns inside N half x: chunk c = [128 x + 64 c + 32 h, + 32), c = 0, 1 -- interleaved between the
+    // two warps of a lane quarter so that K quarter 2 x + c of the next operand is complete when both have stored chunk c
+    const int cb = 32 * h;
 
-    auto signal_a = [&]() {                                 // the next A operand (or nothing) is in place
+    auto signal_a = [&](int quarter) {                      // K quarter of the next A operand (or nothing) is in place
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_remote(BAR(BAR_AREADY), 0);
+      if (lane == 0) mbar_arrive_remote(BAR(BAR_AREADY0 + quarter), 0);
     };
-    auto wait_d = [&]() {
-      mbar_wait(BAR(BAR_DFULL), gcount & 1);
-      ++gcount;
+    auto wait_d0 = [&]() {
+      mbar_wait(BAR(BAR_DFULL0), d0count & 1);
+      ++d0count;
+      tc_fence_after();
+    };
+    auto wait_d1 = [&]() {
+      mbar_wait(BAR(BAR_DFULL1), d1count & 1);
+      ++d1count;
+      tc_fence_after();
+    };
+    auto wait_afree = [&]() {
+      mbar_wait(BAR(BAR_AFREE), afcount & 1);
+      ++afcount;
       tc_fence_after();
     };
 
@@ -313,54 +409,62 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_exac
         }
         rad = valid ? a.obs[j * 4 + 3] : 0.f;
       }
-      signal_a();
+      signal_a(0);
+      if (q4 == 0) TCX_PROF(h, 1);
 
-      // ---- hidden layers: h = relu(W h + b), masks kept for the backward pass
+      // ---- hidden layers: h = relu(W h + b), masks kept for the backward pass.  N half 0 is converted under the MMAs
+      //      of N half 1 and parked in registers until they retire (they read the operand being replaced); N half 1 is
+      //      converted under the next layer's first K half.  Every 64 finished columns are handed over at once.
 #pragma unroll 1
       for (int l = 0; l < 4; ++l) {
-        wait_d();
-        const float* bl = net.b[l] + 128 * h;
+        const float* bl = net.b[l] + cb;
         const float comp = (a.dbg & 4) ? 0.f : (l == 0 ? COMP_K32 : COMP_K256);
-        uint32_t r1[2][32], r2[2][32];                       // double-buffered: chunk c+1 loads under chunk c's math
-        tmem_ld32(tD + 128 * h, r1[0]);
-        tmem_ld32(tD + 256 + 128 * h, r2[0]);
-        tc_wait_ld();
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          if (c < 3) {
-            tmem_ld32(tD + 128 * h + 32 * (c + 1), r1[(c + 1) & 1]);
-            tmem_ld32(tD + 256 + 128 * h + 32 * (c + 1), r2[(c + 1) & 1]);
+        wait_d0();
+        if (q4 == 0) TCX_PROF(h, 10 + l);
+        {
+          uint32_t hh0[16], hl0[16], hh1[16], hl1[16];
+          {                                                   // one chunk at a time: this half hides under MMAs,
+            uint32_t r1[32], r2[32];                          // registers are what is scarce (64 stay parked)
+            tmem_ld32(tD + cb, r1);
+            tmem_ld32(tD + 256 + cb, r2);
+            tc_wait_ld();
+            mk[l][0] = fwd_chunk32(r1, r2, bl, comp, hh0, hl0, range);
+            tmem_ld32(tD + 64 + cb, r1);
+            tmem_ld32(tD + 320 + cb, r2);
+            tc_wait_ld();
+            mk[l][1] = fwd_chunk32(r1, r2, bl + 64, comp, hh1, hl1, range);
           }
-          uint32_t m = 0;                                   // SIGN bits of the pre-activations, column 0 in bit 31
-#pragma unroll
-          for (int j8 = 0; j8 < 4; ++j8) {
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(bl + 32 * c + 8 * j8));
-            const float4 b1 = __ldg(reinterpret_cast<const float4*>(bl + 32 * c + 8 * j8 + 4));
-            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-            uint32_t hw[4], lw[4];
-#pragma unroll
-            for (int p = 0; p < 4; ++p) {
-              const int idx = 8 * j8 + 2 * p;
-              float x0, x1;
-              unpk2(add2(combine2(r1[c & 1][idx], r1[c & 1][idx + 1], r2[c & 1][idx], r2[c & 1][idx + 1], comp),
-                         pk2f(bb[2 * p], bb[2 * p + 1])), x0, x1);
-              m = __funnelshift_l(__float_as_uint(x0), m, 1);
-              m = __funnelshift_l(__float_as_uint(x1), m, 1);
-              split2(fmaxf(x0, 0.f), fmaxf(x1, 0.f), hw[p], lw[p]);
-              range = __vmaxu2(range, hw[p]);
-            }
-            const int ch = 16 * h + 4 * c + j8;             // 8-column chunk of the next A operand
-            *reinterpret_cast<uint4*>(a_hi + ch * A_LBO) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-            *reinterpret_cast<uint4*>(a_lo + ch * A_LBO) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-          }
-          mk[l][c] = m;
-          if (c < 3) tc_wait_ld();
+          if (q4 == 0) TCX_PROF(h, 20 + l);
+          wait_afree();
+          store_chunk32(a_hi, a_lo, 4 * h, hh0, hl0);
+          signal_a(0);
+          store_chunk32(a_hi, a_lo, 8 + 4 * h, hh1, hl1);
+          signal_a(1);
         }
-        signal_a();
+        if (q4 == 0) TCX_PROF(h, 40 + l);
+        wait_d1();
+        if (q4 == 0) TCX_PROF(h, 30 + l);
+        {
+          uint32_t r1[2][32], r2[2][32], hw[16], lw[16];
+          tmem_ld32(tD + 128 + cb, r1[0]);
+          tmem_ld32(tD + 384 + cb, r2[0]);
+          tc_wait_ld();
+          tmem_ld32(tD + 192 + cb, r1[1]);
+          tmem_ld32(tD + 448 + cb, r2[1]);
+          mk[l][2] = fwd_chunk32(r1[0], r2[0], bl + 128, comp, hw, lw, range);
+          store_chunk32(a_hi, a_lo, 16 + 4 * h, hw, lw);
+          signal_a(2);
+          tc_wait_ld();
+          mk[l][3] = fwd_chunk32(r1[1], r2[1], bl + 192, comp, hw, lw, range);
+          store_chunk32(a_hi, a_lo, 24 + 4 * h, hw, lw);
+        }
+        signal_a(3);
+        if (q4 == 0) TCX_PROF(h, 50 + l);
       }
 
       // ---- output layer (no activation): links 0..15 sit in D columns 0..15
-      wait_d();
+      wait_d0();
+      if (q4 == 0) TCX_PROF(h, 60);
       if (h == 0) {
         uint32_t r1[16], r2[16];
         tmem_ld16(tD, r1);
@@ -392,17 +496,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_exac
       }
       if constexpr (BWD) {
         asm volatile("bar.sync 1, 256;" ::: "memory");      // lst visible to the column-half-1 warps
-        // ---- g4 = W5[l*, :] * s4 from the pre-split table
+        // ---- g4 = W5[l*, :] * s4 from the pre-split table, handed over quarter by quarter
         {
           const int ls = lst[row];
-          const uint4* th = a.w4hi + ls * 32 + 16 * h;
-          const uint4* tl = a.w4lo + ls * 32 + 16 * h;
+          const uint4* th = a.w4hi + ls * 32;
+          const uint4* tl = a.w4lo + ls * 32;
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
+          for (int c = 0; c < 4; ++c) {                       // c = 2 x + chunk: N half x, 32-column chunk of this thread
             const uint32_t bits = mk[3][c];
 #pragma unroll
             for (int j8 = 0; j8 < 4; ++j8) {
-              uint4 hi = __ldg(th + 4 * c + j8), lo = __ldg(tl + 4 * c + j8);
+              const int ch = 8 * c + 4 * h + j8;
+              uint4 hi = __ldg(th + ch), lo = __ldg(tl + ch);
               const uint32_t on = ~(bits >> (24 - 8 * j8));     // column 8 j8 + j of this chunk sits in bit 7 - j
               const uint32_t m0 = ((on >> 7) & 1u) * 0xffffu + ((on >> 6) & 1u) * 0xffff0000u;
               const uint32_t m1 = ((on >> 5) & 1u) * 0xffffu + ((on >> 4) & 1u) * 0xffff0000u;
@@ -410,54 +515,64 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_exac
               const uint32_t m3 = ((on >> 1) & 1u) * 0xffffu + (on & 1u) * 0xffff0000u;
               hi.x &= m0; hi.y &= m1; hi.z &= m2; hi.w &= m3;
               lo.x &= m0; lo.y &= m1; lo.z &= m2; lo.w &= m3;
-              const int ch = 16 * h + 4 * c + j8;
               *reinterpret_cast<uint4*>(a_hi + ch * A_LBO) = hi;
               *reinterpret_cast<uint4*>(a_lo + ch * A_LBO) = lo;
             }
+            signal_a(c);
           }
         }
-        signal_a();
+        if (q4 == 0) TCX_PROF(h, 61);
 
-        // ---- g_{l-1} = (W_l^T g_l) * s_{l-1},  l = 3, 2, 1
+        // ---- g_{l-1} = (W_l^T g_l) * s_{l-1},  l = 3, 2, 1 (same half-by-half schedule as the forward layers)
 #pragma unroll 1
         for (int l = 3; l >= 1; --l) {
-          wait_d();
-          uint32_t r1[2][32], r2[2][32];
-          tmem_ld32(tD + 128 * h, r1[0]);
-          tmem_ld32(tD + 256 + 128 * h, r2[0]);
-          tc_wait_ld();
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            if (c < 3) {
-              tmem_ld32(tD + 128 * h + 32 * (c + 1), r1[(c + 1) & 1]);
-              tmem_ld32(tD + 256 + 128 * h + 32 * (c + 1), r2[(c + 1) & 1]);
-              }
-            const uint32_t bits = mk[l - 1][c];
-            const float comp = (a.dbg & 4) ? 0.f : COMP_K256;
-#pragma unroll
-            for (int j8 = 0; j8 < 4; ++j8) {
-              uint32_t hw[4], lw[4];
-#pragma unroll
-              for (int p = 0; p < 4; ++p) {
-                const int idx = 8 * j8 + 2 * p;
-                float x0, x1;
-                unpk2(combine2(r1[c & 1][idx], r1[c & 1][idx + 1], r2[c & 1][idx], r2[c & 1][idx + 1], comp), x0, x1);
-                x0 = (bits & (0x80000000u >> idx)) ? 0.f : x0;          // ReLU of the forward pass was off
-                x1 = (bits & (0x40000000u >> idx)) ? 0.f : x1;
-                split2(x0, x1, hw[p], lw[p]);
-                range = __vmaxu2(range, hw[p] & 0x7fff7fffu);
-              }
-              const int ch = 16 * h + 4 * c + j8;
-              *reinterpret_cast<uint4*>(a_hi + ch * A_LBO) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-              *reinterpret_cast<uint4*>(a_lo + ch * A_LBO) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+          const float comp = (a.dbg & 4) ? 0.f : COMP_K256;
+          wait_d0();
+          if (q4 == 0) TCX_PROF(h, 14 + l);
+          {
+            uint32_t hh0[16], hl0[16], hh1[16], hl1[16];
+            {
+              uint32_t r1[32], r2[32];
+              tmem_ld32(tD + cb, r1);
+              tmem_ld32(tD + 256 + cb, r2);
+              tc_wait_ld();
+              bwd_chunk32(r1, r2, mk[l - 1][0], comp, hh0, hl0, range);
+              tmem_ld32(tD + 64 + cb, r1);
+              tmem_ld32(tD + 320 + cb, r2);
+              tc_wait_ld();
+              bwd_chunk32(r1, r2, mk[l - 1][1], comp, hh1, hl1, range);
             }
-            if (c < 3) tc_wait_ld();
+            if (q4 == 0) TCX_PROF(h, 24 + l);
+            wait_afree();
+            store_chunk32(a_hi, a_lo, 4 * h, hh0, hl0);
+            signal_a(0);
+            store_chunk32(a_hi, a_lo, 8 + 4 * h, hh1, hl1);
+            signal_a(1);
           }
-          signal_a();
+          if (q4 == 0) TCX_PROF(h, 44 + l);
+          wait_d1();
+          if (q4 == 0) TCX_PROF(h, 34 + l);
+          {
+            uint32_t r1[2][32], r2[2][32], hw[16], lw[16];
+            tmem_ld32(tD + 128 + cb, r1[0]);
+            tmem_ld32(tD + 384 + cb, r2[0]);
+            tc_wait_ld();
+            tmem_ld32(tD + 192 + cb, r1[1]);
+            tmem_ld32(tD + 448 + cb, r2[1]);
+            bwd_chunk32(r1[0], r2[0], mk[l - 1][2], comp, hw, lw, range);
+            store_chunk32(a_hi, a_lo, 16 + 4 * h, hw, lw);
+            signal_a(2);
+            tc_wait_ld();
+            bwd_chunk32(r1[1], r2[1], mk[l - 1][3], comp, hw, lw, range);
+            store_chunk32(a_hi, a_lo, 24 + 4 * h, hw, lw);
+          }
+          signal_a(3);
+          if (q4 == 0) TCX_PROF(h, 54 + l);
         }
 
         // ---- a = W_1^T g_1 (N = 32), then the encoding Jacobian dz/dx_c = a[c] + cos(x_c) a[nin+c] - sin(x_c) a[2nin+c]
-        wait_d();
+        wait_d0();
+        if (q4 == 0) TCX_PROF(h, 62);
         if (h == 0) {
           uint32_t r1[32], r2[32];
           tmem_ld32(tD, r1);
@@ -476,6 +591,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_exac
         }
       }
       (void)nenc;
+      if (q4 == 0) TCX_PROF(h, 63);
       // ---- rows whose activations or gradients saturated fp16 are handed to the FFMA arithmetic
       if (((range & 0xffffu) >= 0x7bffu) || ((range >> 16) >= 0x7bffu)) ovf[row] = 1;
       int* fixn = reinterpret_cast<int*>(smem + OFF_FIXN);
@@ -589,41 +705,93 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_exac
       }
   } else if (warp == W_MMA) {
     // =================================== MMA issuer (leader CTA) ===================================
-    constexpr uint32_t idesc256 = make_idesc_f16(256, 256), idesc32 = make_idesc_f16(256, 32);
+    constexpr uint32_t idesc128 = make_idesc_f16(256, 128), idesc32 = make_idesc_f16(256, 32);
     const uint32_t a_hi = sbase + OFF_AHI, a_lo = sbase + OFF_ALO;
-    uint32_t n = 0, gcount = 0;
+    uint32_t slot = 0, par = 0;                               // ring position of the next weight stage
+    uint32_t acount[4] = {0, 0, 0, 0};                        // phases consumed of the four operand-quarter barriers
+    uint32_t adh, adl, bdh, bdl, b_step, d1, d2, idesc;       // the open stage: operand descriptors (low words)
+    constexpr uint32_t a_step = (2 * A_LBO) >> 4;             // one K = 16 step of the A images
+    // open a weight stage: its descriptors, then "weights landed in both CTAs" -- all of it before the operand wait, so
+    // that nothing but the MMAs themselves follows the moment the epilogue hands a K quarter over
+    auto open_stage = [&](uint32_t d_col, uint32_t a_off, uint32_t b_lbo, uint32_t lo_off, uint32_t id) {
+      const uint32_t b_base = sbase + OFF_RING + slot * SLOT_BYTES;
+      adh = make_desc_lo(a_hi + a_off, A_LBO); adl = make_desc_lo(a_lo + a_off, A_LBO);
+      bdh = make_desc_lo(b_base, b_lbo); bdl = make_desc_lo(b_base + lo_off, b_lbo);
+      b_step = (2 * b_lbo) >> 4;
+      d1 = tmem_base + d_col; d2 = tmem_base + 256 + d_col;
+      idesc = id;
+      mbar_wait(BAR(BAR_FULL + slot), par);
+      mbar_wait_cluster(BAR(BAR_PEER + slot), par);
+      TCX_PROF(2, 100 + (int)d_col + (a_off ? 1 : 0));       // weights landed
+    };
+    auto wait_a = [&](int q) {                                // K quarter q of the operand is in place
+      mbar_wait_cluster(BAR(BAR_AREADY0 + q), acount[q]++ & 1);
+      TCX_PROF(2, 92 + q);
+    };
+    auto steps = [&](int nks, bool first) {                   // nks K = 16 steps of the MMA triple
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll 2
+        for (int ks = 0; ks < nks; ++ks) {
+          const uint32_t acc = (first && ks == 0) ? 0u : 1u;
+          mma_ss_2cta_lo(d1, adh, bdh, idesc, acc);          // D1 += A_hi B_hi
+          mma_ss_2cta_lo(d2, adh, bdl, idesc, acc);          // D2 += A_hi B_lo
+          mma_ss_2cta_lo(d2, adl, bdh, idesc, 1u);           // D2 += A_lo B_hi
+          adh += a_step; adl += a_step; bdh += b_step; bdl += b_step;
+        }
+      }
+      __syncwarp();
+    };
+    auto close_stage = [&](int commit_d) {                    // commit_d: 0 / 1 = this stage completes N half 0 / 1, 2 = AFREE
+      if (elect_one()) {
+        mma_commit_2cta(BAR(BAR_EMPTY + slot));              // the slot may be refilled (both CTAs)
+        if (commit_d == 0) mma_commit_2cta(BAR(BAR_DFULL0)); // N half 0 (or a small GEMM) is complete
+        if (commit_d == 1) mma_commit_2cta(BAR(BAR_DFULL1));
+        if (commit_d == 2) mma_commit_2cta(BAR(BAR_AFREE));  // last reader of the operand's K half 0
+      }
+      __syncwarp();
+      if (++slot == NSLOT) { slot = 0; par ^= 1; }
+    };
+    constexpr uint32_t KHALF = 8 * 2 * A_LBO;                 // byte offset of K = 128 in the A images
     for (int tile = pair; tile < n_tiles; tile += npairs)
     for (int t = 1; t <= n_steps; ++t) {
 #pragma unroll 1
-      for (int g = 0; g < NG; ++g, ++gcount) {
-        const bool small = (g == 4 || g == 8);
-        const int nst = (g == 0 || small) ? 1 : 4;
-        const int ksteps = g == 0 ? 2 : (small ? 16 : 4);
-        const uint32_t b_lbo = small ? 16 * 16 : TROWS * 16;
-        const uint32_t lo_off = (g == 0 || small) ? 8192 : 16384;
-        const uint32_t idesc = small ? idesc32 : idesc256;
-        mbar_wait_cluster(BAR(BAR_AREADY), gcount & 1);
-        tc_fence_after();
-        for (int st = 0; st < nst; ++st, ++n) {
-          const uint32_t slot = n % NSLOT, par = (n / NSLOT) & 1;
-          mbar_wait(BAR(BAR_FULL + slot), par);
-          mbar_wait_cluster(BAR(BAR_PEER + slot), par);
-          tc_fence_after();
-          if (elect_one()) {
-            const uint32_t b_hi = sbase + OFF_RING + slot * SLOT_BYTES, b_lo = b_hi + lo_off;
-            for (int ks = 0; ks < ksteps; ++ks) {
-              const uint32_t ka = (uint32_t)(st * 4 + ks) * 2 * A_LBO, kb = (uint32_t)ks * 2 * b_lbo;
-              const uint64_t adh = make_desc(a_hi + ka, A_LBO), adl = make_desc(a_lo + ka, A_LBO);
-              const uint64_t bdh = make_desc(b_hi + kb, b_lbo), bdl = make_desc(b_lo + kb, b_lbo);
-              const uint32_t acc = (st == 0 && ks == 0) ? 0u : 1u;
-              mma_ss_2cta(tmem_base, adh, bdh, idesc, acc);            // D1 += A_hi B_hi
-              mma_ss_2cta(tmem_base + 256, adh, bdl, idesc, acc);      // D2 += A_hi B_lo
-              mma_ss_2cta(tmem_base + 256, adl, bdh, idesc, 1u);       // D2 += A_lo B_hi
-            }
-            mma_commit_2cta(BAR(BAR_EMPTY + slot));                    // the slot may be refilled (both CTAs)
-            if (st == nst - 1) mma_commit_2cta(BAR(BAR_DFULL));        // the layer's accumulators are complete
-          }
+      for (int g = 0; g < NG; ++g) {
+        if (g == 0) {                          // K = 32: one stage per N half, operand (the encoding) in one piece
+          open_stage(0, 0, 64 * 16, 4096, idesc128);
+          wait_a(0);
+          steps(2, true);
+          close_stage(0);
+          open_stage(128, 0, 64 * 16, 4096, idesc128);
+          steps(2, true);
+          if (elect_one()) mma_commit_2cta(BAR(BAR_AFREE));
           __syncwarp();
+          close_stage(1);
+        } else if (g == 4 || g == 8) {         // N = 32, K = 256: one stage, issued quarter by quarter as the operand lands
+          open_stage(0, 0, 16 * 16, 8192, idesc32);
+          wait_a(0); steps(4, true);
+          wait_a(1); steps(4, false);
+          wait_a(2); steps(4, false);
+          wait_a(3); steps(4, false);
+          close_stage(0);
+        } else {
+          // N half 0 follows the operand quarter by quarter: quarters 0, 1 are the previous layer's half-0 epilogue
+          // (parked, stored when that layer's MMAs retired), quarters 2, 3 its half-1 epilogue, whose accumulator
+          // columns N half 1 of this layer then overwrites
+          open_stage(0, 0, 64 * 16, 16384, idesc128);
+          wait_a(0); steps(4, true);
+          wait_a(1); steps(4, false);
+          close_stage(-1);
+          open_stage(0, KHALF, 64 * 16, 16384, idesc128);
+          wait_a(2); steps(4, false);
+          wait_a(3); steps(4, false);
+          close_stage(0);
+          open_stage(128, 0, 64 * 16, 16384, idesc128);
+          steps(8, true);
+          close_stage(2);
+          open_stage(128, KHALF, 64 * 16, 16384, idesc128);
+          steps(8, false);
+          close_stage(1);
         }
       }
     }
@@ -673,35 +841,41 @@ int tcx_build_images(dsmppi_ctx* c, const dsmppi_net* net) {
   for (int rank = 0; rank < 2; ++rank) {
     uint8_t* img = host.data() + (size_t)rank * IMG_BYTES;
     uint32_t off, bytes;
-    // GEMM 0: B[n][k] = W0[n][k], k < nenc
-    stage_info(0, off, bytes);
-    for (int n = 0; n < 128; ++n)
-      for (int k = 0; k < 32; ++k)
-        put(img + off, img + off + 8192, canon(n, k, 128),
-            k < nenc ? net->W_host[0][(size_t)(128 * rank + n) * nenc + k] : 0.f);
-    // GEMMs 1-3 (forward): B[n][k] = W_l[n][k];  GEMMs 5-7 (backward, l = 3, 2, 1): B[n][k] = W_l[k][n]
+    // GEMM 0: B[n][k] = W0[n][k], k < nenc; N half x, this rank's 64 features
+    for (int x = 0; x < 2; ++x) {
+      stage_info(x, off, bytes);
+      for (int n = 0; n < 64; ++n)
+        for (int k = 0; k < 32; ++k)
+          put(img + off, img + off + 4096, canon(n, k, 64),
+              k < nenc ? net->W_host[0][(size_t)(128 * x + 64 * rank + n) * nenc + k] : 0.f);
+    }
+    // GEMMs 1-3 (forward): B[n][k] = W_l[n][k];  GEMMs 5-7 (backward, l = 3, 2, 1): B[n][k] = W_l[k][n];
+    // stage (x, kh) = N half x, K half kh
     for (int g = 0; g < 3; ++g)
-      for (int j = 0; j < 4; ++j) {
-        stage_info(1 + 4 * g + j, off, bytes);
-        const float* W = net->W_host[1 + g];
-        for (int n = 0; n < 128; ++n)
-          for (int k = 0; k < 64; ++k)
-            put(img + off, img + off + 16384, canon(n, k, 128), W[(size_t)(128 * rank + n) * HID + 64 * j + k]);
-        stage_info(14 + 4 * g + j, off, bytes);
-        const float* Wt = net->W_host[3 - g];
-        for (int n = 0; n < 128; ++n)
-          for (int k = 0; k < 64; ++k)
-            put(img + off, img + off + 16384, canon(n, k, 128), Wt[(size_t)(64 * j + k) * HID + 128 * rank + n]);
-      }
+      for (int x = 0; x < 2; ++x)
+        for (int kh = 0; kh < 2; ++kh) {
+          stage_info(2 + 4 * g + 2 * x + kh, off, bytes);
+          const float* W = net->W_host[1 + g];
+          for (int n = 0; n < 64; ++n)
+            for (int k = 0; k < 128; ++k)
+              put(img + off, img + off + 16384, canon(n, k, 64),
+                  W[(size_t)(128 * x + 64 * rank + n) * HID + 128 * kh + k]);
+          stage_info(15 + 4 * g + 2 * x + kh, off, bytes);
+          const float* Wt = net->W_host[3 - g];
+          for (int n = 0; n < 64; ++n)
+            for (int k = 0; k < 128; ++k)
+              put(img + off, img + off + 16384, canon(n, k, 64),
+                  Wt[(size_t)(128 * kh + k) * HID + 128 * x + 64 * rank + n]);
+        }
     // GEMM 4: N = 32 over the pair, links 0..15 on rank 0, padding on rank 1
-    stage_info(13, off, bytes);
+    stage_info(14, off, bytes);
     for (int n = 0; n < 16; ++n)
       for (int k = 0; k < HID; ++k) {
         const int o = 16 * rank + n;
         put(img + off, img + off + 8192, canon(n, k, 16), o < O ? net->W_host[4][(size_t)o * HID + k] : 0.f);
       }
     // GEMM 8: a[e] = sum_k g1[k] W0[k][e], e = 16 * rank + n
-    stage_info(26, off, bytes);
+    stage_info(27, off, bytes);
     for (int n = 0; n < 16; ++n)
       for (int k = 0; k < HID; ++k) {
         const int e = 16 * rank + n;
@@ -772,6 +946,17 @@ int launch_tc_exact(dsmppi_ctx* c, const float* q, int q_stride, const RowSrc& s
   c->fix_parity ^= 1;
   const char* dbg = std::getenv("DSMPPI_TCX_DEBUG");
   a.dbg = dbg ? std::atoi(dbg) : 0;
+  a.prof = nullptr;
+#ifdef DSMPPI_TCX_PROF
+  static long long* prof_buf = nullptr;
+  const char* prof_out = std::getenv("DSMPPI_TCX_PROF_OUT");
+  if (prof_out && src.n_rows >= 100000) {
+    if (!prof_buf) CUDA_TRY(cudaMallocManaged(reinterpret_cast<void**>(&prof_buf), 4 * 2048 * sizeof(long long)));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    std::memset(prof_buf, 0, 4 * 2048 * sizeof(long long));
+    a.prof = prof_buf;
+  }
+#endif
   const long long tiles = ((long long)src.n_rows + 2 * TROWS - 1) / (2 * TROWS);
   long long pairs = c->sm_count / 2;
   if (pairs > tiles) pairs = tiles;
@@ -781,6 +966,15 @@ int launch_tc_exact(dsmppi_ctx* c, const float* q, int q_stride, const RowSrc& s
   else tc_exact_kernel<0><<<grid, NTHREADS, SMEM_BYTES, st>>>(a);
   CUDA_TRY(cudaGetLastError());
   c->launches++;
+#ifdef DSMPPI_TCX_PROF
+  if (a.prof) {
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (FILE* f = std::fopen(prof_out, "wb")) {
+      std::fwrite(prof_buf, sizeof(long long), 4 * 2048, f);
+      std::fclose(f);
+    }
+  }
+#endif
   // the flagged rows again, in IEEE fp32, written over the tensor-core results
   RowSrc fix{};
   fix.mode = ROWS_LIST;

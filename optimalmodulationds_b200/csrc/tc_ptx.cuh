@@ -147,6 +147,26 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_b
   const uint32_t hi = (128u >> 4) | (1u << 14);
   return ((uint64_t)hi << 32) | lo;
 }
+// the same descriptor as two 32-bit words: the low word carries the address and LBO (advancing the operand by `bytes`
+// adds bytes >> 4 to it), the high word is the constant SBO / version part
+__device__ __forceinline__ uint32_t make_desc_lo(uint32_t smem_addr, uint32_t lbo_bytes) {
+  return ((smem_addr >> 4) & 0x3FFF) | (((lbo_bytes >> 4) & 0x3FFF) << 16);
+}
+constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);
+// the issuer's form of mma_ss_2cta: descriptors assembled inside the asm block from their low words, so the compiler
+// has no 64-bit descriptor tables to precompute (and spill) ahead of the first MMA of a stage
+__device__ __forceinline__ void mma_ss_2cta_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 ad, bd;\n\t"
+      "mov.b64 ad, {%1, %5};\n\t"
+      "mov.b64 bd, {%2, %5};\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], ad, bd, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "n"(DESC_HI)
+      : "memory");
+}
+
 // kind::f16 instruction descriptor: fp16 A and B (K-major), fp32 accumulate, dense
 __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
   return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
