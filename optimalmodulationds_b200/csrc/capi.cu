@@ -2,6 +2,7 @@
 // one rollout: per step  [tensor-core prefilter -> candidate band ->] fp32 scoring -> ranking ->
 // fp32 forward+VJP on the K closest -> modulation/integration step.  Everything is stream-ordered; the
 // host never waits inside the horizon loop.
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -225,6 +226,9 @@ int dsmppi_ctx_destroy(dsmppi_ctx* c) {
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
+  for (cudaEvent_t e : c->pipe_ev) cudaEventDestroy(e);
+  if (c->s_in) cudaStreamDestroy(c->s_in);
+  if (c->s_out) cudaStreamDestroy(c->s_out);
   delete c;
   return 0;
 }
@@ -392,8 +396,10 @@ int dsmppi_rollout(dsmppi_ctx* c, const dsmppi_rollout_args* a, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   CUDA_TRY(cudaSetDevice(c->device));
   REQUIRE(c->M >= 1, "obstacles not set");
-  c->ev_used = 0;
-  CUDA_TRY(cudaMemsetAsync(c->counters + 1, 0, 3 * sizeof(int), st));
+  if (!c->keep_counters) {
+    c->ev_used = 0;
+    CUDA_TRY(cudaMemsetAsync(c->counters + 1, 0, 3 * sizeof(int), st));
+  }
   const int d = c->d;
   // Samples never interact, so a very large batch is rolled out in blocks of samples: it bounds the workspace
   // (the (n, M) prefilter matrix is the big one: <= 1 GiB) and keeps every row index inside 31 bits.
@@ -578,8 +584,15 @@ int dsmppi_iteration_host(dsmppi_ctx* c, dsmppi_iteration_host_args* h, void* st
     d2h += (int64_t)(n * sizeof(float));
     return cudaMemcpyAsync(dst, S + o, n * sizeof(float), cudaMemcpyDeviceToHost, st);
   };
-  CUDA_TRY(up(o_q, h->q_cur_host, r.q_cur_is_batch ? N * d : d));
-  if (nk > 0) {
+  // A batch of more than two chunks is pipelined (below); DSMPPI_HOST_CHUNK overrides the chunk size (0 = never).
+  size_t CHUNK = (size_t)1 << 17;
+  if (const char* e = std::getenv("DSMPPI_HOST_CHUNK")) CHUNK = (size_t)std::atoll(e);
+  const bool pipelined = CHUNK > 0 && N > 2 * CHUNK;
+  h2d += (int64_t)((r.q_cur_is_batch ? N * d : d) * sizeof(float)) + (int64_t)(N * nk * (2 * d + 1) * sizeof(float));
+  if (!pipelined || !r.q_cur_is_batch)
+    CUDA_TRY(cudaMemcpyAsync(S + o_q, h->q_cur_host, (r.q_cur_is_batch ? N * d : d) * sizeof(float),
+                             cudaMemcpyHostToDevice, st));
+  if (nk > 0 && !pipelined) {
     // only the live kernel columns travel: (N, 50, d) rows are strided, so copy with a 2-D memcpy
     CUDA_TRY(cudaMemcpy2DAsync(S + o_mu, NKMAX * d * sizeof(float), h->mu_tmp_host, NKMAX * d * sizeof(float),
                                nk * d * sizeof(float), N, cudaMemcpyHostToDevice, st));
@@ -587,7 +600,6 @@ int dsmppi_iteration_host(dsmppi_ctx* c, dsmppi_iteration_host_args* h, void* st
                                nk * d * sizeof(float), N, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpy2DAsync(S + o_sg, NKMAX * sizeof(float), h->sigma_tmp_host, NKMAX * sizeof(float),
                                nk * sizeof(float), N, cudaMemcpyHostToDevice, st));
-    h2d += (int64_t)(N * nk * (2 * d + 1) * sizeof(float));
   }
   CUDA_TRY(up(o_muc, h->mu_c_host, NKMAX * d));
   CUDA_TRY(up(o_sgc, h->sigma_c_host, NKMAX));
@@ -597,12 +609,87 @@ int dsmppi_iteration_host(dsmppi_ctx* c, dsmppi_iteration_host_args* h, void* st
   a.all_traj_dev = S + o_tr; a.closest_dist_all_dev = S + o_cd; a.kernel_val_all_dev = S + o_kv;
   a.dot_products_dev = S + o_dp; a.kernel_activations_dev = S + o_ka; a.qdot_dev = S + o_qd;
   a.nn_grad_all_dev = S + o_gr; a.norm_basis_dev = nullptr;
-  if (dsmppi_rollout(c, &a, stream)) return 1;
   dsmppi_cost_args ca{};
   ca.N = r.N; ca.H = r.H; ca.terms = h->cost_terms;
   for (int i = 0; i < MAXD; ++i) { ca.q_goal[i] = r.q_goal[i]; ca.q_min[i] = h->q_min[i]; ca.q_max[i] = h->q_max[i]; }
   ca.all_traj_dev = a.all_traj_dev; ca.closest_dist_all_dev = a.closest_dist_all_dev; ca.cost_dev = S + o_co;
-  if (launch_cost(c, &ca, st)) return 1;
+  if (!pipelined) {
+    if (dsmppi_rollout(c, &a, stream)) return 1;
+    if (launch_cost(c, &ca, st)) return 1;
+  } else {
+    // ---- large batch: samples never interact before the policy update, so the batch moves through
+    //      [H2D on s_in] -> [rollout + cost on the caller's stream] -> [D2H on s_out] in chunks of samples; with the
+    //      copies of neighbouring chunks under the compute of this one the iteration costs max(copy, compute), not the sum
+    const size_t n_chunks = (N + CHUNK - 1) / CHUNK;
+    if (!c->s_in) CUDA_TRY(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
+    if (!c->s_out) CUDA_TRY(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
+    while (c->pipe_ev.size() < 2 * n_chunks + 2) {
+      cudaEvent_t e;
+      CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      c->pipe_ev.push_back(e);
+    }
+    cudaEvent_t ev_start = c->pipe_ev[2 * n_chunks], ev_drained = c->pipe_ev[2 * n_chunks + 1];
+    CUDA_TRY(cudaEventRecord(ev_start, st));              // the small uploads above, and whatever the caller queued
+    CUDA_TRY(cudaStreamWaitEvent(c->s_in, ev_start, 0));
+    CUDA_TRY(cudaStreamWaitEvent(c->s_out, ev_start, 0));
+    c->ev_used = 0;
+    CUDA_TRY(cudaMemsetAsync(c->counters + 1, 0, 3 * sizeof(int), st));
+    c->keep_counters = 1;
+    int rc = 0;
+    for (size_t k = 0; k < n_chunks && !rc; ++k) {
+      const size_t o = k * CHUNK, n = N - o < CHUNK ? N - o : CHUNK;
+      cudaEvent_t ev_in = c->pipe_ev[2 * k], ev_out = c->pipe_ev[2 * k + 1];
+      if (r.q_cur_is_batch)
+        CUDA_TRY(cudaMemcpyAsync(S + o_q + o * d, h->q_cur_host + o * d, n * d * sizeof(float), cudaMemcpyHostToDevice,
+                                 c->s_in));
+      if (nk > 0) {
+        CUDA_TRY(cudaMemcpy2DAsync(S + o_mu + o * NKMAX * d, NKMAX * d * sizeof(float), h->mu_tmp_host + o * NKMAX * d,
+                                   NKMAX * d * sizeof(float), nk * d * sizeof(float), n, cudaMemcpyHostToDevice, c->s_in));
+        CUDA_TRY(cudaMemcpy2DAsync(S + o_al + o * NKMAX * d, NKMAX * d * sizeof(float), h->alpha_tmp_host + o * NKMAX * d,
+                                   NKMAX * d * sizeof(float), nk * d * sizeof(float), n, cudaMemcpyHostToDevice, c->s_in));
+        CUDA_TRY(cudaMemcpy2DAsync(S + o_sg + o * NKMAX, NKMAX * sizeof(float), h->sigma_tmp_host + o * NKMAX,
+                                   NKMAX * sizeof(float), nk * sizeof(float), n, cudaMemcpyHostToDevice, c->s_in));
+      }
+      CUDA_TRY(cudaEventRecord(ev_in, c->s_in));
+      CUDA_TRY(cudaStreamWaitEvent(st, ev_in, 0));
+      dsmppi_rollout_args b = a;
+      b.N = (int)n;
+      if (r.q_cur_is_batch) b.q_cur_dev = a.q_cur_dev + o * d;
+      b.mu_tmp_dev = a.mu_tmp_dev + o * NKMAX * d; b.sigma_tmp_dev = a.sigma_tmp_dev + o * NKMAX;
+      b.alpha_tmp_dev = a.alpha_tmp_dev + o * NKMAX * d;
+      b.all_traj_dev = a.all_traj_dev + o * H * d; b.closest_dist_all_dev = a.closest_dist_all_dev + o * H;
+      b.kernel_val_all_dev = a.kernel_val_all_dev + o * H * NKMAX; b.dot_products_dev = a.dot_products_dev + o * H;
+      b.kernel_activations_dev = a.kernel_activations_dev + o * H; b.qdot_dev = a.qdot_dev + o * d;
+      b.nn_grad_all_dev = a.nn_grad_all_dev + o * H * d;
+      rc = dsmppi_rollout(c, &b, stream);
+      if (rc) break;
+      dsmppi_cost_args cb = ca;
+      cb.N = (int)n;
+      cb.all_traj_dev = b.all_traj_dev; cb.closest_dist_all_dev = b.closest_dist_all_dev; cb.cost_dev = ca.cost_dev + o;
+      rc = launch_cost(c, &cb, st);
+      if (rc) break;
+      CUDA_TRY(cudaEventRecord(ev_out, st));
+      CUDA_TRY(cudaStreamWaitEvent(c->s_out, ev_out, 0));
+      auto down_c = [&](float* dst, size_t off_f, size_t per_sample) {
+        return cudaMemcpyAsync(dst + o * per_sample, S + off_f + o * per_sample, n * per_sample * sizeof(float),
+                               cudaMemcpyDeviceToHost, c->s_out);
+      };
+      CUDA_TRY(down_c(h->all_traj_host, o_tr, H * d));
+      CUDA_TRY(down_c(h->closest_dist_all_host, o_cd, H));
+      if (nk > 0)
+        CUDA_TRY(cudaMemcpy2DAsync(h->kernel_val_all_host + o * H * NKMAX, NKMAX * sizeof(float),
+                                   S + o_kv + o * H * NKMAX, NKMAX * sizeof(float), nk * sizeof(float), n * H,
+                                   cudaMemcpyDeviceToHost, c->s_out));
+      CUDA_TRY(down_c(h->dot_products_host, o_dp, H));
+      CUDA_TRY(down_c(h->kernel_activations_host, o_ka, H));
+      CUDA_TRY(down_c(h->qdot_host, o_qd, d));
+      CUDA_TRY(down_c(h->cost_host, o_co, 1));
+    }
+    c->keep_counters = 0;
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(ev_drained, c->s_out));
+    CUDA_TRY(cudaStreamWaitEvent(st, ev_drained, 0));      // the caller's stream is done when the last copy-out is
+  }
   dsmppi_update_args ua{};
   ua.N = r.N; ua.H = r.H; ua.n_kernels = r.n_kernels; ua.owns_sample0 = 1; ua.N_global = r.N; ua.variant = h->update_variant;
   ua.ker_thr = h->ker_thr; ua.upd_rate = h->upd_rate;
@@ -613,17 +700,21 @@ int dsmppi_iteration_host(dsmppi_ctx* c, dsmppi_iteration_host_args* h, void* st
   if (launch_cost_stats(c, ua.cost_dev, r.N, c->stats_tmp, st)) return 1;
   if (launch_update_partial(c, &ua, c->stats_tmp, c->packed_tmp, st)) return 1;
   if (launch_update_finalize(c, &ua, c->packed_tmp, reinterpret_cast<int*>(S + o_nu), st)) return 1;
-  CUDA_TRY(down(h->all_traj_host, o_tr, N * H * d));
-  CUDA_TRY(down(h->closest_dist_all_host, o_cd, N * H));
-  if (nk > 0) {
-    CUDA_TRY(cudaMemcpy2DAsync(h->kernel_val_all_host, NKMAX * sizeof(float), S + o_kv, NKMAX * sizeof(float),
-                               nk * sizeof(float), N * H, cudaMemcpyDeviceToHost, st));
-    d2h += (int64_t)(N * H * nk * sizeof(float));
+  if (!pipelined) {
+    CUDA_TRY(down(h->all_traj_host, o_tr, N * H * d));
+    CUDA_TRY(down(h->closest_dist_all_host, o_cd, N * H));
+    if (nk > 0) {
+      CUDA_TRY(cudaMemcpy2DAsync(h->kernel_val_all_host, NKMAX * sizeof(float), S + o_kv, NKMAX * sizeof(float),
+                                 nk * sizeof(float), N * H, cudaMemcpyDeviceToHost, st));
+    }
+    CUDA_TRY(down(h->dot_products_host, o_dp, N * H));
+    CUDA_TRY(down(h->kernel_activations_host, o_ka, N * H));
+    CUDA_TRY(down(h->qdot_host, o_qd, N * d));
+    CUDA_TRY(down(h->cost_host, o_co, N));
+  } else {
+    d2h += (int64_t)((N * H * d + 3 * N * H + N * d + N) * sizeof(float));
   }
-  CUDA_TRY(down(h->dot_products_host, o_dp, N * H));
-  CUDA_TRY(down(h->kernel_activations_host, o_ka, N * H));
-  CUDA_TRY(down(h->qdot_host, o_qd, N * d));
-  CUDA_TRY(down(h->cost_host, o_co, N));
+  if (nk > 0) d2h += (int64_t)(N * H * nk * sizeof(float));
   CUDA_TRY(down(h->mu_c_host, o_muc, NKMAX * d));
   CUDA_TRY(down(h->sigma_c_host, o_sgc, NKMAX));
   CUDA_TRY(down(h->alpha_c_host, o_alc, NKMAX * d));

@@ -124,6 +124,10 @@ struct dsmppi_ctx {
   int ev_kind = 0;                    // 0: FFMA dense scoring, 1: tensor-core pass 1, 2: whole-horizon FFMA kernel,
                                       // 3: tensor-core dense scoring, 4: whole-horizon tensor-core kernel
   int fused_rollout = 1;              // 0 disables the single-launch path (tests compare the two)
+  // host-buffer iteration of a large batch: copy streams + events of the chunk pipeline (capi.cu)
+  cudaStream_t s_in = nullptr, s_out = nullptr;
+  std::vector<cudaEvent_t> pipe_ev;
+  int keep_counters = 0;              // 1 while a chunked iteration calls dsmppi_rollout once per chunk
 };
 
 // exact_mlp.cu

@@ -17,24 +17,36 @@
 // section 3 has the table.
 //
 // Design (B200, one CTA pair per TPC, persistent over 256-row tiles):
-//   * cta_group::2 MMAs, M = 256 (128 rows per CTA = the 128 TMEM lanes), N = 256: D1 and D2 fill the 512 TMEM
-//     columns.  The A operand (activations, then back-propagated gradients) lives in shared memory as two K-major
-//     fp16 images (hi, lo; 2 x 64 KB) that the epilogue warps rewrite in place once a layer's MMAs have retired.
-//   * weights never fit on chip in split form (7 GEMMs x 256 KB), so they stream: each CTA pulls ITS N-half of
-//     every stage (K = 64: 32 KB) from L2 with one bulk TMA copy into a 3-slot ring, running ahead across layer and
-//     tile boundaries (the ring refills while the epilogue runs).  The pair shares every stage, so a tile of 256
-//     rows costs 816 KB of L2 reads per SM for 41 k cycles of MMAs (20 B/cycle/SM, half the L2 limit).
-//   * warp roles: warps 0-7 epilogue (TMEM lane quarter = warp % 4, column half = warp / 4): D1/D2 -> bias, ReLU
-//     (bit masks kept in registers for the backward pass), hi/lo split, st.shared of the next A operand;
-//     warp 8 = TMEM allocator + MMA issuer (leader CTA) / "stage landed" relay (peer CTA); warp 9 = weight loader.
+//   * cta_group::2 MMAs, M = 256 (128 rows per CTA = the 128 TMEM lanes): D1 and D2 of a 256-wide layer fill the 512
+//     TMEM columns.  The A operand (activations, then back-propagated gradients) lives in shared memory as two K-major
+//     fp16 images (hi, lo; 2 x 64 KB) that the epilogue warps rewrite in place.
+//   * weights never fit on chip in split form (7 GEMMs x 256 KB), so they stream: each CTA pulls its share of every
+//     stage (32 KB: N half x K half, hi | lo) from L2 with one bulk TMA copy into a 3-slot ring, running ahead across
+//     layer and tile boundaries.  The pair shares every stage, so a tile of 256 rows costs 816 KB of L2 reads per SM
+//     for 41 k cycles of MMAs (20 B/cycle/SM, half the L2 limit).
+//   * warp roles: warps 0-7 epilogue (TMEM lane quarter = warp % 4; the two warps of a quarter interleave 32-column
+//     chunks): D1/D2 -> bias, ReLU (sign bits kept in registers for the backward pass), hi/lo split, st.shared of the
+//     next A operand; warp 8 = TMEM allocator + MMA issuer (leader CTA) / "stage landed" relay (peer CTA);
+//     warp 9 = weight loader.
 //   * the output layer (N = 32), the one-hot seed g4 = W5[l*, :] * mask and the final W1^T contraction (N = 32)
 //     plus the encoding Jacobian run in the same pipeline: 9 GEMMs per tile with BWD.
-//   * N-half pipelining: D1 and D2 fill TMEM, so a layer has no second accumulator to drain under the next GEMM.
-//     Every hidden GEMM is therefore issued as two N = 128 halves (same MMA rate: tools/tcx_ss_microbench.cu), each
-//     with its own "accumulator complete" barrier.  The epilogue of half 0 runs under the MMAs of half 1 and keeps its
-//     converted operand in 64 registers until those MMAs (which still read the old A operand) have retired; the
-//     epilogue of half 1 runs under the first K half of the NEXT layer's MMAs, which only need the columns half 0
-//     produced.  Per-element arithmetic (k-order, the three MMAs per step) is unchanged, hence bitwise equal results.
+//   * N-half pipelining.  With TMEM full a layer has no second accumulator to drain under the next GEMM, so every
+//     hidden GEMM is issued as two N = 128 halves (same MMA rate, tools/tcx_ss_microbench.cu), each with its own
+//     "accumulator complete" barrier:
+//       - the epilogue of N half 0 runs under the MMAs of N half 1 and parks its converted operand in 64 registers;
+//         it is stored as soon as the last MMAs that read those operand columns have retired (barrier AFREE, after
+//         the first K stage of N half 1), i.e. still under N half 1;
+//       - the epilogue of N half 1 runs under the NEXT layer's N half 0, which follows the operand K quarter by K
+//         quarter (four "operand ready" barriers, 64 columns each);
+//       - the issuer opens a weight stage (descriptors, "weights landed") BEFORE it waits for the operand, and builds
+//         descriptors from 32-bit low words inside the asm block -- nothing but the MMAs follows a hand-over;
+//       - the seed epilogue reads the split rows of W5 from the output layer's weight stage, which the issuer keeps
+//         in its ring slot until the first seed quarter is signalled (no global table look-up on the critical path);
+//       - the two warps of a lane quarter share the input encoding (h = 0 joint angles, h = 1 obstacle point), and a
+//         row's global stores wait until the tile's last hand-over is out: fence.proxy.async is a MEMBAR.ALL.CTA,
+//         which would otherwise wait for their round trip.
+//     Per-element arithmetic (k order, the three MMAs per step) is unchanged: results are bitwise equal to the
+//     unpipelined kernel (tools/tcx_regress.py).  Phase accounting: tools/tcx_prof.py on a -DDSMPPI_TCX_PROF build.
 #include <cuda_fp16.h>
 
 #include <cstdio>
@@ -46,6 +58,17 @@
 #include "step_device.cuh"
 #include "exact_tile.cuh"
 #include "tc_ptx.cuh"
+
+// Experiment switches (tools/tcx_variants.py times the combinations; the defaults are the measured best):
+//   TCX_ENC_PIPE   1 = the next tile's encoding is computed before the current tile's last GEMM completes and stored
+//                      at the tile end; 0 = computed and stored at the top of the tile
+//   TCX_DEFER_STG  1 = a row's results are stored after the tile's last operand hand-over; 0 = where they are produced
+#ifndef TCX_ENC_PIPE
+#define TCX_ENC_PIPE 1
+#endif
+#ifndef TCX_DEFER_STG
+#define TCX_DEFER_STG 1
+#endif
 
 namespace {
 using namespace tcx;
@@ -130,7 +153,8 @@ constexpr int OFF_LST = OFF_TMEMPTR + 16;  // argmin link per row (128 ints)
 constexpr int OFF_OVF = OFF_LST + TROWS * 4;   // "left the fp16 range" flag per row (128 ints)
 constexpr int OFF_FIXN = OFF_OVF + TROWS * 4;   // whole-horizon kernel: flagged rows of this CTA's tile (count + list)
 constexpr int OFF_FIXL = OFF_FIXN + 16;         // (3, 128) ints: samples | obstacles | output rows
-constexpr int SMEM_BYTES = OFF_FIXL + 3 * TROWS * 4;
+constexpr int OFF_B4 = OFF_FIXL + 3 * TROWS * 4;   // output-layer bias (16 floats)
+constexpr int SMEM_BYTES = OFF_B4 + 64;
 static_assert(exact_tile::smem_bytes(32) <= OFF_RING, "the FFMA fallback tile lives in the A operand images");
 constexpr int OFF_SCRATCH = OFF_ALO + 32768;   // final epilogue: a[e][row] fp32 (16 KB) inside the idle A_lo image
 static_assert(NBAR * 8 <= 128, "barrier block");
@@ -145,7 +169,6 @@ static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB shared-memory budget");
 //   s = 27       GEMM 8  backward W1^T        K = 256  N = 32                 16 KB
 constexpr int STAGES_FWD = 15, STAGES_BWD = 28;
 constexpr size_t IMG_BYTES = 16384 + 12 * 32768 + 16384 + 12 * 32768 + 16384;   // 835584
-constexpr size_t W4_TABLE_BYTES = 2 * 16 * HID * 2;                              // [hi | lo] x 16 links x 256 fp16
 __host__ __device__ __forceinline__ void stage_info(int s, uint32_t& off, uint32_t& bytes) {
   if (s <= 1) { off = (uint32_t)s * 8192; bytes = 8192; }
   else if (s <= 13) { off = 16384 + (uint32_t)(s - 2) * 32768; bytes = 32768; }
@@ -155,12 +178,11 @@ __host__ __device__ __forceinline__ void stage_info(int s, uint32_t& off, uint32
 }
 
 struct TxImages {
-  uint8_t* dev = nullptr;      // [rank 0 image | rank 1 image | W4 hi/lo table]
+  uint8_t* dev = nullptr;      // [rank 0 image | rank 1 image]
 };
 
 struct TxArgs {
   const uint8_t* img0; const uint8_t* img1;
-  const uint4* w4hi; const uint4* w4lo;      // (16, 32) uint4 each: fp16 halves of the output layer's rows
   NetDev net;
   RowSrc src;
   const float* q; int q_stride;
@@ -291,6 +313,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_exac
   constexpr int NST = BWD ? STAGES_BWD : STAGES_FWD;
 
   if (MODE != 2 && blockIdx.x == 0 && tid == 0) *a.fix_next = 0;
+  if (tid < 16) reinterpret_cast<float*>(smem + OFF_B4)[tid] = tid < a.net.O ? a.net.b[4][tid] : 0.f;
   if (warp == W_MMA) {
     if (lane == 0) {
       for (int s = 0; s < NSLOT; ++s) {
@@ -350,67 +373,119 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_exac
       tc_fence_after();
     };
 
+    // ---- encoded inputs [x, sin x, cos x], split, K = 32 (network_macros_mod.py:139-140).  The two warps of a lane
+    //      quarter share a row: h = 0 encodes the joint angles (and keeps sin / cos for the Jacobian), h = 1 the obstacle
+    //      point and the zero padding -- every one of the 32 operand columns is written exactly once.  The values of the
+    //      NEXT tile are prepared in registers while the last GEMM of the current one runs (rows looked up and their
+    //      inputs prefetched one GEMM earlier), so the tile boundary itself only stores them.
+    uint32_t en_v[3 * MAXD];                                // element: fp16 hi | fp16 lo << 16
+    float en_sn[MAXD], en_cs[MAXD], en_rad = 0.f;
+    uint32_t en_range = 0;
+    int en_i = 0, en_j = 0;
+    bool en_valid = false;
+    auto enc_compute = [&](int i, int j, bool valid, const float* qsrc, int qstride) {
+      en_i = i; en_j = j; en_valid = valid; en_range = 0;
+      auto prep = [&](float v) -> uint32_t {                // saturating like split8, and range-checked
+        const uint32_t hh = pack_h2(v, 0.f);
+        const uint32_t ll = pack_h2((v - unpack_h2(hh).x) * SPLIT, 0.f);
+        en_range = __vmaxu2(en_range, hh & 0x7fff7fffu);
+        return (hh & 0xffffu) | (ll << 16);
+      };
+      if (h == 0) {
+        float xq[MAXD];
+#pragma unroll
+        for (int c = 0; c < MAXD; ++c) xq[c] = (c < d && valid) ? qsrc[(size_t)i * qstride + c] : 0.f;
+        en_rad = valid ? a.obs[j * 4 + 3] : 0.f;
+#pragma unroll
+        for (int c = 0; c < MAXD; ++c) {
+          en_sn[c] = 0.f; en_cs[c] = 1.f;
+          if (c < d) {
+            en_sn[c] = sinf(xq[c]); en_cs[c] = cosf(xq[c]);
+            en_v[3 * c] = prep(xq[c]); en_v[3 * c + 1] = prep(en_sn[c]); en_v[3 * c + 2] = prep(en_cs[c]);
+          }
+        }
+      } else {
+        float xp[3];                                        // nin - d obstacle coordinates: 3, or 2 for the toy variant
+#pragma unroll
+        for (int c = 0; c < 3; ++c) xp[c] = (valid && d + c < nin) ? a.obs[j * 4 + c] : 0.f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          if (d + c < nin) {
+            en_v[3 * c] = prep(xp[c]); en_v[3 * c + 1] = prep(sinf(xp[c])); en_v[3 * c + 2] = prep(cosf(xp[c]));
+          }
+      }
+    };
+    auto enc_store = [&]() {
+      auto st = [&](int e, uint32_t v) {
+        const int off = (e >> 3) * A_LBO + (e & 7) * 2;
+        *reinterpret_cast<uint16_t*>(a_hi + off) = (uint16_t)v;
+        *reinterpret_cast<uint16_t*>(a_lo + off) = (uint16_t)(v >> 16);
+      };
+      if (h == 0) {
+#pragma unroll
+        for (int c = 0; c < MAXD; ++c)
+          if (c < d) { st(c, en_v[3 * c]); st(nin + c, en_v[3 * c + 1]); st(2 * nin + c, en_v[3 * c + 2]); }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          if (d + c < nin) { st(d + c, en_v[3 * c]); st(nin + d + c, en_v[3 * c + 1]); st(2 * nin + d + c, en_v[3 * c + 2]); }
+        for (int e = 3 * nin; e < 32; ++e) st(e, 0u);
+      }
+    };
+    int nx_i = 0, nx_j = 0;
+    bool nx_valid = false;
+    auto lookup_tile = [&](int tl) {
+      if (tl < n_tiles) {
+        nx_valid = row_lookup(a.src, tl * (2 * TROWS) + (int)rank * TROWS + row, n_rows, nx_i, nx_j);
+        if (nx_valid) {
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(a.q + (size_t)nx_i * a.q_stride));
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(a.obs + nx_j * 4));
+        }
+      }
+    };
+    if (MODE != 2) {
+      lookup_tile(pair);
+      if (TCX_ENC_PIPE) enc_compute(nx_i, nx_j, nx_valid, a.q, a.q_stride);
+    }
+    uint32_t pass = 0;                                      // (tile, step) passes done: locates the output layer's stage
+    bool enc_stored = false;
+
     for (int tile = pair; tile < n_tiles; tile += npairs)
-    for (int t = 1; t <= n_steps; ++t) {
+    for (int t = 1; t <= n_steps; ++t, ++pass) {
       // global row of this thread: consecutive rows of the list, or (whole-horizon) row j of sample i = dense row i * M + j
       int grow = tile * (2 * TROWS) + (int)rank * TROWS + row;
-      int til_i = 0, til_j = 0;
-      bool til_valid = false;
-      if (MODE == 2) {
-        const int sl = row / a.M;
-        til_j = row - sl * a.M;
-        til_i = (tile * 2 + (int)rank) * a.S + sl;
-        til_valid = sl < a.S && til_i < a.sa.N;
-        grow = til_valid ? til_i * a.M + til_j : n_rows;
-      }
       const float* qsrc = MODE == 2 ? a.sa.traj + (size_t)(t - 1) * d : a.q;     // q_prev = all_traj[:, t-1, :]
       const int qstride = MODE == 2 ? a.sa.H * d : a.q_stride;
+      if (MODE == 2) {                                      // the state was written by the step just before: encode now
+        const int sl = row / a.M;
+        const int tj = row - sl * a.M;
+        const int ti = (tile * 2 + (int)rank) * a.S + sl;
+        const bool tv = sl < a.S && ti < a.sa.N;
+        grow = tv ? ti * a.M + tj : n_rows;
+        enc_compute(ti, tj, tv, qsrc, qstride);
+      } else if (!TCX_ENC_PIPE) {
+        enc_compute(nx_i, nx_j, nx_valid, qsrc, qstride);
+      }
       float* out_m = MODE == 2 ? a.m_rows : a.out_m;
       float* out_dist = MODE == 2 ? a.row_dist : a.out_dist;
       float* out_grad = MODE == 2 ? a.row_grad : a.out_grad;
-      float xs[MAXD], sn[MAXD], cs[MAXD];
-      float rad = 0.f;
+      float sn[MAXD], cs[MAXD];
+#pragma unroll
+      for (int c = 0; c < MAXD; ++c) { sn[c] = en_sn[c]; cs[c] = en_cs[c]; }
+      const float rad = en_rad;
       uint32_t mk[4][4];    // sign bits of the pre-activations (set = ReLU off): layer x 32-column chunk, column 0 in bit 31
-      uint32_t range = 0;                                   // largest fp16 magnitude written to the A operand
-      int row_i = 0, row_j = 0;
+      uint32_t range = en_range;                            // largest fp16 magnitude written to the A operand
+      const int row_i = en_i, row_j = en_j;
       int* ovf = reinterpret_cast<int*>(smem + OFF_OVF);
-      // ---- rows -> encoded inputs [x, sin x, cos x], split, K = 32 (network_macros_mod.py:139-140)
-      if (h == 0) {
-        int i = til_i, j = til_j;
-        const bool valid = MODE == 2 ? til_valid : row_lookup(a.src, grow, n_rows, i, j);
-        row_i = i; row_j = j;
-        ovf[row] = 0;
-        const uint4 z4 = make_uint4(0, 0, 0, 0);
-#pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-          *reinterpret_cast<uint4*>(a_hi + ch * A_LBO) = z4;
-          *reinterpret_cast<uint4*>(a_lo + ch * A_LBO) = z4;
-        }
-        auto put = [&](int e, float v) {                  // saturating like split8, and range-checked
-          const uint32_t hh = pack_h2(v, 0.f);
-          const uint32_t ll = pack_h2((v - unpack_h2(hh).x) * SPLIT, 0.f);
-          range = __vmaxu2(range, hh & 0x7fff7fffu);
-          const int off = (e >> 3) * A_LBO + (e & 7) * 2;
-          *reinterpret_cast<uint16_t*>(a_hi + off) = (uint16_t)hh;
-          *reinterpret_cast<uint16_t*>(a_lo + off) = (uint16_t)ll;
-        };
-#pragma unroll
-        for (int c = 0; c < MAXD; ++c) {
-          xs[c] = 0.f; sn[c] = 0.f; cs[c] = 1.f;
-          if (c < d) {
-            const float x = valid ? qsrc[(size_t)i * qstride + c] : 0.f;
-            xs[c] = x; sn[c] = sinf(x); cs[c] = cosf(x);
-            put(c, x); put(nin + c, sn[c]); put(2 * nin + c, cs[c]);
-          }
-        }
-        for (int c = d; c < nin; ++c) {
-          const float x = valid ? a.obs[j * 4 + (c - d)] : 0.f;
-          put(c, x); put(nin + c, sinf(x)); put(2 * nin + c, cosf(x));
-        }
-        rad = valid ? a.obs[j * 4 + 3] : 0.f;
+      if (h == 0) ovf[row] = 0;
+      if (MODE == 2 || !enc_stored) {                       // otherwise stored at the end of the previous tile
+        enc_store();
+        signal_a(0);
       }
-      signal_a(0);
       if (q4 == 0) TCX_PROF(h, 1);
+      // this row's results stay in registers until the tile's last hand-over is out: a global store ahead of a
+      // fence.proxy.async (MEMBAR.ALL.CTA) would put its round trip on the critical path
+      float o_m = 0.f, o_dist = 0.f, o_g[MAXD];
 
       // ---- hidden layers: h = relu(W h + b), masks kept for the backward pass.  N half 0 is converted under the MMAs
       //      of N half 1 and parked in registers until they retire (they read the operand being replaced); N half 1 is
@@ -462,6 +537,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_exac
         if (q4 == 0) TCX_PROF(h, 50 + l);
       }
 
+      if (MODE != 2) {
+        lookup_tile(tile + npairs);
+        if (TCX_ENC_PIPE && !BWD && tile + npairs < n_tiles) enc_compute(nx_i, nx_j, nx_valid, a.q, a.q_stride);
+      }
       // ---- output layer (no activation): links 0..15 sit in D columns 0..15
       wait_d0();
       if (q4 == 0) TCX_PROF(h, 60);
@@ -470,44 +549,69 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_exac
         tmem_ld16(tD, r1);
         tmem_ld16(tD + 256, r2);
         tc_wait_ld();
-        int best = 0;
-        float bv = 0.f, m = 3.0e38f;
+        if (q4 == 0) TCX_PROF(h, 64);
+        // straight-line and branch-free: the same operations on every link, the unused ones masked by o < O
+        const float comp_o = (a.dbg & 4) ? 0.f : COMP_K256;
+        const float* b4s = reinterpret_cast<const float*>(smem + OFF_B4);
+        const bool scaled = net.scale != 1.f;
+        float v[16];
 #pragma unroll
-        for (int o = 0; o < 16; ++o) {
-          if (o < O) {
-            const float v = combine(r1[o], r2[o], (a.dbg & 4) ? 0.f : COMP_K256) + __ldg(net.b[4] + o);
-            if (o == 0 || v < bv) { bv = v; best = o; }     // argmin of the RAW output (robot_sdf.py:155)
-            float y = v;                                      // MPPI.py:236-242: /100, minus radius, ignored := 1e6
-            if (net.scale != 1.f) y = y / 100.f;
-            y -= rad;
-            if ((a.ignore_mask >> o) & 1u) y = 1e6f;
-            m = fminf(m, y);
-          }
+        for (int o = 0; o < 16; ++o) v[o] = combine(r1[o], r2[o], comp_o) + b4s[o];
+        int best = 0;
+        float bv = v[0], m = 3.0e38f;
+#pragma unroll
+        for (int o = 1; o < 16; ++o) {                        // argmin of the RAW output (robot_sdf.py:155)
+          const bool lt = o < O && v[o] < bv;
+          bv = lt ? v[o] : bv;
+          best = lt ? o : best;
         }
-        if (grow < n_rows) {
-          if (out_m) out_m[grow] = m;
-          if (BWD) {
-            float y = bv;                                     // pass-2 distance of the argmin link (MPPI.py:265-274)
-            if (net.scale != 1.f) y = y / 100.f;
-            out_dist[grow] = y - rad;
-          }
+#pragma unroll
+        for (int o = 0; o < 16; ++o) {                        // MPPI.py:236-242: /100, minus radius, ignored := 1e6
+          float y = scaled ? v[o] / 100.f : v[o];
+          y -= rad;
+          if ((a.ignore_mask >> o) & 1u) y = 1e6f;
+          m = o < O ? fminf(m, y) : m;
+        }
+        o_m = m;
+        if (BWD) {
+          float y = bv;                                       // pass-2 distance of the argmin link (MPPI.py:265-274)
+          if (net.scale != 1.f) y = y / 100.f;
+          o_dist = y - rad;
+        }
+        if (!TCX_DEFER_STG && grow < n_rows) {
+          if (out_m) out_m[grow] = o_m;
+          if (BWD) out_dist[grow] = o_dist;
         }
         if (BWD) lst[row] = best;
+        if (q4 == 0) TCX_PROF(h, 65);
       }
       if constexpr (BWD) {
         asm volatile("bar.sync 1, 256;" ::: "memory");      // lst visible to the column-half-1 warps
-        // ---- g4 = W5[l*, :] * s4 from the pre-split table, handed over quarter by quarter
+        if (q4 == 0) TCX_PROF(h, 66);
+        // ---- g4 = W5[l*, :] * s4, handed over quarter by quarter.  The split rows of W5 are read from the weight stage
+        //      of the output layer, which the issuer keeps in its ring slot until the first quarter is signalled: in the
+        //      canonical K-major layout the 8 columns of chunk ch of link l* are exactly one 16-byte core-matrix row
         {
           const int ls = lst[row];
-          const uint4* th = a.w4hi + ls * 32;
-          const uint4* tl = a.w4lo + ls * 32;
+          const uint32_t slot4 = (pass * (uint32_t)NST + 14u) % NSLOT;
+          const uint8_t* wrow = smem + OFF_RING + slot4 * SLOT_BYTES + ls * 16;
+          uint4 whi[16], wlo[16];
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int j8 = 0; j8 < 4; ++j8) {
+              const int ch = 8 * c + 4 * h + j8;
+              whi[4 * c + j8] = *reinterpret_cast<const uint4*>(wrow + ch * 256);
+              wlo[4 * c + j8] = *reinterpret_cast<const uint4*>(wrow + 8192 + ch * 256);
+            }
+          if (q4 == 0) TCX_PROF(h, 67);
 #pragma unroll
           for (int c = 0; c < 4; ++c) {                       // c = 2 x + chunk: N half x, 32-column chunk of this thread
             const uint32_t bits = mk[3][c];
 #pragma unroll
             for (int j8 = 0; j8 < 4; ++j8) {
               const int ch = 8 * c + 4 * h + j8;
-              uint4 hi = __ldg(th + ch), lo = __ldg(tl + ch);
+              uint4 hi = whi[4 * c + j8], lo = wlo[4 * c + j8];
               const uint32_t on = ~(bits >> (24 - 8 * j8));     // column 8 j8 + j of this chunk sits in bit 7 - j
               const uint32_t m0 = ((on >> 7) & 1u) * 0xffffu + ((on >> 6) & 1u) * 0xffff0000u;
               const uint32_t m1 = ((on >> 5) & 1u) * 0xffffu + ((on >> 4) & 1u) * 0xffff0000u;
@@ -519,6 +623,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_exac
               *reinterpret_cast<uint4*>(a_lo + ch * A_LBO) = lo;
             }
             signal_a(c);
+            if (q4 == 0 && c == 0) TCX_PROF(h, 68);
           }
         }
         if (q4 == 0) TCX_PROF(h, 61);
@@ -570,6 +675,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_exac
           if (q4 == 0) TCX_PROF(h, 54 + l);
         }
 
+        if (TCX_ENC_PIPE && MODE != 2 && tile + npairs < n_tiles) enc_compute(nx_i, nx_j, nx_valid, a.q, a.q_stride);
         // ---- a = W_1^T g_1 (N = 32), then the encoding Jacobian dz/dx_c = a[c] + cos(x_c) a[nin+c] - sin(x_c) a[2nin+c]
         wait_d0();
         if (q4 == 0) TCX_PROF(h, 62);
@@ -581,16 +687,34 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_exac
           float* scr = reinterpret_cast<float*>(smem + OFF_SCRATCH) + row;     // a[e] at scr[e * 128]
 #pragma unroll
           for (int e = 0; e < 32; ++e) scr[e * TROWS] = combine(r1[e], r2[e], (a.dbg & 4) ? 0.f : COMP_K256);
-          if (grow < n_rows) {
+#pragma unroll
+          for (int c = 0; c < MAXD; ++c)
+            if (c < d) o_g[c] = scr[c * TROWS] + cs[c] * scr[(nin + c) * TROWS] - sn[c] * scr[(2 * nin + c) * TROWS];
+          if (!TCX_DEFER_STG && grow < n_rows) {
 #pragma unroll
             for (int c = 0; c < MAXD; ++c)
-              if (c < d)
-                out_grad[(size_t)grow * d + c] =
-                    scr[c * TROWS] + cs[c] * scr[(nin + c) * TROWS] - sn[c] * scr[(2 * nin + c) * TROWS];
+              if (c < d) out_grad[(size_t)grow * d + c] = o_g[c];
           }
         }
       }
       (void)nenc;
+      // ---- tile end: the next tile's encoding (prepared above) goes out first, then this tile's rows
+      if (TCX_ENC_PIPE && MODE != 2 && tile + npairs < n_tiles) {
+        enc_store();
+        signal_a(0);
+        enc_stored = true;
+      } else {
+        enc_stored = false;
+      }
+      if (TCX_DEFER_STG && h == 0 && grow < n_rows) {
+        if (out_m) out_m[grow] = o_m;
+        if (BWD) {
+          out_dist[grow] = o_dist;
+#pragma unroll
+          for (int c = 0; c < MAXD; ++c)
+            if (c < d) out_grad[(size_t)grow * d + c] = o_g[c];
+        }
+      }
       if (q4 == 0) TCX_PROF(h, 63);
       // ---- rows whose activations or gradients saturated fp16 are handed to the FFMA arithmetic
       if (((range & 0xffffu) >= 0x7bffu) || ((range >> 16) >= 0x7bffu)) ovf[row] = 1;
@@ -742,9 +866,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_exac
       }
       __syncwarp();
     };
-    auto close_stage = [&](int commit_d) {                    // commit_d: 0 / 1 = this stage completes N half 0 / 1, 2 = AFREE
+    uint32_t held_slot = 0;                                   // the output layer's weight stage, read by the seed epilogue
+    auto close_stage = [&](int commit_d, bool release = true) {   // commit_d: 0 / 1 = completes N half 0 / 1, 2 = AFREE
       if (elect_one()) {
-        mma_commit_2cta(BAR(BAR_EMPTY + slot));              // the slot may be refilled (both CTAs)
+        if (release) mma_commit_2cta(BAR(BAR_EMPTY + slot)); // the slot may be refilled (both CTAs)
         if (commit_d == 0) mma_commit_2cta(BAR(BAR_DFULL0)); // N half 0 (or a small GEMM) is complete
         if (commit_d == 1) mma_commit_2cta(BAR(BAR_DFULL1));
         if (commit_d == 2) mma_commit_2cta(BAR(BAR_AFREE));  // last reader of the operand's K half 0
@@ -773,13 +898,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_exac
           wait_a(1); steps(4, false);
           wait_a(2); steps(4, false);
           wait_a(3); steps(4, false);
-          close_stage(0);
+          held_slot = slot;
+          close_stage(0, !(BWD && g == 4));    // W5's stage stays: the seed epilogue reads its rows from the slot
         } else {
           // N half 0 follows the operand quarter by quarter: quarters 0, 1 are the previous layer's half-0 epilogue
           // (parked, stored when that layer's MMAs retired), quarters 2, 3 its half-1 epilogue, whose accumulator
           // columns N half 1 of this layer then overwrites
           open_stage(0, 0, 64 * 16, 16384, idesc128);
-          wait_a(0); steps(4, true);
+          wait_a(0);
+          if (g == 5) {                        // every seed thread has read W5's rows: hand the slot back in both CTAs
+            if (lane == 0) {
+              mbar_arrive_remote(BAR(BAR_EMPTY + held_slot), 0);
+              mbar_arrive_remote(BAR(BAR_EMPTY + held_slot), 1);
+            }
+            __syncwarp();
+          }
+          steps(4, true);
           wait_a(1); steps(4, false);
           close_stage(-1);
           open_stage(0, KHALF, 64 * 16, 16384, idesc128);
@@ -829,7 +963,7 @@ int tcx_build_images(dsmppi_ctx* c, const dsmppi_net* net) {
   if (c->nenc > 32 || c->O > 16) return 0;          // layer-1 K and the output N are fixed at 32 / 16: FFMA path only
   const char* dis = std::getenv("DSMPPI_DISABLE_TC");
   if (dis && dis[0] == '1') return 0;
-  const size_t total = 2 * IMG_BYTES + W4_TABLE_BYTES;
+  const size_t total = 2 * IMG_BYTES;
   std::vector<uint8_t> host(total, 0);
   const int nenc = c->nenc, O = c->O;
   auto put = [&](uint8_t* part_hi, uint8_t* part_lo, size_t off, float w) {
@@ -867,11 +1001,12 @@ int tcx_build_images(dsmppi_ctx* c, const dsmppi_net* net) {
               put(img + off, img + off + 16384, canon(n, k, 64),
                   Wt[(size_t)(128 * kh + k) * HID + 128 * x + 64 * rank + n]);
         }
-    // GEMM 4: N = 32 over the pair, links 0..15 on rank 0, padding on rank 1
+    // GEMM 4: N = 32 over the pair.  BOTH ranks carry links 0..15 (rank 1's accumulator columns 16..31 are never
+    // read): the seed epilogue of either CTA looks W5[l*, :] up in its own copy of this stage
     stage_info(14, off, bytes);
     for (int n = 0; n < 16; ++n)
       for (int k = 0; k < HID; ++k) {
-        const int o = 16 * rank + n;
+        const int o = n;
         put(img + off, img + off + 8192, canon(n, k, 16), o < O ? net->W_host[4][(size_t)o * HID + k] : 0.f);
       }
     // GEMM 8: a[e] = sum_k g1[k] W0[k][e], e = 16 * rank + n
@@ -882,11 +1017,6 @@ int tcx_build_images(dsmppi_ctx* c, const dsmppi_net* net) {
         put(img + off, img + off + 8192, canon(n, k, 16), e < nenc ? net->W_host[0][(size_t)k * nenc + e] : 0.f);
       }
   }
-  uint8_t* t_hi = host.data() + 2 * IMG_BYTES;
-  uint8_t* t_lo = t_hi + 16 * HID * 2;
-  for (int o = 0; o < 16; ++o)
-    for (int k = 0; k < HID; ++k)
-      put(t_hi, t_lo, ((size_t)o * HID + k) * 2, o < O ? net->W_host[4][(size_t)o * HID + k] : 0.f);
   TxImages* t = new TxImages();
   if (cudaMalloc(reinterpret_cast<void**>(&t->dev), total) != cudaSuccess) {
     dsmppi_set_error("cudaMalloc(split weight images) failed");
@@ -917,8 +1047,6 @@ int launch_tc_exact(dsmppi_ctx* c, const float* q, int q_stride, const RowSrc& s
   TxArgs a;
   a.img0 = t->dev;
   a.img1 = t->dev + IMG_BYTES;
-  a.w4hi = reinterpret_cast<const uint4*>(t->dev + 2 * IMG_BYTES);
-  a.w4lo = reinterpret_cast<const uint4*>(t->dev + 2 * IMG_BYTES + 16 * HID * 2);
   a.net = c->net;
   a.src = src;
   a.q = q;
@@ -951,9 +1079,8 @@ int launch_tc_exact(dsmppi_ctx* c, const float* q, int q_stride, const RowSrc& s
   static long long* prof_buf = nullptr;
   const char* prof_out = std::getenv("DSMPPI_TCX_PROF_OUT");
   if (prof_out && src.n_rows >= 100000) {
-    if (!prof_buf) CUDA_TRY(cudaMallocManaged(reinterpret_cast<void**>(&prof_buf), 4 * 2048 * sizeof(long long)));
-    CUDA_TRY(cudaStreamSynchronize(st));
-    std::memset(prof_buf, 0, 4 * 2048 * sizeof(long long));
+    if (!prof_buf) CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&prof_buf), 4 * 2048 * sizeof(long long)));
+    CUDA_TRY(cudaMemsetAsync(prof_buf, 0, 4 * 2048 * sizeof(long long), st));
     a.prof = prof_buf;
   }
 #endif
@@ -969,8 +1096,10 @@ int launch_tc_exact(dsmppi_ctx* c, const float* q, int q_stride, const RowSrc& s
 #ifdef DSMPPI_TCX_PROF
   if (a.prof) {
     CUDA_TRY(cudaStreamSynchronize(st));
+    std::vector<long long> host(4 * 2048);
+    CUDA_TRY(cudaMemcpy(host.data(), prof_buf, host.size() * sizeof(long long), cudaMemcpyDeviceToHost));
     if (FILE* f = std::fopen(prof_out, "wb")) {
-      std::fwrite(prof_buf, sizeof(long long), 4 * 2048, f);
+      std::fwrite(host.data(), sizeof(long long), host.size(), f);
       std::fclose(f);
     }
   }
@@ -997,8 +1126,6 @@ int launch_tc_rollout(dsmppi_ctx* c, const dsmppi_rollout_args* ra, cudaStream_t
   TxArgs a{};
   a.img0 = t->dev;
   a.img1 = t->dev + IMG_BYTES;
-  a.w4hi = reinterpret_cast<const uint4*>(t->dev + 2 * IMG_BYTES);
-  a.w4lo = reinterpret_cast<const uint4*>(t->dev + 2 * IMG_BYTES + 16 * HID * 2);
   a.net = c->net;
   a.obs = c->obs;
   a.ignore_mask = ra->ignored_link_mask;

@@ -425,3 +425,60 @@ def test_whole_horizon_kernel_is_bitwise_identical_to_per_step_launches(tag, fac
     assert la <= 4 and lb >= 3 * H, (la, lb)      # obstacle encodings (2) + init + fused vs 3 launches per step
     for x, y in zip(a, b):
         assert torch.equal(x, y)
+
+
+def _host_buffers(m, q_cur):
+    N, H, d = m.N_traj, m.dt_H, m.n_dof
+    P = m.Policy
+    pin = lambda x: x.detach().cpu().contiguous().clone().pin_memory()  # noqa: E731
+    return dict(q_cur=pin(q_cur), mu_tmp=pin(P.mu_tmp), sigma_tmp=pin(P.sigma_tmp), alpha_tmp=pin(P.alpha_tmp),
+                mu_c=pin(P.mu_c), sigma_c=pin(P.sigma_c), alpha_c=pin(P.alpha_c),
+                all_traj=pin(torch.empty(N, H, d)), closest_dist_all=pin(torch.empty(N, H)),
+                kernel_val_all=pin(torch.zeros(N, H, 50)), dot_products=pin(torch.empty(N, H)),
+                kernel_activations=pin(torch.empty(N, H)), qdot=pin(torch.empty(N, d)), cost=pin(torch.empty(N)),
+                n_updated=pin(torch.zeros(1, dtype=torch.int32)))
+
+
+@pytest.mark.parametrize("tag,N,H,batch_start", [("planar7", 700, 5, False), ("field2", 1000, 1, True),
+                                                  ("franka_shelf", 333, 3, False)])
+def test_host_buffer_iteration_matches_device_path_and_is_chunk_invariant(tag, N, H, batch_start, factory, monkeypatch):
+    """dsmppi_iteration_host (what a CPU-tensor caller and bench.py's e2e pay) returns exactly what
+    propagate + get_cost + shift_policy_means return, and its chunk pipeline for large batches (H2D | rollout + cost |
+    D2H of neighbouring sample chunks overlapped on three streams) changes no bit: forced here with a 64-sample chunk."""
+    c = load_npz(f"case_{tag}")
+    gen = torch.Generator().manual_seed(11)
+    d = c["q0"].shape[0]
+    q_cur = (c["q_cur"].reshape(-1, d)[:1] + 0.2 * torch.randn(N, d, generator=gen)) if batch_start else c["q_cur"].reshape(-1)[:d]
+
+    def fresh():
+        m = factory.make_mppi(c, device="cuda", H=H, N=N, pass1="auto", copy_policy=False, q_cur=q_cur)
+        g2 = torch.Generator().manual_seed(12)
+        nk = int(c["nk"])
+        P = m.Policy
+        P.mu_tmp.zero_(); P.sigma_tmp.zero_(); P.alpha_tmp.zero_()
+        if nk:
+            P.mu_tmp[:, :nk] = (P.mu_c[:nk].cpu() + 0.05 * torch.randn(N, nk, d, generator=g2)).to(P.mu_tmp.device)
+            P.sigma_tmp[:, :nk] = (P.sigma_c[:nk].cpu() * (1 + 0.1 * torch.rand(N, nk, generator=g2))).to(P.sigma_tmp.device)
+            P.alpha_tmp[:, :nk] = (P.alpha_c[:nk].cpu() + 0.3 * torch.randn(N, nk, d, generator=g2)).to(P.alpha_tmp.device)
+        return m
+
+    m = fresh()
+    host0 = _host_buffers(m, q_cur)
+    traj, dist, kv, dots, acts = m.propagate()
+    cost = m.get_cost()
+    _, n_upd = m.shift_policy_means()
+    want = dict(all_traj=traj, closest_dist_all=dist, dot_products=dots, kernel_activations=acts, qdot=m.qdot, cost=cost,
+                mu_c=m.Policy.mu_c, sigma_c=m.Policy.sigma_c, alpha_c=m.Policy.alpha_c)
+    for chunk in ("0", "64"):
+        monkeypatch.setenv("DSMPPI_HOST_CHUNK", chunk)
+        m2 = fresh()
+        host = {k: v.clone().pin_memory() for k, v in host0.items()}
+        m2.iteration_host(host)
+        torch.cuda.synchronize()
+        # bit patterns, so that NaN == NaN: the H = 1 field case has a 0/0 stagnation cost in both paths
+        bits = lambda x: x.detach().cpu().contiguous().view(torch.int32)  # noqa: E731
+        for k, v in want.items():
+            assert torch.equal(bits(host[k]), bits(v)), f"chunk={chunk}: {k} differs from the device path"
+        nk = int(c["nk"])
+        assert torch.equal(bits(host["kernel_val_all"][:, :, :nk]), bits(kv[:, :, :nk])), f"chunk={chunk}: kernel_val_all"
+        assert int(host["n_updated"][0]) == int(n_upd)

@@ -1,5 +1,6 @@
 """Phase accounting of tc_exact_kernel (build the library with DSMPPI_EXTRA_NVCC_FLAGS=-DDSMPPI_TCX_PROF first).
 `run` (GPU box): scores 600 k planar-2 rows once with the stamps on and writes gpurun_out/tcx_prof.bin;
+`dense`: the same two launches with the product library (for `ncu -k regex:tc_exact_kernel -s 1 -c 1`);
 `show` (anywhere): prints CTA 0's merged timeline (epilogue warps 0 and 4, MMA issuer) for one steady-state tile."""
 import os
 import sys
@@ -14,7 +15,8 @@ NAMES = {1: "enc done, A0 signalled", 60: "out layer: D ready", 61: "seed writte
          63: "tile done", 92: "issuer: got K quarter 0", 93: "issuer: got K quarter 1", 94: "issuer: got K quarter 2",
          95: "issuer: got K quarter 3", 100: "weights landed: N0 k<128", 101: "weights landed: N0 k>=128",
          228: "weights landed: N1 k<128", 229: "weights landed: N1 k>=128"}
-NAMES.update({70: "  L3 parked chunk 0 stored", 71: "  L3 quarter 0 signalled", 72: "  L3 E1: first TMEM load back",
+NAMES.update({64: "  out: TMEM load back", 65: "  out: argmin done", 66: "  out: bar.sync passed", 67: "  seed: W5 rows read",
+              68: "  seed: quarter 0 signalled", 70: "  L3 parked chunk 0 stored", 71: "  L3 quarter 0 signalled", 72: "  L3 E1: first TMEM load back",
               73: "  L3 E1: chunk 0 converted", 74: "  L3 E1: chunk 0 stored", 75: "  L3 E1: quarter 2 signalled",
               76: "  L3 E1: second TMEM load back", 77: "  L3 E1: chunk 1 converted"})
 for l in range(8):
@@ -26,8 +28,12 @@ for l in range(8):
     NAMES[50 + l] = f"{tag}: half1 stored, quarters 2, 3 signalled"
 
 
-def run():
+def run(prof=True):
     import torch
+    from optimalmodulationds_b200 import _capi
+    prof_lib = os.path.join(ROOT, "optimalmodulationds_b200", "libdsmppi_b200_prof.so")
+    if prof and os.path.exists(prof_lib):          # tools/build_prof.sh: the instrumented build beside the product library
+        _capi.LIB_PATH = prof_lib
     from tests.golden_util import load_npz
     from tests.mppi_factory import make_mppi
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
@@ -38,10 +44,12 @@ def run():
     q = ((torch.rand(300000, 2) * 2 - 1) * 2.5).cuda()
     m.distance_repulsion_nn(q)
     torch.cuda.synchronize()
-    os.environ["DSMPPI_TCX_PROF_OUT"] = OUT
+    if prof:
+        os.environ["DSMPPI_TCX_PROF_OUT"] = OUT
     m.distance_repulsion_nn(q)
     torch.cuda.synchronize()
-    print("wrote", OUT, os.path.getsize(OUT))
+    if prof:
+        print("wrote", OUT, os.path.getsize(OUT))
 
 
 def show(tile=3):
@@ -68,4 +76,9 @@ def show(tile=3):
 
 
 if __name__ == "__main__":
-    run() if sys.argv[1] == "run" else show(int(sys.argv[2]) if len(sys.argv) > 2 else 3)
+    if sys.argv[1] == "run":
+        run()
+    elif sys.argv[1] == "dense":          # the same launch with the product library: the target of an ncu capture
+        run(prof=False)
+    else:
+        show(int(sys.argv[2]) if len(sys.argv) > 2 else 3)
