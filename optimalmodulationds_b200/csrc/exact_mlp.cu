@@ -108,9 +108,7 @@ rollout_fused_kernel(NetDev net, StepArgs sa, const float* __restrict__ obs, int
         sel_rows[(size_t)i * K + kk] = i * M + bj;
         last_v = bv; last_j = bj;
       }
-      StepArgs s = sa;
-      s.t = t;
-      step_sample(s, i);
+      step_sample(sa, i, t);
     }
     __syncthreads();                                    // next state written before the next tile reads it
   }

@@ -64,10 +64,11 @@ __device__ __forceinline__ float nan_to_num(float v) {
   return v;
 }
 
-// one sample i of step s.t; every per-sample vector stays in registers
-__device__ __forceinline__ void step_sample(const StepArgs& s, int i) {
+// one sample i of step t (s.t is ignored: the whole-horizon kernels keep ONE argument block in the constant bank and
+// pass the step they are at); every per-sample vector stays in registers
+__device__ __forceinline__ void step_sample(const StepArgs& s, int i, int t) {
   const int d = s.d;
-  const size_t st = (size_t)i * s.H + (s.t - 1);     // state-step index
+  const size_t st = (size_t)i * s.H + (t - 1);       // state-step index
   float q[MAXD], v[MAXD], vhat[MAXD], e0[MAXD], g[MAXD], u[MAXD], vt[MAXD], m[MAXD];
   // S0 nominal DS and its norm (MPPI.py:106-108)
   float ss = 0.f;
@@ -211,27 +212,38 @@ __device__ __forceinline__ void step_sample(const StepArgs& s, int i) {
   // S4 RBF policy (policy.py:186-199, MPPI.py:165-186)
 #pragma unroll
   for (int a = 0; a < MAXD; ++a) u[a] = 0.f;
+  // the sampled policy is read-only for the whole rollout: ld.global.nc, and the loads of the next kernel are issued
+  // under the arithmetic of this one (in the whole-horizon kernels ONE warp per CTA runs this loop between two
+  // network tiles, so every exposed L2 round trip is on the rollout's critical path)
+#pragma unroll 2
   for (int k = 0; k < s.nk; ++k) {
     const float* mu = s.mu + ((size_t)i * NKMAX + k) * d;
+    const float* al = s.alpha + ((size_t)i * NKMAX + k) * d;
+    float muv[MAXD], alv[MAXD];
+#pragma unroll
+    for (int a = 0; a < MAXD; ++a) {
+      muv[a] = a < d ? __ldg(mu + a) : 0.f;
+      alv[a] = a < d ? __ldg(al + a) : 0.f;
+    }
+    const float sg = __ldg(s.sigma + (size_t)i * NKMAX + k);
     float acc = 0.f;
     if (s.p == 2.f) {
 #pragma unroll
       for (int a = 0; a < MAXD; ++a)
-        if (a < d) { const float df = q[a] - mu[a]; acc += df * df; }
+        if (a < d) { const float df = q[a] - muv[a]; acc += df * df; }
       acc = sqrtf(acc);
     } else {
 #pragma unroll
       for (int a = 0; a < MAXD; ++a)
-        if (a < d) acc += powf(fabsf(q[a] - mu[a]), s.p);
+        if (a < d) acc += powf(fabsf(q[a] - muv[a]), s.p);
       acc = powf(acc, 1.f / s.p);
     }
     const float num = acc * acc;                       // norm ** 2
-    const float phi = expf(-s.sigma[(size_t)i * NKMAX + k] * num);
+    const float phi = expf(-sg * num);
     s.kval[st * NKMAX + k] = s.mod.fold_activation ? phi * kv_scale : phi;   // MPPI.py:184
-    const float* al = s.alpha + ((size_t)i * NKMAX + k) * d;
 #pragma unroll
     for (int a = 0; a < MAXD; ++a)
-      if (a < d) u[a] += al[a] * phi;                  // MPPI.py:174-177
+      if (a < d) u[a] += alv[a] * phi;                 // MPPI.py:174-177
   }
   // total velocity and modulation M = l_tau I + (l_nv - l_tau) e0 e0^T  (MPPI.py:158-161,197-209)
   float proj = 0.f;
@@ -256,12 +268,12 @@ __device__ __forceinline__ void step_sample(const StepArgs& s, int i) {
     if (coll) mv = mv * 0.1f + e0[a] * vn * s.mod.repulsion;   // MPPI.py:215-217
     m[a] = mv;
   }
-  if (s.t < s.H) {
+  if (t < s.H) {
 #pragma unroll
     for (int a = 0; a < MAXD; ++a)
       if (a < d) s.traj[(st + 1) * d + a] = q[a] + s.dt * m[a];   // MPPI.py:220-221
   }
-  if (s.t == 1) {
+  if (t == 1) {
 #pragma unroll
     for (int a = 0; a < MAXD; ++a)
       if (a < d) s.qdot[(size_t)i * d + a] = m[a];                // MPPI.py:222-223

@@ -743,6 +743,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_exac
       }
       if constexpr (MODE == 2) {
         asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (q4 == 0) TCX_PROF(h, 80);
         const int nfix = *fixn;
         if (nfix > 0 && tid < exact_tile::nthreads(8)) {
           // the FFMA tile of exact_mlp.cu on warps 0-3, its shared memory carved out of the (idle) A operand images
@@ -786,12 +787,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_exac
               a.sel_rows[(size_t)i * K + kk] = i * M + bj;
               last_v = bv; last_j = bj;
             }
-            StepArgs st = a.sa;
-            st.t = t;
-            step_sample(st, i);
+            if (tid == 0) TCX_PROF(0, 83);
+            step_sample(a.sa, i, t);
           }
         }
+        if (q4 == 0) TCX_PROF(h, 81);
         asm volatile("bar.sync 1, 256;" ::: "memory");      // the next state is written before the next encoding reads it
+        if (q4 == 0) TCX_PROF(h, 82);
       }
     }
   } else {
@@ -1144,6 +1146,15 @@ int launch_tc_rollout(dsmppi_ctx* c, const dsmppi_rollout_args* ra, cudaStream_t
   a.fix_cap = 0;
   const char* dbg = std::getenv("DSMPPI_TCX_DEBUG");
   a.dbg = dbg ? std::atoi(dbg) : 0;
+#ifdef DSMPPI_TCX_PROF
+  static long long* prof_buf = nullptr;
+  const char* prof_out = std::getenv("DSMPPI_TCX_PROF_OUT");
+  if (prof_out) {
+    if (!prof_buf) CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&prof_buf), 4 * 2048 * sizeof(long long)));
+    CUDA_TRY(cudaMemsetAsync(prof_buf, 0, 4 * 2048 * sizeof(long long), st));
+    a.prof = prof_buf;
+  }
+#endif
   const long long tiles = ((long long)ra->N + 2 * a.S - 1) / (2 * a.S);
   long long pairs = c->sm_count / 2;
   if (pairs > tiles) pairs = tiles;
@@ -1151,5 +1162,16 @@ int launch_tc_rollout(dsmppi_ctx* c, const dsmppi_rollout_args* ra, cudaStream_t
   tc_exact_kernel<2><<<dim3((unsigned)(2 * pairs)), NTHREADS, SMEM_BYTES, st>>>(a);
   CUDA_TRY(cudaGetLastError());
   c->launches++;
+#ifdef DSMPPI_TCX_PROF
+  if (a.prof) {
+    CUDA_TRY(cudaStreamSynchronize(st));
+    std::vector<long long> host(4 * 2048);
+    CUDA_TRY(cudaMemcpy(host.data(), prof_buf, host.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    if (FILE* f = std::fopen(prof_out, "wb")) {
+      std::fwrite(host.data(), sizeof(long long), host.size(), f);
+      std::fclose(f);
+    }
+  }
+#endif
   return 0;
 }

@@ -15,7 +15,8 @@ NAMES = {1: "enc done, A0 signalled", 60: "out layer: D ready", 61: "seed writte
          63: "tile done", 92: "issuer: got K quarter 0", 93: "issuer: got K quarter 1", 94: "issuer: got K quarter 2",
          95: "issuer: got K quarter 3", 100: "weights landed: N0 k<128", 101: "weights landed: N0 k>=128",
          228: "weights landed: N1 k<128", 229: "weights landed: N1 k>=128"}
-NAMES.update({64: "  out: TMEM load back", 65: "  out: argmin done", 66: "  out: bar.sync passed", 67: "  seed: W5 rows read",
+NAMES.update({83: "  step: ranking done", 80: "  step: rows visible (bar.sync)", 81: "  step: ranking + modulation step done", 82: "  step: next state visible (bar.sync)",
+              64: "  out: TMEM load back", 65: "  out: argmin done", 66: "  out: bar.sync passed", 67: "  seed: W5 rows read",
               68: "  seed: quarter 0 signalled", 70: "  L3 parked chunk 0 stored", 71: "  L3 quarter 0 signalled", 72: "  L3 E1: first TMEM load back",
               73: "  L3 E1: chunk 0 converted", 74: "  L3 E1: chunk 0 stored", 75: "  L3 E1: quarter 2 signalled",
               76: "  L3 E1: second TMEM load back", 77: "  L3 E1: chunk 1 converted"})
@@ -26,6 +27,26 @@ for l in range(8):
     NAMES[30 + l] = f"{tag}: D half1 ready"
     NAMES[40 + l] = f"{tag}: half0 stored, quarters 0, 1 signalled"
     NAMES[50 + l] = f"{tag}: half1 stored, quarters 2, 3 signalled"
+
+
+def run_rollout(case):
+    """whole-horizon kernel (MODE 2): one propagate() of a golden case with the stamps on"""
+    import torch
+    from optimalmodulationds_b200 import _capi
+    prof_lib = os.path.join(ROOT, "optimalmodulationds_b200", "libdsmppi_b200_prof.so")
+    if os.path.exists(prof_lib):
+        _capi.LIB_PATH = prof_lib
+    from tests.golden_util import load_npz
+    from tests.mppi_factory import make_mppi
+    os.makedirs(os.path.dirname(OUT), exist_ok=True)
+    m = make_mppi(load_npz(f"case_{case}"), device="cuda", pass1="auto")
+    m.set_score_mode("tc_split")
+    m.propagate()
+    torch.cuda.synchronize()
+    os.environ["DSMPPI_TCX_PROF_OUT"] = OUT
+    m.propagate()
+    torch.cuda.synchronize()
+    print("wrote", OUT, os.path.getsize(OUT))
 
 
 def run(prof=True):
@@ -78,6 +99,8 @@ def show(tile=3):
 if __name__ == "__main__":
     if sys.argv[1] == "run":
         run()
+    elif sys.argv[1] == "rollout":
+        run_rollout(sys.argv[2] if len(sys.argv) > 2 else "planar7")
     elif sys.argv[1] == "dense":          # the same launch with the product library: the target of an ncu capture
         run(prof=False)
     else:
