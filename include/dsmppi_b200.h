@@ -268,7 +268,11 @@ int dsmppi_kernel_candidates(dsmppi_ctx* ctx, const dsmppi_candidates_args* args
 
 /* One whole MPPI iteration with HOST buffers (what a CPU-tensor caller of the reference API pays):
  * H2D of q_cur / sampled policy, rollout, cost, policy update, D2H of every output.  Host pointers may be
- * pageable or pinned.  Synchronises `stream` before returning. */
+ * pageable or pinned.  Synchronises `stream` before returning.
+ * A batch of more than 2 x 131072 samples is pipelined in sample chunks over two internal copy streams (H2D of chunk
+ * k+1 and D2H of chunk k-1 under the rollout + cost of chunk k on `stream`; the policy update follows the last
+ * chunk); results are bit-identical to the single pass.  Environment: DSMPPI_HOST_CHUNK=<samples> overrides the
+ * chunk size, 0 disables the pipeline. */
 typedef struct {
   dsmppi_rollout_args rollout;   /* the *_dev fields are ignored; shapes and scalars are used            */
   float q_min[DSMPPI_MAX_DOF];
