@@ -143,6 +143,22 @@ class MPPI:
     def _stream(self):
         return _capi.C.c_void_p(torch.cuda.current_stream(self._dev).cuda_stream)
 
+    def _host_vec(self, t):
+        """Small parameter vectors (goal, joint limits) as Python floats.  A CUDA tensor is copied to the host once per
+        (tensor, in-place version): a `.to('cpu')` on every call would synchronise with the device and keep the CPU
+        from running ahead of the rollout it has just launched."""
+        if isinstance(t, torch.Tensor) and t.is_cuda:
+            cache = self.__dict__.setdefault('_hostvec_cache', {})
+            hit = cache.get(id(t))
+            if hit is not None and hit[0] is t and hit[1] == t._version:
+                return hit[2]
+            vals = t.detach().reshape(-1).to('cpu', torch.float32).tolist()
+            if len(cache) > 64:
+                cache.clear()
+            cache[id(t)] = (t, t._version, vals)
+            return vals
+        return torch.as_tensor(t).detach().reshape(-1).to('cpu', torch.float32).tolist()
+
     def _d(self, t):
         """Tensor on the compute device, fp32, contiguous (no copy when it already is)."""
         return torch.as_tensor(t).detach().to(self._dev, torch.float32).contiguous()
@@ -289,9 +305,9 @@ class MPPI:
         elif self.distance_provider != 'nn':
             raise ValueError("distance_provider must be 'nn' or 'fk'")
         a.lin_thr, a.rbf_p = float(getattr(self.DS, 'lin_thr', 0.0)), float(self.Policy.p)
-        goal = torch.as_tensor(self.DS.q_goal).detach().reshape(-1).to('cpu', torch.float32)
+        goal = self._host_vec(self.DS.q_goal)
         for i in range(self.n_dof):
-            a.q_goal[i] = float(goal[i])
+            a.q_goal[i] = goal[i]
         a.q_cur_dev = q_cur.data_ptr()
         a.mu_tmp_dev, a.sigma_tmp_dev, a.alpha_tmp_dev = mu.data_ptr(), sigma.data_ptr(), alpha.data_ptr()
         a.all_traj_dev = out['all_traj'].data_ptr()
@@ -416,13 +432,11 @@ class MPPI:
         N, H, d = all_traj.shape
         a = _capi.CostArgs()
         a.N, a.H, a.terms = N, H, self._COST_TERMS
-        goal = torch.as_tensor(cost_obj.qf).detach().reshape(-1).to('cpu', torch.float32)
-        qmin = torch.as_tensor(cost_obj.q_min).detach().reshape(-1).to('cpu', torch.float32)
-        qmax = torch.as_tensor(cost_obj.q_max).detach().reshape(-1).to('cpu', torch.float32)
-        if qmin.numel() < d or qmax.numel() < d:
+        goal, qmin, qmax = self._host_vec(cost_obj.qf), self._host_vec(cost_obj.q_min), self._host_vec(cost_obj.q_max)
+        if len(qmin) < d or len(qmax) < d:
             raise ValueError("Cost.q_min / q_max must have n_dof entries")
         for i in range(d):
-            a.q_goal[i], a.q_min[i], a.q_max[i] = float(goal[i]), float(qmin[i]), float(qmax[i])
+            a.q_goal[i], a.q_min[i], a.q_max[i] = goal[i], qmin[i], qmax[i]
         with torch.cuda.device(self._dev):
             tr, cd = self._dev_of(all_traj), self._dev_of(closest_dist_all)
             cost = torch.empty(N, device=self._dev)
@@ -532,10 +546,9 @@ class MPPI:
         out = {k: dummy for k in ('all_traj', 'closest', 'kval', 'dots', 'acts', 'qdot', 'grads')}
         r = self._rollout_args(N, H, int(P.n_kernels), host['q_cur'], dummy, dummy, dummy, out)
         a.rollout = r
-        qmin = torch.as_tensor(self.Cost.q_min).reshape(-1).float()
-        qmax = torch.as_tensor(self.Cost.q_max).reshape(-1).float()
+        qmin, qmax = self._host_vec(self.Cost.q_min), self._host_vec(self.Cost.q_max)
         for i in range(d):
-            a.q_min[i], a.q_max[i] = float(qmin[i]), float(qmax[i])
+            a.q_min[i], a.q_max[i] = qmin[i], qmax[i]
         a.ker_thr, a.upd_rate = float(self.ker_thr), float(self.policy_upd_rate)
         a.cost_terms, a.update_variant = self._COST_TERMS, self._UPDATE_VARIANT
         for name in ('q_cur', 'mu_tmp', 'sigma_tmp', 'alpha_tmp', 'mu_c', 'sigma_c', 'alpha_c', 'all_traj',

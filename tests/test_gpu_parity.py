@@ -482,3 +482,26 @@ def test_host_buffer_iteration_matches_device_path_and_is_chunk_invariant(tag, N
         nk = int(c["nk"])
         assert torch.equal(bits(host["kernel_val_all"][:, :, :nk]), bits(kv[:, :, :nk])), f"chunk={chunk}: kernel_val_all"
         assert int(host["n_updated"][0]) == int(n_upd)
+
+
+def test_parameter_vectors_on_the_device_are_read_at_call_time(factory):
+    """Goal and joint limits handed over as CUDA tensors are cached on the host per (tensor, in-place version) so that
+    a call does not synchronise with the device; an in-place edit or a rebinding must still be seen by the next call
+    (the reference reads the attributes at call time)."""
+    c = load_npz("case_planar7")
+    m = factory.make_mppi(c, device="cuda", pass1="auto")
+    m.propagate()
+    m.Cost.q_max = torch.full_like(m.Cost.q_max, 100.0)          # rebound: nothing violates a joint limit
+    m.Cost.q_min = torch.full_like(m.Cost.q_min, -100.0)
+    base = m.get_cost().clone()
+    assert torch.equal(m.get_cost(), base)                       # served from the cache: same numbers
+    m.Cost.q_max[0] = -100.0                                     # in place: every trajectory now violates a limit
+    assert torch.allclose(m.get_cost(), base + 100.0)
+    m.Cost.q_max[0] = 100.0
+    assert torch.equal(m.get_cost(), base)
+    goal0 = m.DS.q_goal.clone()
+    traj0 = m.propagate()[0].clone()
+    m.DS.q_goal += 0.5                                           # in place: the nominal DS must follow
+    assert not torch.equal(m.propagate()[0], traj0)
+    m.DS.q_goal.copy_(goal0)
+    assert torch.equal(m.propagate()[0], traj0)
