@@ -634,7 +634,11 @@ int dsmppi_iteration_host(dsmppi_ctx* c, dsmppi_iteration_host_args* h, void* st
     CUDA_TRY(cudaStreamWaitEvent(c->s_out, ev_start, 0));
     c->ev_used = 0;
     CUDA_TRY(cudaMemsetAsync(c->counters + 1, 0, 3 * sizeof(int), st));
-    c->keep_counters = 1;
+    struct KeepCounters {                                   // cleared on every exit path, error returns included
+      dsmppi_ctx* c;
+      explicit KeepCounters(dsmppi_ctx* ctx) : c(ctx) { c->keep_counters = 1; }
+      ~KeepCounters() { c->keep_counters = 0; }
+    } keep(c);
     int rc = 0;
     for (size_t k = 0; k < n_chunks && !rc; ++k) {
       const size_t o = k * CHUNK, n = N - o < CHUNK ? N - o : CHUNK;
@@ -685,7 +689,6 @@ int dsmppi_iteration_host(dsmppi_ctx* c, dsmppi_iteration_host_args* h, void* st
       CUDA_TRY(down_c(h->qdot_host, o_qd, d));
       CUDA_TRY(down_c(h->cost_host, o_co, 1));
     }
-    c->keep_counters = 0;
     if (rc) return rc;
     CUDA_TRY(cudaEventRecord(ev_drained, c->s_out));
     CUDA_TRY(cudaStreamWaitEvent(st, ev_drained, 0));      // the caller's stream is done when the last copy-out is

@@ -108,7 +108,7 @@ rollout_fused_kernel(NetDev net, StepArgs sa, const float* __restrict__ obs, int
         sel_rows[(size_t)i * K + kk] = i * M + bj;
         last_v = bv; last_j = bj;
       }
-      step_sample(sa, i, t);
+      step_sample(sa, i, t, step_io_global(sa, i));
     }
     __syncthreads();                                    // next state written before the next tile reads it
   }

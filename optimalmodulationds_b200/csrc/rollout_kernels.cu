@@ -178,7 +178,7 @@ __global__ void blend_kernel(const float* __restrict__ row_dist, const float* __
 
 __global__ void __launch_bounds__(128) step_kernel(StepArgs s) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < s.N) step_sample(s, i, s.t);
+  if (i < s.N) step_sample(s, i, s.t, step_io_global(s, i));
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -6,6 +6,22 @@
 
 #include "internal.cuh"
 
+// phase stamps of ONE thread (block 0, thread 0) inside step_sample, only in -DDSMPPI_TCX_PROF builds (tools/tcx_prof.py)
+#ifdef DSMPPI_TCX_PROF
+__device__ long long* g_step_prof = nullptr;
+__device__ int g_step_prof_n = 0;
+#define STEP_PROF(id)                                                                  \
+  do {                                                                                 \
+    if (g_step_prof && blockIdx.x == 0 && threadIdx.x == 0 && g_step_prof_n < 1000) {  \
+      g_step_prof[2 * g_step_prof_n] = (id);                                           \
+      g_step_prof[2 * g_step_prof_n + 1] = clock64();                                  \
+      ++g_step_prof_n;                                                                 \
+    }                                                                                  \
+  } while (0)
+#else
+#define STEP_PROF(id) do { } while (0)
+#endif
+
 // ------------------------------------------------------------------------------------------------
 // Gradient blend (MPPI.py:270-280): w = softmax(-10 * dist_k), grad = sum_k w_k grad_k, distance = dist_0
 // ------------------------------------------------------------------------------------------------
@@ -64,16 +80,31 @@ __device__ __forceinline__ float nan_to_num(float v) {
   return v;
 }
 
+// Where one sample's step finds its inputs: the differentiated rows (distance, gradient) and the ranked row indices of
+// this sample, and optionally the state itself.  The stand-alone step kernel reads all of it from global memory; the
+// whole-horizon tensor-core kernel keeps the rows in shared memory and the state in registers, because every dependent
+// L2 round trip of the ONE warp that steps a CTA's samples (~2 k cycles on this part) is on the rollout's critical path.
+struct StepIO {
+  const float* row_dist; const float* row_grad; const int* rows;
+  const float* q_in;     // nullptr: all_traj[i, t-1]
+  float* q_next;         // nullptr, or where q + dt * m goes besides all_traj[i, t]
+};
+
+// the stand-alone form: everything from global memory
+__device__ __forceinline__ StepIO step_io_global(const StepArgs& s, int i) {
+  return StepIO{s.row_dist, s.row_grad, s.sel_rows + (size_t)i * s.K, nullptr, nullptr};
+}
+
 // one sample i of step t (s.t is ignored: the whole-horizon kernels keep ONE argument block in the constant bank and
 // pass the step they are at); every per-sample vector stays in registers
-__device__ __forceinline__ void step_sample(const StepArgs& s, int i, int t) {
+__device__ __forceinline__ void step_sample(const StepArgs& s, int i, int t, const StepIO& io) {
   const int d = s.d;
   const size_t st = (size_t)i * s.H + (t - 1);       // state-step index
   float q[MAXD], v[MAXD], vhat[MAXD], e0[MAXD], g[MAXD], u[MAXD], vt[MAXD], m[MAXD];
   // S0 nominal DS and its norm (MPPI.py:106-108)
   float ss = 0.f;
 #pragma unroll
-  for (int a = 0; a < MAXD; ++a) q[a] = a < d ? s.traj[st * d + a] : 0.f;
+  for (int a = 0; a < MAXD; ++a) q[a] = a < d ? (io.q_in ? io.q_in[a] : s.traj[st * d + a]) : 0.f;
   if (s.mod.ds_kind == DSMPPI_DS_MATRIX) {
     // v = (q - q_goal) @ A, not normalised (MPPI_toy.py:89)
 #pragma unroll
@@ -173,9 +204,10 @@ __device__ __forceinline__ void step_sample(const StepArgs& s, int i, int t) {
 #pragma unroll
   for (int a = 0; a < MAXD; ++a) vhat[a] = a < d ? v[a] / vn : 0.f;
 
+  STEP_PROF(201);
   // S2e blended distance / gradient
   float dist;
-  blend(s.row_dist, s.row_grad, s.sel_rows + (size_t)i * s.K, s.K, d, dist, g);
+  blend(io.row_dist, io.row_grad, io.rows, s.K, d, dist, g);
   dist -= s.dst_thr;                                  // MPPI.py:117
   s.closest[st] = dist;
   ss = 0.f;
@@ -192,6 +224,7 @@ __device__ __forceinline__ void step_sample(const StepArgs& s, int i, int t) {
     dot += e0[a] * vhat[a];                           // MPPI.py:129
   }
   s.dots[st] = dot;
+  STEP_PROF(202);
   // S3 modulation coefficients (MPPI.py:132,149-155)
   const float l_vel = gsigmoid(dot, 0.f, 1.f, s.mod.lvel_mid, s.mod.lvel_k);
   const float l_n = gsigmoid(dist, 0.f, 1.f, s.mod.dist_mid, s.mod.dist_k);
@@ -209,6 +242,7 @@ __device__ __forceinline__ void step_sample(const StepArgs& s, int i, int t) {
   const float act = (1.f - l_n) * (1.f - l_vel) * ga;
   s.acts[st] = act;
   const float kv_scale = s.mod.fold_activation ? act : 1.f;   // MPPI_toy.py:178-179
+  STEP_PROF(203);
   // S4 RBF policy (policy.py:186-199, MPPI.py:165-186)
 #pragma unroll
   for (int a = 0; a < MAXD; ++a) u[a] = 0.f;
@@ -245,6 +279,7 @@ __device__ __forceinline__ void step_sample(const StepArgs& s, int i, int t) {
     for (int a = 0; a < MAXD; ++a)
       if (a < d) u[a] += alv[a] * phi;                 // MPPI.py:174-177
   }
+  STEP_PROF(204);
   // total velocity and modulation M = l_tau I + (l_nv - l_tau) e0 e0^T  (MPPI.py:158-161,197-209)
   float proj = 0.f;
 #pragma unroll
@@ -268,11 +303,15 @@ __device__ __forceinline__ void step_sample(const StepArgs& s, int i, int t) {
     if (coll) mv = mv * 0.1f + e0[a] * vn * s.mod.repulsion;   // MPPI.py:215-217
     m[a] = mv;
   }
-  if (t < s.H) {
 #pragma unroll
-    for (int a = 0; a < MAXD; ++a)
-      if (a < d) s.traj[(st + 1) * d + a] = q[a] + s.dt * m[a];   // MPPI.py:220-221
+  for (int a = 0; a < MAXD; ++a) {
+    if (a < d) {
+      const float qn = q[a] + s.dt * m[a];                        // MPPI.py:220-221
+      if (t < s.H) s.traj[(st + 1) * d + a] = qn;
+      if (io.q_next) io.q_next[a] = qn;
+    }
   }
+  STEP_PROF(205);
   if (t == 1) {
 #pragma unroll
     for (int a = 0; a < MAXD; ++a)

@@ -157,6 +157,13 @@ constexpr int OFF_B4 = OFF_FIXL + 3 * TROWS * 4;   // output-layer bias (16 floa
 constexpr int SMEM_BYTES = OFF_B4 + 64;
 static_assert(exact_tile::smem_bytes(32) <= OFF_RING, "the FFMA fallback tile lives in the A operand images");
 constexpr int OFF_SCRATCH = OFF_ALO + 32768;   // final epilogue: a[e][row] fp32 (16 KB) inside the idle A_lo image
+// whole-horizon kernel: the tile's rows (ranking key, distance, gradient) and the stepped states, handed from the row
+// threads to the CTA's step threads and back through the last 16 KB of the A_lo image (idle between the last GEMM of
+// a step and the second half of the next step's first epilogue; the FFMA fallback tile ends below it)
+constexpr int OFF_STAGE = OFF_ALO + 49152;
+constexpr int STG_M = 0, STG_DIST = TROWS, STG_GRAD = 2 * TROWS, STG_Q = 2 * TROWS + TROWS * MAXD;   // float offsets
+static_assert((STG_Q + TROWS * MAXD) * 4 <= 16384, "row staging exceeds the tail of the A_lo image");
+static_assert(exact_tile::smem_bytes(32) <= OFF_STAGE && OFF_SCRATCH + 16384 <= OFF_STAGE, "staging overlaps");
 static_assert(NBAR * 8 <= 128, "barrier block");
 static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB shared-memory budget");
 
@@ -448,6 +455,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_exac
       if (TCX_ENC_PIPE) enc_compute(nx_i, nx_j, nx_valid, a.q, a.q_stride);
     }
     uint32_t pass = 0;                                      // (tile, step) passes done: locates the output layer's stage
+    float qreg[MAXD];                                       // whole-horizon kernel: the state of this thread's sample
+#pragma unroll
+    for (int c = 0; c < MAXD; ++c) qreg[c] = 0.f;
     bool enc_stored = false;
 
     for (int tile = pair; tile < n_tiles; tile += npairs)
@@ -456,19 +466,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_exac
       int grow = tile * (2 * TROWS) + (int)rank * TROWS + row;
       const float* qsrc = MODE == 2 ? a.sa.traj + (size_t)(t - 1) * d : a.q;     // q_prev = all_traj[:, t-1, :]
       const int qstride = MODE == 2 ? a.sa.H * d : a.q_stride;
+      float* stg = reinterpret_cast<float*>(smem + OFF_STAGE);
       if (MODE == 2) {                                      // the state was written by the step just before: encode now
         const int sl = row / a.M;
         const int tj = row - sl * a.M;
         const int ti = (tile * 2 + (int)rank) * a.S + sl;
         const bool tv = sl < a.S && ti < a.sa.N;
         grow = tv ? ti * a.M + tj : n_rows;
-        enc_compute(ti, tj, tv, qsrc, qstride);
+        if (t == 1) enc_compute(ti, tj, tv, qsrc, qstride);
+        else enc_compute(sl, tj, tv, stg + STG_Q, MAXD);    // ... and handed over in shared memory: no L2 round trip
       } else if (!TCX_ENC_PIPE) {
         enc_compute(nx_i, nx_j, nx_valid, qsrc, qstride);
       }
-      float* out_m = MODE == 2 ? a.m_rows : a.out_m;
-      float* out_dist = MODE == 2 ? a.row_dist : a.out_dist;
-      float* out_grad = MODE == 2 ? a.row_grad : a.out_grad;
+      // MODE 2: the rows never leave the SM (they are workspace, not outputs of the rollout)
+      float* out_m = MODE == 2 ? stg + STG_M : a.out_m;
+      float* out_dist = MODE == 2 ? stg + STG_DIST : a.out_dist;
+      float* out_grad = MODE == 2 ? stg + STG_GRAD : a.out_grad;
+      const int orow = MODE == 2 ? row : grow;              // where this row's results go
       float sn[MAXD], cs[MAXD];
 #pragma unroll
       for (int c = 0; c < MAXD; ++c) { sn[c] = en_sn[c]; cs[c] = en_cs[c]; }
@@ -578,7 +592,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_exac
           if (net.scale != 1.f) y = y / 100.f;
           o_dist = y - rad;
         }
-        if (!TCX_DEFER_STG && grow < n_rows) {
+        if (!TCX_DEFER_STG && MODE != 2 && grow < n_rows) {
           if (out_m) out_m[grow] = o_m;
           if (BWD) out_dist[grow] = o_dist;
         }
@@ -690,7 +704,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_exac
 #pragma unroll
           for (int c = 0; c < MAXD; ++c)
             if (c < d) o_g[c] = scr[c * TROWS] + cs[c] * scr[(nin + c) * TROWS] - sn[c] * scr[(2 * nin + c) * TROWS];
-          if (!TCX_DEFER_STG && grow < n_rows) {
+          if (!TCX_DEFER_STG && MODE != 2 && grow < n_rows) {
 #pragma unroll
             for (int c = 0; c < MAXD; ++c)
               if (c < d) out_grad[(size_t)grow * d + c] = o_g[c];
@@ -706,13 +720,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_exac
       } else {
         enc_stored = false;
       }
-      if (TCX_DEFER_STG && h == 0 && grow < n_rows) {
-        if (out_m) out_m[grow] = o_m;
+      if ((TCX_DEFER_STG || MODE == 2) && h == 0 && grow < n_rows) {
+        if (out_m) out_m[orow] = o_m;
         if (BWD) {
-          out_dist[grow] = o_dist;
+          out_dist[orow] = o_dist;
 #pragma unroll
           for (int c = 0; c < MAXD; ++c)
-            if (c < d) out_grad[(size_t)grow * d + c] = o_g[c];
+            if (c < d) out_grad[(size_t)orow * d + c] = o_g[c];
         }
       }
       if (q4 == 0) TCX_PROF(h, 63);
@@ -738,7 +752,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_exac
           atomicAdd(a.fix_total, 1);
           fixl[k] = row_i;
           fixl[TROWS + k] = row_j;
-          fixl[2 * TROWS + k] = grow;
+          fixl[2 * TROWS + k] = row;           // re-scored into the staged rows
         }
       }
       if constexpr (MODE == 2) {
@@ -772,23 +786,42 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_exac
           const int i = (tile * 2 + (int)rank) * a.S + tid;
           if (i < a.sa.N) {
             const int K = a.sa.K, M = a.M;
-            const float* mr = a.m_rows + (size_t)i * M;
+            // the sampled policy rows of this sample on their way into L1 while the ranking and the blend run
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(a.sa.sigma + (size_t)i * NKMAX));
+            for (int b = 0; b < a.sa.nk * d * 4; b += 128) {
+              asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char*>(a.sa.mu + (size_t)i * NKMAX * d) + b));
+              asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char*>(a.sa.alpha + (size_t)i * NKMAX * d) + b));
+            }
+            if (t == 1) {
+#pragma unroll
+              for (int c = 0; c < MAXD; ++c) qreg[c] = c < d ? a.sa.traj[(size_t)i * a.sa.H * d + c] : 0.f;
+            }
+            const float* mr = stg + STG_M + tid * M;         // this sample's rows are staged rows tid * M .. + M
+            int rows[MAXK];
             float last_v = -3.4e38f;
             int last_j = -1;
-            for (int kk = 0; kk < K; ++kk) {
-              float bv = 3.4e38f;
-              int bj = -1;
-              for (int j = 0; j < M; ++j) {
-                const float v = mr[j];
-                const bool after = kk == 0 || v > last_v || (v == last_v && j > last_j);
-                if (after && (bj < 0 || v < bv)) { bv = v; bj = j; }
+#pragma unroll
+            for (int kk = 0; kk < MAXK; ++kk) {
+              rows[kk] = 0;
+              if (kk < K) {
+                float bv = 3.4e38f;
+                int bj = -1;
+                for (int j = 0; j < M; ++j) {
+                  const float v = mr[j];
+                  const bool after = kk == 0 || v > last_v || (v == last_v && j > last_j);
+                  if (after && (bj < 0 || v < bv)) { bv = v; bj = j; }
+                }
+                if (bj < 0) bj = last_j < 0 ? 0 : last_j;
+                rows[kk] = tid * M + bj;
+                last_v = bv; last_j = bj;
               }
-              if (bj < 0) bj = last_j < 0 ? 0 : last_j;
-              a.sel_rows[(size_t)i * K + kk] = i * M + bj;
-              last_v = bv; last_j = bj;
             }
             if (tid == 0) TCX_PROF(0, 83);
-            step_sample(a.sa, i, t);
+            const StepIO io{stg + STG_DIST, stg + STG_GRAD, rows, qreg, qreg};
+            step_sample(a.sa, i, t, io);
+#pragma unroll
+            for (int c = 0; c < MAXD; ++c)
+              if (c < d) stg[STG_Q + tid * MAXD + c] = qreg[c];
           }
         }
         if (q4 == 0) TCX_PROF(h, 81);
@@ -1153,6 +1186,10 @@ int launch_tc_rollout(dsmppi_ctx* c, const dsmppi_rollout_args* ra, cudaStream_t
     if (!prof_buf) CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&prof_buf), 4 * 2048 * sizeof(long long)));
     CUDA_TRY(cudaMemsetAsync(prof_buf, 0, 4 * 2048 * sizeof(long long), st));
     a.prof = prof_buf;
+    long long* region3 = prof_buf + 3 * 2048;              // step_sample's own stamps (step_device.cuh)
+    int zero = 0;
+    CUDA_TRY(cudaMemcpyToSymbolAsync(g_step_prof, &region3, sizeof(region3), 0, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyToSymbolAsync(g_step_prof_n, &zero, sizeof(zero), 0, cudaMemcpyHostToDevice, st));
   }
 #endif
   const long long tiles = ((long long)ra->N + 2 * a.S - 1) / (2 * a.S);

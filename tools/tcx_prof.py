@@ -15,7 +15,8 @@ NAMES = {1: "enc done, A0 signalled", 60: "out layer: D ready", 61: "seed writte
          63: "tile done", 92: "issuer: got K quarter 0", 93: "issuer: got K quarter 1", 94: "issuer: got K quarter 2",
          95: "issuer: got K quarter 3", 100: "weights landed: N0 k<128", 101: "weights landed: N0 k>=128",
          228: "weights landed: N1 k<128", 229: "weights landed: N1 k>=128"}
-NAMES.update({83: "  step: ranking done", 80: "  step: rows visible (bar.sync)", 81: "  step: ranking + modulation step done", 82: "  step: next state visible (bar.sync)",
+NAMES.update({201: "    step_sample: nominal DS done", 202: "    step_sample: blend + e0 + dot done", 203: "    step_sample: sigmoids + activation done",
+              204: "    step_sample: RBF policy done", 205: "    step_sample: modulation + Euler step done", 83: "  step: ranking done", 80: "  step: rows visible (bar.sync)", 81: "  step: ranking + modulation step done", 82: "  step: next state visible (bar.sync)",
               64: "  out: TMEM load back", 65: "  out: argmin done", 66: "  out: bar.sync passed", 67: "  seed: W5 rows read",
               68: "  seed: quarter 0 signalled", 70: "  L3 parked chunk 0 stored", 71: "  L3 quarter 0 signalled", 72: "  L3 E1: first TMEM load back",
               73: "  L3 E1: chunk 0 converted", 74: "  L3 E1: chunk 0 stored", 75: "  L3 E1: quarter 2 signalled",
@@ -76,7 +77,7 @@ def run(prof=True):
 def show(tile=3):
     a = np.fromfile(OUT, dtype=np.int64).reshape(4, 1024, 2)
     ev = []
-    for r, who in enumerate(("epi w0", "epi w4", "issuer", "loader")):
+    for r, who in enumerate(("epi w0", "epi w4", "issuer", "epi w0")):
         for i, t in a[r]:
             if t:
                 ev.append((int(t), who, int(i)))
