@@ -27,6 +27,7 @@ __device__ int g_step_prof_n = 0;
 // ------------------------------------------------------------------------------------------------
 // rows[k] = row of row_dist / row_grad holding the k-th closest obstacle of this sample
 // (no __restrict__: the whole-horizon kernel writes these rows in the same launch that blends them)
+template <int DD = MAXD>
 __device__ __forceinline__ void blend(const float* row_dist, const float* row_grad, const int* rows, int K, int d,
                                       float& dist, float (&g)[MAXD]) {
   float sd[MAXK];
@@ -41,14 +42,14 @@ __device__ __forceinline__ void blend(const float* row_dist, const float* row_gr
   for (int k = 0; k < MAXK; ++k)
     if (k < K) { wk[k] = expf(-10.f * sd[k] - mx); den += wk[k]; }
 #pragma unroll
-  for (int a = 0; a < MAXD; ++a) g[a] = 0.f;
+  for (int a = 0; a < DD; ++a) g[a] = 0.f;
 #pragma unroll
   for (int k = 0; k < MAXK; ++k)
     if (k < K) {
       const float w = wk[k] / den;
       const float* sg = row_grad + (size_t)rr[k] * d;
 #pragma unroll
-      for (int a = 0; a < MAXD; ++a)
+      for (int a = 0; a < DD; ++a)
         if (a < d) g[a] += sg[a] * w;
     }
   dist = sd[0];
@@ -97,21 +98,24 @@ __device__ __forceinline__ StepIO step_io_global(const StepArgs& s, int i) {
 
 // one sample i of step t (s.t is ignored: the whole-horizon kernels keep ONE argument block in the constant bank and
 // pass the step they are at); every per-sample vector stays in registers
-__device__ __forceinline__ void step_sample(const StepArgs& s, int i, int t, const StepIO& io) {
-  const int d = s.d;
+// D > 0: the joint count is a compile-time constant (no predicated padding lanes, no `a < d` tests); D == 0: generic
+template <int D>
+__device__ __forceinline__ void step_sample_t(const StepArgs& s, int i, int t, const StepIO& io) {
+  constexpr int DD = D > 0 ? D : MAXD;               // components actually walked
+  const int d = D > 0 ? D : s.d;
   const size_t st = (size_t)i * s.H + (t - 1);       // state-step index
-  float q[MAXD], v[MAXD], vhat[MAXD], e0[MAXD], g[MAXD], u[MAXD], vt[MAXD], m[MAXD];
+  float q[MAXD], v[MAXD], vhat[MAXD], e0[MAXD], g[MAXD], u[MAXD], vt[MAXD], m[MAXD];   // only [0, DD) is ever touched
   // S0 nominal DS and its norm (MPPI.py:106-108)
   float ss = 0.f;
 #pragma unroll
-  for (int a = 0; a < MAXD; ++a) q[a] = a < d ? (io.q_in ? io.q_in[a] : s.traj[st * d + a]) : 0.f;
+  for (int a = 0; a < DD; ++a) q[a] = a < d ? (io.q_in ? io.q_in[a] : s.traj[st * d + a]) : 0.f;
   if (s.mod.ds_kind == DSMPPI_DS_MATRIX) {
     // v = (q - q_goal) @ A, not normalised (MPPI_toy.py:89)
 #pragma unroll
-    for (int cc = 0; cc < MAXD; ++cc) {
+    for (int cc = 0; cc < DD; ++cc) {
       float acc = 0.f;
 #pragma unroll
-      for (int a = 0; a < MAXD; ++a)
+      for (int a = 0; a < DD; ++a)
         if (a < d && cc < d) acc += (q[a] - s.goal[a]) * s.mod.ds_A[a * MAXD + cc];
       v[cc] = acc;
     }
@@ -127,7 +131,7 @@ __device__ __forceinline__ void step_sample(const StepArgs& s, int i, int t, con
     float x[MAXD], y[MAXD];
     float dst2 = 0.f;
 #pragma unroll
-    for (int a = 0; a < MAXD; ++a) {
+    for (int a = 0; a < DD; ++a) {
       x[a] = a < d ? q[a] - s.goal[a] : 0.f;
       y[a] = 0.f;
       dst2 += x[a] * x[a];
@@ -136,11 +140,11 @@ __device__ __forceinline__ void step_sample(const StepArgs& s, int i, int t, con
     for (int j = 0; j < G; ++j) {                      // responsibilities Priors_j N(x; Mu_j, Sigma_j)  (:28-34,48-49)
       float quad = 0.f;
 #pragma unroll
-      for (int r = 0; r < MAXD; ++r) {
+      for (int r = 0; r < DD; ++r) {
         if (r < d) {
           float row = 0.f;
 #pragma unroll
-          for (int cc = 0; cc < MAXD; ++cc)
+          for (int cc = 0; cc < DD; ++cc)
             if (cc < d) row += (x[cc] - mux[j * d + cc]) * sinv[(j * d + cc) * d + r];
           quad += row * (x[r] - mux[j * d + r]);
         }
@@ -150,11 +154,11 @@ __device__ __forceinline__ void step_sample(const StepArgs& s, int i, int t, con
     for (int j = 0; j < G; ++j) {
       float quad = 0.f;
 #pragma unroll
-      for (int r = 0; r < MAXD; ++r) {
+      for (int r = 0; r < DD; ++r) {
         if (r < d) {
           float row = 0.f;
 #pragma unroll
-          for (int cc = 0; cc < MAXD; ++cc)
+          for (int cc = 0; cc < DD; ++cc)
             if (cc < d) row += (x[cc] - mux[j * d + cc]) * sinv[(j * d + cc) * d + r];
           quad += row * (x[r] - mux[j * d + r]);
         }
@@ -162,11 +166,11 @@ __device__ __forceinline__ void step_sample(const StepArgs& s, int i, int t, con
       float beta = nan_to_num(pri[j] * (expf(-0.5f * quad) / den[j]) / psum);     // :50-51
       beta = fmaxf(beta, 1e-8f);                                                  // :52
 #pragma unroll
-      for (int r = 0; r < MAXD; ++r) {
+      for (int r = 0; r < DD; ++r) {
         if (r < d) {
           float yr = 0.f;
 #pragma unroll
-          for (int cc = 0; cc < MAXD; ++cc)
+          for (int cc = 0; cc < DD; ++cc)
             if (cc < d) yr += Am[(j * d + r) * d + cc] * (x[cc] - mux[j * d + cc]);
           y[r] += beta * (muy[j * d + r] + yr);                                   // :53-59
         }
@@ -174,12 +178,12 @@ __device__ __forceinline__ void step_sample(const StepArgs& s, int i, int t, con
     }
     float yn2 = 0.f;
 #pragma unroll
-    for (int a = 0; a < MAXD; ++a) yn2 += y[a] * y[a];
+    for (int a = 0; a < DD; ++a) yn2 += y[a] * y[a];
     const float ynorm = sqrtf(yn2), dst = sqrtf(dst2);
     const bool far = dst > s.lin_thr;                                             // :63
     const bool weak = ynorm < s.seds_thr;                                         // :72
 #pragma unroll
-    for (int a = 0; a < MAXD; ++a) {
+    for (int a = 0; a < DD; ++a) {
       float va = y[a];
       if (far) va = weak ? -x[a] / dst : y[a] / ynorm;                            // :68-75 (|-x| == dst)
       v[a] = a < d ? va : 0.f;
@@ -187,39 +191,39 @@ __device__ __forceinline__ void step_sample(const StepArgs& s, int i, int t, con
   } else {
     // unit-speed attractor, linear inside lin_thr (LinDS.py:11-21)
 #pragma unroll
-    for (int a = 0; a < MAXD; ++a) {
+    for (int a = 0; a < DD; ++a) {
       v[a] = a < d ? -(q[a] - s.goal[a]) : 0.f;
       ss += v[a] * v[a];
     }
     const float dst = sqrtf(ss);
     if (dst > s.lin_thr) {
 #pragma unroll
-      for (int a = 0; a < MAXD; ++a) v[a] = v[a] / dst;
+      for (int a = 0; a < DD; ++a) v[a] = v[a] / dst;
     }
   }
   ss = 0.f;
 #pragma unroll
-  for (int a = 0; a < MAXD; ++a) ss += v[a] * v[a];
+  for (int a = 0; a < DD; ++a) ss += v[a] * v[a];
   const float vn = sqrtf(ss);
 #pragma unroll
-  for (int a = 0; a < MAXD; ++a) vhat[a] = a < d ? v[a] / vn : 0.f;
+  for (int a = 0; a < DD; ++a) vhat[a] = a < d ? v[a] / vn : 0.f;
 
   STEP_PROF(201);
   // S2e blended distance / gradient
   float dist;
-  blend(io.row_dist, io.row_grad, io.rows, s.K, d, dist, g);
+  blend<DD>(io.row_dist, io.row_grad, io.rows, s.K, d, dist, g);
   dist -= s.dst_thr;                                  // MPPI.py:117
   s.closest[st] = dist;
   ss = 0.f;
 #pragma unroll
-  for (int a = 0; a < MAXD; ++a) {
+  for (int a = 0; a < DD; ++a) {
     if (a < d) s.grads[st * d + a] = g[a];
     ss += g[a] * g[a];
   }
   const float gn = sqrtf(ss);
   float dot = 0.f;
 #pragma unroll
-  for (int a = 0; a < MAXD; ++a) {
+  for (int a = 0; a < DD; ++a) {
     e0[a] = a < d ? g[a] / gn : 0.f;                  // MPPI.py:126
     dot += e0[a] * vhat[a];                           // MPPI.py:129
   }
@@ -234,7 +238,7 @@ __device__ __forceinline__ void step_sample(const StepArgs& s, int i, int t, con
   // activations (MPPI.py:191-196)
   float ga = 0.f;
 #pragma unroll
-  for (int a = 0; a < MAXD; ++a)
+  for (int a = 0; a < DD; ++a)
     if (a < d) ga += sqrtf(fabsf(q[a] - s.goal[a]));
   ga = ga * ga;                                        // (sum |x|^0.5)^(1/0.5)
   ga = fminf(fmaxf(ga, 0.f), 1.f);
@@ -245,7 +249,7 @@ __device__ __forceinline__ void step_sample(const StepArgs& s, int i, int t, con
   STEP_PROF(203);
   // S4 RBF policy (policy.py:186-199, MPPI.py:165-186)
 #pragma unroll
-  for (int a = 0; a < MAXD; ++a) u[a] = 0.f;
+  for (int a = 0; a < DD; ++a) u[a] = 0.f;
   // the sampled policy is read-only for the whole rollout: ld.global.nc, and the loads of the next kernel are issued
   // under the arithmetic of this one (in the whole-horizon kernels ONE warp per CTA runs this loop between two
   // network tiles, so every exposed L2 round trip is on the rollout's critical path)
@@ -255,7 +259,7 @@ __device__ __forceinline__ void step_sample(const StepArgs& s, int i, int t, con
     const float* al = s.alpha + ((size_t)i * NKMAX + k) * d;
     float muv[MAXD], alv[MAXD];
 #pragma unroll
-    for (int a = 0; a < MAXD; ++a) {
+    for (int a = 0; a < DD; ++a) {
       muv[a] = a < d ? __ldg(mu + a) : 0.f;
       alv[a] = a < d ? __ldg(al + a) : 0.f;
     }
@@ -263,12 +267,12 @@ __device__ __forceinline__ void step_sample(const StepArgs& s, int i, int t, con
     float acc = 0.f;
     if (s.p == 2.f) {
 #pragma unroll
-      for (int a = 0; a < MAXD; ++a)
+      for (int a = 0; a < DD; ++a)
         if (a < d) { const float df = q[a] - muv[a]; acc += df * df; }
       acc = sqrtf(acc);
     } else {
 #pragma unroll
-      for (int a = 0; a < MAXD; ++a)
+      for (int a = 0; a < DD; ++a)
         if (a < d) acc += powf(fabsf(q[a] - muv[a]), s.p);
       acc = powf(acc, 1.f / s.p);
     }
@@ -276,20 +280,20 @@ __device__ __forceinline__ void step_sample(const StepArgs& s, int i, int t, con
     const float phi = expf(-sg * num);
     s.kval[st * NKMAX + k] = s.mod.fold_activation ? phi * kv_scale : phi;   // MPPI.py:184
 #pragma unroll
-    for (int a = 0; a < MAXD; ++a)
+    for (int a = 0; a < DD; ++a)
       if (a < d) u[a] += alv[a] * phi;                 // MPPI.py:174-177
   }
   STEP_PROF(204);
   // total velocity and modulation M = l_tau I + (l_nv - l_tau) e0 e0^T  (MPPI.py:158-161,197-209)
   float proj = 0.f;
 #pragma unroll
-  for (int a = 0; a < MAXD; ++a) {
+  for (int a = 0; a < DD; ++a) {
     vt[a] = v[a] + act * u[a] * vn;
     proj += e0[a] * vt[a];
   }
   ss = 0.f;
 #pragma unroll
-  for (int a = 0; a < MAXD; ++a) {
+  for (int a = 0; a < DD; ++a) {
     m[a] = l_tau * vt[a] + (l_nv - l_tau) * e0[a] * proj;
     if (a >= d) m[a] = 0.f;
     ss += m[a] * m[a];
@@ -298,13 +302,13 @@ __device__ __forceinline__ void step_sample(const StepArgs& s, int i, int t, con
   if (mn <= 0.5f) mn = 1.f;                            // MPPI.py:211-212
   const bool coll = dist < 0.f;
 #pragma unroll
-  for (int a = 0; a < MAXD; ++a) {
+  for (int a = 0; a < DD; ++a) {
     float mv = nan_to_num(m[a] / mn);                  // MPPI.py:213
     if (coll) mv = mv * 0.1f + e0[a] * vn * s.mod.repulsion;   // MPPI.py:215-217
     m[a] = mv;
   }
 #pragma unroll
-  for (int a = 0; a < MAXD; ++a) {
+  for (int a = 0; a < DD; ++a) {
     if (a < d) {
       const float qn = q[a] + s.dt * m[a];                        // MPPI.py:220-221
       if (t < s.H) s.traj[(st + 1) * d + a] = qn;
@@ -314,11 +318,18 @@ __device__ __forceinline__ void step_sample(const StepArgs& s, int i, int t, con
   STEP_PROF(205);
   if (t == 1) {
 #pragma unroll
-    for (int a = 0; a < MAXD; ++a)
+    for (int a = 0; a < DD; ++a)
       if (a < d) s.qdot[(size_t)i * d + a] = m[a];                // MPPI.py:222-223
   }
 }
 
+
+// dispatch on the joint counts the shipped robots have (planar 2-DoF, planar / Franka 7-DoF); anything else runs generic
+__device__ __forceinline__ void step_sample(const StepArgs& s, int i, int t, const StepIO& io) {
+  if (s.d == 7) step_sample_t<7>(s, i, t, io);
+  else if (s.d == 2) step_sample_t<2>(s, i, t, io);
+  else step_sample_t<0>(s, i, t, io);
+}
 
 // host side: the argument block of step `t` of rollout `a`
 static inline StepArgs make_step_args(const dsmppi_ctx* c, const dsmppi_rollout_args* a, int t) {

@@ -161,8 +161,9 @@ constexpr int OFF_SCRATCH = OFF_ALO + 32768;   // final epilogue: a[e][row] fp32
 // threads to the CTA's step threads and back through the last 16 KB of the A_lo image (idle between the last GEMM of
 // a step and the second half of the next step's first epilogue; the FFMA fallback tile ends below it)
 constexpr int OFF_STAGE = OFF_ALO + 49152;
-constexpr int STG_M = 0, STG_DIST = TROWS, STG_GRAD = 2 * TROWS, STG_Q = 2 * TROWS + TROWS * MAXD;   // float offsets
-static_assert((STG_Q + TROWS * MAXD) * 4 <= 16384, "row staging exceeds the tail of the A_lo image");
+constexpr int STG_M = 0, STG_DIST = TROWS, STG_GRAD = 2 * TROWS, STG_Q = 2 * TROWS + TROWS * MAXD,          // float offsets
+              STG_ROWS = STG_Q + TROWS * MAXD;                                                          // (128, MAXK) ints
+static_assert((STG_ROWS + TROWS * MAXK) * 4 <= 16384, "row staging exceeds the tail of the A_lo image");
 static_assert(exact_tile::smem_bytes(32) <= OFF_STAGE && OFF_SCRATCH + 16384 <= OFF_STAGE, "staging overlaps");
 static_assert(NBAR * 8 <= 128, "barrier block");
 static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB shared-memory budget");
@@ -407,7 +408,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_exac
         for (int c = 0; c < MAXD; ++c) {
           en_sn[c] = 0.f; en_cs[c] = 1.f;
           if (c < d) {
-            en_sn[c] = sinf(xq[c]); en_cs[c] = cosf(xq[c]);
+            sincosf(xq[c], &en_sn[c], &en_cs[c]);           // same bits as sinf / cosf (tools/tcx_regress.py), half the code
             en_v[3 * c] = prep(xq[c]); en_v[3 * c + 1] = prep(en_sn[c]); en_v[3 * c + 2] = prep(en_cs[c]);
           }
         }
@@ -418,7 +419,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_exac
 #pragma unroll
         for (int c = 0; c < 3; ++c)
           if (d + c < nin) {
-            en_v[3 * c] = prep(xp[c]); en_v[3 * c + 1] = prep(sinf(xp[c])); en_v[3 * c + 2] = prep(cosf(xp[c]));
+            float sp, cp;
+            sincosf(xp[c], &sp, &cp);
+            en_v[3 * c] = prep(xp[c]); en_v[3 * c + 1] = prep(sp); en_v[3 * c + 2] = prep(cp);
           }
       }
     };
@@ -797,24 +800,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_exac
               for (int c = 0; c < MAXD; ++c) qreg[c] = c < d ? a.sa.traj[(size_t)i * a.sa.H * d + c] : 0.f;
             }
             const float* mr = stg + STG_M + tid * M;         // this sample's rows are staged rows tid * M .. + M
-            int rows[MAXK];
-            float last_v = -3.4e38f;
+            int* rows = reinterpret_cast<int*>(stg + STG_ROWS) + tid * MAXK;   // ranked rows, also in shared memory:
+            float last_v = -3.4e38f;                                           // a rolled loop keeps the code short
             int last_j = -1;
-#pragma unroll
-            for (int kk = 0; kk < MAXK; ++kk) {
-              rows[kk] = 0;
-              if (kk < K) {
-                float bv = 3.4e38f;
-                int bj = -1;
-                for (int j = 0; j < M; ++j) {
-                  const float v = mr[j];
-                  const bool after = kk == 0 || v > last_v || (v == last_v && j > last_j);
-                  if (after && (bj < 0 || v < bv)) { bv = v; bj = j; }
-                }
-                if (bj < 0) bj = last_j < 0 ? 0 : last_j;
-                rows[kk] = tid * M + bj;
-                last_v = bv; last_j = bj;
+#pragma unroll 1
+            for (int kk = 0; kk < K; ++kk) {
+              float bv = 3.4e38f;
+              int bj = -1;
+#pragma unroll 1
+              for (int j = 0; j < M; ++j) {
+                const float v = mr[j];
+                const bool after = kk == 0 || v > last_v || (v == last_v && j > last_j);
+                if (after && (bj < 0 || v < bv)) { bv = v; bj = j; }
               }
+              if (bj < 0) bj = last_j < 0 ? 0 : last_j;
+              rows[kk] = tid * M + bj;
+              last_v = bv; last_j = bj;
             }
             if (tid == 0) TCX_PROF(0, 83);
             const StepIO io{stg + STG_DIST, stg + STG_GRAD, rows, qreg, qreg};
