@@ -30,29 +30,27 @@ __device__ int g_step_prof_n = 0;
 template <int DD = MAXD>
 __device__ __forceinline__ void blend(const float* row_dist, const float* row_grad, const int* rows, int K, int d,
                                       float& dist, float (&g)[MAXD]) {
-  float sd[MAXK];
-  int rr[MAXK];
+  // three rolled passes over the K rows (maximum, normaliser, weighted sum) instead of eight unrolled copies: the
+  // exponentials of the last pass are recomputed, which costs K expf and returns the same bits, and the code stays
+  // short -- in the whole-horizon kernels this runs on one warp that is bound by instruction fetch
   float mx = -FLT_MAX;
-#pragma unroll
-  for (int k = 0; k < MAXK; ++k)
-    if (k < K) { rr[k] = rows[k]; sd[k] = row_dist[rr[k]]; mx = fmaxf(mx, -10.f * sd[k]); }
-  float wk[MAXK];
+#pragma unroll 1
+  for (int k = 0; k < K; ++k) mx = fmaxf(mx, -10.f * row_dist[rows[k]]);
   float den = 0.f;
-#pragma unroll
-  for (int k = 0; k < MAXK; ++k)
-    if (k < K) { wk[k] = expf(-10.f * sd[k] - mx); den += wk[k]; }
+#pragma unroll 1
+  for (int k = 0; k < K; ++k) den += expf(-10.f * row_dist[rows[k]] - mx);
 #pragma unroll
   for (int a = 0; a < DD; ++a) g[a] = 0.f;
+#pragma unroll 1
+  for (int k = 0; k < K; ++k) {
+    const int r = rows[k];
+    const float w = expf(-10.f * row_dist[r] - mx) / den;
+    const float* sg = row_grad + (size_t)r * d;
 #pragma unroll
-  for (int k = 0; k < MAXK; ++k)
-    if (k < K) {
-      const float w = wk[k] / den;
-      const float* sg = row_grad + (size_t)rr[k] * d;
-#pragma unroll
-      for (int a = 0; a < DD; ++a)
-        if (a < d) g[a] += sg[a] * w;
-    }
-  dist = sd[0];
+    for (int a = 0; a < DD; ++a)
+      if (a < d) g[a] += sg[a] * w;
+  }
+  dist = row_dist[rows[0]];
 }
 
 // ------------------------------------------------------------------------------------------------
