@@ -79,6 +79,19 @@ __device__ __forceinline__ float nan_to_num(float v) {
   return v;
 }
 
+// ||x||_p for p != 2 (policy.py:186-199 with Policy.p set by a script), out of line: two powf per component would
+// otherwise sit inside the RBF loop of every caller, which in the whole-horizon kernels is bound by instruction fetch
+static_assert(MAXD == 8, "pnorm_general takes the components by value");
+static __device__ __noinline__ float pnorm_general(float x0, float x1, float x2, float x3, float x4, float x5, float x6, float x7,
+                                            int d, float p) {
+  const float x[MAXD] = {x0, x1, x2, x3, x4, x5, x6, x7};
+  float acc = 0.f;
+#pragma unroll
+  for (int a = 0; a < MAXD; ++a)
+    if (a < d) acc += powf(x[a], p);
+  return powf(acc, 1.f / p);
+}
+
 // Where one sample's step finds its inputs: the differentiated rows (distance, gradient) and the ranked row indices of
 // this sample, and optionally the state itself.  The stand-alone step kernel reads all of it from global memory; the
 // whole-horizon tensor-core kernel keeps the rows in shared memory and the state in registers, because every dependent
@@ -248,10 +261,10 @@ __device__ __forceinline__ void step_sample_t(const StepArgs& s, int i, int t, c
   // S4 RBF policy (policy.py:186-199, MPPI.py:165-186)
 #pragma unroll
   for (int a = 0; a < DD; ++a) u[a] = 0.f;
-  // the sampled policy is read-only for the whole rollout: ld.global.nc, and the loads of the next kernel are issued
-  // under the arithmetic of this one (in the whole-horizon kernels ONE warp per CTA runs this loop between two
-  // network tiles, so every exposed L2 round trip is on the rollout's critical path)
-#pragma unroll 2
+  // the sampled policy is read-only for the whole rollout: ld.global.nc (the whole-horizon kernel prefetches the rows
+  // into L1 before it ranks).  A rolled loop: in the whole-horizon kernels ONE warp per CTA runs this between two
+  // network tiles and is bound by instruction fetch, not by arithmetic
+#pragma unroll 1
   for (int k = 0; k < s.nk; ++k) {
     const float* mu = s.mu + ((size_t)i * NKMAX + k) * d;
     const float* al = s.alpha + ((size_t)i * NKMAX + k) * d;
@@ -269,10 +282,10 @@ __device__ __forceinline__ void step_sample_t(const StepArgs& s, int i, int t, c
         if (a < d) { const float df = q[a] - muv[a]; acc += df * df; }
       acc = sqrtf(acc);
     } else {
+      float df[MAXD];
 #pragma unroll
-      for (int a = 0; a < DD; ++a)
-        if (a < d) acc += powf(fabsf(q[a] - muv[a]), s.p);
-      acc = powf(acc, 1.f / s.p);
+      for (int a = 0; a < MAXD; ++a) df[a] = (a < DD && a < d) ? fabsf(q[a] - muv[a]) : 0.f;
+      acc = pnorm_general(df[0], df[1], df[2], df[3], df[4], df[5], df[6], df[7], d, s.p);
     }
     const float num = acc * acc;                       // norm ** 2
     const float phi = expf(-sg * num);

@@ -161,9 +161,12 @@ def test_distance_repulsion_vs_reference(name, factory):
     check(grad, g["nn_grad"], 1e-4, 1e-4 * g["nn_grad"].abs().max().item(), "nn_grad", min_frac=1.0)
 
 
-@pytest.mark.parametrize("name,N,H,M,K", [("franka", 300, 3, 37, 5), ("planar7", 257, 4, 5, 2), ("planar2", 129, 5, 3, 3)])
-def test_rollout_vs_oracle_random_inputs(name, N, H, M, K, factory):
-    """Fresh seeded inputs (ragged sizes: N not a multiple of any tile) against the CPU oracle."""
+@pytest.mark.parametrize("name,N,H,M,K,p", [("franka", 300, 3, 37, 5, 2.0), ("planar7", 257, 4, 5, 2, 2.0),
+                                             ("planar2", 129, 5, 3, 3, 2.0), ("planar7", 131, 3, 4, 1, 3.0),
+                                             ("planar2", 77, 4, 2, 2, 1.5)])
+def test_rollout_vs_oracle_random_inputs(name, N, H, M, K, p, factory):
+    """Fresh seeded inputs (ragged sizes: N not a multiple of any tile) against the CPU oracle; p != 2 exercises the
+    general p-norm of the RBF kernels (policy.py:186-199), which lives out of line in the step."""
     torch.manual_seed(1234)
     d = {"franka": 7, "planar7": 7, "planar2": 2}[name]
     W, b = load_weights(name)
@@ -181,10 +184,11 @@ def test_rollout_vs_oracle_random_inputs(name, N, H, M, K, factory):
     P.sigma_c[:nk] = 0.7
     P.alpha_c[:nk] = torch.randn(nk, d)
     P.alpha_s = 1.5
+    P.p = p
     P.sample_policy()
     ign = base["ignored_links"].tolist()
     prm = orc.RolloutParams(dt=float(base["dt"]), dt_H=1, n_closest_obs=K, dst_thr=float(base["dst_thr"]),
-                            ignored_links=ign, p=2.0, with_basis=False)
+                            ignored_links=ign, p=p, with_basis=False)
     traj, dist, kv, dots, acts = m.propagate()
     # teacher-forced against the oracle, step by step, using the GPU's own states
     for t in range(H):
