@@ -45,6 +45,30 @@ __global__ void rank_kernel(const float* __restrict__ m_rows, const int* __restr
   }
 }
 
+// The same ranking for a handful of obstacles scored densely (M <= 16: the planar and dense-field workloads): one
+// THREAD per sample scans its M rows K times -- a warp per sample would idle 30 lanes and, at 10^6 samples, launch
+// 10^6 warps for 2 x 10^6 floats.  Same order as the warp form: ascending by (distance, obstacle index).
+__global__ void __launch_bounds__(256) rank_small_kernel(const float* __restrict__ m_rows, int M, int n, int K,
+                                                         int rows_out, int* __restrict__ sel) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= n) return;
+  const float* mr = m_rows + (size_t)w * M;
+  float last_v = -FLT_MAX;
+  int last_j = -1;
+  for (int kk = 0; kk < K; ++kk) {
+    float bv = FLT_MAX;
+    int bj = -1;
+    for (int j = 0; j < M; ++j) {
+      const float v = mr[j];
+      const bool after = kk == 0 || v > last_v || (v == last_v && j > last_j);
+      if (after && (bj < 0 || v < bv)) { bv = v; bj = j; }
+    }
+    if (bj < 0) bj = last_j < 0 ? 0 : last_j;            // fewer than K candidates: repeat
+    sel[(size_t)w * K + kk] = rows_out ? w * M + bj : bj;
+    last_v = bv; last_j = bj;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Candidate band from the approximate (tensor-core) distances: every obstacle within `band` of the
 // K-th smallest approximate distance is re-scored in fp32.  One warp per sample.
@@ -752,6 +776,12 @@ __global__ void update_finalize_kernel(const float* __restrict__ packed, int nk,
   } while (0)
 
 int launch_rank_dense(dsmppi_ctx* c, int n, int K, bool rows_out, cudaStream_t st) {
+  if (c->M <= 16) {
+    rank_small_kernel<<<(n + 255) / 256, 256, 0, st>>>(c->m_rows, c->M, n, K, rows_out ? 1 : 0,
+                                                       rows_out ? c->sel_rows : c->sel);
+    LAUNCH_CHECK(c);
+    return 0;
+  }
   const int threads = 128, warps = threads / 32;
   rank_kernel<<<(n + warps - 1) / warps, threads, 0, st>>>(c->m_rows, nullptr, nullptr, nullptr, c->M, n, K,
                                                           rows_out ? 1 : 0, rows_out ? c->sel_rows : c->sel);
