@@ -12,9 +12,11 @@ BASELINE.json configs[2] / the metric's named config: Franka Panda 7-DoF, shelf 
 Prints ONE JSON line (rank 0).  `value` = whole-job state-steps/s with inputs resident in HBM, CUDA-event
 timed, max over ranks; `e2e` = the same through the C ABI host-buffer entry point with pinned host tensors
 (H2D + D2H inside the timed region); `roofline` = tensor-core prefilter kernel vs the measured bf16 peak;
-`cpu_baseline` = the oracle port (torch CPU, all host threads) on a bounded sample.
-`--impl reference` times that CPU port alone (the reference is pure Python/torch and is not shipped to
-the GPU box; the oracle restates it op for op -- oracle/mppi_oracle.py).
+`cpu_baseline` = the reference's own classes (oracle/_ref, staged by oracle/make_ref.sh; torch CPU, all host
+threads) on a bounded sample -- the oracle port only when that tree is absent.
+`--impl reference` times that CPU arm alone with the same --steps / --warmup.
+On N > 1 GPUs the run first proves the NCCL path (`multi_gpu_check`: ranks bit-identical, sharded == single-rank
+update; exit 3 otherwise) and adds `c5`, the BASELINE configs[4] shard shape (125 000 samples x 50 steps per GPU).
 """
 import argparse
 import json
@@ -137,8 +139,57 @@ def seeded_policy(p, N, seed):
 
 
 # ---------------------------------------------------------------------------------------- CPU arm
+def _sample_text(p, N, H, what, cores):
+    return (f"{N} samples x {H} steps of the same workload (M={p['obs'].shape[0]}, K={p['K']}, nk={p['nk']}), "
+            f"propagate+get_cost+shift_policy_means, {what}, torch CPU {cores} threads")
+
+
+def cpu_reference_rate(p, target_seconds, steps=1, warmup=0):
+    """state-steps/s of the REFERENCE'S OWN classes (oracle/_ref staged by oracle/make_ref.sh, imported through
+    oracle/ref_harness.py with its two import shims) on the host cores, on a bounded sample of the workload: the full
+    horizon, as many samples as fit `target_seconds` per step.  Falls back to the oracle port (kind "port") when the
+    staged reference is absent."""
+    from oracle import ref_harness as rh
+    if not rh.available():
+        return cpu_port_rate(p, target_seconds, steps, warmup)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    H = p["H"]
+    q_grid = None
+    if p.get("grid"):
+        g = torch.linspace(-math.pi, math.pi, p["grid"])
+        q_grid = torch.stack(torch.meshgrid(g, g, indexing="ij"), -1).reshape(-1, p["dof"])
+
+    def build(N, Hh):
+        it = rh.ReferenceIteration(p, N, Hh, seed=0, policy=seeded_policy(p, N, 100))
+        if q_grid is not None:
+            it.set_q_cur(q_grid[torch.linspace(0, q_grid.shape[0] - 1, N).long()].contiguous())
+        return it
+
+    def timed(it):
+        import contextlib
+        import io
+        with contextlib.redirect_stdout(io.StringIO()):        # shift_policy_means prints (MPPI.py:343)
+            t0 = time.perf_counter()
+            it.step()
+            return time.perf_counter() - t0
+
+    probe = build(8, min(H, 2))            # the constructor runs the reference's five warm-up rollouts itself
+    timed(probe)
+    rate = 8 * min(H, 2) / timed(probe)
+    N = int(max(2, min(p["N"], rate * target_seconds / H)))
+    it = build(N, H)
+    for _ in range(warmup):
+        timed(it)
+    times = [timed(it) for _ in range(steps)]
+    t = sum(times) / len(times)
+    return dict(value=N * H / t, ms_per_step=t * 1e3, cores=cores, N=N, H=H, kind="reference",
+                sample=_sample_text(p, N, H, "UNMODIFIED reference classes from oracle/_ref (MPPI.py, cost.py, "
+                                             "policy.py, robot_sdf.py)", cores))
+
+
 def cpu_port_rate(p, target_seconds, steps=1, warmup=0):
-    """state-steps/s of the oracle port (torch CPU, all host threads) on a bounded sample of the workload."""
+    """The same measurement on the oracle port (oracle/mppi_oracle.py) -- only when the reference is not staged."""
     from oracle import mppi_oracle as orc
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
@@ -159,15 +210,14 @@ def cpu_port_rate(p, target_seconds, steps=1, warmup=0):
     one(4, 1, 0)                                   # thread-pool / allocator warm-up
     t = one(8, 2, 1)
     rate = 16 / t
-    H = min(p["H"], 10)
-    N = int(max(8, min(p["N"], rate * target_seconds / H)))
+    H = p["H"]
+    N = int(max(2, min(p["N"], rate * target_seconds / H)))
     for _ in range(warmup):
         one(N, H, 2)
     times = [one(N, H, 3 + i) for i in range(steps)]
     t = sum(times) / len(times)
-    return dict(value=N * H / t, ms_per_step=t * 1e3, cores=cores, N=N, H=H,
-                sample=f"{N} samples x {H} steps of the same workload (M={p['obs'].shape[0]}, K={p['K']}, "
-                       f"nk={p['nk']}), propagate+cost+update, torch CPU {cores} threads")
+    return dict(value=N * H / t, ms_per_step=t * 1e3, cores=cores, N=N, H=H, kind="port",
+                sample=_sample_text(p, N, H, "oracle port (reference not staged)", cores))
 
 
 # ---------------------------------------------------------------------------------------- clocks
@@ -208,59 +258,14 @@ class ClockSampler(threading.Thread):
 
 
 # ---------------------------------------------------------------------------------------- GPU arm
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="franka_shelf_2064", choices=sorted(WORKLOADS))
-    ap.add_argument("--samples", type=int, default=0, help="samples per GPU (default: the workload's)")
-    ap.add_argument("--pass1", default="auto", choices=["auto", "exact", "tc_f16", "tc_bf16"])
-    ap.add_argument("--score", default="auto", choices=["auto", "ffma", "tc_split"],
-                    help="arithmetic of the scoring rows: split-fp16 tcgen05 (default) or strict IEEE FFMA")
-    ap.add_argument("--per-step", action="store_true", help="disable the whole-horizon single-launch path")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    args = ap.parse_args()
-    rank = int(os.environ.get("RANK", 0))
-    world = int(os.environ.get("WORLD_SIZE", 1))
-    local_rank = int(os.environ.get("LOCAL_RANK", 0))
-    p = problem(args.workload)
-    if args.samples:
-        p["N"] = args.samples
-    N, H = p["N"], p["H"]
-    M = p["obs"].shape[0]
-    f_fwd, f_bwd, f_step = flops_per_state_step(p)
-    robot = {"franka": "franka_panda_7dof", "planar7": "planar_7dof", "planar2": "planar_2dof"}[p["net"]]
-    config = dict(workload=args.workload, robot=robot,
-                  n_obstacles=M, samples_per_gpu=N, horizon=H, n_closest_obs=p["K"], n_kernels=p["nk"],
-                  weights="tests/golden/weights (shipped checkpoint)", sharding=f"samples x{world}",
-                  l2="flushed between timed steps (256 MiB write, outside the per-step event pairs)")
+C5_SAMPLES_PER_GPU = 125_000       # BASELINE.json configs[4]: 10^6 samples x 50 steps sharded over 8 GPUs
 
-    if args.impl == "reference":
-        if rank != 0:
-            return
-        K = max(1, args.steps)
-        r = cpu_port_rate(p, target_seconds=max(2.0, 60.0 / (K + args.warmup)), steps=K, warmup=min(args.warmup, 1))
-        line = dict(metric="mppi_rollout_state_steps_per_sec", value=r["value"], unit="state-steps/s", n_gpus=0,
-                    steps=K, warmup=min(args.warmup, 1), ms_per_step=r["ms_per_step"], higher_is_better=True,
-                    scaling="weak", vs_baseline=None, dtype="f32", data="synthetic", config=config, impl="reference",
-                    cpu_baseline=dict(value=r["value"], unit="state-steps/s", cores=r["cores"], kind="port",
-                                      sample=r["sample"]),
-                    e2e=dict(value=r["value"], unit="state-steps/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
-        print(json.dumps(line))
-        return
 
-    import torch.distributed as dist
+def build_mppi(p, N, H, dev, args, seed, world):
+    """The drop-in MPPI object on `dev` with the workload's parameters and a seeded sampled policy."""
     from optimalmodulationds_b200 import MPPI, LinDS
     from optimalmodulationds_b200.sdf.robot_sdf import RobotSdfCollisionNet
-    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
-    dev = torch.device("cuda", local_rank)
-    torch.cuda.set_device(dev)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
     W, b, wsrc = load_net_arrays(p["net"])
-    config["weights"] = wsrc
     net = RobotSdfCollisionNet(in_channels=p["dof"] + 3, out_channels=p["out"], layers=[256] * 4, skips=[])
     net.load_arrays(W, b)
     t = lambda x: x.to(dev)  # noqa: E731
@@ -274,22 +279,138 @@ def main():
     mppi.Cost.q_min, mppi.Cost.q_max = t(p["qlim"][0]), t(p["qlim"][1])
     if world > 1:
         mppi.enable_sample_sharding()
+    pol = seeded_policy(p, N, seed)
+    load_policy(mppi, p, pol, dev)
+    return mppi, pol, wsrc
+
+
+def load_policy(mppi, p, pol, dev):
+    mu_c, sigma_c, alpha_c, mu_tmp, sigma_tmp, alpha_tmp = pol
+    P = mppi.Policy
+    P.n_kernels = p["nk"]
+    for dst, src in ((P.mu_c, mu_c), (P.sigma_c, sigma_c), (P.alpha_c, alpha_c), (P.mu_tmp, mu_tmp),
+                     (P.sigma_tmp, sigma_tmp), (P.alpha_tmp, alpha_tmp)):
+        dst.copy_(src.to(dev))
+
+
+def policy_vector(mppi):
+    P = mppi.Policy
+    return torch.cat((P.mu_c.flatten(), P.sigma_c.flatten(), P.alpha_c.flatten())).float()
+
+
+def check_sharding(p, dev, args, rank, world, mppi_main):
+    """Evidence that the NCCL path computes the unsharded update (exit != 0 otherwise):
+      1. after the timed iterations every rank holds bit-identical policy means;
+      2. a small job (256 samples per rank, 8 steps, the workload's obstacles) run sample-sharded over the ranks gives
+         the policy of ONE rank running all world x 256 samples, and the same trajectories for its slice."""
+    import torch.distributed as dist
+    mine = policy_vector(mppi_main)
+    every = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(every, mine)
+    identical = all(torch.equal(every[0], e) for e in every)
+    n_small, h_small = 256, 8
+    pol_all = seeded_policy(p, world * n_small, 4242)                 # the same global draw on every rank
+    lo, hi = rank * n_small, (rank + 1) * n_small
+    sl = (pol_all[0], pol_all[1], pol_all[2], pol_all[3][lo:hi].clone(), pol_all[4][lo:hi].clone(),
+          pol_all[5][lo:hi].clone())
+    sharded, _, _ = build_mppi(p, n_small, h_small, dev, args, 0, world)
+    load_policy(sharded, p, sl, dev)
+    traj_s = sharded.propagate()[0].clone()
+    cost_s = sharded.get_cost().clone()
+    n_upd_s = int(sharded.shift_policy_means()[1])
+    whole, _, _ = build_mppi(p, world * n_small, h_small, dev, args, 0, 1)
+    load_policy(whole, p, pol_all, dev)
+    traj_w = whole.propagate()[0]
+    cost_w = whole.get_cost()
+    n_upd_w = int(whole.shift_policy_means()[1])
+    a, b = policy_vector(sharded), policy_vector(whole)
+    pol_err = float(((a - b).abs() / (b.abs() + 1e-6)).max())
+    traj_err = float((traj_s - traj_w[lo:hi]).abs().max())
+    cost_err = float(((cost_s - cost_w[lo:hi]).abs() / (cost_w[lo:hi].abs() + 1e-6)).max())
+    res = torch.tensor([pol_err, traj_err, cost_err, float(n_upd_s != n_upd_w), float(not identical)], device=dev)
+    dist.all_reduce(res, op=dist.ReduceOp.MAX)
+    out = dict(ranks_hold_identical_policy=bool(res[4] == 0), sharded_vs_single_rank_policy_max_rel=float(res[0]),
+               sharded_vs_single_rank_traj_max_abs=float(res[1]), sharded_vs_single_rank_cost_max_rel=float(res[2]),
+               n_updated_equal=bool(res[3] == 0), small_job=f"{world} x {n_small} samples x {h_small} steps",
+               tolerance="policy 1e-4 rel, trajectories 1e-5 abs, cost 1e-4 rel")
+    out["ok"] = bool(out["ranks_hold_identical_policy"] and out["n_updated_equal"] and res[0] <= 1e-4 and
+                     res[1] <= 1e-5 and res[2] <= 1e-4)
+    del sharded, whole
+    torch.cuda.empty_cache()
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="franka_shelf_2064", choices=sorted(WORKLOADS))
+    ap.add_argument("--samples", type=int, default=0, help="samples per GPU (default: the workload's)")
+    ap.add_argument("--pass1", default="auto", choices=["auto", "exact", "tc_f16", "tc_bf16"])
+    ap.add_argument("--score", default="auto", choices=["auto", "ffma", "tc_split"],
+                    help="arithmetic of the scoring rows: split-fp16 tcgen05 (default) or strict IEEE FFMA")
+    ap.add_argument("--per-step", action="store_true", help="disable the whole-horizon single-launch path")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-c5", action="store_true", help="skip the configs[4]-shaped record of multi-GPU runs")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    p = problem(args.workload)
+    if args.samples:
+        p["N"] = args.samples
+    N, H = p["N"], p["H"]
+    M = p["obs"].shape[0]
+    f_fwd, f_bwd, f_step = flops_per_state_step(p)
+    robot = {"franka": "franka_panda_7dof", "planar7": "planar_7dof", "planar2": "planar_2dof"}[p["net"]]
+    warm = max(args.warmup, 3)
+    # `config` is the same dictionary in both arms (the driver compares them); run-time diagnostics go to "diagnostics"
+    config = dict(workload=args.workload, robot=robot,
+                  n_obstacles=M, samples_per_gpu=N, horizon=H, n_closest_obs=p["K"], n_kernels=p["nk"],
+                  weights="shipped checkpoint (tests/golden/weights == mlp_learn/models/*.pt)",
+                  sharding=f"samples x{world}",
+                  l2="flushed between timed steps (256 MiB write, outside the per-step event pairs)")
+    if world > 1 and args.workload.startswith("franka_shelf") and not args.no_c5:
+        config["c5"] = dict(workload="BASELINE.json configs[4] shard shape", samples_per_gpu=C5_SAMPLES_PER_GPU,
+                            horizon=H, n_obstacles=M, timed_iterations=2)
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        K = max(1, args.steps)
+        r = cpu_reference_rate(p, target_seconds=max(1.0, 75.0 / (K + warm)), steps=K, warmup=warm)
+        line = dict(metric="mppi_rollout_state_steps_per_sec", value=r["value"], unit="state-steps/s", n_gpus=0,
+                    steps=K, warmup=warm, ms_per_step=r["ms_per_step"], higher_is_better=True,
+                    scaling="weak", vs_baseline=None, dtype="f32", data="synthetic", config=config, impl="reference",
+                    cpu_baseline=dict(value=r["value"], unit="state-steps/s", cores=r["cores"], kind=r["kind"],
+                                      sample=r["sample"]),
+                    e2e=dict(value=r["value"], unit="state-steps/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                    gpu_launches=0)
+        print(json.dumps(line))
+        return
+
+    import torch.distributed as dist
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    t = lambda x: x.to(dev)  # noqa: E731
+    mppi, pol, wsrc = build_mppi(p, N, H, dev, args, 100 + rank, world)
+    mu_c, sigma_c, alpha_c, mu_tmp, sigma_tmp, alpha_tmp = pol
     q_start = p["q0"]
     if p.get("grid"):            # dense field: every sample starts at its own grid point (MPPI.py:99 broadcast)
         g = torch.linspace(-math.pi, math.pi, p["grid"])
         q_start = torch.stack(torch.meshgrid(g, g, indexing="ij"), -1).reshape(-1, p["dof"])[:N].contiguous()
         mppi.q_cur = t(q_start)
-    mu_c, sigma_c, alpha_c, mu_tmp, sigma_tmp, alpha_tmp = seeded_policy(p, N, 100 + rank)
-    P = mppi.Policy
-    P.n_kernels = p["nk"]
-    P.mu_c.copy_(t(mu_c)); P.sigma_c.copy_(t(sigma_c)); P.alpha_c.copy_(t(alpha_c))
-    P.mu_tmp.copy_(t(mu_tmp)); P.sigma_tmp.copy_(t(sigma_tmp)); P.alpha_tmp.copy_(t(alpha_tmp))
     flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
 
-    def step():
-        mppi.propagate()
-        mppi.get_cost()
-        mppi.shift_policy_means()
+    def step(m=mppi):
+        m.propagate()
+        m.get_cost()
+        m.shift_policy_means()
 
     def sync_all():
         torch.cuda.synchronize(dev)
@@ -297,40 +418,56 @@ def main():
             dist.barrier()
             torch.cuda.synchronize(dev)
 
-    for _ in range(max(args.warmup, 3)):
+    def timed_steps(m, n_steps, with_kernel_timing):
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_steps)]
+        kt_ms, kt_n, name = 0.0, 0, "exact_mlp_kernel"
+        sync_all()
+        for a, bq in evs:
+            flush.fill_(1.0)
+            a.record()
+            step(m)
+            bq.record()
+            bq.synchronize()
+            if with_kernel_timing:
+                kt = m.kernel_timing_ex()
+                name = kt["kernel"]
+                kt_ms += kt["ms"] * kt["launches"]
+                kt_n += kt["launches"]
+        sync_all()
+        ms = torch.tensor([sum(a.elapsed_time(bq) for a, bq in evs) / n_steps], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms), kt_ms, kt_n, name
+
+    for _ in range(warm):
         step()
     sync_all()
     mppi.enable_kernel_timing(True)
     sampler = ClockSampler(local_rank)
     sampler.start()
     launches0 = mppi.launch_count()
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    kt_ms, kt_n, kern_name = 0.0, 0, "exact_mlp_kernel"
-    sync_all()
-    for a, bq in evs:
-        flush.fill_(1.0)
-        a.record()
-        step()
-        bq.record()
-        bq.synchronize()
-        kt = mppi.kernel_timing_ex()
-        kern_name = kt["kernel"]
-        kt_ms += kt["ms"] * kt["launches"]
-        kt_n += kt["launches"]
-    sync_all()
-    total_ms = sum(a.elapsed_time(bq) for a, bq in evs)
+    ms_per_step, kt_ms, kt_n, kern_name = timed_steps(mppi, args.steps, True)
     launches = mppi.launch_count() - launches0
     sampler.stop_flag = True
     sampler.join()
-    ms = torch.tensor([total_ms / args.steps], device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_per_step = float(ms)
     value = world * N * H / (ms_per_step * 1e-3)
     stats = mppi.pass1_stats()
+    xstats = mppi.exactness_stats()
     mppi.enable_kernel_timing(False)
 
-    # ---- e2e: the same iteration through the C ABI with pinned HOST buffers (H2D + D2H inside the timed region)
+    # ---- multi-GPU: prove the NCCL path before reporting it
+    mg_check = None
+    if world > 1:
+        mg_check = check_sharding(p, dev, args, rank, world, mppi)
+        if not mg_check["ok"]:
+            if rank == 0:
+                print(json.dumps(dict(error="sample-sharded update disagrees with the single-rank update",
+                                      multi_gpu_check=mg_check)), file=sys.stderr)
+            dist.destroy_process_group()
+            sys.exit(3)
+
+    # ---- e2e: the same iteration through the C ABI with pinned HOST buffers (H2D + D2H inside the timed region);
+    #      on several GPUs it stays sample-sharded: the library calls back for the two all-reduces (NCCL)
     pin = lambda x: x.contiguous().pin_memory()  # noqa: E731
     d = p["dof"]
     host = dict(q_cur=pin(q_start), mu_tmp=pin(mu_tmp), sigma_tmp=pin(sigma_tmp), alpha_tmp=pin(alpha_tmp),
@@ -339,8 +476,6 @@ def main():
                 kernel_val_all=pin(torch.zeros(N, H, 50)), dot_products=pin(torch.empty(N, H)),
                 kernel_activations=pin(torch.empty(N, H)), qdot=pin(torch.empty(N, d)), cost=pin(torch.empty(N)),
                 n_updated=pin(torch.zeros(1, dtype=torch.int32)))
-    saved = mppi._shard
-    mppi._shard = None            # the host-buffer entry point is a single-GPU call: every rank runs its own shard
     for _ in range(2):
         h2d, d2h = mppi.iteration_host(host)
     sync_all()
@@ -352,8 +487,30 @@ def main():
     e_ms = torch.tensor([(time.perf_counter() - t0) * 1e3 / e_steps], device=dev)
     if world > 1:
         dist.all_reduce(e_ms, op=dist.ReduceOp.MAX)
-    mppi._shard = saved
+        hp = torch.cat((host["mu_c"].flatten(), host["sigma_c"], host["alpha_c"].flatten())).to(dev)
+        every = [torch.empty_like(hp) for _ in range(world)]
+        dist.all_gather(every, hp)
+        mg_check["e2e_ranks_hold_identical_policy"] = all(torch.equal(every[0], e) for e in every)
+        if not mg_check["e2e_ranks_hold_identical_policy"]:
+            if rank == 0:
+                print(json.dumps(dict(error="ranks disagree after the sharded host-buffer iteration")), file=sys.stderr)
+            dist.destroy_process_group()
+            sys.exit(3)
     e2e_value = world * N * H / (float(e_ms) * 1e-3)
+
+    # ---- configs[4]: 10^6 samples x 50 steps over 8 GPUs = 125 000 samples per GPU, sample-sharded
+    c5 = None
+    if "c5" in config:
+        del mppi, host
+        torch.cuda.empty_cache()
+        m5, _, _ = build_mppi(p, C5_SAMPLES_PER_GPU, H, dev, args, 500 + rank, world)
+        step(m5)
+        ms5, _, _, _ = timed_steps(m5, 2, False)
+        c5 = dict(samples_per_gpu=C5_SAMPLES_PER_GPU, samples_total=world * C5_SAMPLES_PER_GPU, horizon=H,
+                  n_obstacles=M, ms_per_iteration=ms5, timed_iterations=2, warmup=1,
+                  value=world * C5_SAMPLES_PER_GPU * H / (ms5 * 1e-3), unit="state-steps/s",
+                  timing="CUDA events per iteration, max over ranks", exactness=m5.exactness_stats())
+        mppi = m5
 
     if rank != 0:
         if world > 1:
@@ -372,12 +529,13 @@ def main():
     if not tensor_kernel:
         peak_tf, peak_src = 74.0, "FFMA nominal 74 TFLOP/s (IEEE fp32 scoring kernel; no tensor cores in this mode)"
     kern_ms = kt_ms / max(kt_n, 1)
-    traffic = None
+    traffic, traffic_src = None, None
     try:      # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed ncu capture
         prof = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
         ent = prof.get(f"{args.workload}:{kern_name}")
         if ent and ent.get("samples") == N:
             traffic = ent["dram_bytes_per_launch"]
+            traffic_src = ent.get("source")
     except Exception:  # noqa: BLE001
         pass
     # algorithmic FLOPs of the dominant kernel: the all-pairs forward (tensor-core prefilter, or the scoring kernel's
@@ -398,6 +556,7 @@ def main():
                 kern_name, "fp32 FFMA (compute-bound; no tensor cores)")
     roofline = dict(bound="tensor", pipe=pipe, kernel=kern_name,
                     achieved=achieved, peak=peak_tf, unit="TFLOP/s", frac=achieved / peak_tf, traffic=traffic,
+                    traffic_source=traffic_src,
                     peak_source=peak_src, flops_per_launch=flops_per_launch, ms_per_launch=kern_ms, launches_timed=kt_n,
                     share_of_step=kt_ms / args.steps / ms_per_step)
     if kern_name.startswith("tc_exact"):
@@ -405,23 +564,34 @@ def main():
         roofline["mma_flops_per_algorithmic_flop"] = 3
         roofline["frac_of_split_ceiling"] = 3 * achieved / peak_tf
     line = dict(metric="mppi_rollout_state_steps_per_sec", value=value, unit="state-steps/s", n_gpus=world,
-                steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=ms_per_step, higher_is_better=True,
+                steps=args.steps, warmup=warm, ms_per_step=ms_per_step, higher_is_better=True,
                 scaling="weak", vs_baseline=None,
                 dtype=("f32 (scoring: split-fp16 tcgen05, fp32 accumulate, fp32-accurate; obstacle-ranking prefilter: "
                        "f16 tcgen05)" if sstats["mode"] == "tc_split" else
                        "f32 (IEEE FFMA scoring; obstacle-ranking prefilter: f16 tcgen05, f32 accumulate)"),
-                data="synthetic", config=dict(config, pass1=mode, score=sstats["mode"],
-                                              range_fixup_rows=sstats["range_fixup_rows"],
-                                              rescored_pairs_per_state_step=stats["rescored_pairs"] / (N * H),
-                                              band_overflows=stats["band_overflows"], flops_per_state_step=f_step),
+                data="synthetic", config=config,
+                diagnostics=dict(pass1=mode, score=sstats["mode"], weights_source=wsrc,
+                                 range_fixup_rows=sstats["range_fixup_rows"],
+                                 rescored_pairs_per_state_step=stats["rescored_pairs"] / (N * H),
+                                 crowded_bands=stats["band_overflows"], guard_band_m=xstats["guard_band"],
+                                 prefilter_calibration_error_m=xstats["calibration_error"],
+                                 capacity_retries=xstats["capacity_retries"], exact_fallbacks=xstats["exact_fallbacks"],
+                                 flops_per_state_step=f_step),
                 clocks=sampler.summary(),
                 e2e=dict(value=e2e_value, unit="state-steps/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
-                         ms_per_step=float(e_ms), api="dsmppi_iteration_host (C ABI, pinned host buffers)"),
+                         ms_per_step=float(e_ms),
+                         api="dsmppi_iteration_host (C ABI, pinned host buffers" +
+                             (", sample-sharded: two NCCL all-reduces per iteration through the exchange hook)"
+                              if world > 1 else ")")),
                 gpu_launches=launches, roofline=roofline,
                 ms_per_mppi_iteration=ms_per_step)
+    if mg_check is not None:
+        line["multi_gpu_check"] = mg_check
+    if c5 is not None:
+        line["c5"] = c5
     if world == 1 and not args.no_cpu_baseline:
-        r = cpu_port_rate(p, target_seconds=15.0)
-        line["cpu_baseline"] = dict(value=r["value"], unit="state-steps/s", cores=r["cores"], kind="port",
+        r = cpu_reference_rate(p, target_seconds=15.0)
+        line["cpu_baseline"] = dict(value=r["value"], unit="state-steps/s", cores=r["cores"], kind=r["kind"],
                                     sample=r["sample"])
     print(json.dumps(line))
     if world > 1:

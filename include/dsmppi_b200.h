@@ -176,6 +176,7 @@ void dsmppi_modulation_toy(dsmppi_modulation* out);       /* MPPI_toy.py constan
 int dsmppi_ctx_create(dsmppi_ctx** out, const dsmppi_net* net, const float* dh_params_host,
                       int32_t capacity, int32_t device);
 int dsmppi_ctx_destroy(dsmppi_ctx* ctx);
+/* guard_band > 0 fixes the prefilter's guard band (metres); 0 = calibrate it for the network (dsmppi_exactness_stats) */
 int dsmppi_set_pass1_mode(dsmppi_ctx* ctx, int32_t mode, float guard_band);
 int dsmppi_set_score_mode(dsmppi_ctx* ctx, int32_t mode);     /* DSMPPI_SCORE_*; default AUTO */
 /* Small obstacle sets scored in fp32 (M <= 16, or M <= 32 with a latency-bound batch) are rolled out over the whole
@@ -233,11 +234,12 @@ int dsmppi_cost(dsmppi_ctx* ctx, const dsmppi_cost_args* args, void* stream);
 
 /* MPPI.shift_policy_means -> TensorPolicyMPPI.update_policy (MPPI.py:331-345, policy.py:88-113), split in
  * the three phases a sample-sharded job needs:
- *   cost_stats : stats_dev[0..3] = { sum cost, min cost, argmin (as float), N }          -> allreduce #1
- *   partial    : packed_dev[L], L = dsmppi_update_packed_len(nk, d)                      -> allreduce #2
+ *   cost_stats : stats_dev[0..3] = { sum cost, N, min cost, argmin (as float) }
+ *                                                  -> allreduce #1: SUM of stats_dev[0..1] (beta = sum / N / 50)
+ *   partial    : packed_dev[L], L = dsmppi_update_packed_len(nk, d)                      -> allreduce #2: SUM
  *   finalize   : EMA of mu_c / sigma_c / alpha_c, n_updated_dev[0] = number of kernels updated.
- * On one GPU call them back to back; `beta_dev` is cost mean / 50 computed by the caller or by
- * dsmppi_update_beta from the (all-reduced) stats. */
+ * On one GPU call them back to back.  Entries [2..3] (minimum cost and its local index) are per shard; get_qdot
+ * reduces them separately when a caller asks for the best sample. */
 int32_t dsmppi_update_packed_len(int32_t n_kernels, int32_t n_dof);
 int dsmppi_update_cost_stats(dsmppi_ctx* ctx, const float* cost_dev, int32_t N, float* stats_dev, void* stream);
 int dsmppi_update_partial(dsmppi_ctx* ctx, const dsmppi_update_args* args, const float* stats_dev,
@@ -273,6 +275,8 @@ int dsmppi_kernel_candidates(dsmppi_ctx* ctx, const dsmppi_candidates_args* args
  * k+1 and D2H of chunk k-1 under the rollout + cost of chunk k on `stream`; the policy update follows the last
  * chunk); results are bit-identical to the single pass.  Environment: DSMPPI_HOST_CHUNK=<samples> overrides the
  * chunk size, 0 disables the pipeline. */
+enum { DSMPPI_EXCHANGE_COST_STATS = 0, DSMPPI_EXCHANGE_PACKED_SUMS = 1 };
+typedef int (*dsmppi_exchange_fn)(void* user, int32_t phase);
 typedef struct {
   dsmppi_rollout_args rollout;   /* the *_dev fields are ignored; shapes and scalars are used            */
   float q_min[DSMPPI_MAX_DOF];
@@ -296,14 +300,34 @@ typedef struct {
   float* cost_host;              /* (N,)       */
   int32_t* n_updated_host;       /* (1,)       */
   int64_t h2d_bytes, d2h_bytes;  /* filled in: bytes moved by this call                                 */
+  /* Sample-sharded job: when `exchange` is set this call runs ONE SHARD of the iteration and calls
+   * exchange(exchange_user, phase) twice, after it has enqueued the producer of the buffer named by `phase` on
+   * `stream`; the hook all-reduces (SUM) that caller-owned device buffer over the ranks on the same stream
+   * (torch.distributed / NCCL) and returns 0.  NULL = single-GPU iteration (the fields below are ignored). */
+  dsmppi_exchange_fn exchange;
+  void* exchange_user;
+  float* stats_dev;              /* (4,)  DSMPPI_EXCHANGE_COST_STATS: SUM over ranks of stats_dev[0..1]   */
+  float* packed_dev;             /* (dsmppi_update_packed_len,)  DSMPPI_EXCHANGE_PACKED_SUMS: SUM of all  */
+  int32_t owns_sample0;          /* 1 on the rank holding global sample 0                                 */
+  int32_t reserved2;
+  int64_t N_global;              /* samples over all ranks                                                */
 } dsmppi_iteration_host_args;
 int dsmppi_iteration_host(dsmppi_ctx* ctx, dsmppi_iteration_host_args* args, void* stream);
 
 /* Introspection used by bench.py / tests: launches issued by the library since ctx creation, pass-1
- * statistics of the last rollout (re-scored pairs, band overflows), and the resolved pass-1 mode. */
+ * statistics of the last rollout (re-scored pairs; `band_overflows` = sample-steps whose guard band held more than
+ * 16 obstacles -- informational: they all get a row), and the resolved pass-1 mode. */
 int64_t dsmppi_launch_count(const dsmppi_ctx* ctx);
 int dsmppi_pass1_stats(dsmppi_ctx* ctx, int64_t* rescored_pairs, int64_t* band_overflows, int32_t* mode,
                        void* stream);
+/* The prefilter path is exact by construction: EVERY obstacle within the guard band of the K-th smallest approximate
+ * distance is re-scored in fp32; when a step's candidates do not fit the shared row list the rollout is repeated with
+ * a larger list (`capacity_retries`), past 2^27 rows with every pair scored in fp32 (`exact_fallbacks`) -- never
+ * truncated.  `guard_band` is the band in effect (metres): the caller's (dsmppi_set_pass1_mode) or the one
+ * calibrated for this network and obstacle set = 3 x `calibration_error`, the largest |prefilter - fp32 scoring|
+ * over 256 random joint vectors + the first states of the calling batch x every obstacle. */
+int dsmppi_exactness_stats(dsmppi_ctx* ctx, int64_t* capacity_retries, int64_t* exact_fallbacks, float* guard_band,
+                           float* calibration_error);
 /* Scoring arithmetic in effect (DSMPPI_SCORE_FFMA / _TC_SPLIT) and, for the tensor-core path, how many rows left the
  * fp16 range of its split operands and were re-scored by the FFMA kernel since the context was created
  * (`dropped_rows` > 0 means the re-scoring list overflowed: results of those rows are saturated, not exact). */

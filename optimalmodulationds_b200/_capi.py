@@ -88,6 +88,10 @@ class CandidatesArgs(C.Structure):
     ]
 
 
+EXCHANGE_COST_STATS, EXCHANGE_PACKED_SUMS = 0, 1
+ExchangeFn = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int32)
+
+
 class IterationHostArgs(C.Structure):
     _fields_ = [
         ("rollout", RolloutArgs),
@@ -99,6 +103,8 @@ class IterationHostArgs(C.Structure):
         ("dot_products_host", _fp), ("kernel_activations_host", _fp), ("qdot_host", _fp),
         ("cost_host", _fp), ("n_updated_host", _fp),
         ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
+        ("exchange", ExchangeFn), ("exchange_user", C.c_void_p), ("stats_dev", _fp), ("packed_dev", _fp),
+        ("owns_sample0", C.c_int32), ("reserved2", C.c_int32), ("N_global", C.c_int64),
     ]
 
 
@@ -131,6 +137,8 @@ EXPORTS = {
     "dsmppi_launch_count": (C.c_int64, [C.c_void_p]),
     "dsmppi_pass1_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int32),
                                      C.c_void_p]),
+    "dsmppi_exactness_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_float),
+                                         C.POINTER(C.c_float)]),
     "dsmppi_score_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_int64),
                                      C.c_void_p]),
     "dsmppi_enable_kernel_timing": (C.c_int, [C.c_void_p, C.c_int32]),

@@ -31,14 +31,23 @@ def build(force=False, verbose=False):
     objs = []
     procs = []
     os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    headers += [os.path.join(ROOT, "include", "dsmppi_b200.h"), os.path.abspath(__file__)]
+    flag_stamp = " ".join(NVCC_FLAGS) + os.environ.get("DSMPPI_EXTRA_NVCC_FLAGS", "")
     for src in SOURCES:
         obj = os.path.join(HERE, "build", src.replace(".cu", ".o"))
+        objs.append(obj)
+        stamp = obj + ".flags"
+        # per-object incremental build: an object is reused while its source, every header and the flags are older
+        if (not force and os.path.exists(obj) and os.path.exists(stamp) and open(stamp).read() == flag_stamp and
+                all(os.path.getmtime(d) < os.path.getmtime(obj) for d in [os.path.join(CSRC, src)] + headers)):
+            continue
+        open(stamp, "w").write(flag_stamp)
         cmd = [nvcc, *NVCC_FLAGS, *os.environ.get("DSMPPI_EXTRA_NVCC_FLAGS", "").split(), "-c", os.path.join(CSRC, src),
                "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
-        objs.append(obj)
     for src, p in procs:
         out, _ = p.communicate()
         if verbose or p.returncode != 0:

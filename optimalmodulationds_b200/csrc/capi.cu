@@ -75,36 +75,39 @@ int timing_mark(dsmppi_ctx* c, int kind, cudaStream_t st) {
 }  // namespace
 
 int ensure_workspace(dsmppi_ctx* c, int n, int M) {
-  if (n <= c->ws_n && M <= c->ws_M) return 0;
+  // The sizes below depend on the resolved pass-1 mode, and AUTO flips with the obstacle count (prefilter from 64
+  // obstacles on, dense fp32 scoring below): a workspace sized for one mode must not be taken for the other.
+  const int mode = resolved_mode(c);
+  const size_t list_rows_now = cand_list_cap(c, n);
+  if (n <= c->ws_n && M <= c->ws_M && mode == c->ws_mode && list_rows_now <= c->rowlist_cap) return 0;
   const int nn = n > c->ws_n ? n : c->ws_n;
   const int mm = M > c->ws_M ? M : c->ws_M;
   const int d = c->d;
-  size_t cap;
   if (nn > c->ws_n) {
-    if (alloc(c->q_work, (size_t)nn * d) || alloc(c->cand_obs, (size_t)nn * CAND_MAX) || alloc(c->cand_cnt, (size_t)nn) ||
+    if (alloc(c->q_work, (size_t)nn * d) || alloc(c->cand_cnt, (size_t)nn) ||
         alloc(c->row_base, (size_t)nn) || alloc(c->sel, (size_t)nn * MAXK) ||
         alloc(c->sel_rows, (size_t)nn * MAXK) || alloc(c->dist_tmp, (size_t)nn) || alloc(c->grad_tmp, (size_t)nn * d))
       return 1;
   }
-  // rows scored in fp32: dense n*M when the prefilter is off, at most n*CAND_MAX when it is on.  Sized
-  // for the dense case only while that stays small; the tensor path needs n*CAND_MAX.
-  const int mode = resolved_mode(c);
-  size_t rows = (mode == DSMPPI_PASS1_EXACT_FP32) ? (size_t)nn * mm : (size_t)nn * CAND_MAX;
-  if (rows < (size_t)nn * CAND_MAX) rows = (size_t)nn * CAND_MAX;
+  // rows scored in fp32: dense n*M when the prefilter is off, the candidate list when it is on
+  const size_t list_rows = cand_list_cap(c, nn);
+  size_t rows = (mode == DSMPPI_PASS1_EXACT_FP32) ? (size_t)nn * mm : list_rows;
+  if (rows < list_rows) rows = list_rows;
   if (grow(c->m_rows, c->m_rows_cap, rows)) return 1;
   // rows that get a distance + gradient: all candidates (fused single launch) or the K selected
-  size_t drows = (size_t)nn * CAND_MAX;
+  size_t drows = list_rows;
   if (mm <= WHOLE_M_MAX && (size_t)nn * mm > drows) drows = (size_t)nn * mm;
   if (grow(c->row_dist, c->row_dist_cap, drows)) return 1;
   if (grow(c->row_grad, c->row_grad_cap, drows * d)) return 1;
-  cap = c->rowlist_cap;
-  if (grow(c->row_sample, cap, (size_t)nn * CAND_MAX)) return 1;
-  if (grow(c->row_obs, c->rowlist_cap, (size_t)nn * CAND_MAX)) return 1;
+  size_t cap = c->rowlist_cap;
+  if (grow(c->row_sample, cap, list_rows)) return 1;
+  if (grow(c->row_obs, c->rowlist_cap, list_rows)) return 1;
   if (mode != DSMPPI_PASS1_EXACT_FP32) {
     if (grow(c->mdist, c->mdist_cap, (size_t)nn * mm)) return 1;
   }
   c->ws_n = nn;
   c->ws_M = mm;
+  c->ws_mode = mode;
   return 0;
 }
 
@@ -197,6 +200,7 @@ int dsmppi_ctx_create(dsmppi_ctx** out, const dsmppi_net* net, const float* dh_p
   }
   c->net.W4 = c->weights_blob + off_w4;
   for (int l = 0; l < 5; ++l) c->net.b[l] = c->weights_blob + off_bias[l];
+  if (exact_set_attributes()) { delete c; return 1; }
   if (tc_build_images(c, net)) { delete c; return 1; }
   if (tcx_build_images(c, net)) { delete c; return 1; }
   c->upd_blocks = c->sm_count * 2;
@@ -207,8 +211,9 @@ int dsmppi_ctx_create(dsmppi_ctx** out, const dsmppi_net* net, const float* dh_p
   CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c->stats_ticket), sizeof(unsigned int)));
   CUDA_TRY(cudaMemset(c->stats_ticket, 0, sizeof(unsigned int)));
   CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c->packed_tmp), dsmppi_update_packed_len(NKMAX, MAXD) * sizeof(float)));
-  CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c->counters), 8 * sizeof(int)));
-  CUDA_TRY(cudaMemset(c->counters, 0, 8 * sizeof(int)));
+  CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c->counters), N_COUNTERS * sizeof(int)));
+  CUDA_TRY(cudaMemset(c->counters, 0, N_COUNTERS * sizeof(int)));
+  CUDA_TRY(cudaMallocHost(reinterpret_cast<void**>(&c->counters_host), N_COUNTERS * sizeof(int)));
   *out = c;
   return 0;
 }
@@ -225,6 +230,7 @@ int dsmppi_ctx_destroy(dsmppi_ctx* c) {
                   c->packed_tmp, c->stage};
   for (void* p : ptrs)
     if (p) cudaFree(p);
+  if (c->counters_host) cudaFreeHost(c->counters_host);
   for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
   for (cudaEvent_t e : c->pipe_ev) cudaEventDestroy(e);
   if (c->s_in) cudaStreamDestroy(c->s_in);
@@ -237,10 +243,8 @@ int dsmppi_set_pass1_mode(dsmppi_ctx* c, int32_t mode, float guard_band) {
   REQUIRE(c, "null ctx");
   REQUIRE(mode >= 0 && mode <= 3, "bad pass-1 mode");
   c->pass1_mode = mode;
-  if (guard_band > 0.f) c->guard_band = guard_band;
-  c->ws_n = 0;   // force re-sizing of the workspace for the new mode
-  c->ws_M = 0;
-  return 0;
+  c->guard_band = guard_band > 0.f ? guard_band : 0.f;   // 0: the band calibrated for this network (calibrate_band)
+  return 0;       // ensure_workspace re-sizes when the resolved mode differs from the one it sized for
 }
 
 int dsmppi_set_score_mode(dsmppi_ctx* c, int32_t mode) {
@@ -318,6 +322,57 @@ int dsmppi_set_obstacles_host(dsmppi_ctx* c, const float* obs_host, int32_t M, v
   return dsmppi_set_obstacles(c, obs_host, M, stream);   // cudaMemcpyDefault handles host sources
 }
 
+// ---- guard band of the prefilter, calibrated per network ------------------------------------------------------
+// The tensor-core prefilter ranks obstacles on reduced-precision distances; every obstacle within `band` of the
+// K-th smallest is re-scored in fp32.  The band must exceed twice the prefilter's error, which depends on the
+// network's weights: it is MEASURED for the network (and obstacle set) in hand instead of assumed -- CAL_Q random
+// joint vectors in [-pi, pi]^d plus the first states of the calling batch, against every current obstacle, fp32
+// scoring kernel vs prefilter; band = CAL_SAFETY x the largest difference.  One-off (re-run when the obstacle count
+// changes); costs two launches and one host synchronisation.  dsmppi_set_pass1_mode(.., band > 0) overrides it.
+constexpr int CAL_Q = 256;
+constexpr float CAL_SAFETY = 3.f;
+
+static int calibrate_band(dsmppi_ctx* c, const float* q, int q_stride, int n, uint32_t ignore_mask, int mode,
+                          cudaStream_t st) {
+  const int slot = mode == DSMPPI_PASS1_TC_BF16 ? 1 : 0;
+  const int d = c->d, M = c->M;
+  const int n_act = n < CAL_Q ? n : CAL_Q;
+  const int nq = CAL_Q + n_act;
+  std::vector<float> hq((size_t)nq * d);
+  uint64_t lcg = 0x9E3779B97F4A7C15ull;
+  for (size_t i = 0; i < (size_t)CAL_Q * d; ++i) {
+    lcg = lcg * 6364136223846793005ull + 1442695040888963407ull;
+    hq[i] = ((float)((lcg >> 40) & 0xFFFFFF) / 16777216.f * 2.f - 1.f) * 3.14159265f;
+  }
+  float *dq = nullptr, *ref = nullptr, *err = nullptr;
+  CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&dq), (size_t)nq * d * sizeof(float)));
+  CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&ref), (size_t)nq * M * sizeof(float)));
+  CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&err), sizeof(float)));
+  CUDA_TRY(cudaMemcpyAsync(dq, hq.data(), (size_t)CAL_Q * d * sizeof(float), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpy2DAsync(dq + (size_t)CAL_Q * d, d * sizeof(float), q, (size_t)q_stride * sizeof(float),
+                             d * sizeof(float), n_act, cudaMemcpyDeviceToDevice, st));
+  int rc = ensure_workspace(c, nq, M);
+  RowSrc src{};
+  src.mode = ROWS_DENSE; src.M = M; src.n_rows = nq * M;
+  if (!rc) rc = launch_exact_forward(c, dq, d, src, ignore_mask, ref, st);
+  if (!rc) rc = tc_pass1(c, dq, d, nq, ignore_mask, mode, st);
+  if (!rc) rc = launch_max_abs_diff(c, ref, c->mdist, (long long)nq * M, err, st);
+  float h = 0.f;
+  if (!rc) {
+    CUDA_TRY(cudaMemcpyAsync(&h, err, sizeof(float), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+  }
+  cudaFree(dq); cudaFree(ref); cudaFree(err);
+  if (rc) return rc;
+  c->band_cal_err[slot] = h;
+  float band = CAL_SAFETY * h;
+  const float floor_band = (c->O == 9 ? 1e-3f : 1e-2f);      // never below 1 mm (cm-scaled net) / 1 cm
+  if (!(band > floor_band)) band = floor_band;
+  c->band_cal[slot] = band;
+  c->band_cal_M[slot] = M;
+  return 0;
+}
+
 // distance + gradient of n states q (row stride q_stride floats) against the current obstacles: fills
 // c->row_dist / c->row_grad and the ranked row indices c->sel_rows (n, K)
 static int distance_pipeline(dsmppi_ctx* c, const float* q, int q_stride, int n, int K, uint32_t ignore_mask,
@@ -325,8 +380,13 @@ static int distance_pipeline(dsmppi_ctx* c, const float* q, int q_stride, int n,
   REQUIRE(c->M >= 1, "obstacles not set");
   REQUIRE(K >= 1 && K <= MAXK, "n_closest_obs out of range (1..8)");
   REQUIRE(K <= c->M, "n_closest_obs exceeds the number of obstacles");
-  if (ensure_workspace(c, n, c->M)) return 1;
   const int mode = resolved_mode(c);
+  if (mode != DSMPPI_PASS1_EXACT_FP32 && c->guard_band <= 0.f) {
+    const int slot = mode == DSMPPI_PASS1_TC_BF16 ? 1 : 0;
+    if (c->band_cal[slot] <= 0.f || c->band_cal_M[slot] != c->M)
+      if (calibrate_band(c, q, q_stride, n, ignore_mask, mode, st)) return 1;
+  }
+  if (ensure_workspace(c, n, c->M)) return 1;
   RowSrc src{};
   src.M = c->M;
   src.K = K;
@@ -357,15 +417,15 @@ static int distance_pipeline(dsmppi_ctx* c, const float* q, int q_stride, int n,
     return launch_identity_rows(c, n, K, st);
   }
   // tensor-core prefilter -> candidate band -> one fp32 launch (ranking key + distance + gradient) -> rank
+  c->prefilter_used = 1;
   if (timing_mark(c, 1, st)) return 1;
   if (tc_pass1(c, q, q_stride, n, ignore_mask, mode, st)) return 1;
   if (timing_mark(c, 1, st)) return 1;
-  // default guard band = ~2.5x the largest fp16 prefilter error measured on the shipped nets
-  float band = c->guard_band;
-  if (band <= 0.f) band = (c->O == 9 ? 0.006f : 0.05f) * (mode == DSMPPI_PASS1_TC_BF16 ? 6.f : 1.f);
-  if (launch_select_candidates(c, n, K, band, st)) return 1;
+  const float band = c->guard_band > 0.f ? c->guard_band : c->band_cal[mode == DSMPPI_PASS1_TC_BF16 ? 1 : 0];
+  const size_t cap_rows = cand_list_cap(c, n);
+  if (launch_select_candidates(c, n, K, band, cap_rows, st)) return 1;
   src.mode = ROWS_LIST;
-  src.n_rows = n * CAND_MAX;
+  src.n_rows = (int)(cap_rows < 0x7fffffffu ? cap_rows : 0x7fffffffu);
   src.n_rows_dev = c->counters;
   src.row_sample = c->row_sample;
   src.row_obs = c->row_obs;
@@ -376,30 +436,36 @@ static int distance_pipeline(dsmppi_ctx* c, const float* q, int q_stride, int n,
   return launch_rank_candidates(c, n, K, st);
 }
 
-int dsmppi_rollout(dsmppi_ctx* c, const dsmppi_rollout_args* a, void* stream) {
-  REQUIRE(c && a, "null argument");
-  REQUIRE(a->N >= 1 && a->H >= 1, "N and H must be positive");
-  REQUIRE(a->n_kernels >= 0 && a->n_kernels <= NKMAX, "n_kernels out of range");
-  REQUIRE(a->q_cur_dev && a->all_traj_dev && a->closest_dist_all_dev && a->kernel_val_all_dev &&
-              a->dot_products_dev && a->kernel_activations_dev && a->qdot_dev && a->nn_grad_all_dev,
-          "null device pointer");
-  REQUIRE(a->n_kernels == 0 || (a->mu_tmp_dev && a->sigma_tmp_dev && a->alpha_tmp_dev), "null policy pointer");
-  REQUIRE(a->distance_provider == DSMPPI_DISTANCE_NN || a->distance_provider == DSMPPI_DISTANCE_FK,
-          "unknown distance_provider");
-  REQUIRE(a->distance_provider != DSMPPI_DISTANCE_FK || (c->P == 3 && a->fk_n_pts >= 1 && a->fk_n_pts <= DSMPPI_FK_MAX_PTS),
-          "the FK distance provider needs 3-D obstacles and 1..32 points per link");
-  REQUIRE(a->mod.ds_kind == DSMPPI_DS_LINEAR_ATTRACTOR || a->mod.ds_kind == DSMPPI_DS_MATRIX ||
-              a->mod.ds_kind == DSMPPI_DS_SEDS, "unknown mod.ds_kind");
-  REQUIRE(a->mod.ds_kind != DSMPPI_DS_SEDS || (c->seds && c->seds_G > 0), "SEDS parameters not set (dsmppi_set_seds)");
-  REQUIRE(a->mod.lvel_k != 0.f && a->mod.dist_k != 0.f,
-          "rollout_args.mod is not initialised (dsmppi_modulation_default / _toy)");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  CUDA_TRY(cudaSetDevice(c->device));
-  REQUIRE(c->M >= 1, "obstacles not set");
-  if (!c->keep_counters) {
-    c->ev_used = 0;
-    CUDA_TRY(cudaMemsetAsync(c->counters + 1, 0, 3 * sizeof(int), st));
+// After a call that went through the prefilter: did every step's candidate list fit, and did every row that left the
+// fp16 range of the split operands get its FFMA re-score?  One small D2H copy + a stream synchronisation -- only on the
+// prefilter path, whose rollouts take milliseconds.  verdict: 0 exact, 1 repeat (the list has been re-budgeted, or the
+// call must fall back to scoring every pair in fp32: *exact_mode = 1).
+static int prefilter_verdict(dsmppi_ctx* c, int n_max, cudaStream_t st, int* verdict, int* exact_mode) {
+  *verdict = 0;
+  *exact_mode = 0;
+  if (!c->prefilter_used) return 0;
+  CUDA_TRY(cudaMemcpyAsync(c->counters_host, c->counters, N_COUNTERS * sizeof(int), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  const int* h = c->counters_host;
+  REQUIRE(h[7] == 0, "tensor-core scoring: rows left the fp16 range and did not fit the FFMA re-scoring list "
+                     "(use dsmppi_set_score_mode(DSMPPI_SCORE_FFMA) for this network)");
+  const size_t high = (size_t)(unsigned)h[8];
+  if (high <= cand_list_cap(c, n_max)) return 0;
+  *verdict = 1;
+  // room for the worst step seen plus a quarter; the list costs 44 bytes per row (indices, key, distance, gradient)
+  const size_t want = high + high / 4;
+  if (want > ((size_t)1 << 27)) {          // > 5.9 GB of rows: score every pair of this call in fp32 instead
+    *exact_mode = 1;
+    c->exact_fallbacks++;
+  } else {
+    c->cand_rows_want = want;
+    c->capacity_retries++;
   }
+  return 0;
+}
+
+// one pass over the batch (in blocks of samples) with the context's current pass-1 mode and list budget
+static int rollout_once(dsmppi_ctx* c, const dsmppi_rollout_args* a, cudaStream_t st) {
   const int d = c->d;
   // Samples never interact, so a very large batch is rolled out in blocks of samples: it bounds the workspace
   // (the (n, M) prefilter matrix is the big one: <= 1 GiB) and keeps every row index inside 31 bits.
@@ -455,6 +521,56 @@ int dsmppi_rollout(dsmppi_ctx* c, const dsmppi_rollout_args* a, void* stream) {
   return 0;
 }
 
+int dsmppi_rollout(dsmppi_ctx* c, const dsmppi_rollout_args* a, void* stream) {
+  REQUIRE(c && a, "null argument");
+  REQUIRE(a->N >= 1 && a->H >= 1, "N and H must be positive");
+  REQUIRE(a->n_kernels >= 0 && a->n_kernels <= NKMAX, "n_kernels out of range");
+  REQUIRE(a->q_cur_dev && a->all_traj_dev && a->closest_dist_all_dev && a->kernel_val_all_dev &&
+              a->dot_products_dev && a->kernel_activations_dev && a->qdot_dev && a->nn_grad_all_dev,
+          "null device pointer");
+  REQUIRE(a->n_kernels == 0 || (a->mu_tmp_dev && a->sigma_tmp_dev && a->alpha_tmp_dev), "null policy pointer");
+  REQUIRE(a->distance_provider == DSMPPI_DISTANCE_NN || a->distance_provider == DSMPPI_DISTANCE_FK,
+          "unknown distance_provider");
+  REQUIRE(a->distance_provider != DSMPPI_DISTANCE_FK || (c->P == 3 && a->fk_n_pts >= 1 && a->fk_n_pts <= DSMPPI_FK_MAX_PTS),
+          "the FK distance provider needs 3-D obstacles and 1..32 points per link");
+  REQUIRE(a->mod.ds_kind == DSMPPI_DS_LINEAR_ATTRACTOR || a->mod.ds_kind == DSMPPI_DS_MATRIX ||
+              a->mod.ds_kind == DSMPPI_DS_SEDS, "unknown mod.ds_kind");
+  REQUIRE(a->mod.ds_kind != DSMPPI_DS_SEDS || (c->seds && c->seds_G > 0), "SEDS parameters not set (dsmppi_set_seds)");
+  REQUIRE(a->mod.lvel_k != 0.f && a->mod.dist_k != 0.f,
+          "rollout_args.mod is not initialised (dsmppi_modulation_default / _toy)");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CUDA_TRY(cudaSetDevice(c->device));
+  REQUIRE(c->M >= 1, "obstacles not set");
+  if (!c->keep_counters) c->ev_used = 0;
+  const int ev_start = c->ev_used;
+  long long block = (1LL << 28) / c->M;
+  if (block > (1 << 18)) block = 1 << 18;
+  const int n_max = (int)(a->N < block ? a->N : (block < 1 ? 1 : block));
+  // The prefilter path is exact by construction: a step whose candidates did not all fit the row list is detected
+  // after the rollout (high-water mark, prefilter_verdict) and the rollout is run again with a list that holds them
+  // -- or, past 2^27 rows, with every pair scored in fp32.  The repeat recomputes from the same inputs.
+  for (int attempt = 0;; ++attempt) {
+    c->ev_used = ev_start;
+    c->prefilter_used = 0;
+    if (!c->keep_counters || attempt > 0) CUDA_TRY(cudaMemsetAsync(c->counters + 1, 0, 3 * sizeof(int), st));
+    CUDA_TRY(cudaMemsetAsync(c->counters + 8, 0, sizeof(int), st));
+    if (rollout_once(c, a, st)) return 1;
+    int verdict = 0, exact = 0;
+    if (prefilter_verdict(c, n_max, st, &verdict, &exact)) return 1;
+    if (!verdict) break;
+    REQUIRE(attempt < 4, "candidate row list still too small after four attempts");
+    if (exact) {
+      const int saved = c->pass1_mode;
+      c->pass1_mode = DSMPPI_PASS1_EXACT_FP32;
+      c->ev_used = ev_start;
+      const int rc = rollout_once(c, a, st);
+      c->pass1_mode = saved;
+      return rc;
+    }
+  }
+  return 0;
+}
+
 int dsmppi_distance_grad(dsmppi_ctx* c, const float* q_dev, int32_t n, int32_t n_closest, uint32_t ignored_link_mask,
                          float* distance_dev, float* nn_grad_dev, void* stream) {
   REQUIRE(c && q_dev && distance_dev && nn_grad_dev, "null argument");
@@ -465,10 +581,22 @@ int dsmppi_distance_grad(dsmppi_ctx* c, const float* q_dev, int32_t n, int32_t n
   long long block = (1LL << 28) / c->M;
   if (block > (1 << 18)) block = 1 << 18;
   if (block < 1) block = 1;
+  const int saved_mode = c->pass1_mode;
   for (long long off = 0; off < n; off += block) {
     const int nb = (int)(n - off < block ? n - off : block);
-    if (distance_pipeline(c, q_dev + off * c->d, c->d, nb, n_closest, ignored_link_mask, st)) return 1;
-    if (launch_blend(c, nb, n_closest, distance_dev + off, nn_grad_dev + off * c->d, st)) return 1;
+    for (int attempt = 0;; ++attempt) {                 // same exactness protocol as dsmppi_rollout, per block
+      c->prefilter_used = 0;
+      CUDA_TRY(cudaMemsetAsync(c->counters + 8, 0, sizeof(int), st));
+      int rc = distance_pipeline(c, q_dev + off * c->d, c->d, nb, n_closest, ignored_link_mask, st);
+      if (!rc) rc = launch_blend(c, nb, n_closest, distance_dev + off, nn_grad_dev + off * c->d, st);
+      int verdict = 0, exact = 0;
+      if (!rc) rc = prefilter_verdict(c, nb, st, &verdict, &exact);
+      if (rc) { c->pass1_mode = saved_mode; return rc; }
+      if (!verdict) break;
+      if (attempt >= 4) { c->pass1_mode = saved_mode; REQUIRE(false, "candidate row list still too small"); }
+      if (exact) c->pass1_mode = DSMPPI_PASS1_EXACT_FP32;
+    }
+    c->pass1_mode = saved_mode;
   }
   return 0;
 }
@@ -492,7 +620,6 @@ int dsmppi_debug_pass1(dsmppi_ctx* c, const float* q_dev, int32_t n, uint32_t ig
   CUDA_TRY(cudaSetDevice(c->device));
   const int saved = c->pass1_mode;
   c->pass1_mode = mode;
-  c->ws_n = c->ws_M = 0;
   const int rc = ensure_workspace(c, n, c->M);
   c->pass1_mode = saved;
   if (rc) return rc;
@@ -507,8 +634,7 @@ int dsmppi_debug_pass1(dsmppi_ctx* c, const float* q_dev, int32_t n, uint32_t ig
     if (tc_pass1(c, q_dev, c->d, n, ignored_link_mask, mode, st)) return 1;
     CUDA_TRY(cudaMemcpyAsync(out_dev, c->mdist, bytes, cudaMemcpyDeviceToDevice, st));
   }
-  c->ws_n = c->ws_M = 0;   // the next rollout re-sizes for its own mode
-  return 0;
+  return 0;                // the next rollout re-sizes for its own mode (ensure_workspace keys on it)
 }
 
 int dsmppi_norm_basis(dsmppi_ctx* c, const float* grad_dev, int64_t n, float* basis_dev, void* stream) {
@@ -693,16 +819,27 @@ int dsmppi_iteration_host(dsmppi_ctx* c, dsmppi_iteration_host_args* h, void* st
     CUDA_TRY(cudaEventRecord(ev_drained, c->s_out));
     CUDA_TRY(cudaStreamWaitEvent(st, ev_drained, 0));      // the caller's stream is done when the last copy-out is
   }
+  // sample-sharded caller: the two exchanges of SURVEY 8(e) happen inside this call through the caller's hook (it
+  // all-reduces its own device buffers on `stream`); without a hook this is the single-GPU iteration
+  const bool sharded = h->exchange != nullptr;
+  REQUIRE(!sharded || (h->stats_dev && h->packed_dev && h->N_global >= r.N),
+          "a sharded iteration needs stats_dev, packed_dev and N_global");
+  float* stats_buf = sharded ? h->stats_dev : c->stats_tmp;
+  float* packed_buf = sharded ? h->packed_dev : c->packed_tmp;
   dsmppi_update_args ua{};
-  ua.N = r.N; ua.H = r.H; ua.n_kernels = r.n_kernels; ua.owns_sample0 = 1; ua.N_global = r.N; ua.variant = h->update_variant;
+  ua.N = r.N; ua.H = r.H; ua.n_kernels = r.n_kernels; ua.variant = h->update_variant;
+  ua.owns_sample0 = sharded ? h->owns_sample0 : 1;
+  ua.N_global = sharded ? h->N_global : r.N;
   ua.ker_thr = h->ker_thr; ua.upd_rate = h->upd_rate;
   ua.cost_dev = S + o_co; ua.kernel_val_all_dev = a.kernel_val_all_dev;
   ua.kernel_activations_dev = a.kernel_activations_dev;
   ua.mu_tmp_dev = a.mu_tmp_dev; ua.sigma_tmp_dev = a.sigma_tmp_dev; ua.alpha_tmp_dev = a.alpha_tmp_dev;
   ua.mu_c_dev = S + o_muc; ua.sigma_c_dev = S + o_sgc; ua.alpha_c_dev = S + o_alc;
-  if (launch_cost_stats(c, ua.cost_dev, r.N, c->stats_tmp, st)) return 1;
-  if (launch_update_partial(c, &ua, c->stats_tmp, c->packed_tmp, st)) return 1;
-  if (launch_update_finalize(c, &ua, c->packed_tmp, reinterpret_cast<int*>(S + o_nu), st)) return 1;
+  if (launch_cost_stats(c, ua.cost_dev, r.N, stats_buf, st)) return 1;
+  if (sharded) REQUIRE(h->exchange(h->exchange_user, DSMPPI_EXCHANGE_COST_STATS) == 0, "exchange hook failed (cost stats)");
+  if (launch_update_partial(c, &ua, stats_buf, packed_buf, st)) return 1;
+  if (sharded) REQUIRE(h->exchange(h->exchange_user, DSMPPI_EXCHANGE_PACKED_SUMS) == 0, "exchange hook failed (packed sums)");
+  if (launch_update_finalize(c, &ua, packed_buf, reinterpret_cast<int*>(S + o_nu), st)) return 1;
   if (!pipelined) {
     CUDA_TRY(down(h->all_traj_host, o_tr, N * H * d));
     CUDA_TRY(down(h->closest_dist_all_host, o_cd, N * H));
@@ -744,6 +881,18 @@ int dsmppi_pass1_stats(dsmppi_ctx* c, int64_t* rescored_pairs, int64_t* band_ove
     *rescored_pairs = (int64_t)v;
   }
   if (mode) *mode = resolved_mode(c);
+  return 0;
+}
+
+int dsmppi_exactness_stats(dsmppi_ctx* c, int64_t* capacity_retries, int64_t* exact_fallbacks, float* guard_band,
+                           float* calibration_error) {
+  REQUIRE(c, "null ctx");
+  const int mode = resolved_mode(c);
+  const int slot = mode == DSMPPI_PASS1_TC_BF16 ? 1 : 0;
+  if (capacity_retries) *capacity_retries = c->capacity_retries;
+  if (exact_fallbacks) *exact_fallbacks = c->exact_fallbacks;
+  if (guard_band) *guard_band = c->guard_band > 0.f ? c->guard_band : c->band_cal[slot];
+  if (calibration_error) *calibration_error = c->band_cal_err[slot];
   return 0;
 }
 

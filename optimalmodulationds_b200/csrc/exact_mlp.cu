@@ -145,12 +145,6 @@ template <bool BWD, int RPT, int FT>
 int launch_variant(dsmppi_ctx* c, const float* q, int q_stride, const RowSrc& src, uint32_t ignore_mask, float* out_m,
                    float* out_dist, float* out_grad, cudaStream_t st) {
   constexpr int R = 4 * RPT;
-  static bool init = false;
-  if (!init) {
-    CUDA_TRY(cudaFuncSetAttribute(exact_mlp_kernel<BWD, RPT, FT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)smem_bytes(R)));
-    init = true;
-  }
   const long long grid = ((long long)src.n_rows + R - 1) / R;
   exact_mlp_kernel<BWD, RPT, FT><<<(unsigned)grid, nthreads(FT), smem_bytes(R), st>>>(
       c->net, src, q, q_stride, c->obs, ignore_mask, out_m, out_dist, out_grad);
@@ -180,12 +174,6 @@ int launch(dsmppi_ctx* c, const float* q, int q_stride, const RowSrc& src, uint3
 template <int RPT, int FT>
 int launch_fused_variant(dsmppi_ctx* c, const dsmppi_rollout_args* a, cudaStream_t st) {
   constexpr int R = 4 * RPT;
-  static bool init = false;
-  if (!init) {
-    CUDA_TRY(cudaFuncSetAttribute(rollout_fused_kernel<RPT, FT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)smem_bytes(R)));
-    init = true;
-  }
   const int S = R / c->M;
   const long long grid = ((long long)a->N + S - 1) / S;
   const StepArgs sa = make_step_args(c, a, 0);
@@ -196,7 +184,28 @@ int launch_fused_variant(dsmppi_ctx* c, const dsmppi_rollout_args* a, cudaStream
   return 0;
 }
 
+template <int RPT, int FT>
+int set_attributes_variant() {
+  constexpr int R = 4 * RPT;
+  CUDA_TRY(cudaFuncSetAttribute(exact_mlp_kernel<true, RPT, FT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)smem_bytes(R)));
+  CUDA_TRY(cudaFuncSetAttribute(exact_mlp_kernel<false, RPT, FT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)smem_bytes(R)));
+  CUDA_TRY(cudaFuncSetAttribute(rollout_fused_kernel<RPT, FT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)smem_bytes(R)));
+  return 0;
+}
+
 }  // namespace
+
+// The dynamic shared-memory opt-in is a per-DEVICE function attribute: dsmppi_ctx_create calls this after
+// cudaSetDevice, so a second context on another GPU of the same process gets it too (a process-wide "done" flag
+// would leave that device without it).
+int exact_set_attributes() {
+  if (set_attributes_variant<8, 8>()) return 1;
+  if (set_attributes_variant<8, 4>()) return 1;
+  return set_attributes_variant<4, 4>();
+}
 
 // whole-horizon single launch; the caller has checked M <= 32 and initialised all_traj[:, 0]
 int launch_rollout_fused(dsmppi_ctx* c, const dsmppi_rollout_args* a, cudaStream_t st) {
@@ -211,14 +220,6 @@ int launch_rollout_fused(dsmppi_ctx* c, const dsmppi_rollout_args* a, cudaStream
 int launch_exact_fixup(dsmppi_ctx* c, const float* q, int q_stride, const RowSrc& src, uint32_t ignore_mask,
                        float* m_rows, float* row_dist, float* row_grad, bool bwd, cudaStream_t st) {
   constexpr int RPT = 8, FT = 8, R = 4 * RPT;
-  static bool init = false;
-  if (!init) {
-    CUDA_TRY(cudaFuncSetAttribute(exact_mlp_kernel<true, RPT, FT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)smem_bytes(R)));
-    CUDA_TRY(cudaFuncSetAttribute(exact_mlp_kernel<false, RPT, FT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)smem_bytes(R)));
-    init = true;
-  }
   long long grid = ((long long)src.n_rows + R - 1) / R;
   if (grid > 4LL * c->sm_count) grid = 4LL * c->sm_count;       // usually no row is flagged: keep the launch tiny
   if (bwd)

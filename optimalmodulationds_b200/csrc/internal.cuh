@@ -12,7 +12,10 @@
 #define MAXO DSMPPI_MAX_LINKS
 #define MAXK DSMPPI_MAX_CLOSEST
 #define NKMAX DSMPPI_N_KERNEL_MAX
-#define CAND_MAX 16            // candidates kept per sample by the tensor-core prefilter
+#define CAND_MAX 16            // candidate rows budgeted per sample by the tensor-core prefilter (the band usually
+                               // holds K + 1; a sample may take more while the shared row list has room, and a list
+                               // that runs out of room makes dsmppi_rollout grow it and run again -- never truncation)
+#define N_COUNTERS 16
 
 void dsmppi_set_error(const std::string& msg);
 
@@ -70,7 +73,10 @@ struct dsmppi_ctx {
   int capacity = 0;
   int M = 0;
   int pass1_mode = DSMPPI_PASS1_AUTO;
-  float guard_band = 0.f;
+  float guard_band = 0.f;             // caller-set guard band (dsmppi_set_pass1_mode); 0 = calibrated per network
+  float band_cal[2] = {0.f, 0.f};     // calibrated guard band of the fp16 / bf16 prefilter (capi.cu: calibrate_band)
+  int band_cal_M[2] = {0, 0};         // obstacle count the calibration ran on (re-run when it changes)
+  float band_cal_err[2] = {0.f, 0.f}; // largest |prefilter - fp32 scoring| seen by the calibration
   NetDev net{};
   DhTable dh{};
   float* weights_blob = nullptr;      // all fp32 weights
@@ -88,6 +94,12 @@ struct dsmppi_ctx {
   float* seds = nullptr; int seds_G = 0; float seds_thr = 0.f;
   // workspace (grown on demand)
   int ws_n = 0, ws_M = 0;
+  int ws_mode = -1;                   // resolved pass-1 mode the workspace was sized for (AUTO flips with M)
+  size_t cand_rows_want = 0;          // row-list capacity asked for after a rollout ran out of candidate rows
+  int* counters_host = nullptr;       // pinned mirror of `counters` for the end-of-rollout exactness check
+  int prefilter_used = 0;             // set by distance_pipeline when a call went through the tensor-core prefilter
+  int64_t capacity_retries = 0;       // rollouts that were run again with a larger candidate row list
+  int64_t exact_fallbacks = 0;        // rollouts that were run again with every pair scored in fp32
   float* q_work = nullptr;            // (n, d) states of the current step
   float* m_rows = nullptr;            // exact masked min distance per scored row
   size_t m_rows_cap = 0;
@@ -98,8 +110,11 @@ struct dsmppi_ctx {
   int* cand_cnt = nullptr;            // (n)
   int* row_base = nullptr;            // (n)
   int* row_sample = nullptr; int* row_obs = nullptr; size_t rowlist_cap = 0;
-  int* counters = nullptr;            // [0] n_rows, [1] band overflows, [2..3] rescored pairs (u64), [4..5] range-fixup
-                                      // row counts (ping-pong), [6] rows re-scored in FFMA so far, [7] rows dropped
+  int* counters = nullptr;            // [0] candidate rows reserved this step, [1] samples x steps whose band held more
+                                      // than CAND_MAX obstacles (informational), [2..3] rescored pairs (u64), [4..5]
+                                      // range-fixup row counts (ping-pong), [6] rows re-scored in FFMA so far, [7] rows
+                                      // that did not fit the range-fixup list, [8] largest [0] of any step of this
+                                      // rollout (> capacity: the rollout is repeated with a larger list)
   int* sel = nullptr;                 // (n, K) selected obstacle indices (two-launch fp32 path)
   int* sel_rows = nullptr;            // (n, K) rows of row_dist / row_grad holding the K closest, ranked
   float* row_dist = nullptr;          // pass-2 distance of every differentiated row
@@ -160,7 +175,15 @@ int tc_pass1(dsmppi_ctx* c, const float* q, int q_stride, int n, uint32_t ignore
 int launch_rank_dense(dsmppi_ctx* c, int n, int K, bool rows_out, cudaStream_t st);
 int launch_identity_rows(dsmppi_ctx* c, int n, int K, cudaStream_t st);
 int launch_pack_obstacles(dsmppi_ctx* c, const float* raw, int M, int P, cudaStream_t st);
-int launch_select_candidates(dsmppi_ctx* c, int n, int K, float band, cudaStream_t st);
+int launch_select_candidates(dsmppi_ctx* c, int n, int K, float band, size_t cap_rows, cudaStream_t st);
+int launch_max_abs_diff(dsmppi_ctx* c, const float* a, const float* b, long long n, float* out, cudaStream_t st);
+// exact_mlp.cu: opt the FFMA kernels into their dynamic shared memory on the context's device
+int exact_set_attributes();
+// rows the candidate list of the prefilter path can hold for a batch of n samples
+inline size_t cand_list_cap(const dsmppi_ctx* c, int n) {
+  const size_t base = (size_t)n * CAND_MAX;
+  return base > c->cand_rows_want ? base : c->cand_rows_want;
+}
 int launch_rank_candidates(dsmppi_ctx* c, int n, int K, cudaStream_t st);
 int launch_blend(dsmppi_ctx* c, int n, int K, float* dist_out, float* grad_out, cudaStream_t st);
 int launch_step(dsmppi_ctx* c, const dsmppi_rollout_args* a, int t, cudaStream_t st);

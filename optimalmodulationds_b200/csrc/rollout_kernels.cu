@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(256) rank_small_kernel(const float* __restrict
 // K-th smallest approximate distance is re-scored in fp32.  One warp per sample.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) select_candidates_kernel(const float* __restrict__ mdist, int M, int n, int K,
-                                                                float band, int* __restrict__ cand_cnt,
+                                                                float band, int cap_rows, int* __restrict__ cand_cnt,
                                                                 int* __restrict__ row_base, int* __restrict__ row_sample,
                                                                 int* __restrict__ row_obs, int* __restrict__ counters) {
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -122,49 +122,36 @@ __global__ void __launch_bounds__(128) select_candidates_kernel(const float* __r
     }
   }
   const float thr = last_v + band;
-  // count, reserve a contiguous row range, then fill (ascending obstacle index within the sample)
+  // count, reserve a contiguous row range, then fill (ascending obstacle index within the sample).  EVERY obstacle
+  // inside the band gets a row: a crowded band simply takes more of the shared list (budgeted at CAND_MAX rows per
+  // sample, typically a third used).  If the list itself runs out, the high-water mark in counters[8] tells the host,
+  // which grows the list and runs the rollout again (capi.cu: prefilter_verdict) -- nothing is ever dropped silently.
   int mine = 0;
 #pragma unroll 4
   for (int t = lane; t < M; t += 32) mine += (md[t] <= thr) ? 1 : 0;
   int total = mine;
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) total += __shfl_xor_sync(0xffffffffu, total, off);
-  int keep = total;
-  float thr_use = thr;
-  if (total > CAND_MAX) {
-    // band overflow: fall back to the CAND_MAX smallest approximate values (counted, reported)
-    if (lane == 0) atomicAdd(&counters[1], 1);
-    float lv = -FLT_MAX; int lj = -1; bool fst = true;
-    for (int kk = 0; kk < CAND_MAX; ++kk) {
-      float bv = FLT_MAX; int bj = 0x7fffffff;
-      for (int t = lane; t < M; t += 32) {
-        const float v = md[t];
-        const bool after = fst || v > lv || (v == lv && t > lj);
-        if (after && (v < bv || (v == bv && t < bj))) { bv = v; bj = t; }
-      }
-#pragma unroll
-      for (int off = 16; off > 0; off >>= 1) {
-        const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
-        const int oj = __shfl_xor_sync(0xffffffffu, bj, off);
-        if (ov < bv || (ov == bv && oj < bj)) { bv = ov; bj = oj; }
-      }
-      lv = bv; lj = bj; fst = false;
-    }
-    thr_use = lv;
-    keep = CAND_MAX;
-  }
   int base = 0;
   if (lane == 0) {
-    base = atomicAdd(&counters[0], keep);
-    atomicAdd(reinterpret_cast<unsigned long long*>(&counters[2]), (unsigned long long)keep);
-    cand_cnt[w] = keep;
-    row_base[w] = base;
+    base = atomicAdd(&counters[0], total);
+    atomicMax(&counters[8], base + total);
+    if (total > CAND_MAX) atomicAdd(&counters[1], 1);
   }
   base = __shfl_sync(0xffffffffu, base, 0);
+  // rows of this sample that fit (all of them unless the list is exhausted; the rows written stay valid indices, so
+  // the scoring launch that follows reads nothing out of bounds before the rollout is repeated)
+  const int room = base < cap_rows ? cap_rows - base : 0;
+  const int keep = total < room ? total : room;
+  if (lane == 0) {
+    atomicAdd(reinterpret_cast<unsigned long long*>(&counters[2]), (unsigned long long)keep);
+    cand_cnt[w] = keep;
+    row_base[w] = base < cap_rows ? base : 0;
+  }
   int written = 0;
   for (int t0 = 0; t0 < M && written < keep; t0 += 32) {
     const int t = t0 + lane;
-    const bool in = t < M && md[t] <= thr_use;
+    const bool in = t < M && md[t] <= thr;
     const unsigned bal = __ballot_sync(0xffffffffu, in);
     const int pos = written + __popc(bal & ((1u << lane) - 1u));
     if (in && pos < keep) {
@@ -173,6 +160,20 @@ __global__ void __launch_bounds__(128) select_candidates_kernel(const float* __r
     }
     written += __popc(bal);
   }
+}
+
+// largest |a - b| over n elements (guard-band calibration of the prefilter); out[0] must be zeroed beforehand.
+// Non-negative floats order like their bit patterns, so the grid-wide maximum is an integer atomicMax.
+__global__ void max_abs_diff_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n,
+                                    float* __restrict__ out) {
+  float m = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float df = fabsf(a[i] - b[i]);
+    if (df == df) m = fmaxf(m, df);
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+  if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(out), __float_as_int(m));
 }
 
 __global__ void pack_obstacles_kernel(const float* __restrict__ raw, int M, int P, float* __restrict__ obs) {
@@ -547,7 +548,8 @@ __global__ void __launch_bounds__(128) basis_kernel(const float* __restrict__ gr
 // ------------------------------------------------------------------------------------------------
 // Policy update (MPPI.py:331-345, policy.py:88-113) as three reductions
 // ------------------------------------------------------------------------------------------------
-// stats = { sum cost, min cost, argmin, N }.  Fixed order => deterministic: every CTA reduces a contiguous chunk of
+// stats = { sum cost, N, min cost, argmin }: the two entries a sample-sharded job SUM-all-reduces are adjacent.
+// Fixed order => deterministic: every CTA reduces a contiguous chunk of
 // samples to (sum, min, argmin) and the last CTA to finish (ticket counter) combines the chunks in index order.
 // HBM-bound: 4 B per sample, read once, coalesced.
 constexpr int STATS_MAX_BLOCKS = 1024;
@@ -595,7 +597,7 @@ __global__ void __launch_bounds__(1024) cost_stats_kernel(const float* __restric
   }
   block_reduce();
   if (nb == 1) {
-    if (threadIdx.x == 0) { stats[0] = s; stats[1] = mn; stats[2] = (float)mi; stats[3] = (float)N; }
+    if (threadIdx.x == 0) { stats[0] = s; stats[1] = (float)N; stats[2] = mn; stats[3] = (float)mi; }
     return;
   }
   if (threadIdx.x == 0) {
@@ -617,7 +619,7 @@ __global__ void __launch_bounds__(1024) cost_stats_kernel(const float* __restric
   __syncthreads();
   block_reduce();
   if (threadIdx.x == 0) {
-    stats[0] = s; stats[1] = mn; stats[2] = (float)mi; stats[3] = (float)N;
+    stats[0] = s; stats[1] = (float)N; stats[2] = mn; stats[3] = (float)mi;
     *ticket = 0;                               // ready for the next launch
   }
 }
@@ -646,7 +648,7 @@ __global__ void __launch_bounds__(UPD_T) update_partial_kernel(UpdArgs u) {
   __shared__ float red[UPD_W][32 * E];
   const int nk = u.nk, d = u.d, H = u.H, L = u.L;
   const int o_mu = 1, o_sg = o_mu + nk * d, o_al = o_sg + nk, o_mx = o_al + nk * d, o_b0 = o_mx + nk;
-  const float beta = (u.stats[0] / u.stats[3]) / 50.f;               // MPPI.py:332
+  const float beta = (u.stats[0] / u.stats[1]) / 50.f;               // MPPI.py:332
   const float nib = -1.f / beta;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long chunk = ((long long)u.N + gridDim.x - 1) / gridDim.x;
@@ -801,11 +803,22 @@ int launch_pack_obstacles(dsmppi_ctx* c, const float* raw, int M, int P, cudaStr
   return 0;
 }
 
-int launch_select_candidates(dsmppi_ctx* c, int n, int K, float band, cudaStream_t st) {
+int launch_select_candidates(dsmppi_ctx* c, int n, int K, float band, size_t cap_rows, cudaStream_t st) {
   CUDA_TRY(cudaMemsetAsync(c->counters, 0, sizeof(int), st));   // row counter only; stats accumulate
   const int threads = 128, warps = threads / 32;
+  const int cap = (int)(cap_rows < 0x7fffffffu ? cap_rows : 0x7fffffffu);
   select_candidates_kernel<<<(n + warps - 1) / warps, threads, 0, st>>>(
-      c->mdist, c->M, n, K, band, c->cand_cnt, c->row_base, c->row_sample, c->row_obs, c->counters);
+      c->mdist, c->M, n, K, band, cap, c->cand_cnt, c->row_base, c->row_sample, c->row_obs, c->counters);
+  LAUNCH_CHECK(c);
+  return 0;
+}
+
+int launch_max_abs_diff(dsmppi_ctx* c, const float* a, const float* b, long long n, float* out, cudaStream_t st) {
+  CUDA_TRY(cudaMemsetAsync(out, 0, sizeof(float), st));
+  long long blocks = (n + 255) / 256;
+  if (blocks > 4LL * c->sm_count) blocks = 4LL * c->sm_count;
+  if (blocks < 1) blocks = 1;
+  max_abs_diff_kernel<<<(unsigned)blocks, 256, 0, st>>>(a, b, n, out);
   LAUNCH_CHECK(c);
   return 0;
 }

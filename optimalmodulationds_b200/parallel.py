@@ -4,8 +4,10 @@ Samples never interact inside propagate/get_cost, so rank r simply owns N/G of t
 weights and policy means are replicated.  The policy update needs exactly two tiny exchanges per iteration,
 both plain NCCL all-reduces over NVLink/NVSwitch on the packed vectors produced by the CUDA reduction
 kernels:
-  1. cost statistics  [sum cost, min cost, argmin, N]  -> global beta = mean(cost)/50
-  2. packed weighted sums (<= 3.2 KB)                  -> every rank applies the identical EMA
+  1. cost statistics  SUM of [sum cost, N]             -> global beta = mean(cost)/50
+  2. packed weighted sums (<= 3.4 KB), SUM             -> every rank applies the identical EMA
+Neither needs the host: the global sample count is known when sharding is enabled, so an iteration enqueues two
+collectives and never synchronises.
 The functions below operate on torch tensors on any device so the same logic is exercised with the gloo
 backend on CPU in tests/test_parallel_gloo.py.
 """
@@ -21,14 +23,23 @@ def shard_range(n_total, rank, world):
 
 
 def allreduce_cost_stats(stats, group=None):
-    """stats = [sum cost, min cost, argmin (local), N] per rank -> global sum / min / N in place.
-    Returns the global sample count."""
-    sums = torch.stack((stats[0], stats[3]))
-    mn = stats[1:2].clone()
-    dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
-    dist.all_reduce(mn, op=dist.ReduceOp.MIN, group=group)
-    stats[0], stats[3], stats[1] = sums[0], sums[1], mn[0]
-    return int(round(float(sums[1])))
+    """stats = [sum cost, N, min cost, argmin (local)] per rank (cost_stats_kernel): sums the first two entries over
+    the ranks, in place, with ONE collective.  Entries 2..3 stay per-shard (see allreduce_best)."""
+    dist.all_reduce(stats[0:2], op=dist.ReduceOp.SUM, group=group)
+    return stats
+
+
+def allreduce_best(stats, rank_offset, group=None):
+    """Global (min cost, global sample index) from per-rank stats -- only get_qdot('best') on a sharded job needs it.
+    Returns a 2-vector on stats' device; ties go to the lowest global index like torch.argmin."""
+    world = dist.get_world_size(group)
+    mine = torch.stack((stats[2], stats[3] + float(rank_offset)))
+    allv = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(allv, mine, group=group)
+    allv = torch.stack(allv)
+    order = torch.argsort(allv[:, 1])
+    allv = allv[order]
+    return allv[torch.argmin(allv[:, 0])]
 
 
 def allreduce_packed(packed, group=None):

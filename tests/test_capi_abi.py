@@ -44,7 +44,8 @@ def test_struct_layout_matches_the_c_compiler(capi, tmp_path):
               "dsmppi_seds": ["seds_thr", "priors_host", "A_host"],
               "dsmppi_cost_args": ["terms", "q_max", "cost_dev"],
               "dsmppi_update_args": ["variant", "N_global", "ker_thr", "alpha_c_dev"],
-              "dsmppi_iteration_host_args": ["q_min", "cost_terms", "q_cur_host", "n_updated_host", "d2h_bytes"],
+              "dsmppi_iteration_host_args": ["q_min", "cost_terms", "q_cur_host", "n_updated_host", "d2h_bytes", "exchange",
+                                             "stats_dev", "owns_sample0", "N_global"],
               "dsmppi_net": ["W_host", "b_host"]}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "dsmppi_b200.h"', 'int main(void){']
     for s, fields in probes.items():

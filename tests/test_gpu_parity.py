@@ -297,9 +297,10 @@ def test_sharded_update_kernels_match_unsharded(factory):
         s_ = torch.empty(4, device="cuda")
         _capi.check(lib.dsmppi_update_cost_stats(ctx, m.cur_cost[lo:hi].contiguous().data_ptr(), hi - lo, s_.data_ptr(), st))
         stats.append(s_)
-    g = torch.stack((stats[0][0] + stats[1][0], torch.minimum(stats[0][1], stats[1][1]), stats[0][2],
-                     stats[0][3] + stats[1][3]))
-    assert int(g[3]) == N
+    # layout [sum cost, N, min cost, argmin]: the SUM all-reduce acts on the first two entries
+    g = torch.stack((stats[0][0] + stats[1][0], stats[0][1] + stats[1][1], torch.minimum(stats[0][2], stats[1][2]),
+                     stats[0][3]))
+    assert int(g[1]) == N
     total = torch.zeros(L, device="cuda")
     args = None
     for r, (lo, hi) in enumerate(halves):

@@ -44,10 +44,15 @@ def _worker(rank, world, port, out):
         lo, hi = parallel.shard_range(N, rank, world)
         cost = c["cost"][lo:hi]
         # phase 1: local cost statistics -> all-reduce -> global beta
-        stats = torch.stack((cost.sum(), cost.min(), cost.argmin().float(), torch.tensor(float(hi - lo))))
-        n_global = parallel.allreduce_cost_stats(stats)
+        # the layout of cost_stats_kernel: [sum cost, N, min cost, argmin (local)]
+        stats = torch.stack((cost.sum(), torch.tensor(float(hi - lo)), cost.min(), cost.argmin().float()))
+        parallel.allreduce_cost_stats(stats)                # ONE collective: SUM of the first two entries
+        n_global = int(stats[1])
         assert n_global == N
-        beta = (stats[0] / stats[3]) / 50
+        assert float(stats[2]) == float(cost.min())         # min / argmin stay per shard ...
+        best = parallel.allreduce_best(stats, lo)           # ... until a caller asks for the global best sample
+        assert int(best[1]) == int(c["cost"].argmin()) and float(best[0]) == float(c["cost"].min())
+        beta = (stats[0] / stats[1]) / 50
         # phase 2: packed partial sums -> all-reduce
         packed = orc.policy_update_partials(cost, kv[lo:hi], c["kernel_activations"][lo:hi], mu[lo:hi], sg[lo:hi],
                                             al[lo:hi], nk, beta, owns_sample0=(rank == 0))
@@ -55,7 +60,7 @@ def _worker(rank, world, port, out):
         # phase 3: identical finalize on every rank
         mu1, sg1, al1, n_upd = parallel.finalize_from_packed(packed, nk, d, n_global, float(c["ker_thr"]), 0.1,
                                                             c["mu_c0"], c["sigma_c0"], c["alpha_c0"])
-        out[rank] = (mu1, sg1, al1, n_upd, float(stats[1]))
+        out[rank] = (mu1, sg1, al1, n_upd, float(best[0]))
     finally:
         dist.destroy_process_group()
 
