@@ -1,0 +1,143 @@
+"""The reference's OWN scripts, byte for byte, driven through the drop-in (run with -m gpu).
+
+north_star: "standalonePlanar2d.py, standalonePlanar7d.py and the Franka shelf scripts run unchanged".  The scripts
+live in oracle/_ref/ (staged from the reference by oracle/make_ref.sh, git-ignored, shipped to the GPU box with the
+snapshot; a sha256 manifest pins them).  Each is started exactly as its README says -- `python <script>.py` from its own
+directory -- with ONE change to the environment: optimalmodulationds_b200/dropin is first on PYTHONPATH, so
+`from MPPI import *`, `from LinDS import *`, `from sdf.robot_sdf import RobotSdfCollisionNet` resolve to this package
+(checked: the child reports which file `MPPI` came from).  matplotlib is absent in this image; the drop-in `plots`
+module is headless, so no display shim is involved on this path."""
+import hashlib
+import os
+import re
+import signal
+import subprocess
+import sys
+import time
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DROPIN = os.path.join(ROOT, "optimalmodulationds_b200", "dropin")
+REF = os.path.join(ROOT, "oracle", "_ref")
+DS_MPPI = os.path.join(REF, "python_scripts", "ds_mppi")
+
+needs_ref = pytest.mark.skipif(not os.path.isdir(DS_MPPI),
+                               reason="oracle/_ref is not staged (run oracle/make_ref.sh in the build container)")
+
+# sitecustomize-free way to learn, from inside the unmodified script's process, which MPPI module it imported: a
+# PYTHONSTARTUP-like hook is not available for scripts, so the check runs as a separate probe with the same environment
+PROBE = "import sys; sys.path.append('../functions/'); sys.path.append('functions'); import MPPI; print(MPPI.__file__)"
+
+
+def _env():
+    env = dict(os.environ)
+    env["PYTHONPATH"] = DROPIN + os.pathsep + env.get("PYTHONPATH", "")
+    env["PYTHONUNBUFFERED"] = "1"
+    return env
+
+
+def _verify_manifest():
+    """The staged files are the reference's, unedited: every sha256 of MANIFEST.sha256 still holds."""
+    bad = []
+    for line in open(os.path.join(REF, "MANIFEST.sha256")):
+        digest, rel = line.split(None, 1)
+        rel = rel.strip()
+        with open(os.path.join(REF, rel), "rb") as f:
+            if hashlib.sha256(f.read()).hexdigest() != digest:
+                bad.append(rel)
+    assert not bad, f"staged reference files were modified: {bad}"
+
+
+def _run(script, cwd, timeout):
+    """Runs `python script` in cwd until it exits or `timeout` seconds pass; returns (returncode | None, output)."""
+    proc = subprocess.Popen([sys.executable, "-u", script], cwd=cwd, env=_env(), stdout=subprocess.PIPE,
+                            stderr=subprocess.STDOUT, text=True, start_new_session=True)
+    try:
+        out, _ = proc.communicate(timeout=timeout)
+        return proc.returncode, out
+    except subprocess.TimeoutExpired:
+        os.killpg(proc.pid, signal.SIGTERM)
+        try:
+            out, _ = proc.communicate(timeout=20)
+        except subprocess.TimeoutExpired:
+            os.killpg(proc.pid, signal.SIGKILL)
+            out, _ = proc.communicate()
+        return None, out
+
+
+@needs_ref
+def test_staged_reference_is_unmodified_and_imports_resolve_to_the_dropin():
+    _verify_manifest()
+    out = subprocess.run([sys.executable, "-c", PROBE], cwd=os.path.join(DS_MPPI, "scripts"), env=_env(),
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert os.path.join("optimalmodulationds_b200", "dropin", "MPPI.py") in out.stdout, out.stdout
+
+
+@needs_ref
+@pytest.mark.parametrize("script,min_iters", [("standalonePlanar7d.py", 100), ("standalonePlanar2d.py", 40)])
+def test_unmodified_standalone_script_runs_to_the_goal(script, min_iters):
+    """The script's own loop (standalonePlanar7d.py:119-185 / standalonePlanar2d.py:145-212): planner MPPI + 1 x 1
+    stepper MPPI, kernel adding through check_traj_for_kernels / add_kernel / norm_basis, CPU tensors in and out.  It
+    ends when the arm is within the script's tolerance of the goal (or after its own 10 000-iteration cap) and then
+    prints its timing summary."""
+    rc, out = _run(script, os.path.join(DS_MPPI, "scripts"), timeout=900)
+    tail = out[-3000:]
+    assert rc == 0, f"{script} exited with {rc}:\n{tail}"
+    assert "Weights loaded!" in out, tail
+    iters = [int(m.group(1)) for m in re.finditer(r"Iteration:\s*(\d+),", out)]
+    assert iters and iters[-1] >= min_iters, f"only {iters[-1] if iters else 0} iterations:\n{tail}"
+    assert "Time per rollout step" in out, tail
+    reached = iters[-1] < 10000
+    kernels = [int(m.group(1)) for m in re.finditer(r"Kernel count:\s*(\d+)", out)]
+    hz = re.search(r"Time per iteration:\s*([0-9.e-]+)\s*Hz:\s*([0-9.e+-]+)", out)
+    print(f"{script}: {iters[-1]} iterations, goal {'reached' if reached else 'NOT reached (iteration cap)'}, "
+          f"{kernels[-1] if kernels else 0} kernels, {hz.group(2) if hz else '?'} Hz")
+    assert reached, f"{script} hit its 10 000-iteration cap without reaching the goal"
+
+
+@needs_ref
+def test_unmodified_franka_shelf_processes_run():
+    """The live Franka shelf setup of ds_mppi/Readme.MD:3-11: obstacleStreamer.py (294-sphere shelf at 120 Hz),
+    frankaPlanner.py (40 samples x 10 steps, kernel adding, policy publishing) and frankaIntegrator.py (1 sample x 2
+    steps control tick) as three processes coupled by ZeroMQ on localhost, all unmodified; planner and integrator
+    import the drop-in.  They loop forever by design: run for a bounded time, then check what they printed."""
+    import zmq  # noqa: F401  (the scripts need pyzmq)
+    procs, logs = [], {}
+    try:
+        for name in ("obstacleStreamer.py", "frankaPlanner.py", "frankaIntegrator.py"):
+            procs.append((name, subprocess.Popen([sys.executable, "-u", name], cwd=DS_MPPI, env=_env(),
+                                                 stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
+                                                 start_new_session=True)))
+            time.sleep(1.0)
+        deadline = time.time() + 75
+        while time.time() < deadline and all(p.poll() is None for _, p in procs):
+            time.sleep(1.0)
+    finally:
+        for name, p in procs:
+            if p.poll() is None:
+                os.killpg(p.pid, signal.SIGTERM)
+        for name, p in procs:
+            try:
+                logs[name], _ = p.communicate(timeout=20)
+            except subprocess.TimeoutExpired:
+                os.killpg(p.pid, signal.SIGKILL)
+                logs[name], _ = p.communicate()
+    for name in logs:
+        assert "Traceback" not in logs[name], f"{name} crashed:\n{logs[name][-3000:]}"
+    plan, integ = logs["frankaPlanner.py"], logs["frankaIntegrator.py"]
+    p_iters = [int(m.group(1)) for m in re.finditer(r"Iteration:\s*(\d+),", plan)]
+    i_iters = [int(m.group(1)) for m in re.finditer(r"\(\s*(\d+) total\)", integ)]
+    assert p_iters and p_iters[-1] >= 50, f"planner made {p_iters[-1] if p_iters else 0} iterations:\n{plan[-2000:]}"
+    assert i_iters and i_iters[-1] >= 200, f"integrator made {i_iters[-1] if i_iters else 0} ticks:\n{integ[-2000:]}"
+    assert "Best cost:" in plan
+    p_hz = [float(m.group(1)) for m in re.finditer(r"Avg\. frequency:\s*([0-9.]+)", plan)]
+    i_hz = [float(m.group(1)) for m in re.finditer(r"Avg\. frequency:\s*([0-9.]+)", integ)]
+    kern = [int(m.group(1)) for m in re.finditer(r"Kernel count:\s*(\d+)", integ)]
+    reached = len(re.findall(r"1: Goal reached", integ))
+    print(f"franka shelf: planner {p_iters[-1]} iterations ({p_hz[-1] if p_hz else 0:.0f} Hz avg), integrator "
+          f"{i_iters[-1]} ticks ({i_hz[-1] if i_hz else 0:.0f} Hz avg), kernels received {max(kern) if kern else 0}, "
+          f"goal reached {reached}x")
