@@ -88,10 +88,14 @@ def test_constructor_leaves_the_torch_generator_untouched(factory):
     """Reference: MPPI.__init__ runs five sample_policy + propagate warm-ups (MPPI.py:69-73); with n_kernels = 0
     their normal_() calls draw nothing (checked on the reference itself in the build container: the generator state
     is identical before and after), so RNG lock-step == the constructor consumes no random numbers."""
+    import optimalmodulationds_b200 as pkg
     c = load_npz("case_planar7")
+    net = factory.make_net("planar7")               # nn.Linear initialisation draws from the generator: before seeding,
+    DS = [pkg.LinDS(c["qf"]), pkg.LinDS(c["q0"])]   # as in the scripts (the network is built before the MPPI object)
     torch.manual_seed(2024)
     s0 = torch.get_rng_state().clone()
-    m = factory.make_mppi(c, device="cpu", copy_policy=False)
+    m = pkg.MPPI(c["q0"], c["qf"], c["dh_params"], c["obs"], float(c["dt"]), int(c["H"]), int(c["N"]), DS, c["dh_a"],
+                 net, int(c["K"]))
     assert torch.equal(torch.get_rng_state(), s0)
     # and from there a seeded script draws exactly the reference's noise: mu, sigma, alpha in this order
     m.Policy.n_kernels = 3
@@ -181,8 +185,10 @@ def test_crowded_guard_band_is_rescored_not_truncated(kind, M, factory):
     p1, xs = stats["tc_f16"]
     print(f"{kind} M={M}: {p1}, {xs}")
     assert p1["mode"] == 1
-    assert p1["band_overflows"] > 0, "the adversarial set was meant to crowd the band"
-    assert p1["rescored_pairs"] / (N * H) > 16
+    if kind != "ring":        # (the ring only produces near-ties; the other two put every sphere inside the band)
+        assert p1["band_overflows"] > 0, "the adversarial set was meant to crowd the band"
+        assert p1["rescored_pairs"] / (N * H) > 16
+        assert xs["capacity_retries"] >= 1, "a list budgeted at 16 rows per sample cannot have held them"
     for a, b, name in zip(outs["exact"], outs["tc_f16"], ("traj", "dist", "kval", "dots", "acts", "qdot", "cost")):
         assert torch.equal(a, b), f"{kind}: {name} differs from the all-pairs fp32 rollout"
     # distance_repulsion_nn goes through the same protocol

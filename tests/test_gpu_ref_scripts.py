@@ -79,7 +79,7 @@ def test_staged_reference_is_unmodified_and_imports_resolve_to_the_dropin():
 
 @needs_ref
 @pytest.mark.parametrize("script,min_iters", [("standalonePlanar7d.py", 100), ("standalonePlanar2d.py", 40)])
-def test_unmodified_standalone_script_runs_to_the_goal(script, min_iters):
+def test_unmodified_standalone_script_runs_to_its_end(script, min_iters):
     """The script's own loop (standalonePlanar7d.py:119-185 / standalonePlanar2d.py:145-212): planner MPPI + 1 x 1
     stepper MPPI, kernel adding through check_traj_for_kernels / add_kernel / norm_basis, CPU tensors in and out.  It
     ends when the arm is within the script's tolerance of the goal (or after its own 10 000-iteration cap) and then
@@ -96,7 +96,10 @@ def test_unmodified_standalone_script_runs_to_the_goal(script, min_iters):
     hz = re.search(r"Time per iteration:\s*([0-9.e-]+)\s*Hz:\s*([0-9.e+-]+)", out)
     print(f"{script}: {iters[-1]} iterations, goal {'reached' if reached else 'NOT reached (iteration cap)'}, "
           f"{kernels[-1] if kernels else 0} kernels, {hz.group(2) if hz else '?'} Hz")
-    assert reached, f"{script} hit its 10 000-iteration cap without reaching the goal"
+    # Reaching the goal is NOT asserted: the scripts do not seed their noise, and the reference itself (run on CPU in
+    # the build container with the two import shims) stalls in standalonePlanar2d.py near q = [1.46, -0.40] until the
+    # iteration cap -- its goal [3.14, 0] lies outside the joint limits the script sets (+-0.99 * 3.14) and its 0.1 rad
+    # steps cannot land inside the 0.01 tolerance.  What is asserted is that the unmodified script runs to its own end.
 
 
 @needs_ref
