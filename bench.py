@@ -121,15 +121,19 @@ def load_net_arrays(name):
     return [l.weight.detach() for l in lin], [l.bias.detach() for l in lin], "random-init"
 
 
-def seeded_policy(p, N, seed):
-    """nk kernels pre-placed along q0 + 0.1 k and one Gaussian draw of the weights."""
-    g = torch.Generator().manual_seed(seed)
+def seeded_policy(p, N, seed, mean_seed=100):
+    """nk kernels pre-placed along q0 + 0.1 k and one Gaussian draw of the weights.  The policy MEANS
+    come from `mean_seed` (every rank of a sharded job holds the same means); the per-sample noise from
+    `seed` (each rank draws its own samples; seed == mean_seed continues the same stream)."""
+    g = torch.Generator().manual_seed(mean_seed)
     nk, d = p["nk"], p["dof"]
     mu_c = torch.zeros(50, d); sigma_c = torch.zeros(50); alpha_c = torch.zeros(50, d)
     for k in range(nk):
         mu_c[k] = p["q0"] + 0.1 * k
     sigma_c[:nk] = p["sigma"]
     alpha_c[:nk] = 0.5 * torch.randn(nk, d, generator=g)
+    if seed != mean_seed:
+        g = torch.Generator().manual_seed(seed)
     mu_tmp = torch.zeros(N, 50, d); sigma_tmp = torch.zeros(N, 50); alpha_tmp = torch.zeros(N, 50, d)
     mu_tmp[:, :nk] = mu_c[:nk]
     sigma_tmp[:, :nk] = sigma_c[:nk]
@@ -309,7 +313,7 @@ def check_sharding(p, dev, args, rank, world, mppi_main):
     dist.all_gather(every, mine)
     identical = all(torch.equal(every[0], e) for e in every)
     n_small, h_small = 256, 8
-    pol_all = seeded_policy(p, world * n_small, 4242)                 # the same global draw on every rank
+    pol_all = seeded_policy(p, world * n_small, 4242, mean_seed=4242)  # the same global draw on every rank
     lo, hi = rank * n_small, (rank + 1) * n_small
     sl = (pol_all[0], pol_all[1], pol_all[2], pol_all[3][lo:hi].clone(), pol_all[4][lo:hi].clone(),
           pol_all[5][lo:hi].clone())
