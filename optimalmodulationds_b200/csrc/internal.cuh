@@ -171,6 +171,7 @@ int tc_build_images(dsmppi_ctx* c, const dsmppi_net* net);
 void tc_free_images(dsmppi_ctx* c);
 int tc_set_obstacles(dsmppi_ctx* c, cudaStream_t st);
 int tc_pass1(dsmppi_ctx* c, const float* q, int q_stride, int n, uint32_t ignore_mask, int mode, cudaStream_t st);
+int tc_sample_table(dsmppi_ctx* c, const float* q, int q_stride, int n, int mode, cudaStream_t st);
 // rollout_kernels.cu
 int launch_rank_dense(dsmppi_ctx* c, int n, int K, bool rows_out, cudaStream_t st);
 int launch_identity_rows(dsmppi_ctx* c, int n, int K, cudaStream_t st);

@@ -2,12 +2,20 @@
 //
 // Every (sample, obstacle) pair is pushed through the 5-layer distance MLP on the 5th-generation tensor
 // cores (tcgen05.mma, kind::f16, fp32 accumulation in TMEM) to get an APPROXIMATE masked minimum link
-// distance; the exact fp32 path (exact_mlp.cu) then re-scores only the obstacles inside a guard band of
+// distance; the fp32-accurate scoring path then re-scores only the obstacles inside a guard band of
 // the K-th smallest, so the final ranking, distances and gradients are fp32-exact.
 //
 // Design (B200, one CTA pair per TPC, persistent):
-//   * cta_group::2 MMAs with M = 256 (128 pair-rows per CTA): each CTA keeps HALF of every weight matrix
-//     resident in shared memory for the whole kernel (16 + 3*64 + 8 KB of fp16 + 4 KB of biases = 220 KB),
+//   * layer 1 is SEPARABLE in its input [q, p]:  W1 enc([q, p]) + b1 = (W1q enc(q) + b1) + W1p enc(p).  The
+//     per-sample part A_i (n x 256) and the per-obstacle part B_j (M x 256) are small tables (fp32 arithmetic,
+//     stored as fp16 / bf16 pairs); a pair row's first hidden activation is relu(A_i + B_j) -- two packed
+//     half-precision instructions per two features, read straight into the layer-2 operand.  The (M N, d + 4)
+//     input of MPPI.py:93-95 is never materialised, layer 1 costs no tensor-core time and, above all, no
+//     accumulator round trip: a K = 60 GEMM kept the tensor pipe waiting for a full 256-column epilogue per tile
+//     (31 % of the pipe's cycles were idle in the first version of this kernel, profiles/r1_tc_pass1_*).  The next
+//     tile's operand is prepared under the current tile's last MMAs.
+//   * cta_group::2 MMAs with M = 256 (128 pair-rows per CTA): each CTA keeps HALF of every remaining weight
+//     matrix resident in shared memory for the whole kernel (3 x 64 + 8 KB of fp16 + 3 KB of biases = 203 KB),
 //     loaded once with bulk TMA copies (cp.async.bulk, UBLKCP) -- no weight traffic afterwards.
 //   * activations never touch shared memory or HBM: the A operand of every layer lives in TMEM
 //     (tcgen05.mma "ts" form); the epilogue warps read the fp32 accumulator with tcgen05.ld, add bias, ReLU,
@@ -15,9 +23,6 @@
 //   * TMEM (512 columns): A operands of two row tiles X,Y (2 x 128 columns) + two 128-column accumulator
 //     halves D_lo/D_hi shared by both tiles.  While the epilogue warps of X drain D_lo/D_hi, the tensor core
 //     already works on Y, so in steady state the MMA pipe never waits for an epilogue.
-//   * layer 1 consumes [enc_hi | enc_lo] (two fp16 halves of the fp32 encoding, K = 64) so the only
-//     quantisation is in weights/activations; the per-sample and per-obstacle parts of the encoding are
-//     pre-packed (128 B each) and OR-ed together per pair.
 //   * warp roles: warps 0-3 rows of tile X, warps 4-7 rows of tile Y (TMEM lane quarter = warp % 4),
 //     warp 8 = TMEM allocator + weight loader + MMA issuer (one elected thread, leader CTA only).
 #include <cuda_bf16.h>
@@ -34,7 +39,7 @@
 namespace {
 
 constexpr int ROWS = 128;                 // pair-rows per CTA per tile slot
-constexpr int K0 = 64;                    // layer-1 K: 32 "hi" + 32 "lo" halves of the encoding
+constexpr int NHID = 3;                   // hidden GEMMs on the tensor cores (network layers 2..4)
 constexpr int MMA_WARP = 8;               // warps 0..7: rows (2 tile slots x 4 TMEM lane quarters)
 // Three warpgroups: two of row warps and one holding the MMA issuer (warp 8; warps 9..11 only exist so that the
 // third warpgroup is complete and can hand its registers over with setmaxnreg).  A 9-warp CTA would leave the
@@ -44,15 +49,13 @@ constexpr int NTHREADS = 12 * 32;
 constexpr int ROW_REGS = 232, ISSUER_REGS = 40;   // 128*(168-40) freed == 2*128*(232-168) claimed
 
 // ---- shared-memory map (bytes); the weight part is a verbatim copy of the per-CTA global image
-constexpr int OFF_W1 = 0;                          // 2 halves x (64 rows x K0) fp16
-constexpr int SZ_W1H = 64 * K0 * 2;                // 8 KB per half
-constexpr int OFF_WH = OFF_W1 + 2 * SZ_W1H;        // layers 2..4: 3 x 2 halves x (64 rows x 256) fp16
+constexpr int OFF_WH = 0;                          // layers 2..4: 3 x 2 halves x (64 rows x 256) fp16
 constexpr int SZ_WHH = 64 * HID * 2;               // 32 KB per half
-constexpr int OFF_W5 = OFF_WH + 3 * 2 * SZ_WHH;    // output layer: 16 rows x 256 fp16
+constexpr int OFF_W5 = OFF_WH + NHID * 2 * SZ_WHH; // output layer: 16 rows x 256 fp16
 constexpr int SZ_W5 = 16 * HID * 2;                // 8 KB
-constexpr int OFF_BIAS = OFF_W5 + SZ_W5;           // 4 x 256 fp32 + 16 fp32
-constexpr int SZ_BIAS = (4 * HID + 16) * 4;
-constexpr int IMG_BYTES = OFF_BIAS + SZ_BIAS;      // 225344
+constexpr int OFF_BIAS = OFF_W5 + SZ_W5;           // 3 x 256 fp32 (layers 2..4) + 16 fp32 (output)
+constexpr int SZ_BIAS = (NHID * HID + 16) * 4;
+constexpr int IMG_BYTES = OFF_BIAS + SZ_BIAS;      // 207936
 constexpr int OFF_BAR = IMG_BYTES;                 // mbarriers (8 B each)
 constexpr int NBAR = 12;
 constexpr int OFF_TMEMPTR = OFF_BAR + NBAR * 8;
@@ -259,42 +262,46 @@ __host__ __device__ constexpr uint32_t make_idesc(int fmt /*0 f16, 1 bf16*/, int
 }
 
 // ------------------------------------------------------------------------------------------------
-// Encoding tables: per sample / per obstacle 64 halves = [hi(32) | lo(32)] of enc = [x, sin x, cos x]
-// with zeros at the positions the other table fills (row operand = bitwise OR of the two)
+// Layer-1 tables (network_macros_mod.py:139-141 with the input split into its q and p columns):
+//   A_i[k] = b1[k] + sum_{c < d} W1[k][c] q_c + W1[k][nin + c] sin q_c + W1[k][2 nin + c] cos q_c          (n, 256)
+//   B_j[k] =         sum_{c < P} W1[k][d + c] p_c + W1[k][nin + d + c] sin p_c + W1[k][2 nin + d + c] cos p_c
+// fp32 FMAs over the fp32 weights, rounded once to fp16 / bf16.  A is row-major (a warp's rows share one sample, so
+// its 16-byte reads are broadcasts); B is stored [k / 8][j][k % 8] so that the 32 consecutive obstacles of a warp read
+// 32 consecutive 16-byte groups (one coalesced 512-byte request per instruction).
 // ------------------------------------------------------------------------------------------------
 template <bool BF16>
-__device__ __forceinline__ void split_store(uint16_t* row, int pos, float v) {
-  if (BF16) {
-    const __nv_bfloat16 h = __float2bfloat16_rn(v);
-    const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
-    row[pos] = __bfloat16_as_ushort(h);
-    row[32 + pos] = __bfloat16_as_ushort(l);
-  } else {
-    const __half h = __float2half_rn(v);
-    const __half l = __float2half_rn(v - __half2float(h));
-    row[pos] = __half_as_ushort(h);
-    row[32 + pos] = __half_as_ushort(l);
-  }
+__device__ __forceinline__ uint16_t to_half_bits(float v) {
+  // clamped to half the fp16 range so that A_i + B_j can never overflow to infinity in the packed add (everything
+  // downstream converts with .satfinite); the shipped networks stay below 1e2 here
+  v = fminf(fmaxf(v, -30000.f), 30000.f);
+  if (BF16) return __bfloat16_as_ushort(__float2bfloat16_rn(v));
+  return __half_as_ushort(__float2half_rn(v));
 }
 
+// one CTA of 256 threads per sample / obstacle; Wf0 = W1^T, [3 nin][256] (coalesced over the feature index)
 template <bool BF16>
-__global__ void encode_kernel(const float* __restrict__ x, int x_stride, int x_off, int n, int ncomp, int comp0, int nin,
-                              uint16_t* __restrict__ out) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  uint16_t row[64];
-#pragma unroll
-  for (int k = 0; k < 64; ++k) row[k] = 0;
-  for (int c = 0; c < ncomp; ++c) {
-    const float v = x[(size_t)i * x_stride + x_off + c];
-    split_store<BF16>(row, comp0 + c, v);
-    split_store<BF16>(row, nin + comp0 + c, sinf(v));
-    split_store<BF16>(row, 2 * nin + comp0 + c, cosf(v));
+__global__ void __launch_bounds__(HID) l1_table_kernel(const float* __restrict__ x, int x_stride, int n, int ncomp,
+                                                       int comp0, int nin, const float* __restrict__ Wf0,
+                                                       const float* __restrict__ bias, int transposed, int M,
+                                                       uint16_t* __restrict__ out) {
+  const int i = blockIdx.x, k = threadIdx.x;
+  __shared__ float xs[3 * MAXD];
+  if (k < ncomp) {
+    const float v = x[(size_t)i * x_stride + k];
+    float sn, cs;
+    sincosf(v, &sn, &cs);
+    xs[3 * k] = v; xs[3 * k + 1] = sn; xs[3 * k + 2] = cs;
   }
-  uint4* o = reinterpret_cast<uint4*>(out + (size_t)i * 64);
-  const uint4* r = reinterpret_cast<const uint4*>(row);
-#pragma unroll
-  for (int k = 0; k < 8; ++k) o[k] = r[k];
+  __syncthreads();
+  float acc = bias ? bias[k] : 0.f;
+  for (int c = 0; c < ncomp; ++c) {
+    acc = fmaf(Wf0[(size_t)(comp0 + c) * HID + k], xs[3 * c], acc);
+    acc = fmaf(Wf0[(size_t)(nin + comp0 + c) * HID + k], xs[3 * c + 1], acc);
+    acc = fmaf(Wf0[(size_t)(2 * nin + comp0 + c) * HID + k], xs[3 * c + 2], acc);
+  }
+  const size_t o = transposed ? ((size_t)(k >> 3) * M + i) * 8 + (k & 7) : (size_t)i * HID + k;
+  out[o] = to_half_bits<BF16>(acc);
+  (void)n;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -302,13 +309,14 @@ __global__ void encode_kernel(const float* __restrict__ x, int x_stride, int x_o
 // ------------------------------------------------------------------------------------------------
 struct TcArgs {
   const uint8_t* img0; const uint8_t* img1;    // per-CTA-rank weight images
-  const uint4* encq; const uint4* encp;        // (n, 8) and (M, 8) uint4
+  const uint4* tabA; const uint4* tabB;        // layer-1 tables: (n, 32) and (32, M) groups of 8 halves
   const float* obs;                            // (M, 4)
   float* mdist;                                // (n * M)
   long long n_rows;                            // n * M
   int n, M, O;
   uint32_t ignore_mask;
   float inv_scale_div;                         // 100 for the 9-link net else 1
+  uint32_t zero;                               // 0 (an opaque zero for scheduling dependencies, see first_layer)
   long long* prof;                             // DSMPPI_TC_PROF builds only: [block][warp][8] cycle counters
 };
 
@@ -327,9 +335,9 @@ struct TcArgs {
 
 // bias + ReLU + fp16/bf16 pair packing of 32 accumulator columns into pk[OFF .. OFF+16): per pair of columns one
 // packed fp32 add and one converting ReLU (the epilogue's issue slots are what the two tile slots compete for)
-template <bool BF16, int OFF>
+template <bool BF16, int OFF, int NPK>
 __device__ __forceinline__ void relu_pack32(const uint32_t (&v)[32], const float* __restrict__ bias32,
-                                            uint32_t (&pk)[64]) {
+                                            uint32_t (&pk)[NPK]) {
   const float4* b4 = reinterpret_cast<const float4*>(bias32);
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
@@ -340,6 +348,73 @@ __device__ __forceinline__ void relu_pack32(const uint32_t (&v)[32], const float
     pk[OFF + 2 * k + 0] = pack2_relu<BF16>(s0, s1);
     pk[OFF + 2 * k + 1] = pack2_relu<BF16>(s2, s3);
   }
+}
+
+// relu(a + b) on two packed half-precision values: the first hidden activation from the layer-1 tables
+template <bool BF16>
+__device__ __forceinline__ uint32_t add_relu_h2(uint32_t a, uint32_t b) {
+  uint32_t r;
+  if (BF16) {
+    asm("{\n\t.reg .b32 t;\n\tadd.rn.bf16x2 t, %1, %2;\n\tmax.bf16x2 %0, t, %3;\n\t}" : "=r"(r) : "r"(a), "r"(b), "r"(0u));
+  } else {
+    asm("{\n\t.reg .b32 t;\n\tadd.rn.f16x2 t, %1, %2;\n\tmax.f16x2 %0, t, %3;\n\t}" : "=r"(r) : "r"(a), "r"(b), "r"(0u));
+  }
+  return r;
+}
+
+__device__ __forceinline__ uint4 ldg_nc_v4(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+
+// first hidden activation of pair (sample i, obstacle j): relu(A_i + B_j), 256 features = 128 packed words, the
+// layer-2 operand as it goes into TMEM.  64 independent 16-byte loads (the A half is a warp-wide broadcast), issued
+// as two halves of 32: all 64 at once would not fit next to the packed result, one small chunk at a time would expose
+// the L2 latency many times over (the volatile loads keep that order).  (Free functions, not lambdas: a lambda taking
+// the register array by reference that is not inlined would push the array into local memory.)
+template <bool BF16>
+__device__ __forceinline__ void first_layer(const TcArgs& a, int i, int j, uint32_t dep, uint32_t (&pk)[128]) {
+  // `dep` is zero at run time but opaque to ptxas (it is derived from a kernel argument): the load addresses carry it,
+  // so the assembler cannot hoist the 64 loads above the value `dep` was derived from, nor merge the two halves
+  // (a first build had all 64 loads = 256 registers in flight inside the previous layer's epilogue and spilled 3 KB)
+  if (i < a.n) {
+    const uint4* ta = a.tabA + (size_t)i * 32 + dep;
+    const uint4* tb = a.tabB + j + dep;
+    // the row stride of table B carries `dep` too: as a loop invariant its 32 multiples (64 registers of addresses)
+    // would be hoisted out of the tile loop and held across the hidden-layer epilogues
+    const uint32_t strideM = (uint32_t)a.M + dep;
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      uint4 x[16], y[16];
+#pragma unroll
+      for (int kb = 0; kb < 16; ++kb) {
+        x[kb] = ldg_nc_v4(ta + 16 * hf + kb);
+        y[kb] = ldg_nc_v4(tb + (size_t)((16 * hf + kb) * strideM));
+      }
+#pragma unroll
+      for (int kb = 0; kb < 16; ++kb) {
+        pk[64 * hf + 4 * kb + 0] = add_relu_h2<BF16>(x[kb].x, y[kb].x);
+        pk[64 * hf + 4 * kb + 1] = add_relu_h2<BF16>(x[kb].y, y[kb].y);
+        pk[64 * hf + 4 * kb + 2] = add_relu_h2<BF16>(x[kb].z, y[kb].z);
+        pk[64 * hf + 4 * kb + 3] = add_relu_h2<BF16>(x[kb].w, y[kb].w);
+      }
+      if (hf == 0) {
+        const uint32_t d2 = (pk[3] | pk[11] | pk[19] | pk[27] | pk[35] | pk[43] | pk[51] | pk[59] | pk[63]) & a.zero;
+        ta += d2;
+        tb += d2;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 128; ++k) pk[k] = 0u;
+  }
+}
+__device__ __forceinline__ void store_operand(uint32_t tA, const uint32_t (&pk)[128]) {
+  tmem_st32<0>(tA, pk);
+  tmem_st32<32>(tA + 32, pk);
+  tmem_st32<64>(tA + 64, pk);
+  tmem_st32<96>(tA + 96, pk);
 }
 
 template <bool BF16>
@@ -409,32 +484,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_pass
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(bar, 0);
     };
-    // layer-1 operand of pair (sample i, obstacle j): [enc_hi | enc_lo] = per-sample part OR per-obstacle part
-    auto load_input = [&](int i, int j, uint32_t (&v)[32]) {
-      if (i < a.n) {
-        const uint4* eq = a.encq + (size_t)i * 8;
-        const uint4* ep = a.encp + (size_t)j * 8;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const uint4 x = __ldg(eq + k), y = __ldg(ep + k);
-          v[4 * k + 0] = x.x | y.x; v[4 * k + 1] = x.y | y.y; v[4 * k + 2] = x.z | y.z; v[4 * k + 3] = x.w | y.w;
-        }
-      } else {
-#pragma unroll
-        for (int k = 0; k < 32; ++k) v[k] = 0u;
-      }
-    };
-
     // pair-row of this thread: r = tile*256 + rank*128 + row = i*M + j, advanced by a constant stride per
     // iteration (no 64-bit division inside the loop)
     const long long stride = 2LL * npairs * (2 * ROWS);
     const int di = (int)(stride / a.M), dj = (int)(stride % a.M);
     const long long r0 = ((long long)slot * npairs + pair) * (2 * ROWS) + (long long)rank * ROWS + row;
     int i_cur = (int)min(r0 / a.M, (long long)a.n), j_cur = (int)(r0 % a.M);
-    uint32_t vin[32];
     if ((long long)pair < n_tiles) {
-      load_input(i_cur, j_cur, vin);
-      tmem_st32<0>(tA, vin);
+      uint32_t pk[128];
+      first_layer<BF16>(a, i_cur, j_cur, a.zero, pk);
+      store_operand(tA, pk);
       tc_wait_st();
       signal(bar_aready);
     }
@@ -445,13 +504,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_pass
       const bool more = ((it + 1) * 2) * npairs + pair < n_tiles;
       int i_next = min(i_cur + di, a.n), j_next = j_cur + dj;
       if (j_next >= a.M) { j_next -= a.M; i_next = min(i_next + 1, a.n); }
+      uint32_t tile_dep = 0;
 #pragma unroll
-      for (int l = 0; l < 4; ++l) {          // unrolled: the prefetch registers of layer 4 must not be loop-carried
+      for (int l = 0; l < NHID; ++l) {       // network layers 2..4
         const float* bl = bias + l * HID;
         uint32_t pk[64], raw[4][32];
         PROF_ADD(7);
-        // ---- D_lo (features 0..127) while the tensor core is still producing D_hi
-        mbar_wait(bar_full_lo, (uint32_t)((it + l) & 1));          // phase 5*it + l of this slot's D_lo
+        // ---- D_lo (features 0..127) while the tensor core is still producing D_hi.  Per tile a slot uses D_lo four
+        //      times (three hidden layers + the output layer) and D_hi three times: phase parities below
+        mbar_wait(bar_full_lo, (uint32_t)(l & 1));
         tc_fence_after();
         PROF_ADD(0);
         tmem_ld32(tDlo, raw[0]);
@@ -467,7 +528,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_pass
         relu_pack32<BF16, 48>(raw[3], bl + 96, pk);
         PROF_ADD(2);
         // ---- D_hi (features 128..255); its completion also retires every MMA that read the old A operand
-        mbar_wait(bar_full_hi, (uint32_t)(l & 1));                 // phase 4*it + l of this slot's D_hi
+        mbar_wait(bar_full_hi, (uint32_t)((it + l) & 1));          // phase 3*it + l of this slot's D_hi
         tc_fence_after();
         PROF_ADD(3);
         tmem_ld32(tDhi, raw[0]);
@@ -479,7 +540,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_pass
         tc_wait_ld();
         signal(BAR(BAR_DFREE1));                                    // D_hi drained
         PROF_ADD(4);
-        if (l == 3 && more) load_input(i_next, j_next, vin);        // next tile's layer-1 operand, latency hidden below
         relu_pack32<BF16, 0>(raw[0], bl + 128, pk);
         relu_pack32<BF16, 16>(raw[1], bl + 160, pk);
         relu_pack32<BF16, 32>(raw[2], bl + 192, pk);
@@ -488,31 +548,45 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_pass
         tmem_st32<32>(tA + 96, pk);
         tc_wait_st();
         signal(bar_aready);                                         // next layer's A operand is in TMEM
+        if (l == NHID - 1) tile_dep = (pk[7] | pk[23] | pk[39] | pk[63]) & a.zero;
         PROF_ADD(5);
       }
-      // ---- output layer of this tile
+      // ---- output layer of this tile; under its MMAs (and the other tile's last hidden layer) the NEXT tile's
+      //      first activation is read from the tables, so that the tile boundary costs one tcgen05.st
       const bool valid = i_cur < a.n;
       float rad = 0.f;
       if (valid) rad = __ldg(a.obs + (size_t)j_cur * 4 + 3);
-      PROF_ADD(6);
-      mbar_wait(bar_full_lo, (uint32_t)((it + 4) & 1));
-      tc_fence_after();
-      PROF_ADD(0);
       uint32_t v[16];
-      tmem_ld16(tDlo, v);
-      if (more) tmem_st32<0>(tA, vin);          // the output-layer MMA has retired: A may be overwritten
-      tc_wait_ld();
-      signal(BAR(BAR_DFREE0));
+      // (one branch holds the whole life of the 128-register operand: split into two `if (more)` blocks around the
+      // wait, the compiler kept it conditionally live through the hidden-layer epilogues and spilled 3 KB per thread)
       if (more) {
+        uint32_t nxt[128];
+        first_layer<BF16>(a, i_next, j_next, tile_dep, nxt);
+        PROF_ADD(6);
+        mbar_wait(bar_full_lo, 1u);                                 // fourth use of D_lo in this tile
+        tc_fence_after();
+        PROF_ADD(0);
+        tmem_ld16(tDlo, v);
+        store_operand(tA, nxt);                 // the output-layer MMA has retired: A may be overwritten
+        tc_wait_ld();
+        signal(BAR(BAR_DFREE0));
         tc_wait_st();
         signal(bar_aready);
+      } else {
+        PROF_ADD(6);
+        mbar_wait(bar_full_lo, 1u);
+        tc_fence_after();
+        PROF_ADD(0);
+        tmem_ld16(tDlo, v);
+        tc_wait_ld();
+        signal(BAR(BAR_DFREE0));
       }
       if (valid) {                           // masked minimum link distance (MPPI.py:236-242)
         float m = 3.0e38f;
 #pragma unroll
         for (int o = 0; o < 16; ++o) {
           if (o < a.O) {
-            float y = __uint_as_float(v[o]) + bias[4 * HID + o];
+            float y = __uint_as_float(v[o]) + bias[NHID * HID + o];
             y = y / a.inv_scale_div - rad;
             if ((a.ignore_mask >> o) & 1u) y = 1e6f;
             m = fminf(m, y);
@@ -548,10 +622,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_pass
       ph_free[h] ^= 1;
       tc_fence_after();
       PROF_ADD(1);
-      constexpr uint32_t boff = l == 0 ? OFF_W1 + h * SZ_W1H : (l < 4 ? OFF_WH + ((l - 1) * 2 + h) * SZ_WHH : OFF_W5);
-      constexpr uint32_t lbo = l < 4 ? 64 * 16 : 16 * 16;
-      constexpr int ksteps = l == 0 ? K0 / 16 : HID / 16;
-      constexpr uint32_t idesc = l < 4 ? idesc128 : idesc32;
+      constexpr uint32_t boff = l < NHID ? OFF_WH + (l * 2 + h) * SZ_WHH : OFF_W5;
+      constexpr uint32_t lbo = l < NHID ? 64 * 16 : 16 * 16;
+      constexpr int ksteps = HID / 16;
+      constexpr uint32_t idesc = l < NHID ? idesc128 : idesc32;
       constexpr uint32_t dcol = h ? TM_DHI : TM_DLO, acol = s ? TM_A1 : TM_A0;
       if (elect_one()) {
         mma_group<dcol, acol, boff, lbo, idesc>(tmem_base, sb4, std::make_integer_sequence<int, ksteps>{});
@@ -569,7 +643,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_pass
         tc_fence_after();
         PROF_ADD(0);
         group(L, S, std::integral_constant<int, 0>{});
-        if constexpr (l < 4) group(L, S, std::integral_constant<int, 1>{});
+        if constexpr (l < NHID) group(L, S, std::integral_constant<int, 1>{});
       };
       slot(std::integral_constant<int, 0>{});
       slot(std::integral_constant<int, 1>{});
@@ -581,7 +655,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_pass
       layer(std::integral_constant<int, 1>{});
       layer(std::integral_constant<int, 2>{});
       layer(std::integral_constant<int, 3>{});
-      layer(std::integral_constant<int, 4>{});
     }
     PROF_ADD(2);
     PROF_FLUSH(a, MMA_WARP);
@@ -621,7 +694,7 @@ inline size_t canon(int n, int k, int rows) {
 
 int tc_build_images(dsmppi_ctx* c, const dsmppi_net* net) {
   c->tc_blob = nullptr;
-  if (c->nenc > 32 || c->O > 16) return 0;          // layer-1 operand is fixed at K = 2 x 32; fall back to fp32
+  if (c->O > 16) return 0;                          // output N is fixed at 16 links; fall back to fp32
   const char* dis = std::getenv("DSMPPI_DISABLE_TC");
   if (dis && dis[0] == '1') return 0;
   TcImages* t = new TcImages();
@@ -633,7 +706,6 @@ int tc_build_images(dsmppi_ctx* c, const dsmppi_net* net) {
     return 1;
   }
   std::vector<uint8_t> host((size_t)4 * IMG_BYTES, 0);
-  const int nenc = c->nenc;
   for (int fmt = 0; fmt < 2; ++fmt)
     for (int rank = 0; rank < 2; ++rank) {
       uint8_t* img = host.data() + (size_t)(fmt * 2 + rank) * IMG_BYTES;
@@ -641,29 +713,22 @@ int tc_build_images(dsmppi_ctx* c, const dsmppi_net* net) {
         const uint16_t u = fmt ? f2bf(v) : f2h(v);
         std::memcpy(img + off, &u, 2);
       };
-      const int r_eff = rank;
       for (int h = 0; h < 2; ++h)
         for (int n = 0; n < 64; ++n) {
-          const int feat = 128 * h + 64 * r_eff + n;       // output feature held by this CTA in half h
-          // layer 1: K = [hi(32) | lo(32)], both multiply the same weight column
-          for (int k = 0; k < K0; ++k) {
-            const int e = k & 31;
-            const float w = e < nenc ? net->W_host[0][(size_t)feat * nenc + e] : 0.f;
-            put(OFF_W1 + h * SZ_W1H + canon(n, k, 64), w);
-          }
-          for (int l = 1; l < 4; ++l)
+          const int feat = 128 * h + 64 * rank + n;        // output feature held by this CTA in half h
+          for (int l = 0; l < NHID; ++l)                   // network layers 2..4 (layer 1 comes from the tables)
             for (int k = 0; k < HID; ++k)
-              put(OFF_WH + ((l - 1) * 2 + h) * SZ_WHH + canon(n, k, 64), net->W_host[l][(size_t)feat * HID + k]);
+              put(OFF_WH + (l * 2 + h) * SZ_WHH + canon(n, k, 64), net->W_host[l + 1][(size_t)feat * HID + k]);
         }
       for (int n = 0; n < 16; ++n) {
-        const int o = 16 * r_eff + n;                      // N = 32 over the pair: links 0..15 | 16..31 (padding)
+        const int o = 16 * rank + n;                       // N = 32 over the pair: links 0..15 | 16..31 (padding)
         for (int k = 0; k < HID; ++k)
           put(OFF_W5 + canon(n, k, 16), o < c->O ? net->W_host[4][(size_t)o * HID + k] : 0.f);
       }
       float* bias = reinterpret_cast<float*>(img + OFF_BIAS);
-      for (int l = 0; l < 4; ++l)
-        for (int k = 0; k < HID; ++k) bias[l * HID + k] = net->b_host[l][k];
-      for (int o = 0; o < 16; ++o) bias[4 * HID + o] = o < c->O ? net->b_host[4][o] : 0.f;
+      for (int l = 0; l < NHID; ++l)
+        for (int k = 0; k < HID; ++k) bias[l * HID + k] = net->b_host[l + 1][k];
+      for (int o = 0; o < 16; ++o) bias[NHID * HID + o] = o < c->O ? net->b_host[4][o] : 0.f;
     }
   CUDA_TRY(cudaMemcpy(dev, host.data(), host.size(), cudaMemcpyHostToDevice));
   t->img[0] = dev;
@@ -672,7 +737,6 @@ int tc_build_images(dsmppi_ctx* c, const dsmppi_net* net) {
   c->tc_blob_bytes = host.size();
   CUDA_TRY(cudaFuncSetAttribute(tc_pass1_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(tc_pass1_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-  if (c->guard_band <= 0.f) c->guard_band = 0.f;
   return 0;
 }
 
@@ -685,8 +749,8 @@ void tc_free_images(dsmppi_ctx* c) {
 }
 
 int tc_set_obstacles(dsmppi_ctx* c, cudaStream_t st) {
-  // per-obstacle packed encodings, both formats (fp16 at [0, M), bf16 at [M, 2M))
-  const size_t need = (size_t)2 * c->M * 128;
+  // per-obstacle layer-1 table B, both formats (fp16 first, bf16 after it): M x 256 halves each
+  const size_t need = (size_t)2 * c->M * HID * 2;
   if (need > c->obs_enc_cap) {
     if (c->obs_enc) CUDA_TRY(cudaFree(c->obs_enc));
     c->obs_enc = nullptr;
@@ -694,11 +758,29 @@ int tc_set_obstacles(dsmppi_ctx* c, cudaStream_t st) {
     c->obs_enc_cap = need;
   }
   uint16_t* out = static_cast<uint16_t*>(c->obs_enc);
-  const int th = 128, bl = (c->M + th - 1) / th;
-  encode_kernel<false><<<bl, th, 0, st>>>(c->obs, 4, 0, c->M, c->P, c->d, c->nin, out);
-  encode_kernel<true><<<bl, th, 0, st>>>(c->obs, 4, 0, c->M, c->P, c->d, c->nin, out + (size_t)c->M * 64);
+  l1_table_kernel<false><<<c->M, HID, 0, st>>>(c->obs, 4, c->M, c->P, c->d, c->nin, c->net.Wf[0], nullptr, 1, c->M, out);
+  l1_table_kernel<true><<<c->M, HID, 0, st>>>(c->obs, 4, c->M, c->P, c->d, c->nin, c->net.Wf[0], nullptr, 1, c->M,
+                                              out + (size_t)c->M * HID);
   CUDA_TRY(cudaGetLastError());
   c->launches += 2;
+  return 0;
+}
+
+// the per-sample layer-1 table A of n states (row stride q_stride floats) in the format of `mode`
+int tc_sample_table(dsmppi_ctx* c, const float* q, int q_stride, int n, int mode, cudaStream_t st) {
+  const bool bf16 = mode == DSMPPI_PASS1_TC_BF16;
+  const size_t need = (size_t)n * HID * 2;
+  if (need > c->enc_q_cap) {
+    if (c->enc_q) CUDA_TRY(cudaFree(c->enc_q));
+    c->enc_q = nullptr;
+    CUDA_TRY(cudaMalloc(&c->enc_q, need));
+    c->enc_q_cap = need;
+  }
+  uint16_t* ta = static_cast<uint16_t*>(c->enc_q);
+  if (bf16) l1_table_kernel<true><<<n, HID, 0, st>>>(q, q_stride, n, c->d, 0, c->nin, c->net.Wf[0], c->net.b[0], 0, 0, ta);
+  else l1_table_kernel<false><<<n, HID, 0, st>>>(q, q_stride, n, c->d, 0, c->nin, c->net.Wf[0], c->net.b[0], 0, 0, ta);
+  CUDA_TRY(cudaGetLastError());
+  c->launches++;
   return 0;
 }
 
@@ -706,25 +788,13 @@ int tc_pass1(dsmppi_ctx* c, const float* q, int q_stride, int n, uint32_t ignore
   REQUIRE(c->tc_blob, "tensor-core images not built");
   TcImages* t = static_cast<TcImages*>(c->tc_blob);
   const bool bf16 = mode == DSMPPI_PASS1_TC_BF16;
-  const size_t need = (size_t)n * 128;
-  if (need > c->enc_q_cap) {
-    if (c->enc_q) CUDA_TRY(cudaFree(c->enc_q));
-    c->enc_q = nullptr;
-    CUDA_TRY(cudaMalloc(&c->enc_q, need));
-    c->enc_q_cap = need;
-  }
-  uint16_t* eq = static_cast<uint16_t*>(c->enc_q);
-  const int th = 128, bl = (n + th - 1) / th;
-  if (bf16) encode_kernel<true><<<bl, th, 0, st>>>(q, q_stride, 0, n, c->d, 0, c->nin, eq);
-  else encode_kernel<false><<<bl, th, 0, st>>>(q, q_stride, 0, n, c->d, 0, c->nin, eq);
-  CUDA_TRY(cudaGetLastError());
-  c->launches++;
+  if (tc_sample_table(c, q, q_stride, n, mode, st)) return 1;
   TcArgs a;
   const uint8_t* base = t->img[0] + (size_t)(bf16 ? 2 : 0) * IMG_BYTES;
   a.img0 = base;
   a.img1 = base + IMG_BYTES;
-  a.encq = reinterpret_cast<const uint4*>(eq);
-  a.encp = reinterpret_cast<const uint4*>(static_cast<uint16_t*>(c->obs_enc) + (bf16 ? (size_t)c->M * 64 : 0));
+  a.tabA = reinterpret_cast<const uint4*>(c->enc_q);
+  a.tabB = reinterpret_cast<const uint4*>(static_cast<uint16_t*>(c->obs_enc) + (bf16 ? (size_t)c->M * HID : 0));
   a.obs = c->obs;
   a.mdist = c->mdist;
   a.n_rows = (long long)n * c->M;
@@ -733,6 +803,7 @@ int tc_pass1(dsmppi_ctx* c, const float* q, int q_stride, int n, uint32_t ignore
   a.O = c->O;
   a.ignore_mask = ignore_mask;
   a.inv_scale_div = (c->O == 9) ? 100.f : 1.f;
+  a.zero = 0u;
   a.prof = nullptr;
 #ifdef DSMPPI_TC_PROF
   a.prof = reinterpret_cast<long long*>(c->stage);   // the micro-benchmark parks its counter buffer here
