@@ -211,12 +211,15 @@ class MPPI:
         code = {'exact': _capi.PASS1_EXACT_FP32, 'tc_f16': _capi.PASS1_TC_F16, 'tc_bf16': _capi.PASS1_TC_BF16,
                 'auto': _capi.PASS1_AUTO}[mode]
         _capi.check(self._lib.dsmppi_set_pass1_mode(self._ctx, code, float(guard_band)))
+        self._pass1_forced = mode
+        self.__dict__.pop('_tick', None)
 
     def set_score_mode(self, mode='auto'):
         """Arithmetic of the rows that produce outputs: 'ffma' (IEEE fp32 on the CUDA cores, the strict mode),
         'tc_split' (tcgen05 with split-fp16 operands, fp32-accurate) or 'auto' (tc_split when the network fits)."""
         code = {'ffma': _capi.SCORE_FFMA, 'tc_split': _capi.SCORE_TC_SPLIT, 'auto': _capi.SCORE_AUTO}[mode]
         _capi.check(self._lib.dsmppi_set_score_mode(self._ctx, code))
+        self.__dict__.pop('_tick', None)
 
     def score_stats(self):
         """Scoring arithmetic in effect and the rows the tensor-core path handed to the FFMA kernel (fp16 range)."""
@@ -229,6 +232,7 @@ class MPPI:
     def set_whole_horizon(self, on=True):
         """Small obstacle sets are rolled out by one launch over the whole horizon; False forces per-step launches."""
         _capi.check(self._lib.dsmppi_set_whole_horizon(self._ctx, 1 if on else 0))
+        self.__dict__.pop('_tick', None)
 
     def _upload_obstacles(self):
         # scripts hand the same tensor back every iteration (frankaPlanner.py:129-130 re-assigns the last message):
@@ -355,11 +359,125 @@ class MPPI:
         a.norm_basis_dev = None
         return a
 
+    # ------------------------------------------------------------------ control tick: one CUDA graph per rollout
+    # The integrator process calls propagate() with ONE sample and TWO steps every control tick, on CPU tensors
+    # (frankaIntegrator.py:101-121).  At that size the rollout itself is one ~90 us launch and the tick is spent in
+    # the wrapper: seven allocations, four uploads, the ctypes call, six downloads (each a stream synchronisation).
+    # For small batches of CPU-tensor callers the whole tick -- upload of the state, the live policy columns and the
+    # obstacles from pinned staging buffers, the library's launch sequence, download of every output -- is captured
+    # ONCE into a CUDA graph and replayed: one cudaGraphLaunch and one synchronisation per tick.  Kernel arguments are
+    # baked into a graph, so it is keyed by the bytes of the argument block (time step, thresholds, goal, n_kernels,
+    # obstacle count, ...) and re-captured when a script changes any of them; results are those of the normal path
+    # bit for bit (the same launches).  DSMPPI_GRAPH_TICK=0 disables it.
+    _TICK_MAX_STATE_STEPS = 4096
+
+    def _tick_eligible(self, q_cur):
+        if os.environ.get('DSMPPI_GRAPH_TICK', '1') == '0' or self.tensor_args['device'].type != 'cpu':
+            return False
+        if self.N_traj * self.dt_H > self._TICK_MAX_STATE_STEPS or self.distance_provider != 'nn':
+            return False
+        if self._shard is not None or hasattr(self.DS, 'Mu') or getattr(self, '_timing_on', False):
+            return False
+        if int(self.obs.shape[0]) >= 64 or getattr(self, '_pass1_forced', 'auto') not in ('auto', 'exact'):
+            return False            # the prefilter path ends with a host-side verdict: not capturable
+        obs = self.obs
+        return (isinstance(obs, torch.Tensor) and obs.dim() == 2 and obs.shape[1] == self._point_dim + 1
+                and obs.dtype == torch.float32 and q_cur.dtype == torch.float32)
+
+    def _tick_build(self, nk, q_batch):
+        """Staging buffers + capture for the current shapes / parameters."""
+        N, H, d, K50 = self.N_traj, self.dt_H, self.n_dof, self.Policy.N_KERNEL_MAX
+        dev, M = self._dev, int(self.obs.shape[0])
+        pin = lambda *shape: torch.zeros(*shape).pin_memory()  # noqa: E731
+        t = dict(nk=nk, M=M, q_batch=q_batch)
+        t['h_in'] = dict(q=pin(N, d) if q_batch else pin(d), mu=pin(N, max(nk, 1), d), sigma=pin(N, max(nk, 1)),
+                         alpha=pin(N, max(nk, 1), d), obs=pin(M, self._point_dim + 1))
+        t['h_out'] = dict(all_traj=pin(N, H, d), closest=pin(N, H), kval=pin(N, H, max(nk, 1)), dots=pin(N, H),
+                          acts=pin(N, H), qdot=pin(N, d), grads=pin(N, H, d))
+        with torch.cuda.device(dev):
+            t['d_in'] = dict(q=torch.zeros_like(t['h_in']['q'], device=dev), mu=torch.zeros(N, K50, d, device=dev),
+                             sigma=torch.zeros(N, K50, device=dev), alpha=torch.zeros(N, K50, d, device=dev),
+                             obs=torch.zeros(M, self._point_dim + 1, device=dev))
+            t['d_out'] = dict(all_traj=torch.empty(N, H, d, device=dev), closest=torch.empty(N, H, device=dev),
+                              kval=torch.zeros(N, H, K50, device=dev), dots=torch.empty(N, H, device=dev),
+                              acts=torch.empty(N, H, device=dev), qdot=torch.empty(N, d, device=dev),
+                              grads=torch.empty(N, H, d, device=dev))
+        return t
+
+    def _tick_run(self, t):
+        """The launch sequence that gets captured (and is also run once, eagerly, as the capture's warm-up)."""
+        hi, di, do, ho, nk = t['h_in'], t['d_in'], t['d_out'], t['h_out'], t['nk']
+        di['q'].copy_(hi['q'], non_blocking=True)
+        di['obs'].copy_(hi['obs'], non_blocking=True)
+        if nk > 0:
+            di['mu'][:, :nk].copy_(hi['mu'], non_blocking=True)
+            di['sigma'][:, :nk].copy_(hi['sigma'], non_blocking=True)
+            di['alpha'][:, :nk].copy_(hi['alpha'], non_blocking=True)
+        st = self._stream()
+        _capi.check(self._lib.dsmppi_set_obstacles(self._ctx, di['obs'].data_ptr(), t['M'], st))
+        _capi.check(self._lib.dsmppi_rollout(self._ctx, _capi.C.byref(t['args']), st))
+        for k in ('all_traj', 'closest', 'dots', 'acts', 'qdot', 'grads'):
+            ho[k].copy_(do[k], non_blocking=True)
+        if nk > 0:
+            ho['kval'].copy_(do['kval'][:, :, :nk], non_blocking=True)
+
+    def _propagate_tick(self, q_cur_user, nk):
+        N, H, d = self.N_traj, self.dt_H, self.n_dof
+        P = self.Policy
+        q_batch = q_cur_user.dim() == 2
+        t = self.__dict__.get('_tick')
+        if t is None or t['nk'] != nk or t['M'] != int(self.obs.shape[0]) or t['q_batch'] != q_batch:
+            t = self._tick = self._tick_build(nk, q_batch)
+            t['key'] = None
+        hi = t['h_in']
+        hi['q'].copy_(q_cur_user)
+        hi['obs'].copy_(self.obs)
+        if nk > 0:
+            hi['mu'].copy_(P.mu_tmp[:, :nk]); hi['sigma'].copy_(P.sigma_tmp[:, :nk]); hi['alpha'].copy_(P.alpha_tmp[:, :nk])
+        di, do = t['d_in'], t['d_out']
+        args = self._rollout_args(N, H, nk, di['q'], di['mu'], di['sigma'], di['alpha'], do)
+        key = bytes(args)
+        with torch.cuda.device(self._dev):
+            if key != t['key']:
+                t['args'] = args
+                side = torch.cuda.Stream(self._dev)
+                side.wait_stream(torch.cuda.current_stream(self._dev))
+                with torch.cuda.stream(side):
+                    self._tick_run(t)                         # warm-up: sizes the library's workspace outside the capture
+                side.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=side):
+                    self._tick_run(t)
+                t['graph'], t['key'] = g, key
+            t['graph'].replay()
+            torch.cuda.current_stream(self._dev).synchronize()
+        ho = t['h_out']
+        self._mirror = {}
+        self._obs_uploaded = None
+        self._norm_basis = None
+        out = {k: ho[k].clone() for k in ('all_traj', 'closest', 'dots', 'acts', 'qdot')}
+        kv = torch.zeros(N, H, P.N_KERNEL_MAX)
+        if nk > 0:
+            kv[:, :, :nk] = ho['kval']
+        self._dev_last = dict(grads=None, grads_host=ho['grads'].clone(), nk=nk)   # (the graph's buffers are reused)
+        self.all_traj, self.closest_dist_all, self.kernel_val_all = out['all_traj'], out['closest'], kv
+        self.dot_products, self.kernel_activations, self.qdot = out['dots'], out['acts'], out['qdot']
+        self.nn_grad = ho['grads'][:, H - 1, :].clone()
+        self.ker_w = self.kernel_val_all[:, H - 1, :nk].unsqueeze(2)
+        return (self.all_traj, self.closest_dist_all, self.kernel_val_all[:, :, 0:nk], self.dot_products,
+                self.kernel_activations)
+
     def propagate(self):
         N, H, d = self.N_traj, self.dt_H, self.n_dof
         P = self.Policy
         nk = int(P.n_kernels)
         dev = self._dev
+        q_user = torch.as_tensor(self.q_cur)
+        if self._tick_eligible(q_user):
+            if q_user.shape not in ((d,), (N, d)):
+                raise ValueError(f"q_cur must be ({d},) or ({N}, {d}), got {tuple(q_user.shape)}")
+            with _stage_tags(_ROLLOUT_TAGS):
+                return self._propagate_tick(q_user, nk)
         with torch.cuda.device(dev):
             q_cur = self._d(self.q_cur)
             if q_cur.shape not in ((d,), (N, d)):
@@ -404,6 +522,8 @@ class MPPI:
         from the stored blended gradients (keeps 4*d*d bytes per state-step off the rollout)."""
         if self._norm_basis is None:
             g = self._dev_last['grads']
+            if g is None:
+                g = self._d(self._dev_last['grads_host'])
             N, H, d = g.shape
             with torch.cuda.device(self._dev):
                 E = torch.empty(N, H, d, d, device=self._dev)
@@ -664,6 +784,7 @@ class MPPI:
 
     def enable_kernel_timing(self, on=True):
         _capi.check(self._lib.dsmppi_enable_kernel_timing(self._ctx, 1 if on else 0))
+        self._timing_on = bool(on)
 
     def kernel_timing_ex(self):
         """(kernel name, ms per launch, launches) of the dominant kernel in the last rollout."""

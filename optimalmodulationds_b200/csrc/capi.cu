@@ -375,16 +375,20 @@ static int calibrate_band(dsmppi_ctx* c, const float* q, int q_stride, int n, ui
 
 // distance + gradient of n states q (row stride q_stride floats) against the current obstacles: fills
 // c->row_dist / c->row_grad and the ranked row indices c->sel_rows (n, K)
+// table_ready / defer_rank: the rollout loop of the prefilter path hands the per-sample layer-1 table over from the
+// previous step and ranks inside its fused step launch (launch_rank_step)
 static int distance_pipeline(dsmppi_ctx* c, const float* q, int q_stride, int n, int K, uint32_t ignore_mask,
-                             cudaStream_t st) {
+                             cudaStream_t st, bool table_ready = false, bool defer_rank = false) {
   REQUIRE(c->M >= 1, "obstacles not set");
   REQUIRE(K >= 1 && K <= MAXK, "n_closest_obs out of range (1..8)");
   REQUIRE(K <= c->M, "n_closest_obs exceeds the number of obstacles");
   const int mode = resolved_mode(c);
   if (mode != DSMPPI_PASS1_EXACT_FP32 && c->guard_band <= 0.f) {
     const int slot = mode == DSMPPI_PASS1_TC_BF16 ? 1 : 0;
-    if (c->band_cal[slot] <= 0.f || c->band_cal_M[slot] != c->M)
+    if (c->band_cal[slot] <= 0.f || c->band_cal_M[slot] != c->M) {
       if (calibrate_band(c, q, q_stride, n, ignore_mask, mode, st)) return 1;
+      table_ready = false;                 // the calibration wrote ITS states' table over the one handed in
+    }
   }
   if (ensure_workspace(c, n, c->M)) return 1;
   RowSrc src{};
@@ -418,11 +422,11 @@ static int distance_pipeline(dsmppi_ctx* c, const float* q, int q_stride, int n,
   }
   // tensor-core prefilter -> candidate band -> one fp32 launch (ranking key + distance + gradient) -> rank
   c->prefilter_used = 1;
-  if (timing_mark(c, 1, st)) return 1;
-  if (tc_pass1(c, q, q_stride, n, ignore_mask, mode, st)) return 1;
-  if (timing_mark(c, 1, st)) return 1;
   const float band = c->guard_band > 0.f ? c->guard_band : c->band_cal[mode == DSMPPI_PASS1_TC_BF16 ? 1 : 0];
   const size_t cap_rows = cand_list_cap(c, n);
+  if (timing_mark(c, 1, st)) return 1;
+  if (tc_pass1(c, q, q_stride, n, ignore_mask, mode, st, table_ready)) return 1;
+  if (timing_mark(c, 1, st)) return 1;
   if (launch_select_candidates(c, n, K, band, cap_rows, st)) return 1;
   src.mode = ROWS_LIST;
   src.n_rows = (int)(cap_rows < 0x7fffffffu ? cap_rows : 0x7fffffffu);
@@ -433,6 +437,7 @@ static int distance_pipeline(dsmppi_ctx* c, const float* q, int q_stride, int n,
   if (launch_exact_fwdbwd(c, q, q_stride, src, ignore_mask, c->m_rows, c->row_dist, c->row_grad,
                           (long long)n * (K + 1), st))
     return 1;
+  if (defer_rank) return 0;
   return launch_rank_candidates(c, n, K, st);
 }
 
@@ -508,6 +513,24 @@ static int rollout_once(dsmppi_ctx* c, const dsmppi_rollout_args* a, cudaStream_
       if (timing_mark(c, tcx ? 4 : 2, st)) return 1;
       if (tcx ? launch_tc_rollout(c, &b, st) : launch_rollout_fused(c, &b, st)) return 1;
       if (timing_mark(c, tcx ? 4 : 2, st)) return 1;
+      continue;
+    }
+    const int mode = resolved_mode(c);
+    if (mode != DSMPPI_PASS1_EXACT_FP32) {
+      // prefilter path, four launches per step: tc_pass1 (all-pairs prefilter) -> select_candidates (guard band) ->
+      // tc_exact / exact_mlp (fp32 scoring + VJP of the band; + its normally empty FFMA range fix-up) -> rank_step
+      // (ranking, modulation step, and the next step's per-sample layer-1 table)
+      if (tc_reserve_sample_table(c, b.N)) return 1;
+      for (int t = 1; t <= b.H; ++t) {
+        const float* q = b.all_traj_dev + (size_t)(t - 1) * d;        // q_prev = all_traj[:, t-1, :]
+        // (the first call may calibrate the guard band, which runs the prefilter on other states: no table hand-over)
+        const bool handed = t > 1 && c->table_valid;
+        c->table_valid = 0;
+        if (distance_pipeline(c, q, b.H * d, b.N, b.n_closest, b.ignored_link_mask, st, handed, true)) return 1;
+        if (launch_rank_step(c, &b, t, mode, st)) return 1;
+        c->table_valid = 1;
+      }
+      c->table_valid = 0;
       continue;
     }
     for (int t = 1; t <= b.H; ++t) {

@@ -97,6 +97,7 @@ struct dsmppi_ctx {
   int ws_mode = -1;                   // resolved pass-1 mode the workspace was sized for (AUTO flips with M)
   size_t cand_rows_want = 0;          // row-list capacity asked for after a rollout ran out of candidate rows
   int* counters_host = nullptr;       // pinned mirror of `counters` for the end-of-rollout exactness check
+  int table_valid = 0;                // c->enc_q holds the layer-1 table of the states the next prefilter launch scores
   int prefilter_used = 0;             // set by distance_pipeline when a call went through the tensor-core prefilter
   int64_t capacity_retries = 0;       // rollouts that were run again with a larger candidate row list
   int64_t exact_fallbacks = 0;        // rollouts that were run again with every pair scored in fp32
@@ -170,7 +171,10 @@ inline bool use_tc_scoring(const dsmppi_ctx* c) { return c->tcx_blob && c->score
 int tc_build_images(dsmppi_ctx* c, const dsmppi_net* net);
 void tc_free_images(dsmppi_ctx* c);
 int tc_set_obstacles(dsmppi_ctx* c, cudaStream_t st);
-int tc_pass1(dsmppi_ctx* c, const float* q, int q_stride, int n, uint32_t ignore_mask, int mode, cudaStream_t st);
+// table_ready: the per-sample layer-1 table (c->enc_q) of these n states has already been written
+int tc_pass1(dsmppi_ctx* c, const float* q, int q_stride, int n, uint32_t ignore_mask, int mode, cudaStream_t st,
+             bool table_ready = false);
+int tc_reserve_sample_table(dsmppi_ctx* c, int n);
 int tc_sample_table(dsmppi_ctx* c, const float* q, int q_stride, int n, int mode, cudaStream_t st);
 // rollout_kernels.cu
 int launch_rank_dense(dsmppi_ctx* c, int n, int K, bool rows_out, cudaStream_t st);
@@ -188,6 +192,8 @@ inline size_t cand_list_cap(const dsmppi_ctx* c, int n) {
 int launch_rank_candidates(dsmppi_ctx* c, int n, int K, cudaStream_t st);
 int launch_blend(dsmppi_ctx* c, int n, int K, float* dist_out, float* grad_out, cudaStream_t st);
 int launch_step(dsmppi_ctx* c, const dsmppi_rollout_args* a, int t, cudaStream_t st);
+// prefilter path: ranking of the candidate rows + the step + (table_mode >= 0) the layer-1 table of the next state
+int launch_rank_step(dsmppi_ctx* c, const dsmppi_rollout_args* a, int t, int table_mode, cudaStream_t st);
 int launch_init_traj(dsmppi_ctx* c, const dsmppi_rollout_args* a, cudaStream_t st);
 int launch_cost(dsmppi_ctx* c, const dsmppi_cost_args* a, cudaStream_t st);
 int launch_basis(dsmppi_ctx* c, const float* grad, int64_t n, float* basis, cudaStream_t st);

@@ -5,6 +5,8 @@
 
 #include "internal.cuh"
 #include "step_device.cuh"
+#include "select_device.cuh"
+#include "l1_table.cuh"
 
 namespace {
 
@@ -81,85 +83,8 @@ __global__ void __launch_bounds__(128) select_candidates_kernel(const float* __r
   const int lane = threadIdx.x & 31;
   if (w >= n) return;
   const float* md = mdist + (size_t)w * M;
-  // K-th smallest approximate value (with multiplicity), one streaming pass: every lane keeps the K smallest of
-  // its own elements sorted in registers (ties: lower obstacle index first), then the warp merges the 32 lists
-  float lv[MAXK];
-  int lj[MAXK];
-#pragma unroll
-  for (int k = 0; k < MAXK; ++k) { lv[k] = FLT_MAX; lj[k] = 0x7fffffff; }
-#pragma unroll 4
-  for (int t = lane; t < M; t += 32) {
-    float v = md[t];
-    int j = t;
-    if (v < lv[MAXK - 1]) {
-#pragma unroll
-      for (int k = 0; k < MAXK; ++k) {
-        if (v < lv[k]) {                      // strict: an equal value seen later (higher index) stays behind
-          const float tv = lv[k]; lv[k] = v; v = tv;
-          const int tj = lj[k]; lj[k] = j; j = tj;
-        }
-      }
-    }
-  }
-  float last_v = -FLT_MAX;
-  for (int kk = 0; kk < K; ++kk) {
-    float bv = lv[0];
-    int bj = lj[0];
-    int src = lane;
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
-      const int oj = __shfl_xor_sync(0xffffffffu, bj, off);
-      const int os = __shfl_xor_sync(0xffffffffu, src, off);
-      if (ov < bv || (ov == bv && oj < bj)) { bv = ov; bj = oj; src = os; }
-    }
-    last_v = bv;
-    if (lane == src) {                         // pop the winner's head
-#pragma unroll
-      for (int k = 0; k + 1 < MAXK; ++k) { lv[k] = lv[k + 1]; lj[k] = lj[k + 1]; }
-      lv[MAXK - 1] = FLT_MAX;
-      lj[MAXK - 1] = 0x7fffffff;
-    }
-  }
-  const float thr = last_v + band;
-  // count, reserve a contiguous row range, then fill (ascending obstacle index within the sample).  EVERY obstacle
-  // inside the band gets a row: a crowded band simply takes more of the shared list (budgeted at CAND_MAX rows per
-  // sample, typically a third used).  If the list itself runs out, the high-water mark in counters[8] tells the host,
-  // which grows the list and runs the rollout again (capi.cu: prefilter_verdict) -- nothing is ever dropped silently.
-  int mine = 0;
-#pragma unroll 4
-  for (int t = lane; t < M; t += 32) mine += (md[t] <= thr) ? 1 : 0;
-  int total = mine;
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) total += __shfl_xor_sync(0xffffffffu, total, off);
-  int base = 0;
-  if (lane == 0) {
-    base = atomicAdd(&counters[0], total);
-    atomicMax(&counters[8], base + total);
-    if (total > CAND_MAX) atomicAdd(&counters[1], 1);
-  }
-  base = __shfl_sync(0xffffffffu, base, 0);
-  // rows of this sample that fit (all of them unless the list is exhausted; the rows written stay valid indices, so
-  // the scoring launch that follows reads nothing out of bounds before the rollout is repeated)
-  const int room = base < cap_rows ? cap_rows - base : 0;
-  const int keep = total < room ? total : room;
-  if (lane == 0) {
-    atomicAdd(reinterpret_cast<unsigned long long*>(&counters[2]), (unsigned long long)keep);
-    cand_cnt[w] = keep;
-    row_base[w] = base < cap_rows ? base : 0;
-  }
-  int written = 0;
-  for (int t0 = 0; t0 < M && written < keep; t0 += 32) {
-    const int t = t0 + lane;
-    const bool in = t < M && md[t] <= thr;
-    const unsigned bal = __ballot_sync(0xffffffffu, in);
-    const int pos = written + __popc(bal & ((1u << lane) - 1u));
-    if (in && pos < keep) {
-      row_sample[base + pos] = w;
-      row_obs[base + pos] = t;
-    }
-    written += __popc(bal);
-  }
+  select_candidates_warp([md](int t) { return md[t]; }, M, K, band, cap_rows, w, lane, cand_cnt, row_base, row_sample,
+                         row_obs, counters);
 }
 
 // largest |a - b| over n elements (guard-band calibration of the prefilter); out[0] must be zeroed beforehand.
@@ -204,6 +129,84 @@ __global__ void blend_kernel(const float* __restrict__ row_dist, const float* __
 __global__ void __launch_bounds__(128) step_kernel(StepArgs s) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < s.N) step_sample(s, i, s.t, step_io_global(s, i));
+}
+
+// ------------------------------------------------------------------------------------------------
+// Prefilter path, ONE launch after the scoring kernel: a WARP per sample
+//   1. ranks the sample's re-scored candidate rows -- the K closest, ascending by (fp32 key, obstacle index): the
+//      second half of MPPI.py:245-253's sort (the body of rank_kernel);
+//   2. lane 0 runs the modulation / policy / Euler step (step_sample, MPPI.py:101-223) on those rows;
+//   3. all lanes write the layer-1 table row of the NEXT state for the next step's prefilter (l1_table.cuh).
+// Replaces rank_kernel + step_kernel + l1_table_kernel.  The step is a 5 k-instruction dependent chain per sample:
+// with one sample per warp an SM holds ~28 such chains on 28 warps instead of one warp with 28 active lanes, so the
+// schedulers have something to switch to.
+// ------------------------------------------------------------------------------------------------
+struct RankStepArgs {
+  const float* m_rows; const int* row_base; const int* cand_cnt; const int* row_obs;
+  const float* Wf0; const float* b0; uint16_t* tabA;      // tabA == nullptr: no table (last step, or no prefilter next)
+  int nin; int bf16;
+};
+
+// GL lanes per sample (a power of two <= 32): 128 / GL samples per CTA.  With GL = 32 the step's registers (~128 per
+// thread, allocated for all 32 lanes of a warp that uses one) allow 16 samples per SM and 4096 samples need two waves
+// of the 26 us chain; GL = 8 runs four chains per warp and fits them in one.
+template <int GL>
+__global__ void __launch_bounds__(128) rank_step_kernel(StepArgs s, RankStepArgs r) {
+  constexpr int SPB = 128 / GL;                     // samples per CTA
+  __shared__ int rows_s[SPB][MAXK];
+  __shared__ float qn_s[SPB][MAXD];
+  __shared__ float xs_s[SPB][3 * MAXD];
+  const int g = threadIdx.x / GL, gl = threadIdx.x % GL;
+  const int w = blockIdx.x * SPB + g;
+  const bool live = w < s.N;                        // (no early return: the shuffles below are warp-wide)
+  const int K = s.K;
+  {
+    const int base = live ? r.row_base[w] : 0, c = live ? r.cand_cnt[w] : 0;
+    float last_v = -FLT_MAX;
+    int last_j = -1, last_t = 0;
+    bool first = true;
+    for (int kk = 0; kk < K; ++kk) {
+      float bv = FLT_MAX;
+      int bj = 0x7fffffff, bt = 0;
+      for (int t = gl; t < c; t += GL) {
+        const float v = r.m_rows[base + t];
+        const int j = r.row_obs[base + t];
+        const bool after = first || v > last_v || (v == last_v && j > last_j);
+        if (after && (v < bv || (v == bv && j < bj))) { bv = v; bj = j; bt = t; }
+      }
+#pragma unroll
+      for (int off = GL / 2; off > 0; off >>= 1) {   // xor offsets below GL stay inside the aligned group
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
+        const int oj = __shfl_xor_sync(0xffffffffu, bj, off);
+        const int ot = __shfl_xor_sync(0xffffffffu, bt, off);
+        if (ov < bv || (ov == bv && oj < bj)) { bv = ov; bj = oj; bt = ot; }
+      }
+      if (bj == 0x7fffffff) { bj = last_j < 0 ? 0 : last_j; bt = last_t; }   // fewer than K candidates: repeat
+      if (gl == 0) rows_s[g][kk] = base + bt;
+      last_v = bv; last_j = bj; last_t = bt; first = false;
+    }
+  }
+  __syncwarp();
+  if (gl == 0 && live) step_sample(s, w, s.t, StepIO{s.row_dist, s.row_grad, rows_s[g], nullptr, qn_s[g]});
+  __syncwarp();
+  if (r.tabA != nullptr && s.t < s.H && live) {
+    const int d = s.d;
+    if (gl < d) {
+      const float v = qn_s[g][gl];
+      float sn, cs;
+      sincosf(v, &sn, &cs);
+      xs_s[g][3 * gl] = v; xs_s[g][3 * gl + 1] = sn; xs_s[g][3 * gl + 2] = cs;
+    }
+  }
+  __syncwarp();
+  if (r.tabA != nullptr && s.t < s.H && live) {
+    const int d = s.d;
+#pragma unroll 2
+    for (int u = 0; u < HID / GL; ++u) {
+      const int k = gl + GL * u;
+      r.tabA[(size_t)w * HID + k] = l1_to_half_bits(l1_feature(r.Wf0, r.b0, k, xs_s[g], d, 0, r.nin), r.bf16 != 0);
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -865,6 +868,19 @@ int launch_step(dsmppi_ctx* c, const dsmppi_rollout_args* a, int t, cudaStream_t
   // one thread per sample, a long dependent chain each: spread small batches over all SMs (one warp per CTA)
   const int bs = a->N <= c->sm_count * 128 ? 32 : 128;
   step_kernel<<<(a->N + bs - 1) / bs, bs, 0, st>>>(s);
+  LAUNCH_CHECK(c);
+  return 0;
+}
+
+int launch_rank_step(dsmppi_ctx* c, const dsmppi_rollout_args* a, int t, int table_mode, cudaStream_t st) {
+  const StepArgs s = make_step_args(c, a, t);
+  RankStepArgs r;
+  r.m_rows = c->m_rows; r.row_base = c->row_base; r.cand_cnt = c->cand_cnt; r.row_obs = c->row_obs;
+  r.Wf0 = c->net.Wf[0]; r.b0 = c->net.b[0];
+  r.tabA = (table_mode >= 0 && t < a->H) ? static_cast<uint16_t*>(c->enc_q) : nullptr;
+  r.nin = c->nin; r.bf16 = table_mode == DSMPPI_PASS1_TC_BF16 ? 1 : 0;
+  static_assert(MAXD <= 8, "the table part reads one joint per lane of an 8-lane group");
+  rank_step_kernel<8><<<(a->N + 15) / 16, 128, 0, st>>>(s, r);
   LAUNCH_CHECK(c);
   return 0;
 }

@@ -35,6 +35,7 @@
 #include <vector>
 
 #include "internal.cuh"
+#include "l1_table.cuh"
 
 namespace {
 
@@ -57,15 +58,20 @@ constexpr int OFF_BIAS = OFF_W5 + SZ_W5;           // 3 x 256 fp32 (layers 2..4)
 constexpr int SZ_BIAS = (NHID * HID + 16) * 4;
 constexpr int IMG_BYTES = OFF_BIAS + SZ_BIAS;      // 207936
 constexpr int OFF_BAR = IMG_BYTES;                 // mbarriers (8 B each)
-constexpr int NBAR = 12;
+constexpr int NBAR = 20;
 constexpr int OFF_TMEMPTR = OFF_BAR + NBAR * 8;
-constexpr int SMEM_BYTES = OFF_TMEMPTR + 16;
+// hand-over of a tile's 128 distances from the row warps of a slot to that slot's writer warp (warp 9 / 10): two
+// buffers per slot, so the row warps never wait for the writer
+constexpr int OFF_MBUF = OFF_TMEMPTR + 16;         // [slot][buffer][128] floats
+constexpr int SMEM_BYTES = OFF_MBUF + 2 * 2 * ROWS * 4;
 static_assert(IMG_BYTES % 16 == 0, "bulk copies need 16-byte granularity");
 static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB shared-memory budget");
 
 // barrier indices
 enum { BAR_W = 0, BAR_AREADY0 = 1, BAR_AREADY1 = 2, BAR_DFREE0 = 3, BAR_DFREE1 = 4,
-       BAR_DFULL00 = 5, BAR_DFULL01 = 6, BAR_DFULL10 = 7, BAR_DFULL11 = 8 };
+       BAR_DFULL00 = 5, BAR_DFULL01 = 6, BAR_DFULL10 = 7, BAR_DFULL11 = 8,
+       BAR_MFULL = 9,      // + slot * 2 + buffer: the slot's four row warps have written their distances (count 4)
+       BAR_MEMPTY = 13 };  // + slot * 2 + buffer: the writer warp has read them (count 1)
 
 // TMEM columns
 constexpr uint32_t TM_A0 = 0, TM_A1 = 128, TM_DLO = 256, TM_DHI = 384;
@@ -88,6 +94,9 @@ __device__ __forceinline__ void cluster_sync_all() {
 }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_local(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
@@ -262,23 +271,11 @@ __host__ __device__ constexpr uint32_t make_idesc(int fmt /*0 f16, 1 bf16*/, int
 }
 
 // ------------------------------------------------------------------------------------------------
-// Layer-1 tables (network_macros_mod.py:139-141 with the input split into its q and p columns):
-//   A_i[k] = b1[k] + sum_{c < d} W1[k][c] q_c + W1[k][nin + c] sin q_c + W1[k][2 nin + c] cos q_c          (n, 256)
-//   B_j[k] =         sum_{c < P} W1[k][d + c] p_c + W1[k][nin + d + c] sin p_c + W1[k][2 nin + d + c] cos p_c
-// fp32 FMAs over the fp32 weights, rounded once to fp16 / bf16.  A is row-major (a warp's rows share one sample, so
-// its 16-byte reads are broadcasts); B is stored [k / 8][j][k % 8] so that the 32 consecutive obstacles of a warp read
-// 32 consecutive 16-byte groups (one coalesced 512-byte request per instruction).
+// Layer-1 tables (l1_table.cuh).  A is row-major (a warp's rows share one sample, so its 16-byte reads are
+// broadcasts); B is stored [k / 8][j][k % 8] so that the 32 consecutive obstacles of a warp read 32 consecutive
+// 16-byte groups (one coalesced 512-byte request per instruction).
 // ------------------------------------------------------------------------------------------------
-template <bool BF16>
-__device__ __forceinline__ uint16_t to_half_bits(float v) {
-  // clamped to half the fp16 range so that A_i + B_j can never overflow to infinity in the packed add (everything
-  // downstream converts with .satfinite); the shipped networks stay below 1e2 here
-  v = fminf(fmaxf(v, -30000.f), 30000.f);
-  if (BF16) return __bfloat16_as_ushort(__float2bfloat16_rn(v));
-  return __half_as_ushort(__float2half_rn(v));
-}
-
-// one CTA of 256 threads per sample / obstacle; Wf0 = W1^T, [3 nin][256] (coalesced over the feature index)
+// one CTA of 256 threads per sample / obstacle
 template <bool BF16>
 __global__ void __launch_bounds__(HID) l1_table_kernel(const float* __restrict__ x, int x_stride, int n, int ncomp,
                                                        int comp0, int nin, const float* __restrict__ Wf0,
@@ -293,14 +290,9 @@ __global__ void __launch_bounds__(HID) l1_table_kernel(const float* __restrict__
     xs[3 * k] = v; xs[3 * k + 1] = sn; xs[3 * k + 2] = cs;
   }
   __syncthreads();
-  float acc = bias ? bias[k] : 0.f;
-  for (int c = 0; c < ncomp; ++c) {
-    acc = fmaf(Wf0[(size_t)(comp0 + c) * HID + k], xs[3 * c], acc);
-    acc = fmaf(Wf0[(size_t)(nin + comp0 + c) * HID + k], xs[3 * c + 1], acc);
-    acc = fmaf(Wf0[(size_t)(2 * nin + comp0 + c) * HID + k], xs[3 * c + 2], acc);
-  }
+  const float acc = l1_feature(Wf0, bias, k, xs, ncomp, comp0, nin);
   const size_t o = transposed ? ((size_t)(k >> 3) * M + i) * 8 + (k & 7) : (size_t)i * HID + k;
-  out[o] = to_half_bits<BF16>(acc);
+  out[o] = l1_to_half_bits(acc, BF16);
   (void)n;
 }
 
@@ -317,6 +309,7 @@ struct TcArgs {
   uint32_t ignore_mask;
   float inv_scale_div;                         // 100 for the 9-link net else 1
   uint32_t zero;                               // 0 (an opaque zero for scheduling dependencies, see first_layer)
+  int use_writers;                             // 1: warps 9 / 10 store the distances (0: the row warps do, see there)
   long long* prof;                             // DSMPPI_TC_PROF builds only: [block][warp][8] cycle counters
 };
 
@@ -432,6 +425,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_pass
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
 
   // ---- one-time setup: barriers, TMEM, resident weights
+  float* mbuf = reinterpret_cast<float*>(smem + OFF_MBUF);
   if (warp == MMA_WARP) {
     if (lane == 0) {
       mbar_init(BAR(BAR_W), 1);
@@ -440,6 +434,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_pass
       mbar_init(BAR(BAR_DFREE0), 8);      // 4 draining warps x 2 CTAs
       mbar_init(BAR(BAR_DFREE1), 8);
       for (int i = BAR_DFULL00; i <= BAR_DFULL11; ++i) mbar_init(BAR(i), 1);   // tcgen05.commit arrives
+      for (int i = 0; i < 4; ++i) { mbar_init(BAR(BAR_MFULL + i), 4); mbar_init(BAR(BAR_MEMPTY + i), 1); }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
@@ -581,8 +576,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_pass
         tc_wait_ld();
         signal(BAR(BAR_DFREE0));
       }
-      if (valid) {                           // masked minimum link distance (MPPI.py:236-242)
-        float m = 3.0e38f;
+      float m = 3.0e38f;                     // masked minimum link distance (MPPI.py:236-242)
+      if (valid) {
 #pragma unroll
         for (int o = 0; o < 16; ++o) {
           if (o < a.O) {
@@ -592,6 +587,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_pass
             m = fminf(m, y);
           }
         }
+      }
+      if (a.use_writers) {
+        // hand the distance to this slot's writer warp through shared memory (one st.shared + one mbarrier arrival
+        // per warp): this warp is on the tensor core's critical path, a global store and its address arithmetic are
+        // not free there (2.51 -> 2.39 ms per launch)
+        const int b = (int)(it & 1);
+        if (it >= 2) mbar_wait(BAR(BAR_MEMPTY + slot * 2 + b), (uint32_t)(((it >> 1) - 1) & 1));
+        mbuf[(slot * 2 + b) * ROWS + row] = m;
+        __syncwarp();
+        if (lane == 0) mbar_arrive_local(BAR(BAR_MFULL + slot * 2 + b));
+      } else if (valid) {
         a.mdist[(size_t)i_cur * a.M + j_cur] = m;
       }
       i_cur = i_next;
@@ -658,6 +664,39 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_pass
     }
     PROF_ADD(2);
     PROF_FLUSH(a, MMA_WARP);
+  }
+  if ((warp == MMA_WARP + 1 || warp == MMA_WARP + 2) && a.use_writers) {
+    // =================================== distance writers (warps 9, 10: one per tile slot) ========================
+    // Per tile: the slot's 128 distances from shared memory to the (n, M) scratch matrix, 128 bytes per store
+    // instruction; the matrix stays in L2 for select_candidates_kernel, which follows.
+    //
+    // Measured alternatives (B200, Franka shelf 2064, 4096 samples; ms per launch): row warps store directly 2.51;
+    // writer warps 2.39 (this form).  Taking the guard band of a sample INSIDE this kernel as soon as its M distances
+    // are complete (one atomic per sample and tile on a writer warp: free, 2.36) was tried three ways and lost each
+    // time: on the writer warp itself 6.1 (while it selects, its slot's row warps run out of hand-over buffers and,
+    // the issuer alternating the slots strictly, the whole CTA pair stops); on a dedicated warp with the sample staged
+    // in shared memory 7.4 (the 24 KB of staging came out of the L1 that serves the table loads and the spills); on a
+    // dedicated warp at this warpgroup's 40 registers 20 (spilled loop variables, every spill an L2 round trip).  The
+    // stand-alone kernel takes 36 us per step with sixteen warps per SM hiding that latency.
+    const int slot = warp - (MMA_WARP + 1);
+    for (long long it = 0;; ++it) {
+      const long long tX = (it * 2) * npairs + pair;
+      if (tX >= n_tiles) break;                              // the row warps of both slots loop on slot X's tile
+      const long long tile = (it * 2 + slot) * npairs + pair;
+      const int b = (int)(it & 1);
+      mbar_wait(BAR(BAR_MFULL + slot * 2 + b), (uint32_t)((it >> 1) & 1));
+      float vals[4];
+#pragma unroll
+      for (int w = 0; w < 4; ++w) vals[w] = mbuf[(slot * 2 + b) * ROWS + 32 * w + lane];
+      __syncwarp();
+      if (lane == 0) mbar_arrive_local(BAR(BAR_MEMPTY + slot * 2 + b));
+      const long long r0 = tile * (2 * ROWS) + (long long)rank * ROWS;       // pair-row r = i * M + j: mdist index
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        const long long r = r0 + 32 * w + lane;
+        if (r < a.n_rows) a.mdist[r] = vals[w];
+      }
+    }
   }
   // ---- teardown
   tc_fence_before();
@@ -767,15 +806,20 @@ int tc_set_obstacles(dsmppi_ctx* c, cudaStream_t st) {
 }
 
 // the per-sample layer-1 table A of n states (row stride q_stride floats) in the format of `mode`
-int tc_sample_table(dsmppi_ctx* c, const float* q, int q_stride, int n, int mode, cudaStream_t st) {
-  const bool bf16 = mode == DSMPPI_PASS1_TC_BF16;
+int tc_reserve_sample_table(dsmppi_ctx* c, int n) {
   const size_t need = (size_t)n * HID * 2;
   if (need > c->enc_q_cap) {
     if (c->enc_q) CUDA_TRY(cudaFree(c->enc_q));
     c->enc_q = nullptr;
-    CUDA_TRY(cudaMalloc(&c->enc_q, need));
-    c->enc_q_cap = need;
+    CUDA_TRY(cudaMalloc(&c->enc_q, need + need / 8));
+    c->enc_q_cap = need + need / 8;
   }
+  return 0;
+}
+
+int tc_sample_table(dsmppi_ctx* c, const float* q, int q_stride, int n, int mode, cudaStream_t st) {
+  const bool bf16 = mode == DSMPPI_PASS1_TC_BF16;
+  if (tc_reserve_sample_table(c, n)) return 1;
   uint16_t* ta = static_cast<uint16_t*>(c->enc_q);
   if (bf16) l1_table_kernel<true><<<n, HID, 0, st>>>(q, q_stride, n, c->d, 0, c->nin, c->net.Wf[0], c->net.b[0], 0, 0, ta);
   else l1_table_kernel<false><<<n, HID, 0, st>>>(q, q_stride, n, c->d, 0, c->nin, c->net.Wf[0], c->net.b[0], 0, 0, ta);
@@ -784,11 +828,13 @@ int tc_sample_table(dsmppi_ctx* c, const float* q, int q_stride, int n, int mode
   return 0;
 }
 
-int tc_pass1(dsmppi_ctx* c, const float* q, int q_stride, int n, uint32_t ignore_mask, int mode, cudaStream_t st) {
+int tc_pass1(dsmppi_ctx* c, const float* q, int q_stride, int n, uint32_t ignore_mask, int mode, cudaStream_t st,
+             bool table_ready) {
   REQUIRE(c->tc_blob, "tensor-core images not built");
   TcImages* t = static_cast<TcImages*>(c->tc_blob);
   const bool bf16 = mode == DSMPPI_PASS1_TC_BF16;
-  if (tc_sample_table(c, q, q_stride, n, mode, st)) return 1;
+  // the per-sample table of these states: written by the fused step kernel of the previous rollout step, else here
+  if (!table_ready && tc_sample_table(c, q, q_stride, n, mode, st)) return 1;
   TcArgs a;
   const uint8_t* base = t->img[0] + (size_t)(bf16 ? 2 : 0) * IMG_BYTES;
   a.img0 = base;
@@ -804,6 +850,7 @@ int tc_pass1(dsmppi_ctx* c, const float* q, int q_stride, int n, uint32_t ignore
   a.ignore_mask = ignore_mask;
   a.inv_scale_div = (c->O == 9) ? 100.f : 1.f;
   a.zero = 0u;
+  a.use_writers = 1;
   a.prof = nullptr;
 #ifdef DSMPPI_TC_PROF
   a.prof = reinterpret_cast<long long*>(c->stage);   // the micro-benchmark parks its counter buffer here

@@ -252,3 +252,47 @@ def test_profiler_sees_the_reference_stage_tags(factory, score_mode):
                 "TAG: evaluate NN_4 (forward+backward pass)"):
         assert tag in names, f"{tag} missing from the profiler trace"
     m.propagate()        # and without a profiler attached nothing is opened (no per-call overhead)
+
+
+def test_graphed_control_tick_equals_the_plain_path(factory, monkeypatch):
+    """The integrator's shape (N = 1, H = 2, CPU tensors: frankaIntegrator.py:101-121) and the planner's (40 x 10) run
+    as ONE replayed CUDA graph per propagate(); outputs must equal the plain launch path bit for bit, follow obstacle
+    and state changes from tick to tick, and re-capture when a script pokes a parameter that is baked into the graph."""
+    c = load_npz("case_franka_shelf")
+    obs = c["obs"][:28].clone()
+    for N, H in ((1, 2), (40, 10)):
+        torch.manual_seed(5)
+        q_start = c["q0"] + 0.05 * torch.randn(7)
+        objs = {}
+        for mode in ("graph", "plain"):
+            monkeypatch.setenv("DSMPPI_GRAPH_TICK", "1" if mode == "graph" else "0")
+            m = factory.make_mppi(dict(c, obs=obs.clone()), device="cpu", N=N, H=H, pass1="auto", copy_policy=False)
+            m.Policy.alpha_s = 1.0
+            objs[mode] = m
+        outs = {k: [] for k in objs}
+        for tick in range(6):
+            for mode, m in objs.items():
+                monkeypatch.setenv("DSMPPI_GRAPH_TICK", "1" if mode == "graph" else "0")
+                if tick == 2:
+                    m.dst_thr = 0.03                          # parameter poke -> re-capture
+                if tick == 3:
+                    m.update_obstacles(m.obs + torch.tensor([0.01, 0.0, -0.01, 0.0]))   # streamed obstacles, same count
+                if tick == 4:
+                    m.Policy.n_kernels = 3                    # fewer live kernels -> new staging shapes
+                torch.manual_seed(100 + tick)
+                m.Policy.sample_policy()
+                m.q_cur = q_start + 0.01 * tick
+                traj, dist, kv, dots, acts = m.propagate()
+                outs[mode].append([t.clone() for t in (traj, dist, kv, dots, acts, m.qdot, m.nn_grad,
+                                                       m.norm_basis, m.kernel_val_all)])
+        assert "_tick" in objs["graph"].__dict__ and "_tick" not in objs["plain"].__dict__
+        for tick, (a, b) in enumerate(zip(outs["graph"], outs["plain"])):
+            for x, y, name in zip(a, b, ("traj", "dist", "kval", "dots", "acts", "qdot", "nn_grad", "norm_basis",
+                                         "kernel_val_all")):
+                assert x.device.type == "cpu" and x.shape == y.shape, (N, tick, name)
+                assert torch.equal(x, y), f"N={N} tick {tick}: {name} differs between the graphed and the plain path"
+        # cost / update keep working on the graphed outputs
+        g = objs["graph"]
+        cost = g.get_cost()
+        assert cost.shape == (N,) and torch.isfinite(cost).all()
+        g.shift_policy_means()
