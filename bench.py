@@ -302,6 +302,48 @@ def policy_vector(mppi):
     return torch.cat((P.mu_c.flatten(), P.sigma_c.flatten(), P.alpha_c.flatten())).float()
 
 
+def measure_control_tick(dev_index, ticks=400, n_obs=28):
+    """The integrator process's loop (frankaIntegrator.py:101-121): ONE sample, TWO steps per control tick, CPU tensors
+    in and out as that script uses them -- update_obstacles, sample_policy, propagate, q += qdot * dt, clamp.  Wall
+    clock per tick, everything included (this is a latency figure, the reference logs ~500 Hz for it).  The drop-in
+    replays one CUDA graph per propagate() at this size (MPPI._propagate_tick)."""
+    from optimalmodulationds_b200 import MPPI, LinDS
+    from optimalmodulationds_b200.sdf.robot_sdf import RobotSdfCollisionNet
+    p = problem("franka_shelf_294")
+    obs = p["obs"][:n_obs].clone()
+    W, b, _ = load_net_arrays("franka")
+    net = RobotSdfCollisionNet(in_channels=10, out_channels=9, layers=[256] * 4, skips=[])
+    net.load_arrays(W, b)
+    os.environ.setdefault("DSMPPI_DEVICE", str(dev_index))
+    m = MPPI(p["q0"].clone(), p["qf"].clone(), p["dh"], obs, 0.01, 2, 1, [LinDS(p["qf"].clone()), LinDS(p["q0"].clone())],
+             p["dh_a"], net, p["K"])
+    m.dst_thr = 0.03
+    P = m.Policy
+    P.alpha_s, P.sigma_c_nominal = 0.0, 1.0
+    for k in range(5):                                     # the planner has published a few kernels
+        P.add_kernel(p["q0"] + 0.1 * k, 0.1, torch.eye(7))
+    P.alpha_c[:5] = 0.3
+
+    def tick():
+        m.update_obstacles(obs)
+        P.sample_policy()
+        m.propagate()
+        m.q_cur = torch.clamp(m.q_cur + m.qdot[0, :] * 0.01, m.Cost.q_min, m.Cost.q_max)
+
+    for _ in range(30):
+        tick()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(ticks):
+        tick()
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / ticks
+    return dict(hz=1.0 / dt, ms_per_tick=dt * 1e3, ticks=ticks, graphed="_tick" in m.__dict__,
+                config=f"Franka net, {n_obs} spheres, N=1, H=2, K={p['K']}, 5 kernels, CPU caller tensors, "
+                       "loop of frankaIntegrator.py:101-121 (update_obstacles, sample_policy, propagate, q += qdot dt)",
+                timing="wall clock per tick incl. host wrapper, H2D, launch, D2H")
+
+
 def check_sharding(p, dev, args, rank, world, mppi_main):
     """Evidence that the NCCL path computes the unsharded update (exit != 0 otherwise):
       1. after the timed iterations every rank holds bit-identical policy means;
@@ -593,6 +635,10 @@ def main():
         line["multi_gpu_check"] = mg_check
     if c5 is not None:
         line["c5"] = c5
+    if world == 1:
+        del mppi
+        torch.cuda.empty_cache()
+        line["control_tick"] = measure_control_tick(local_rank)
     if world == 1 and not args.no_cpu_baseline:
         r = cpu_reference_rate(p, target_seconds=15.0)
         line["cpu_baseline"] = dict(value=r["value"], unit="state-steps/s", cores=r["cores"], kind=r["kind"],

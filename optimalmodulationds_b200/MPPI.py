@@ -174,7 +174,7 @@ class MPPI:
         """Small parameter vectors (goal, joint limits) as Python floats.  A CUDA tensor is copied to the host once per
         (tensor, in-place version): a `.to('cpu')` on every call would synchronise with the device and keep the CPU
         from running ahead of the rollout it has just launched."""
-        if isinstance(t, torch.Tensor) and t.is_cuda:
+        if isinstance(t, torch.Tensor):
             cache = self.__dict__.setdefault('_hostvec_cache', {})
             hit = cache.get(id(t))
             if hit is not None and hit[0] is t and hit[1] == t._version:
@@ -385,41 +385,60 @@ class MPPI:
                 and obs.dtype == torch.float32 and q_cur.dtype == torch.float32)
 
     def _tick_build(self, nk, q_batch):
-        """Staging buffers + capture for the current shapes / parameters."""
+        """Staging for the current shapes: ONE pinned input block [q | obs | mu | sigma | alpha] and ONE output block
+        [all_traj | closest | dots | acts | qdot | grads | kval] on each side, so a tick moves two copies."""
         N, H, d, K50 = self.N_traj, self.dt_H, self.n_dof, self.Policy.N_KERNEL_MAX
-        dev, M = self._dev, int(self.obs.shape[0])
-        pin = lambda *shape: torch.zeros(*shape).pin_memory()  # noqa: E731
+        dev, M, P1 = self._dev, int(self.obs.shape[0]), self._point_dim + 1
+
+        def carve(total_buf, shapes):
+            out, off = {}, 0
+            for name, shape in shapes:
+                n = 1
+                for x in shape:
+                    n *= x
+                out[name] = total_buf[off:off + n].view(*shape)
+                off += (n + 3) // 4 * 4                       # 16-byte aligned pieces
+            return out
+
+        def total(shapes):
+            t = 0
+            for _, shape in shapes:
+                n = 1
+                for x in shape:
+                    n *= x
+                t += (n + 3) // 4 * 4
+            return t
+
+        in_shapes = [('q', (N, d) if q_batch else (d,)), ('obs', (M, P1)), ('mu', (N, K50, d)), ('sigma', (N, K50)),
+                     ('alpha', (N, K50, d))]
+        out_shapes = [('all_traj', (N, H, d)), ('closest', (N, H)), ('dots', (N, H)), ('acts', (N, H)), ('qdot', (N, d)),
+                      ('grads', (N, H, d)), ('kval', (N, H, K50))]
         t = dict(nk=nk, M=M, q_batch=q_batch)
-        t['h_in'] = dict(q=pin(N, d) if q_batch else pin(d), mu=pin(N, max(nk, 1), d), sigma=pin(N, max(nk, 1)),
-                         alpha=pin(N, max(nk, 1), d), obs=pin(M, self._point_dim + 1))
-        t['h_out'] = dict(all_traj=pin(N, H, d), closest=pin(N, H), kval=pin(N, H, max(nk, 1)), dots=pin(N, H),
-                          acts=pin(N, H), qdot=pin(N, d), grads=pin(N, H, d))
+        t['h_in_buf'] = torch.zeros(total(in_shapes)).pin_memory()
+        t['h_out_buf'] = torch.zeros(total(out_shapes)).pin_memory()
         with torch.cuda.device(dev):
-            t['d_in'] = dict(q=torch.zeros_like(t['h_in']['q'], device=dev), mu=torch.zeros(N, K50, d, device=dev),
-                             sigma=torch.zeros(N, K50, device=dev), alpha=torch.zeros(N, K50, d, device=dev),
-                             obs=torch.zeros(M, self._point_dim + 1, device=dev))
-            t['d_out'] = dict(all_traj=torch.empty(N, H, d, device=dev), closest=torch.empty(N, H, device=dev),
-                              kval=torch.zeros(N, H, K50, device=dev), dots=torch.empty(N, H, device=dev),
-                              acts=torch.empty(N, H, device=dev), qdot=torch.empty(N, d, device=dev),
-                              grads=torch.empty(N, H, d, device=dev))
+            t['d_in_buf'] = torch.zeros(total(in_shapes), device=dev)
+            t['d_out_buf'] = torch.zeros(total(out_shapes), device=dev)
+        t['h_in'], t['d_in'] = carve(t['h_in_buf'], in_shapes), carve(t['d_in_buf'], in_shapes)
+        t['h_out'], t['d_out'] = carve(t['h_out_buf'], out_shapes), carve(t['d_out_buf'], out_shapes)
         return t
 
     def _tick_run(self, t):
         """The launch sequence that gets captured (and is also run once, eagerly, as the capture's warm-up)."""
-        hi, di, do, ho, nk = t['h_in'], t['d_in'], t['d_out'], t['h_out'], t['nk']
-        di['q'].copy_(hi['q'], non_blocking=True)
-        di['obs'].copy_(hi['obs'], non_blocking=True)
-        if nk > 0:
-            di['mu'][:, :nk].copy_(hi['mu'], non_blocking=True)
-            di['sigma'][:, :nk].copy_(hi['sigma'], non_blocking=True)
-            di['alpha'][:, :nk].copy_(hi['alpha'], non_blocking=True)
+        t['d_in_buf'].copy_(t['h_in_buf'], non_blocking=True)
         st = self._stream()
-        _capi.check(self._lib.dsmppi_set_obstacles(self._ctx, di['obs'].data_ptr(), t['M'], st))
+        _capi.check(self._lib.dsmppi_set_obstacles(self._ctx, t['d_in']['obs'].data_ptr(), t['M'], st))
         _capi.check(self._lib.dsmppi_rollout(self._ctx, _capi.C.byref(t['args']), st))
-        for k in ('all_traj', 'closest', 'dots', 'acts', 'qdot', 'grads'):
-            ho[k].copy_(do[k], non_blocking=True)
-        if nk > 0:
-            ho['kval'].copy_(do['kval'][:, :, :nk], non_blocking=True)
+        t['h_out_buf'].copy_(t['d_out_buf'], non_blocking=True)
+
+    def _tick_key(self, nk):
+        """Everything dsmppi_rollout_args bakes into the captured kernel arguments, cheaply (the argument block itself
+        is only rebuilt when this changes)."""
+        DS = self.DS
+        A = getattr(DS, 'A', None)
+        return (nk, int(self.n_closest_obs), self._ignore_mask(), float(self.dt), float(self.dst_thr),
+                float(self.Policy.p), type(DS), tuple(self._host_vec(DS.q_goal)), float(getattr(DS, 'lin_thr', 0.0)),
+                None if A is None else tuple(self._host_vec(A)))
 
     def _propagate_tick(self, q_cur_user, nk):
         N, H, d = self.N_traj, self.dt_H, self.n_dof
@@ -433,13 +452,12 @@ class MPPI:
         hi['q'].copy_(q_cur_user)
         hi['obs'].copy_(self.obs)
         if nk > 0:
-            hi['mu'].copy_(P.mu_tmp[:, :nk]); hi['sigma'].copy_(P.sigma_tmp[:, :nk]); hi['alpha'].copy_(P.alpha_tmp[:, :nk])
-        di, do = t['d_in'], t['d_out']
-        args = self._rollout_args(N, H, nk, di['q'], di['mu'], di['sigma'], di['alpha'], do)
-        key = bytes(args)
-        with torch.cuda.device(self._dev):
-            if key != t['key']:
-                t['args'] = args
+            hi['mu'].copy_(P.mu_tmp); hi['sigma'].copy_(P.sigma_tmp); hi['alpha'].copy_(P.alpha_tmp)
+        key = self._tick_key(nk)
+        if key != t['key']:
+            with torch.cuda.device(self._dev):
+                di, do = t['d_in'], t['d_out']
+                t['args'] = self._rollout_args(N, H, nk, di['q'], di['mu'], di['sigma'], di['alpha'], do)
                 side = torch.cuda.Stream(self._dev)
                 side.wait_stream(torch.cuda.current_stream(self._dev))
                 with torch.cuda.stream(side):
@@ -449,20 +467,31 @@ class MPPI:
                 with torch.cuda.graph(g, stream=side):
                     self._tick_run(t)
                 t['graph'], t['key'] = g, key
+                t['done'] = torch.cuda.Event()
+        if torch.cuda.current_device() == self._dev.index:
             t['graph'].replay()
-            torch.cuda.current_stream(self._dev).synchronize()
-        ho = t['h_out']
+            t['done'].record()
+            t['done'].synchronize()
+        else:
+            with torch.cuda.device(self._dev):
+                t['graph'].replay()
+                t['done'].record()
+                t['done'].synchronize()
+        # fresh tensors every call, like the reference's reset_tensors (MPPI.py:86-91): one clone of the output block
+        blk = t['h_out_buf'].clone()
+        off = 0
+        outs = {}
+        for name, view in t['h_out'].items():
+            n = view.numel()
+            outs[name] = blk[off:off + n].view(view.shape)
+            off += (n + 3) // 4 * 4
         self._mirror = {}
         self._obs_uploaded = None
         self._norm_basis = None
-        out = {k: ho[k].clone() for k in ('all_traj', 'closest', 'dots', 'acts', 'qdot')}
-        kv = torch.zeros(N, H, P.N_KERNEL_MAX)
-        if nk > 0:
-            kv[:, :, :nk] = ho['kval']
-        self._dev_last = dict(grads=None, grads_host=ho['grads'].clone(), nk=nk)   # (the graph's buffers are reused)
-        self.all_traj, self.closest_dist_all, self.kernel_val_all = out['all_traj'], out['closest'], kv
-        self.dot_products, self.kernel_activations, self.qdot = out['dots'], out['acts'], out['qdot']
-        self.nn_grad = ho['grads'][:, H - 1, :].clone()
+        self._dev_last = dict(grads=None, grads_host=outs['grads'], nk=nk)   # (the graph's buffers are reused)
+        self.all_traj, self.closest_dist_all, self.kernel_val_all = outs['all_traj'], outs['closest'], outs['kval']
+        self.dot_products, self.kernel_activations, self.qdot = outs['dots'], outs['acts'], outs['qdot']
+        self.nn_grad = outs['grads'][:, H - 1, :]
         self.ker_w = self.kernel_val_all[:, H - 1, :nk].unsqueeze(2)
         return (self.all_traj, self.closest_dist_all, self.kernel_val_all[:, :, 0:nk], self.dot_products,
                 self.kernel_activations)

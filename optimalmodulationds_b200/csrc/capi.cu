@@ -203,7 +203,7 @@ int dsmppi_ctx_create(dsmppi_ctx** out, const dsmppi_net* net, const float* dh_p
   if (exact_set_attributes()) { delete c; return 1; }
   if (tc_build_images(c, net)) { delete c; return 1; }
   if (tcx_build_images(c, net)) { delete c; return 1; }
-  c->upd_blocks = c->sm_count * 2;
+  c->upd_blocks = c->sm_count * 4;       // update_partial_kernel: four 256-thread CTAs per SM (56 registers per thread)
   CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c->upd_partials),
                       (size_t)c->upd_blocks * dsmppi_update_packed_len(NKMAX, MAXD) * sizeof(float)));
   CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c->stats_tmp), 4 * sizeof(float)));
@@ -314,7 +314,7 @@ int dsmppi_set_obstacles(dsmppi_ctx* c, const float* obs_dev, int32_t M, void* s
     if (launch_pack_obstacles(c, c->obs_raw, M, c->P, st)) return 1;
   }
   c->M = M;
-  if (c->tc_blob) return tc_set_obstacles(c, st);
+  c->obs_tables_dirty = 1;      // the prefilter's per-obstacle table is rebuilt by the next launch that needs it
   return 0;
 }
 

@@ -647,7 +647,7 @@ constexpr int UPD_EMAX = (UPD_LMAX + 31) / 32;                             // pa
 // count, and with it the number of resident warps, where a latency-bound kernel needs them.  Fixed order: per-warp
 // sums over its samples, warps combined in index order, CTAs combined by update_block_sum_kernel.
 template <int E>
-__global__ void __launch_bounds__(UPD_T) update_partial_kernel(UpdArgs u) {
+__global__ void __launch_bounds__(UPD_T, E <= 3 ? 4 : 2) update_partial_kernel(UpdArgs u) {
   __shared__ float red[UPD_W][32 * E];
   const int nk = u.nk, d = u.d, H = u.H, L = u.L;
   const int o_mu = 1, o_sg = o_mu + nk * d, o_al = o_sg + nk, o_mx = o_al + nk * d, o_b0 = o_mx + nk;

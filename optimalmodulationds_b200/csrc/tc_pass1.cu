@@ -833,6 +833,10 @@ int tc_pass1(dsmppi_ctx* c, const float* q, int q_stride, int n, uint32_t ignore
   REQUIRE(c->tc_blob, "tensor-core images not built");
   TcImages* t = static_cast<TcImages*>(c->tc_blob);
   const bool bf16 = mode == DSMPPI_PASS1_TC_BF16;
+  if (c->obs_tables_dirty) {              // (small obstacle sets never get here: they are scored densely in fp32)
+    if (tc_set_obstacles(c, st)) return 1;
+    c->obs_tables_dirty = 0;
+  }
   // the per-sample table of these states: written by the fused step kernel of the previous rollout step, else here
   if (!table_ready && tc_sample_table(c, q, q_stride, n, mode, st)) return 1;
   TcArgs a;
