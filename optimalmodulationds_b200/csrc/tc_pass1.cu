@@ -639,28 +639,39 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_pass
       }
       __syncwarp();
     };
-    auto layer = [&](auto L) {
-      constexpr int l = decltype(L)::value;
-      auto slot = [&](auto S) {
-        constexpr int s = decltype(S)::value;
-        PROF_ADD(2);
-        mbar_wait(BAR(s ? BAR_AREADY1 : BAR_AREADY0), ph_a[s]);
-        ph_a[s] ^= 1;
-        tc_fence_after();
-        PROF_ADD(0);
-        group(L, S, std::integral_constant<int, 0>{});
-        if constexpr (l < NHID) group(L, S, std::integral_constant<int, 1>{});
-      };
-      slot(std::integral_constant<int, 0>{});
-      slot(std::integral_constant<int, 1>{});
+    // one (slot, layer) step: wait for the slot's operand, then its accumulator halves
+    auto step = [&](auto S, auto L) {
+      constexpr int l = decltype(L)::value, s = decltype(S)::value;
+      PROF_ADD(2);
+      mbar_wait(BAR(s ? BAR_AREADY1 : BAR_AREADY0), ph_a[s]);
+      ph_a[s] ^= 1;
+      tc_fence_after();
+      PROF_ADD(0);
+      group(L, S, std::integral_constant<int, 0>{});
+      if constexpr (l < NHID) group(L, S, std::integral_constant<int, 1>{});
     };
-    for (long long it = 0;; ++it) {
-      const long long tX = (it * 2) * npairs + pair;
-      if (tX >= n_tiles) break;
-      layer(std::integral_constant<int, 0>{});
-      layer(std::integral_constant<int, 1>{});
-      layer(std::integral_constant<int, 2>{});
-      layer(std::integral_constant<int, 3>{});
+    using I0 = std::integral_constant<int, 0>;
+    using I1 = std::integral_constant<int, 1>;
+    using I2 = std::integral_constant<int, 2>;
+    using I3 = std::integral_constant<int, 3>;
+    // The two tile slots run HALF A TILE APART: X is two layers ahead of Y.  A slot's tile boundary -- drain the output
+    // layer, read the next tile's first activation from the tables (L2 latency), store it -- takes ~2.5 k cycles during
+    // which that slot has no MMA to offer; with both slots at the boundary together the tensor pipe idled for it (27 %
+    // of its cycles in the ncu capture of the un-staggered order).  Staggered, one slot's boundary falls under a full
+    // hidden layer (2.1 k cycles of MMAs) of the other.
+    const long long n_it = (n_tiles - pair + 2LL * npairs - 1) / (2LL * npairs);   // iterations of this pair
+    if (n_it > 0) {
+      step(I0{}, I0{});
+      step(I0{}, I1{});
+    }
+    for (long long it = 0; it < n_it; ++it) {
+      const bool more = it + 1 < n_it;
+      step(I0{}, I2{}); step(I1{}, I0{});
+      step(I0{}, I3{}); step(I1{}, I1{});
+      if (more) step(I0{}, I0{});
+      step(I1{}, I2{});
+      if (more) step(I0{}, I1{});
+      step(I1{}, I3{});
     }
     PROF_ADD(2);
     PROF_FLUSH(a, MMA_WARP);
