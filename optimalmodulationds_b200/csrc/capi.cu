@@ -203,6 +203,7 @@ int dsmppi_ctx_create(dsmppi_ctx** out, const dsmppi_net* net, const float* dh_p
   if (exact_set_attributes()) { delete c; return 1; }
   if (tc_build_images(c, net)) { delete c; return 1; }
   if (tcx_build_images(c, net)) { delete c; return 1; }
+  if (const char* e = std::getenv("DSMPPI_HALF_TILES")) c->half_tiles = std::atoi(e) != 0;
   c->upd_blocks = c->sm_count * 4;       // update_partial_kernel: four 256-thread CTAs per SM (56 registers per thread)
   CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c->upd_partials),
                       (size_t)c->upd_blocks * dsmppi_update_packed_len(NKMAX, MAXD) * sizeof(float)));

@@ -98,6 +98,7 @@ struct dsmppi_ctx {
   size_t cand_rows_want = 0;          // row-list capacity asked for after a rollout ran out of candidate rows
   int* counters_host = nullptr;       // pinned mirror of `counters` for the end-of-rollout exactness check
   int obs_tables_dirty = 1;           // c->obs changed since tc_set_obstacles built the per-obstacle layer-1 table
+  int half_tiles = 1;                 // whole-horizon tensor-core rollout: 64-row tiles while one wave covers the batch
   int table_valid = 0;                // c->enc_q holds the layer-1 table of the states the next prefilter launch scores
   int prefilter_used = 0;             // set by distance_pipeline when a call went through the tensor-core prefilter
   int64_t capacity_retries = 0;       // rollouts that were run again with a larger candidate row list

@@ -288,22 +288,40 @@ __device__ __forceinline__ void bwd_chunk32(const uint32_t (&r1)[32], const uint
   }
 }
 // 32 converted columns -> four 8-column chunks (ch0 ..) of this thread's row in the two A images
+template <uint32_t LBO>
 __device__ __forceinline__ void store_chunk32(uint8_t* a_hi, uint8_t* a_lo, int ch0, const uint32_t (&hw)[16],
                                               const uint32_t (&lw)[16]) {
 #pragma unroll
   for (int j8 = 0; j8 < 4; ++j8) {
-    *reinterpret_cast<uint4*>(a_hi + (ch0 + j8) * A_LBO) = make_uint4(hw[4 * j8], hw[4 * j8 + 1], hw[4 * j8 + 2], hw[4 * j8 + 3]);
-    *reinterpret_cast<uint4*>(a_lo + (ch0 + j8) * A_LBO) = make_uint4(lw[4 * j8], lw[4 * j8 + 1], lw[4 * j8 + 2], lw[4 * j8 + 3]);
+    *reinterpret_cast<uint4*>(a_hi + (ch0 + j8) * LBO) = make_uint4(hw[4 * j8], hw[4 * j8 + 1], hw[4 * j8 + 2], hw[4 * j8 + 3]);
+    *reinterpret_cast<uint4*>(a_lo + (ch0 + j8) * LBO) = make_uint4(lw[4 * j8], lw[4 * j8 + 1], lw[4 * j8 + 2], lw[4 * j8 + 3]);
   }
 }
 
 // MODE 0: forward only, 1: forward + VJP on a list of rows, 2: whole-horizon rollout (forward + VJP + ranking + step, H times)
-template <int MODE>
+//
+// HM ("half M"): the MMAs run with M = 128 over the CTA pair -- 64 rows per CTA -- instead of 256.  tcgen05's issue
+// floor is max(M, 128) N / 512 cycles per K = 16 step at cta_group::2, so a half tile takes half the tensor-pipe time
+// (tools/tcx_m128_microbench.cu: 3076 instead of 6148 cycles per split K = 256 layer), and each epilogue thread has
+// half the columns: a rollout that is latency-bound on ONE tile per step (planar robots, the control tick, the
+// planner's 40 samples) steps in little more than half the time, on twice the CTA pairs.  The accumulator of an
+// M = 128 pair MMA uses the "2 x 2" layout: TMEM lanes 0-63 hold the CTA's 64 rows x the first N / 2 columns, lanes
+// 64-127 the same rows x the second N / 2 -- which are the output features of CTA rank 0's / rank 1's half of B.  So a
+// row has FOUR epilogue threads (lane half fb = feature block, warp half h = 32-column chunk) instead of two, each
+// hands over ONE 32-column chunk per N half, and K quarter 2 x + fb of the next operand is complete after 8 (not 16)
+// warp arrivals.  Everything else -- weight images, stage order, arithmetic per element -- is the same, so HM results
+// are bitwise equal to the full-tile kernel.
+template <int MODE, bool HM = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_exact_kernel(TxArgs a) {
   constexpr bool BWD = MODE >= 1;
+  constexpr int RPC = HM ? 64 : TROWS;                 // rows per CTA per tile
+  constexpr uint32_t ALBO = RPC * 16;                  // bytes between consecutive 8-element K chunks of the A images
+  constexpr uint32_t DHALF = HM ? 64 : 128;            // TMEM columns of one N = 128 accumulator half
+  constexpr uint32_t D2B = HM ? 128 : 256;             // first TMEM column of D2
+  static_assert(!HM || MODE == 2, "half tiles are built for the whole-horizon mode");
   extern __shared__ __align__(1024) uint8_t smem[];
   const int n_rows = MODE == 2 ? a.sa.N * a.M : (a.src.n_rows_dev ? min(*a.src.n_rows_dev, a.src.n_rows) : a.src.n_rows);
-  const int n_tiles = MODE == 2 ? (a.sa.N + 2 * a.S - 1) / (2 * a.S) : (n_rows + 2 * TROWS - 1) / (2 * TROWS);
+  const int n_tiles = MODE == 2 ? (a.sa.N + 2 * a.S - 1) / (2 * a.S) : (n_rows + 2 * RPC - 1) / (2 * RPC);
   const int n_steps = MODE == 2 ? a.sa.H : 1;
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
   if (pair >= n_tiles) return;               // both CTAs of the pair leave together, before any allocation
@@ -329,7 +347,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_exac
         mbar_init(BAR(BAR_PEER + s), 1);     // leader only: the peer's relay
         mbar_init(BAR(BAR_EMPTY + s), 1);    // tcgen05.commit
       }
-      for (int q = 0; q < 4; ++q) mbar_init(BAR(BAR_AREADY0 + q), 16);   // leader only: 8 epilogue warps x 2 CTAs
+      // leader only: 8 epilogue warps x 2 CTAs (half tiles: the 4 warps of the quarter's feature block x 2 CTAs)
+      for (int q = 0; q < 4; ++q) mbar_init(BAR(BAR_AREADY0 + q), HM ? 8 : 16);
       mbar_init(BAR(BAR_DFULL0), 1);         // tcgen05.commit
       mbar_init(BAR(BAR_DFULL1), 1);
       mbar_init(BAR(BAR_AFREE), 1);
@@ -348,7 +367,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_exac
     // =================================== epilogue warps ===================================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(EPI_REGS));
     const int q4 = warp & 3, h = warp >> 2;
-    const int row = q4 * 32 + lane;                         // row within the CTA's 128 == TMEM lane
+    const int fb = HM ? (q4 >> 1) : 0;                      // half tiles: which 64-feature block of an N half
+    const int row = HM ? ((q4 & 1) * 32 + lane) : (q4 * 32 + lane);   // row within the CTA's tile (full tiles: == TMEM lane)
     const uint32_t tD = tmem_base + ((uint32_t)(q4 * 32) << 16);
     uint8_t* a_hi = smem + OFF_AHI + row * 16;
     uint8_t* a_lo = smem + OFF_ALO + row * 16;
@@ -393,6 +413,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_exac
     bool en_valid = false;
     auto enc_compute = [&](int i, int j, bool valid, const float* qsrc, int qstride) {
       en_i = i; en_j = j; en_valid = valid; en_range = 0;
+      if (HM && fb != 0) return;                            // a row's encoding is written by its fb == 0 threads
       auto prep = [&](float v) -> uint32_t {                // saturating like split8, and range-checked
         const uint32_t hh = pack_h2(v, 0.f);
         const uint32_t ll = pack_h2((v - unpack_h2(hh).x) * SPLIT, 0.f);
@@ -431,8 +452,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_exac
       }
     };
     auto enc_store = [&]() {
+      if (HM && fb != 0) return;
       auto st = [&](int e, uint32_t v) {
-        const int off = (e >> 3) * A_LBO + (e & 7) * 2;
+        const int off = (e >> 3) * ALBO + (e & 7) * 2;
         *reinterpret_cast<uint16_t*>(a_hi + off) = (uint16_t)v;
         *reinterpret_cast<uint16_t*>(a_lo + off) = (uint16_t)(v >> 16);
       };
@@ -451,7 +473,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_exac
     bool nx_valid = false;
     auto lookup_tile = [&](int tl) {
       if (tl < n_tiles) {
-        nx_valid = row_lookup(a.src, tl * (2 * TROWS) + (int)rank * TROWS + row, n_rows, nx_i, nx_j);
+        nx_valid = row_lookup(a.src, tl * (2 * RPC) + (int)rank * RPC + row, n_rows, nx_i, nx_j);
         if (nx_valid) {
           asm volatile("prefetch.global.L1 [%0];" ::"l"(a.q + (size_t)nx_i * a.q_stride));
           asm volatile("prefetch.global.L1 [%0];" ::"l"(a.obs + nx_j * 4));
@@ -471,7 +493,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_exac
     for (int tile = pair; tile < n_tiles; tile += npairs)
     for (int t = 1; t <= n_steps; ++t, ++pass) {
       // global row of this thread: consecutive rows of the list, or (whole-horizon) row j of sample i = dense row i * M + j
-      int grow = tile * (2 * TROWS) + (int)rank * TROWS + row;
+      int grow = tile * (2 * RPC) + (int)rank * RPC + row;
       const float* qsrc = MODE == 2 ? a.sa.traj + (size_t)(t - 1) * d : a.q;     // q_prev = all_traj[:, t-1, :]
       const int qstride = MODE == 2 ? a.sa.H * d : a.q_stride;
       float* stg = reinterpret_cast<float*>(smem + OFF_STAGE);
@@ -499,10 +521,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_exac
       uint32_t range = en_range;                            // largest fp16 magnitude written to the A operand
       const int row_i = en_i, row_j = en_j;
       int* ovf = reinterpret_cast<int*>(smem + OFF_OVF);
-      if (h == 0) ovf[row] = 0;
+      if (h == 0 && fb == 0) ovf[row] = 0;
       if (MODE == 2 || !enc_stored) {                       // otherwise stored at the end of the previous tile
         enc_store();
-        signal_a(0);
+        if (!HM || fb == 0) signal_a(0);                    // (K = 32 operand: quarter 0 only)
       }
       if (q4 == 0) TCX_PROF(h, 1);
       // this row's results stay in registers until the tile's last hand-over is out: a global store ahead of a
@@ -516,6 +538,34 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_exac
       for (int l = 0; l < 4; ++l) {
         const float* bl = net.b[l] + cb;
         const float comp = (a.dbg & 4) ? 0.f : (l == 0 ? COMP_K32 : COMP_K256);
+        if constexpr (HM) {
+          // one 32-column chunk per N half: features 128 x + 64 fb + 32 h + [0, 32) -> K quarter 2 x + fb
+          wait_d0();
+          {
+            uint32_t hh0[16], hl0[16];
+            {
+              uint32_t r1[32], r2[32];
+              tmem_ld32(tD + cb, r1);
+              tmem_ld32(tD + D2B + cb, r2);
+              tc_wait_ld();
+              mk[l][0] = fwd_chunk32(r1, r2, bl + 64 * fb, comp, hh0, hl0, range);
+            }
+            wait_afree();
+            store_chunk32<ALBO>(a_hi, a_lo, 8 * fb + 4 * h, hh0, hl0);
+            signal_a(fb);
+          }
+          wait_d1();
+          {
+            uint32_t r1[32], r2[32], hw[16], lw[16];
+            tmem_ld32(tD + DHALF + cb, r1);
+            tmem_ld32(tD + D2B + DHALF + cb, r2);
+            tc_wait_ld();
+            mk[l][1] = fwd_chunk32(r1, r2, bl + 128 + 64 * fb, comp, hw, lw, range);
+            store_chunk32<ALBO>(a_hi, a_lo, 16 + 8 * fb + 4 * h, hw, lw);
+          }
+          signal_a(2 + fb);
+          continue;
+        }
         wait_d0();
         if (q4 == 0) TCX_PROF(h, 10 + l);
         {
@@ -533,9 +583,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_exac
           }
           if (q4 == 0) TCX_PROF(h, 20 + l);
           wait_afree();
-          store_chunk32(a_hi, a_lo, 4 * h, hh0, hl0);
+          store_chunk32<ALBO>(a_hi, a_lo, 4 * h, hh0, hl0);
           signal_a(0);
-          store_chunk32(a_hi, a_lo, 8 + 4 * h, hh1, hl1);
+          store_chunk32<ALBO>(a_hi, a_lo, 8 + 4 * h, hh1, hl1);
           signal_a(1);
         }
         if (q4 == 0) TCX_PROF(h, 40 + l);
@@ -549,11 +599,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_exac
           tmem_ld32(tD + 192 + cb, r1[1]);
           tmem_ld32(tD + 448 + cb, r2[1]);
           mk[l][2] = fwd_chunk32(r1[0], r2[0], bl + 128, comp, hw, lw, range);
-          store_chunk32(a_hi, a_lo, 16 + 4 * h, hw, lw);
+          store_chunk32<ALBO>(a_hi, a_lo, 16 + 4 * h, hw, lw);
           signal_a(2);
           tc_wait_ld();
           mk[l][3] = fwd_chunk32(r1[1], r2[1], bl + 192, comp, hw, lw, range);
-          store_chunk32(a_hi, a_lo, 24 + 4 * h, hw, lw);
+          store_chunk32<ALBO>(a_hi, a_lo, 24 + 4 * h, hw, lw);
         }
         signal_a(3);
         if (q4 == 0) TCX_PROF(h, 50 + l);
@@ -566,10 +616,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_exac
       // ---- output layer (no activation): links 0..15 sit in D columns 0..15
       wait_d0();
       if (q4 == 0) TCX_PROF(h, 60);
-      if (h == 0) {
+      if (h == 0 && fb == 0) {
         uint32_t r1[16], r2[16];
         tmem_ld16(tD, r1);
-        tmem_ld16(tD + 256, r2);
+        tmem_ld16(tD + D2B, r2);
         tc_wait_ld();
         if (q4 == 0) TCX_PROF(h, 64);
         // straight-line and branch-free: the same operations on every link, the unused ones masked by o < O
@@ -617,6 +667,38 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_exac
           const int ls = lst[row];
           const uint32_t slot4 = (pass * (uint32_t)NST + 14u) % NSLOT;
           const uint8_t* wrow = smem + OFF_RING + slot4 * SLOT_BYTES + ls * 16;
+          if constexpr (HM) {
+            // this thread's two chunks: K quarters fb and 2 + fb (the columns whose ReLU bits it holds in mk[3][0 / 1])
+            uint4 whi[8], wlo[8];
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc)
+#pragma unroll
+              for (int j8 = 0; j8 < 4; ++j8) {
+                const int ch = 8 * (2 * cc + fb) + 4 * h + j8;
+                whi[4 * cc + j8] = *reinterpret_cast<const uint4*>(wrow + ch * 256);
+                wlo[4 * cc + j8] = *reinterpret_cast<const uint4*>(wrow + 8192 + ch * 256);
+              }
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc) {
+              const int c = 2 * cc + fb;
+              const uint32_t bits = mk[3][cc];
+#pragma unroll
+              for (int j8 = 0; j8 < 4; ++j8) {
+                const int ch = 8 * c + 4 * h + j8;
+                uint4 hi = whi[4 * cc + j8], lo = wlo[4 * cc + j8];
+                const uint32_t on = ~(bits >> (24 - 8 * j8));
+                const uint32_t m0 = ((on >> 7) & 1u) * 0xffffu + ((on >> 6) & 1u) * 0xffff0000u;
+                const uint32_t m1 = ((on >> 5) & 1u) * 0xffffu + ((on >> 4) & 1u) * 0xffff0000u;
+                const uint32_t m2 = ((on >> 3) & 1u) * 0xffffu + ((on >> 2) & 1u) * 0xffff0000u;
+                const uint32_t m3 = ((on >> 1) & 1u) * 0xffffu + (on & 1u) * 0xffff0000u;
+                hi.x &= m0; hi.y &= m1; hi.z &= m2; hi.w &= m3;
+                lo.x &= m0; lo.y &= m1; lo.z &= m2; lo.w &= m3;
+                *reinterpret_cast<uint4*>(a_hi + ch * ALBO) = hi;
+                *reinterpret_cast<uint4*>(a_lo + ch * ALBO) = lo;
+              }
+              signal_a(c);
+            }
+          } else {
           uint4 whi[16], wlo[16];
 #pragma unroll
           for (int c = 0; c < 4; ++c)
@@ -641,19 +723,47 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_exac
               const uint32_t m3 = ((on >> 1) & 1u) * 0xffffu + (on & 1u) * 0xffff0000u;
               hi.x &= m0; hi.y &= m1; hi.z &= m2; hi.w &= m3;
               lo.x &= m0; lo.y &= m1; lo.z &= m2; lo.w &= m3;
-              *reinterpret_cast<uint4*>(a_hi + ch * A_LBO) = hi;
-              *reinterpret_cast<uint4*>(a_lo + ch * A_LBO) = lo;
+              *reinterpret_cast<uint4*>(a_hi + ch * ALBO) = hi;
+              *reinterpret_cast<uint4*>(a_lo + ch * ALBO) = lo;
             }
             signal_a(c);
             if (q4 == 0 && c == 0) TCX_PROF(h, 68);
           }
         }
+          }
         if (q4 == 0) TCX_PROF(h, 61);
 
         // ---- g_{l-1} = (W_l^T g_l) * s_{l-1},  l = 3, 2, 1 (same half-by-half schedule as the forward layers)
 #pragma unroll 1
         for (int l = 3; l >= 1; --l) {
           const float comp = (a.dbg & 4) ? 0.f : COMP_K256;
+          if constexpr (HM) {
+            wait_d0();
+            {
+              uint32_t hh0[16], hl0[16];
+              {
+                uint32_t r1[32], r2[32];
+                tmem_ld32(tD + cb, r1);
+                tmem_ld32(tD + D2B + cb, r2);
+                tc_wait_ld();
+                bwd_chunk32(r1, r2, mk[l - 1][0], comp, hh0, hl0, range);
+              }
+              wait_afree();
+              store_chunk32<ALBO>(a_hi, a_lo, 8 * fb + 4 * h, hh0, hl0);
+              signal_a(fb);
+            }
+            wait_d1();
+            {
+              uint32_t r1[32], r2[32], hw[16], lw[16];
+              tmem_ld32(tD + DHALF + cb, r1);
+              tmem_ld32(tD + D2B + DHALF + cb, r2);
+              tc_wait_ld();
+              bwd_chunk32(r1, r2, mk[l - 1][1], comp, hw, lw, range);
+              store_chunk32<ALBO>(a_hi, a_lo, 16 + 8 * fb + 4 * h, hw, lw);
+            }
+            signal_a(2 + fb);
+            continue;
+          }
           wait_d0();
           if (q4 == 0) TCX_PROF(h, 14 + l);
           {
@@ -671,9 +781,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_exac
             }
             if (q4 == 0) TCX_PROF(h, 24 + l);
             wait_afree();
-            store_chunk32(a_hi, a_lo, 4 * h, hh0, hl0);
+            store_chunk32<ALBO>(a_hi, a_lo, 4 * h, hh0, hl0);
             signal_a(0);
-            store_chunk32(a_hi, a_lo, 8 + 4 * h, hh1, hl1);
+            store_chunk32<ALBO>(a_hi, a_lo, 8 + 4 * h, hh1, hl1);
             signal_a(1);
           }
           if (q4 == 0) TCX_PROF(h, 44 + l);
@@ -687,11 +797,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_exac
             tmem_ld32(tD + 192 + cb, r1[1]);
             tmem_ld32(tD + 448 + cb, r2[1]);
             bwd_chunk32(r1[0], r2[0], mk[l - 1][2], comp, hw, lw, range);
-            store_chunk32(a_hi, a_lo, 16 + 4 * h, hw, lw);
+            store_chunk32<ALBO>(a_hi, a_lo, 16 + 4 * h, hw, lw);
             signal_a(2);
             tc_wait_ld();
             bwd_chunk32(r1[1], r2[1], mk[l - 1][3], comp, hw, lw, range);
-            store_chunk32(a_hi, a_lo, 24 + 4 * h, hw, lw);
+            store_chunk32<ALBO>(a_hi, a_lo, 24 + 4 * h, hw, lw);
           }
           signal_a(3);
           if (q4 == 0) TCX_PROF(h, 54 + l);
@@ -701,7 +811,26 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_exac
         // ---- a = W_1^T g_1 (N = 32), then the encoding Jacobian dz/dx_c = a[c] + cos(x_c) a[nin+c] - sin(x_c) a[2nin+c]
         wait_d0();
         if (q4 == 0) TCX_PROF(h, 62);
-        if (h == 0) {
+        if constexpr (HM) {
+          // N = 32 over the pair: a[0..15] (rank 0's rows of B) sit on lanes 0-63, a[16..31] on lanes 64-127 -- the
+          // row's two h == 0 threads each put their sixteen into the scratch, then the fb == 0 one applies the Jacobian
+          if (h == 0) {
+            uint32_t r1[16], r2[16];
+            tmem_ld16(tD, r1);
+            tmem_ld16(tD + D2B, r2);
+            tc_wait_ld();
+            float* scr = reinterpret_cast<float*>(smem + OFF_SCRATCH) + row;
+#pragma unroll
+            for (int e = 0; e < 16; ++e) scr[(16 * fb + e) * TROWS] = combine(r1[e], r2[e], (a.dbg & 4) ? 0.f : COMP_K256);
+          }
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          if (h == 0 && fb == 0) {
+            const float* scr = reinterpret_cast<const float*>(smem + OFF_SCRATCH) + row;
+#pragma unroll
+            for (int c = 0; c < MAXD; ++c)
+              if (c < d) o_g[c] = scr[c * TROWS] + cs[c] * scr[(nin + c) * TROWS] - sn[c] * scr[(2 * nin + c) * TROWS];
+          }
+        } else if (h == 0) {
           uint32_t r1[32], r2[32];
           tmem_ld32(tD, r1);
           tmem_ld32(tD + 256, r2);
@@ -728,7 +857,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_exac
       } else {
         enc_stored = false;
       }
-      if ((TCX_DEFER_STG || MODE == 2) && h == 0 && grow < n_rows) {
+      if ((TCX_DEFER_STG || MODE == 2) && h == 0 && fb == 0 && grow < n_rows) {
         if (out_m) out_m[orow] = o_m;
         if (BWD) {
           out_dist[orow] = o_dist;
@@ -744,7 +873,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_exac
       int* fixl = reinterpret_cast<int*>(smem + OFF_FIXL);
       if (MODE == 2 && tid == 0) *fixn = 0;
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (h == 0 && grow < n_rows && ovf[row]) {
+      if (h == 0 && fb == 0 && grow < n_rows && ovf[row]) {
         if (MODE != 2) {                       // device-wide list, re-scored by launch_exact_fixup after this kernel
           const int k = atomicAdd(a.fix_count, 1);
           atomicAdd(a.fix_total, 1);
@@ -870,20 +999,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_exac
       }
   } else if (warp == W_MMA) {
     // =================================== MMA issuer (leader CTA) ===================================
-    constexpr uint32_t idesc128 = make_idesc_f16(256, 128), idesc32 = make_idesc_f16(256, 32);
+    constexpr uint32_t idesc128 = make_idesc_f16(HM ? 128 : 256, 128), idesc32 = make_idesc_f16(HM ? 128 : 256, 32);
     const uint32_t a_hi = sbase + OFF_AHI, a_lo = sbase + OFF_ALO;
     uint32_t slot = 0, par = 0;                               // ring position of the next weight stage
     uint32_t acount[4] = {0, 0, 0, 0};                        // phases consumed of the four operand-quarter barriers
     uint32_t adh, adl, bdh, bdl, b_step, d1, d2, idesc;       // the open stage: operand descriptors (low words)
-    constexpr uint32_t a_step = (2 * A_LBO) >> 4;             // one K = 16 step of the A images
+    constexpr uint32_t a_step = (2 * ALBO) >> 4;              // one K = 16 step of the A images
     // open a weight stage: its descriptors, then "weights landed in both CTAs" -- all of it before the operand wait, so
     // that nothing but the MMAs themselves follows the moment the epilogue hands a K quarter over
     auto open_stage = [&](uint32_t d_col, uint32_t a_off, uint32_t b_lbo, uint32_t lo_off, uint32_t id) {
       const uint32_t b_base = sbase + OFF_RING + slot * SLOT_BYTES;
-      adh = make_desc_lo(a_hi + a_off, A_LBO); adl = make_desc_lo(a_lo + a_off, A_LBO);
+      adh = make_desc_lo(a_hi + a_off, ALBO); adl = make_desc_lo(a_lo + a_off, ALBO);
       bdh = make_desc_lo(b_base, b_lbo); bdl = make_desc_lo(b_base + lo_off, b_lbo);
       b_step = (2 * b_lbo) >> 4;
-      d1 = tmem_base + d_col; d2 = tmem_base + 256 + d_col;
+      d1 = tmem_base + d_col; d2 = tmem_base + D2B + d_col;
       idesc = id;
       mbar_wait(BAR(BAR_FULL + slot), par);
       mbar_wait_cluster(BAR(BAR_PEER + slot), par);
@@ -918,7 +1047,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_exac
       __syncwarp();
       if (++slot == NSLOT) { slot = 0; par ^= 1; }
     };
-    constexpr uint32_t KHALF = 8 * 2 * A_LBO;                 // byte offset of K = 128 in the A images
+    constexpr uint32_t KHALF = 8 * 2 * ALBO;                  // byte offset of K = 128 in the A images
     for (int tile = pair; tile < n_tiles; tile += npairs)
     for (int t = 1; t <= n_steps; ++t) {
 #pragma unroll 1
@@ -928,7 +1057,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_exac
           wait_a(0);
           steps(2, true);
           close_stage(0);
-          open_stage(128, 0, 64 * 16, 4096, idesc128);
+          open_stage(DHALF, 0, 64 * 16, 4096, idesc128);
           steps(2, true);
           if (elect_one()) mma_commit_2cta(BAR(BAR_AFREE));
           __syncwarp();
@@ -947,24 +1076,29 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_exac
           // columns N half 1 of this layer then overwrites
           open_stage(0, 0, 64 * 16, 16384, idesc128);
           wait_a(0);
-          if (g == 5) {                        // every seed thread has read W5's rows: hand the slot back in both CTAs
+          auto release_held = [&]() {          // every seed thread has read W5's rows: hand the slot back in both CTAs
             if (lane == 0) {
               mbar_arrive_remote(BAR(BAR_EMPTY + held_slot), 0);
               mbar_arrive_remote(BAR(BAR_EMPTY + held_slot), 1);
             }
             __syncwarp();
-          }
+          };
+          if (g == 5 && !HM) release_held();
           steps(4, true);
-          wait_a(1); steps(4, false);
+          wait_a(1);
+          // (half tiles: quarter 0 is signalled by the fb == 0 warps only; the fb == 1 warps have read their rows of W5
+          // once quarter 1 is in as well)
+          if (g == 5 && HM) release_held();
+          steps(4, false);
           close_stage(-1);
           open_stage(0, KHALF, 64 * 16, 16384, idesc128);
           wait_a(2); steps(4, false);
           wait_a(3); steps(4, false);
           close_stage(0);
-          open_stage(128, 0, 64 * 16, 16384, idesc128);
+          open_stage(DHALF, 0, 64 * 16, 16384, idesc128);
           steps(8, true);
           close_stage(2);
-          open_stage(128, KHALF, 64 * 16, 16384, idesc128);
+          open_stage(DHALF, KHALF, 64 * 16, 16384, idesc128);
           steps(8, false);
           close_stage(1);
         }
@@ -1069,6 +1203,7 @@ int tcx_build_images(dsmppi_ctx* c, const dsmppi_net* net) {
   CUDA_TRY(cudaFuncSetAttribute(tc_exact_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(tc_exact_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(tc_exact_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  CUDA_TRY(cudaFuncSetAttribute(tc_exact_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   return 0;
 }
 
@@ -1172,7 +1307,12 @@ int launch_tc_rollout(dsmppi_ctx* c, const dsmppi_rollout_args* ra, cudaStream_t
   a.ignore_mask = ra->ignored_link_mask;
   a.sa = make_step_args(c, ra, 0);
   a.M = c->M;
-  a.S = TROWS / c->M;
+  // Half tiles (64 rows per CTA, tc_exact_kernel<2, true>) while they still cover the batch in one wave of CTA pairs:
+  // the rollout is then latency-bound on one tile per step, and a half tile takes about half the time.
+  const long long pairs_all = c->sm_count / 2;
+  const int s_half = c->M <= 64 ? 64 / c->M : 0;
+  const bool half_tiles = c->half_tiles && s_half >= 1 && ((long long)ra->N + 2 * s_half - 1) / (2 * s_half) <= pairs_all;
+  a.S = half_tiles ? s_half : TROWS / c->M;
   a.m_rows = c->m_rows;
   a.row_dist = c->row_dist;
   a.row_grad = c->row_grad;
@@ -1202,7 +1342,8 @@ int launch_tc_rollout(dsmppi_ctx* c, const dsmppi_rollout_args* ra, cudaStream_t
   long long pairs = c->sm_count / 2;
   if (pairs > tiles) pairs = tiles;
   if (pairs < 1) pairs = 1;
-  tc_exact_kernel<2><<<dim3((unsigned)(2 * pairs)), NTHREADS, SMEM_BYTES, st>>>(a);
+  if (half_tiles) tc_exact_kernel<2, true><<<dim3((unsigned)(2 * pairs)), NTHREADS, SMEM_BYTES, st>>>(a);
+  else tc_exact_kernel<2><<<dim3((unsigned)(2 * pairs)), NTHREADS, SMEM_BYTES, st>>>(a);
   CUDA_TRY(cudaGetLastError());
   c->launches++;
 #ifdef DSMPPI_TCX_PROF
