@@ -314,6 +314,36 @@ typedef struct {
 } dsmppi_iteration_host_args;
 int dsmppi_iteration_host(dsmppi_ctx* ctx, dsmppi_iteration_host_args* args, void* stream);
 
+/* One control tick with HOST buffers as ONE replayed CUDA graph (frankaIntegrator.py:101-121: update_obstacles,
+ * propagate with one sample and two steps, every tick; frankaPlanner.py's 40 x 10 rollouts fit too).  At such sizes the
+ * rollout is a single ~0.1 ms launch and the tick is spent around it, so the whole sequence -- H2D of the state, the
+ * obstacles and the FULL (N, 50, ..) policy rows from one pinned staging block, dsmppi_set_obstacles, dsmppi_rollout,
+ * D2H of every output into one pinned block -- is captured once per parameter set and then costs one cudaGraphLaunch
+ * and one synchronisation.  Kernel arguments are baked into a graph: it is re-captured when any scalar of `rollout`,
+ * N, H or n_obs differs from the captured one.  Only for obstacle sets that take the dense fp32 scoring path (the
+ * prefilter path ends with a host-side exactness verdict): returns an error otherwise, as it does on a SEDS nominal DS.
+ * Runs on an internal stream ordered after `stream`; synchronises before returning. */
+typedef struct {
+  dsmppi_rollout_args rollout;   /* the *_dev fields are ignored; shapes and scalars are used            */
+  int32_t n_obs;                 /* M                                                                    */
+  int32_t reserved;
+  const float* q_cur_host;       /* (d,) or (N, d)                                                       */
+  const float* obs_host;         /* (M, P + 1)                                                           */
+  const float* mu_tmp_host;      /* (N, 50, d) or NULL when n_kernels == 0                               */
+  const float* sigma_tmp_host;   /* (N, 50)                                                              */
+  const float* alpha_tmp_host;   /* (N, 50, d)                                                           */
+  float* all_traj_host;          /* (N, H, d)                                                            */
+  float* closest_dist_all_host;  /* (N, H)                                                               */
+  float* kernel_val_all_host;    /* (N, H, 50): dead columns are written as zeros                        */
+  float* dot_products_host;      /* (N, H)                                                               */
+  float* kernel_activations_host;/* (N, H)                                                               */
+  float* qdot_host;              /* (N, d)                                                               */
+  float* nn_grad_all_host;       /* (N, H, d)                                                            */
+  int32_t recaptured;            /* filled in: 1 when this call had to (re)capture the graph             */
+  int32_t reserved2;
+} dsmppi_tick_args;
+int dsmppi_tick(dsmppi_ctx* ctx, dsmppi_tick_args* args, void* stream);
+
 /* Introspection used by bench.py / tests: launches issued by the library since ctx creation, pass-1
  * statistics of the last rollout (re-scored pairs; `band_overflows` = sample-steps whose guard band held more than
  * 16 obstacles -- informational: they all get a row), and the resolved pass-1 mode. */

@@ -363,12 +363,12 @@ class MPPI:
     # The integrator process calls propagate() with ONE sample and TWO steps every control tick, on CPU tensors
     # (frankaIntegrator.py:101-121).  At that size the rollout itself is one ~90 us launch and the tick is spent in
     # the wrapper: seven allocations, four uploads, the ctypes call, six downloads (each a stream synchronisation).
-    # For small batches of CPU-tensor callers the whole tick -- upload of the state, the live policy columns and the
-    # obstacles from pinned staging buffers, the library's launch sequence, download of every output -- is captured
-    # ONCE into a CUDA graph and replayed: one cudaGraphLaunch and one synchronisation per tick.  Kernel arguments are
-    # baked into a graph, so it is keyed by the bytes of the argument block (time step, thresholds, goal, n_kernels,
-    # obstacle count, ...) and re-captured when a script changes any of them; results are those of the normal path
-    # bit for bit (the same launches).  DSMPPI_GRAPH_TICK=0 disables it.
+    # For small batches of CPU-tensor callers the whole tick -- upload of the state, the policy rows and the obstacles
+    # from a pinned staging block, the library's launch sequence, download of every output -- is captured ONCE into a
+    # CUDA graph inside the library (dsmppi_tick) and replayed: one C call, one cudaGraphLaunch and one synchronisation
+    # per tick.  Kernel arguments are baked into a graph, so the library keys it by the bytes of the argument block
+    # (time step, thresholds, goal, n_kernels, obstacle count, ...) and re-captures when a script changes any of them;
+    # results are those of the normal path bit for bit (the same launches).  DSMPPI_GRAPH_TICK=0 disables it.
     _TICK_MAX_STATE_STEPS = 4096
 
     def _tick_eligible(self, q_cur):
@@ -384,117 +384,55 @@ class MPPI:
         return (isinstance(obs, torch.Tensor) and obs.dim() == 2 and obs.shape[1] == self._point_dim + 1
                 and obs.dtype == torch.float32 and q_cur.dtype == torch.float32)
 
-    def _tick_build(self, nk, q_batch):
-        """Staging for the current shapes: ONE pinned input block [q | obs | mu | sigma | alpha] and ONE output block
-        [all_traj | closest | dots | acts | qdot | grads | kval] on each side, so a tick moves two copies."""
-        N, H, d, K50 = self.N_traj, self.dt_H, self.n_dof, self.Policy.N_KERNEL_MAX
-        dev, M, P1 = self._dev, int(self.obs.shape[0]), self._point_dim + 1
-
-        def carve(total_buf, shapes):
-            out, off = {}, 0
-            for name, shape in shapes:
-                n = 1
-                for x in shape:
-                    n *= x
-                out[name] = total_buf[off:off + n].view(*shape)
-                off += (n + 3) // 4 * 4                       # 16-byte aligned pieces
-            return out
-
-        def total(shapes):
-            t = 0
-            for _, shape in shapes:
-                n = 1
-                for x in shape:
-                    n *= x
-                t += (n + 3) // 4 * 4
-            return t
-
-        in_shapes = [('q', (N, d) if q_batch else (d,)), ('obs', (M, P1)), ('mu', (N, K50, d)), ('sigma', (N, K50)),
-                     ('alpha', (N, K50, d))]
-        out_shapes = [('all_traj', (N, H, d)), ('closest', (N, H)), ('dots', (N, H)), ('acts', (N, H)), ('qdot', (N, d)),
-                      ('grads', (N, H, d)), ('kval', (N, H, K50))]
-        t = dict(nk=nk, M=M, q_batch=q_batch)
-        t['h_in_buf'] = torch.zeros(total(in_shapes)).pin_memory()
-        t['h_out_buf'] = torch.zeros(total(out_shapes)).pin_memory()
-        with torch.cuda.device(dev):
-            t['d_in_buf'] = torch.zeros(total(in_shapes), device=dev)
-            t['d_out_buf'] = torch.zeros(total(out_shapes), device=dev)
-        t['h_in'], t['d_in'] = carve(t['h_in_buf'], in_shapes), carve(t['d_in_buf'], in_shapes)
-        t['h_out'], t['d_out'] = carve(t['h_out_buf'], out_shapes), carve(t['d_out_buf'], out_shapes)
-        return t
-
-    def _tick_run(self, t):
-        """The launch sequence that gets captured (and is also run once, eagerly, as the capture's warm-up)."""
-        t['d_in_buf'].copy_(t['h_in_buf'], non_blocking=True)
-        st = self._stream()
-        _capi.check(self._lib.dsmppi_set_obstacles(self._ctx, t['d_in']['obs'].data_ptr(), t['M'], st))
-        _capi.check(self._lib.dsmppi_rollout(self._ctx, _capi.C.byref(t['args']), st))
-        t['h_out_buf'].copy_(t['d_out_buf'], non_blocking=True)
-
-    def _tick_key(self, nk):
+    def _tick_key(self, nk, q_batch):
         """Everything dsmppi_rollout_args bakes into the captured kernel arguments, cheaply (the argument block itself
-        is only rebuilt when this changes)."""
+        is only rebuilt when this changes; the library compares the block's bytes and re-captures its graph)."""
         DS = self.DS
         A = getattr(DS, 'A', None)
-        return (nk, int(self.n_closest_obs), self._ignore_mask(), float(self.dt), float(self.dst_thr),
+        return (nk, q_batch, int(self.n_closest_obs), self._ignore_mask(), float(self.dt), float(self.dst_thr),
                 float(self.Policy.p), type(DS), tuple(self._host_vec(DS.q_goal)), float(getattr(DS, 'lin_thr', 0.0)),
                 None if A is None else tuple(self._host_vec(A)))
 
     def _propagate_tick(self, q_cur_user, nk):
+        """propagate() of a small CPU-tensor batch through dsmppi_tick: one C call per tick."""
         N, H, d = self.N_traj, self.dt_H, self.n_dof
         P = self.Policy
         q_batch = q_cur_user.dim() == 2
+        key = self._tick_key(nk, q_batch)
         t = self.__dict__.get('_tick')
-        if t is None or t['nk'] != nk or t['M'] != int(self.obs.shape[0]) or t['q_batch'] != q_batch:
-            t = self._tick = self._tick_build(nk, q_batch)
-            t['key'] = None
-        hi = t['h_in']
-        hi['q'].copy_(q_cur_user)
-        hi['obs'].copy_(self.obs)
+        if t is None or t['key'] != key:
+            dummy = torch.empty(1, device=self._dev)
+            probe = torch.empty((N, d) if q_batch else (d,), device='meta')
+            out = {k: dummy for k in ('all_traj', 'closest', 'kval', 'dots', 'acts', 'qdot', 'grads')}
+            ta = _capi.TickArgs()
+            ta.rollout = self._rollout_args(N, H, nk, dummy, dummy, dummy, dummy, out)
+            ta.rollout.q_cur_is_batch = 1 if probe.dim() == 2 else 0
+            t = self._tick = dict(key=key, args=ta, keep=dummy)
+        ta = t['args']
+        obs = self.obs if self.obs.is_contiguous() else self.obs.contiguous()
+        q = q_cur_user if q_cur_user.is_contiguous() else q_cur_user.contiguous()
+        ta.n_obs = int(obs.shape[0])
+        ta.q_cur_host, ta.obs_host = q.data_ptr(), obs.data_ptr()
+        mu, sg, al = P.mu_tmp, P.sigma_tmp, P.alpha_tmp
         if nk > 0:
-            hi['mu'].copy_(P.mu_tmp); hi['sigma'].copy_(P.sigma_tmp); hi['alpha'].copy_(P.alpha_tmp)
-        key = self._tick_key(nk)
-        if key != t['key']:
-            with torch.cuda.device(self._dev):
-                di, do = t['d_in'], t['d_out']
-                t['args'] = self._rollout_args(N, H, nk, di['q'], di['mu'], di['sigma'], di['alpha'], do)
-                side = torch.cuda.Stream(self._dev)
-                side.wait_stream(torch.cuda.current_stream(self._dev))
-                with torch.cuda.stream(side):
-                    self._tick_run(t)                         # warm-up: sizes the library's workspace outside the capture
-                side.synchronize()
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, stream=side):
-                    self._tick_run(t)
-                t['graph'], t['key'] = g, key
-                t['done'] = torch.cuda.Event()
-        if torch.cuda.current_device() == self._dev.index:
-            t['graph'].replay()
-            t['done'].record()
-            t['done'].synchronize()
-        else:
-            with torch.cuda.device(self._dev):
-                t['graph'].replay()
-                t['done'].record()
-                t['done'].synchronize()
-        # fresh tensors every call, like the reference's reset_tensors (MPPI.py:86-91): one clone of the output block
-        blk = t['h_out_buf'].clone()
-        off = 0
-        outs = {}
-        for name, view in t['h_out'].items():
-            n = view.numel()
-            outs[name] = blk[off:off + n].view(view.shape)
-            off += (n + 3) // 4 * 4
+            if not (mu.is_contiguous() and sg.is_contiguous() and al.is_contiguous()):
+                mu, sg, al = mu.contiguous(), sg.contiguous(), al.contiguous()
+            ta.mu_tmp_host, ta.sigma_tmp_host, ta.alpha_tmp_host = mu.data_ptr(), sg.data_ptr(), al.data_ptr()
+        traj, closest, kv = torch.empty(N, H, d), torch.empty(N, H), torch.empty(N, H, P.N_KERNEL_MAX)
+        dots, acts, qdot, grads = torch.empty(N, H), torch.empty(N, H), torch.empty(N, d), torch.empty(N, H, d)
+        ta.all_traj_host, ta.closest_dist_all_host, ta.kernel_val_all_host = traj.data_ptr(), closest.data_ptr(), kv.data_ptr()
+        ta.dot_products_host, ta.kernel_activations_host = dots.data_ptr(), acts.data_ptr()
+        ta.qdot_host, ta.nn_grad_all_host = qdot.data_ptr(), grads.data_ptr()
+        _capi.check(self._lib.dsmppi_tick(self._ctx, _capi.C.byref(ta), self._stream()))
         self._mirror = {}
         self._obs_uploaded = None
         self._norm_basis = None
-        self._dev_last = dict(grads=None, grads_host=outs['grads'], nk=nk)   # (the graph's buffers are reused)
-        self.all_traj, self.closest_dist_all, self.kernel_val_all = outs['all_traj'], outs['closest'], outs['kval']
-        self.dot_products, self.kernel_activations, self.qdot = outs['dots'], outs['acts'], outs['qdot']
-        self.nn_grad = outs['grads'][:, H - 1, :]
-        self.ker_w = self.kernel_val_all[:, H - 1, :nk].unsqueeze(2)
-        return (self.all_traj, self.closest_dist_all, self.kernel_val_all[:, :, 0:nk], self.dot_products,
-                self.kernel_activations)
+        self._dev_last = dict(grads=None, grads_host=grads, nk=nk)
+        self.all_traj, self.closest_dist_all, self.kernel_val_all = traj, closest, kv
+        self.dot_products, self.kernel_activations, self.qdot = dots, acts, qdot
+        self.nn_grad = grads[:, H - 1, :]
+        self.ker_w = kv[:, H - 1, :nk].unsqueeze(2)
+        return (traj, closest, kv[:, :, 0:nk], dots, acts)
 
     def propagate(self):
         N, H, d = self.N_traj, self.dt_H, self.n_dof

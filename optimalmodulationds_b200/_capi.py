@@ -108,6 +108,16 @@ class IterationHostArgs(C.Structure):
     ]
 
 
+class TickArgs(C.Structure):
+    _fields_ = [
+        ("rollout", RolloutArgs), ("n_obs", C.c_int32), ("reserved", C.c_int32),
+        ("q_cur_host", _fp), ("obs_host", _fp), ("mu_tmp_host", _fp), ("sigma_tmp_host", _fp), ("alpha_tmp_host", _fp),
+        ("all_traj_host", _fp), ("closest_dist_all_host", _fp), ("kernel_val_all_host", _fp),
+        ("dot_products_host", _fp), ("kernel_activations_host", _fp), ("qdot_host", _fp), ("nn_grad_all_host", _fp),
+        ("recaptured", C.c_int32), ("reserved2", C.c_int32),
+    ]
+
+
 EXPORTS = {
     # name: (restype, argtypes)
     "dsmppi_last_error": (C.c_char_p, []),
@@ -134,6 +144,7 @@ EXPORTS = {
     "dsmppi_update_partial": (C.c_int, [C.c_void_p, C.POINTER(UpdateArgs), _fp, _fp, C.c_void_p]),
     "dsmppi_update_finalize": (C.c_int, [C.c_void_p, C.POINTER(UpdateArgs), _fp, _fp, C.c_void_p]),
     "dsmppi_iteration_host": (C.c_int, [C.c_void_p, C.POINTER(IterationHostArgs), C.c_void_p]),
+    "dsmppi_tick": (C.c_int, [C.c_void_p, C.POINTER(TickArgs), C.c_void_p]),
     "dsmppi_launch_count": (C.c_int64, [C.c_void_p]),
     "dsmppi_pass1_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int32),
                                      C.c_void_p]),

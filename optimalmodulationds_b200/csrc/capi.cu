@@ -111,6 +111,8 @@ int ensure_workspace(dsmppi_ctx* c, int n, int M) {
   return 0;
 }
 
+namespace { void tick_free(dsmppi_ctx* c); }
+
 extern "C" {
 
 const char* dsmppi_last_error(void) { return g_last_error.c_str(); }
@@ -231,6 +233,9 @@ int dsmppi_ctx_destroy(dsmppi_ctx* c) {
                   c->packed_tmp, c->stage};
   for (void* p : ptrs)
     if (p) cudaFree(p);
+  tick_free(c);
+  if (c->s_tick) cudaStreamDestroy(c->s_tick);
+  if (c->tick_ev) cudaEventDestroy(c->tick_ev);
   if (c->counters_host) cudaFreeHost(c->counters_host);
   for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
   for (cudaEvent_t e : c->pipe_ev) cudaEventDestroy(e);
@@ -975,3 +980,146 @@ int dsmppi_kernel_timing(dsmppi_ctx* c, double* pass1_ms, int32_t* pass1_n, doub
 }
 
 }  // extern "C"
+
+// ---- control tick ------------------------------------------------------------------------------------------------
+namespace {
+struct TickLayout {
+  size_t q, obs, mu, sg, al, in_total;
+  size_t tr, cd, dp, ka, qd, gr, kv, out_total;
+};
+TickLayout tick_layout(const dsmppi_ctx* c, const dsmppi_rollout_args& r, int M) {
+  TickLayout L{};
+  const size_t N = r.N, H = r.H, d = c->d, P1 = c->P + 1;
+  size_t off = 0;
+  auto take = [&](size_t n) { size_t o = off; off += (n + 3) / 4 * 4; return o; };
+  L.q = take(r.q_cur_is_batch ? N * d : d); L.obs = take((size_t)M * P1);
+  L.mu = take(N * NKMAX * d); L.sg = take(N * NKMAX); L.al = take(N * NKMAX * d);
+  L.in_total = off;
+  off = 0;
+  L.tr = take(N * H * d); L.cd = take(N * H); L.dp = take(N * H); L.ka = take(N * H); L.qd = take(N * d);
+  L.gr = take(N * H * d); L.kv = take(N * H * NKMAX);
+  L.out_total = off;
+  return L;
+}
+void tick_free(dsmppi_ctx* c) {
+  if (c->tick_exec) cudaGraphExecDestroy(c->tick_exec);
+  if (c->tick_graph) cudaGraphDestroy(c->tick_graph);
+  c->tick_exec = nullptr; c->tick_graph = nullptr;
+  if (c->tick_h_in) cudaFreeHost(c->tick_h_in);
+  if (c->tick_h_out) cudaFreeHost(c->tick_h_out);
+  if (c->tick_d_in) cudaFree(c->tick_d_in);
+  if (c->tick_d_out) cudaFree(c->tick_d_out);
+  c->tick_h_in = c->tick_h_out = c->tick_d_in = c->tick_d_out = nullptr;
+  c->tick_in_floats = c->tick_out_floats = 0;
+  c->tick_key.clear();
+}
+}  // namespace
+
+extern "C" int dsmppi_tick(dsmppi_ctx* c, dsmppi_tick_args* t, void* stream) {
+  REQUIRE(c && t, "null argument");
+  const dsmppi_rollout_args& r = t->rollout;
+  REQUIRE(r.N >= 1 && r.H >= 1 && t->n_obs >= 1, "N, H and n_obs must be positive");
+  REQUIRE(t->q_cur_host && t->obs_host && t->all_traj_host && t->closest_dist_all_host && t->kernel_val_all_host &&
+              t->dot_products_host && t->kernel_activations_host && t->qdot_host && t->nn_grad_all_host,
+          "null host pointer");
+  REQUIRE(r.n_kernels == 0 || (t->mu_tmp_host && t->sigma_tmp_host && t->alpha_tmp_host), "null policy pointer");
+  REQUIRE(r.mod.ds_kind != DSMPPI_DS_SEDS && r.distance_provider == DSMPPI_DISTANCE_NN,
+          "the graphed tick covers the linear / matrix nominal DS with the network distance");
+  CUDA_TRY(cudaSetDevice(c->device));
+  {   // the prefilter path cannot be captured (it ends with a host-side verdict)
+    const int saved = c->M;
+    c->M = t->n_obs;
+    const int mode = resolved_mode(c);
+    c->M = saved;
+    REQUIRE(mode == DSMPPI_PASS1_EXACT_FP32, "the graphed tick needs the dense fp32 scoring path (few obstacles)");
+  }
+  REQUIRE(!c->timing, "kernel timing events cannot be recorded into a graph");
+  cudaStream_t caller = static_cast<cudaStream_t>(stream);
+  if (!c->s_tick) {
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->s_tick, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&c->tick_ev, cudaEventDisableTiming));
+  }
+  const TickLayout L = tick_layout(c, r, t->n_obs);
+  const size_t d = c->d, N = r.N, H = r.H, P1 = c->P + 1;
+  // key: every scalar of the argument block (device pointers zeroed) + M
+  dsmppi_rollout_args k = r;
+  k.q_cur_dev = k.mu_tmp_dev = k.sigma_tmp_dev = k.alpha_tmp_dev = nullptr;
+  k.all_traj_dev = k.closest_dist_all_dev = k.kernel_val_all_dev = k.dot_products_dev = k.kernel_activations_dev = nullptr;
+  k.qdot_dev = k.nn_grad_all_dev = k.norm_basis_dev = nullptr;
+  std::vector<unsigned char> key(sizeof(k) + sizeof(int32_t) + 3 * sizeof(int));
+  std::memcpy(key.data(), &k, sizeof(k));
+  std::memcpy(key.data() + sizeof(k), &t->n_obs, sizeof(int32_t));
+  const int modes[3] = {c->pass1_mode, c->score_mode, c->fused_rollout};
+  std::memcpy(key.data() + sizeof(k) + sizeof(int32_t), modes, sizeof(modes));
+  const bool rebuild = !c->tick_exec || key != c->tick_key;
+  t->recaptured = rebuild ? 1 : 0;
+  if (rebuild) {
+    CUDA_TRY(cudaStreamSynchronize(c->s_tick));
+    if (L.in_total != c->tick_in_floats || L.out_total != c->tick_out_floats) {
+      tick_free(c);
+      CUDA_TRY(cudaMallocHost(reinterpret_cast<void**>(&c->tick_h_in), L.in_total * sizeof(float)));
+      CUDA_TRY(cudaMallocHost(reinterpret_cast<void**>(&c->tick_h_out), L.out_total * sizeof(float)));
+      CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c->tick_d_in), L.in_total * sizeof(float)));
+      CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c->tick_d_out), L.out_total * sizeof(float)));
+      std::memset(c->tick_h_in, 0, L.in_total * sizeof(float));
+      c->tick_in_floats = L.in_total; c->tick_out_floats = L.out_total;
+    } else {
+      if (c->tick_exec) cudaGraphExecDestroy(c->tick_exec);
+      if (c->tick_graph) cudaGraphDestroy(c->tick_graph);
+      c->tick_exec = nullptr; c->tick_graph = nullptr;
+    }
+    CUDA_TRY(cudaMemset(c->tick_d_out, 0, L.out_total * sizeof(float)));     // dead kernel_val columns stay zero
+    CUDA_TRY(cudaDeviceSynchronize());
+  }
+  // inputs -> pinned staging
+  float* hi = c->tick_h_in;
+  std::memcpy(hi + L.q, t->q_cur_host, (r.q_cur_is_batch ? N * d : d) * sizeof(float));
+  std::memcpy(hi + L.obs, t->obs_host, (size_t)t->n_obs * P1 * sizeof(float));
+  if (r.n_kernels > 0) {
+    std::memcpy(hi + L.mu, t->mu_tmp_host, N * NKMAX * d * sizeof(float));
+    std::memcpy(hi + L.sg, t->sigma_tmp_host, N * NKMAX * sizeof(float));
+    std::memcpy(hi + L.al, t->alpha_tmp_host, N * NKMAX * d * sizeof(float));
+  }
+  dsmppi_rollout_args a = r;
+  float* di = c->tick_d_in; float* do_ = c->tick_d_out;
+  a.q_cur_dev = di + L.q; a.mu_tmp_dev = di + L.mu; a.sigma_tmp_dev = di + L.sg; a.alpha_tmp_dev = di + L.al;
+  a.all_traj_dev = do_ + L.tr; a.closest_dist_all_dev = do_ + L.cd; a.kernel_val_all_dev = do_ + L.kv;
+  a.dot_products_dev = do_ + L.dp; a.kernel_activations_dev = do_ + L.ka; a.qdot_dev = do_ + L.qd;
+  a.nn_grad_all_dev = do_ + L.gr; a.norm_basis_dev = nullptr;
+  auto sequence = [&](cudaStream_t st) -> int {
+    CUDA_TRY(cudaMemcpyAsync(di, hi, L.in_total * sizeof(float), cudaMemcpyHostToDevice, st));
+    if (dsmppi_set_obstacles(c, di + L.obs, t->n_obs, st)) return 1;
+    if (dsmppi_rollout(c, &a, st)) return 1;
+    CUDA_TRY(cudaMemcpyAsync(c->tick_h_out, do_, L.out_total * sizeof(float), cudaMemcpyDeviceToHost, st));
+    return 0;
+  };
+  CUDA_TRY(cudaEventRecord(c->tick_ev, caller));                 // ordered after whatever the caller has queued
+  CUDA_TRY(cudaStreamWaitEvent(c->s_tick, c->tick_ev, 0));
+  if (rebuild) {
+    if (sequence(c->s_tick)) return 1;                           // eager pass: sizes the workspace outside the capture
+    CUDA_TRY(cudaStreamSynchronize(c->s_tick));
+    CUDA_TRY(cudaStreamBeginCapture(c->s_tick, cudaStreamCaptureModeThreadLocal));
+    const int rc = sequence(c->s_tick);
+    cudaGraph_t g = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(c->s_tick, &g);
+    if (rc || e != cudaSuccess) {
+      if (g) cudaGraphDestroy(g);
+      if (!rc) dsmppi_set_error(std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+      return 1;
+    }
+    c->tick_graph = g;
+    CUDA_TRY(cudaGraphInstantiate(&c->tick_exec, g, 0));
+    c->tick_key = key;
+  }
+  CUDA_TRY(cudaGraphLaunch(c->tick_exec, c->s_tick));
+  CUDA_TRY(cudaStreamSynchronize(c->s_tick));
+  const float* ho = c->tick_h_out;
+  std::memcpy(t->all_traj_host, ho + L.tr, N * H * d * sizeof(float));
+  std::memcpy(t->closest_dist_all_host, ho + L.cd, N * H * sizeof(float));
+  std::memcpy(t->dot_products_host, ho + L.dp, N * H * sizeof(float));
+  std::memcpy(t->kernel_activations_host, ho + L.ka, N * H * sizeof(float));
+  std::memcpy(t->qdot_host, ho + L.qd, N * d * sizeof(float));
+  std::memcpy(t->nn_grad_all_host, ho + L.gr, N * H * d * sizeof(float));
+  std::memcpy(t->kernel_val_all_host, ho + L.kv, N * H * NKMAX * sizeof(float));
+  return 0;
+}

@@ -145,6 +145,12 @@ struct dsmppi_ctx {
   // host-buffer iteration of a large batch: copy streams + events of the chunk pipeline (capi.cu)
   cudaStream_t s_in = nullptr, s_out = nullptr;
   std::vector<cudaEvent_t> pipe_ev;
+  // control tick (dsmppi_tick): the captured graph, its key and its staging blocks
+  cudaStream_t s_tick = nullptr; cudaEvent_t tick_ev = nullptr;
+  cudaGraph_t tick_graph = nullptr; cudaGraphExec_t tick_exec = nullptr;
+  std::vector<unsigned char> tick_key;
+  float* tick_h_in = nullptr; float* tick_h_out = nullptr; float* tick_d_in = nullptr; float* tick_d_out = nullptr;
+  size_t tick_in_floats = 0, tick_out_floats = 0;
   int keep_counters = 0;              // 1 while a chunked iteration calls dsmppi_rollout once per chunk
 };
 

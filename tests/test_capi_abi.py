@@ -38,7 +38,8 @@ def test_library_exports_every_declared_symbol(capi):
 
 def test_struct_layout_matches_the_c_compiler(capi, tmp_path):
     structs = {"dsmppi_net": capi.Net, "dsmppi_rollout_args": capi.RolloutArgs, "dsmppi_cost_args": capi.CostArgs,
-               "dsmppi_update_args": capi.UpdateArgs, "dsmppi_iteration_host_args": capi.IterationHostArgs, "dsmppi_modulation": capi.Modulation, "dsmppi_seds": capi.Seds}
+               "dsmppi_update_args": capi.UpdateArgs, "dsmppi_iteration_host_args": capi.IterationHostArgs, "dsmppi_modulation": capi.Modulation, "dsmppi_seds": capi.Seds,
+               "dsmppi_tick_args": capi.TickArgs}
     probes = {"dsmppi_rollout_args": ["q_goal", "mod", "distance_provider", "fk_span", "q_cur_dev", "norm_basis_dev"],
               "dsmppi_modulation": ["lvel_mid", "repulsion", "ds_A"],
               "dsmppi_seds": ["seds_thr", "priors_host", "A_host"],
@@ -46,6 +47,7 @@ def test_struct_layout_matches_the_c_compiler(capi, tmp_path):
               "dsmppi_update_args": ["variant", "N_global", "ker_thr", "alpha_c_dev"],
               "dsmppi_iteration_host_args": ["q_min", "cost_terms", "q_cur_host", "n_updated_host", "d2h_bytes", "exchange",
                                              "stats_dev", "owns_sample0", "N_global"],
+              "dsmppi_tick_args": ["n_obs", "q_cur_host", "alpha_tmp_host", "nn_grad_all_host", "recaptured"],
               "dsmppi_net": ["W_host", "b_host"]}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "dsmppi_b200.h"', 'int main(void){']
     for s, fields in probes.items():
