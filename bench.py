@@ -46,6 +46,10 @@ WORKLOADS = {
     # path, standalonePlanar2d_policyPlots.py:160,257-259): H = 1, per-sample start states
     "field_1m": dict(net="planar2", n_pts=None, N=1_000_000, H=1, K=1, nk=10, dt=0.05, dst_thr=0.25, ker_thr=1e-3,
                      alpha_s=2.0, sigma=0.5, ignored=[], grid=1000),
+    # the integrator process's control tick (frankaIntegrator.py:101-121): ONE sample, TWO steps, 28
+    # spheres, CPU caller tensors -- a latency workload: `value` = 2 x tick rate, `ms_per_step` = wall clock per tick
+    "integrator": dict(net="franka", n_pts=12, N=1, H=2, K=5, nk=5, dt=0.01, dst_thr=0.03, ker_thr=0.1,
+                       alpha_s=0.0, sigma=1.0, ignored=[0, 1, 2], n_obs=28),
 }
 
 
@@ -79,6 +83,8 @@ def problem(name):
         q0 = torch.tensor([-0.88, 0.38, 0.5, -1, 0.45, 1.9, 0.31])
         qf = torch.tensor([-1.24, 1.53, 1.22, -1.21, -0.21, 1.55, 0.08])
         obs = shelf(w["n_pts"])
+        if w.get("n_obs"):
+            obs = obs[:w["n_obs"]].clone()
         qlim = (torch.tensor([-2.8973, -1.7628, -2.8973, -3.0718, -2.8973, -0.0175, -2.8973]),
                 torch.tensor([2.8973, 1.7628, 2.8973, -0.0698, 2.8973, 3.7525, 2.8973]))
         dof, out = 7, 9
@@ -441,6 +447,27 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
+    if args.workload == "integrator":
+        # a latency workload: no batch to shard, every rank would run the same tick -- rank 0 reports it
+        if rank != 0:
+            return
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        tick = measure_control_tick(local_rank, ticks=max(200, 100 * args.steps))
+        sampler.stop_flag = True
+        sampler.join()
+        line = dict(metric="mppi_rollout_state_steps_per_sec", value=2 * tick["hz"], unit="state-steps/s", n_gpus=1,
+                    steps=tick["ticks"], warmup=30, ms_per_step=tick["ms_per_tick"], higher_is_better=True,
+                    scaling="weak", vs_baseline=None, dtype="f32 (scoring: split-fp16 tcgen05, fp32-accurate)",
+                    data="synthetic", config=config, clocks=sampler.summary(), control_tick=tick,
+                    e2e=dict(value=2 * tick["hz"], unit="state-steps/s", h2d_bytes_per_step=4 * (7 + 28 * 4 + 50 * 15),
+                             d2h_bytes_per_step=4 * (2 * 7 * 2 + 2 * 3 + 2 * 50 + 7), ms_per_step=tick["ms_per_tick"],
+                             api="MPPI.propagate on CPU tensors -> dsmppi_tick (C ABI, one replayed CUDA graph)"),
+                    gpu_launches=2 * tick["ticks"], roofline=None,
+                    note="latency workload: the tick IS the end-to-end call (host tensors in and out); reference logs "
+                         "~500 Hz for this loop (experiment_logs/my_*.txt)")
+        print(json.dumps(line))
+        return
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     t = lambda x: x.to(dev)  # noqa: E731

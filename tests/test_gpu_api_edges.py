@@ -296,3 +296,46 @@ def test_graphed_control_tick_equals_the_plain_path(factory, monkeypatch):
         cost = g.get_cost()
         assert cost.shape == (N,) and torch.isfinite(cost).all()
         g.shift_policy_means()
+
+
+def test_half_tiles_equal_full_tiles_bitwise(factory, monkeypatch):
+    """tc_exact_kernel<2, true> (M = 128 over the CTA pair, 64 rows per CTA) against the full-tile kernel on the
+    whole-horizon workloads it serves: planar-7 / planar-2 planner batches and a Franka control tick."""
+    cases = [("case_planar7", {}), ("case_c1_planar2", {}), ("case_franka_shelf", dict(obs_n=28, N=3, H=4))]
+    for tag, opt in cases:
+        c = load_npz(tag)
+        if "obs_n" in opt:
+            c = dict(c, obs=c["obs"][:opt["obs_n"]].clone())
+        outs = {}
+        for half in ("1", "0"):
+            monkeypatch.setenv("DSMPPI_HALF_TILES", half)
+            m = factory.make_mppi(c, device="cuda", N=opt.get("N"), H=opt.get("H"), pass1="auto",
+                                  copy_policy="N" not in opt)
+            if "N" in opt:
+                m.Policy.alpha_s = 1.0
+                torch.manual_seed(3)
+                m.Policy.sample_policy()
+            outs[half] = _rollout_outputs(m) + [m.get_cost().clone()]
+        for a, b, name in zip(outs["1"], outs["0"], ("traj", "dist", "kval", "dots", "acts", "qdot", "cost")):
+            assert torch.equal(a, b), f"{tag}: {name} differs between half and full tiles"
+
+
+def test_tick_entry_point_refuses_what_it_cannot_capture(factory):
+    """dsmppi_tick covers the dense fp32 scoring path only: with 64+ obstacles (prefilter + host-side verdict) the
+    drop-in falls back to the plain path by itself, and the C entry point reports an error instead of capturing."""
+    from optimalmodulationds_b200 import _capi
+    c = load_npz("case_franka_shelf")                       # 294 spheres
+    m = factory.make_mppi(c, device="cpu", N=2, H=2, pass1="auto", copy_policy=False)
+    m.propagate()
+    assert "_tick" not in m.__dict__                        # not eligible: took the plain path
+    ta = _capi.TickArgs()
+    dummy = torch.empty(1, device="cuda")
+    out = {k: dummy for k in ("all_traj", "closest", "kval", "dots", "acts", "qdot", "grads")}
+    ta.rollout = m._rollout_args(2, 2, 0, dummy, dummy, dummy, dummy, out)
+    ta.n_obs = 294
+    host = torch.zeros(4096)
+    for f in ("q_cur_host", "obs_host", "all_traj_host", "closest_dist_all_host", "kernel_val_all_host",
+              "dot_products_host", "kernel_activations_host", "qdot_host", "nn_grad_all_host"):
+        setattr(ta, f, host.data_ptr())
+    rc = m._lib.dsmppi_tick(m._ctx, _capi.C.byref(ta), m._stream())
+    assert rc != 0 and b"dense fp32 scoring path" in m._lib.dsmppi_last_error()
