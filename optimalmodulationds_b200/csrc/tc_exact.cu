@@ -849,6 +849,48 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_exac
         }
       }
       (void)nenc;
+      int* fixn = reinterpret_cast<int*>(smem + OFF_FIXN);
+      int* fixl = reinterpret_cast<int*>(smem + OFF_FIXL);
+      if constexpr (MODE == 1) {
+        // ---- rows whose activations or gradients saturated fp16 are re-scored in IEEE FFMA right here (round 1 queued
+        //      them for a launch of their own after this one -- an empty launch per rollout step in the normal case):
+        //      the FFMA tile of exact_mlp.cu on warps 0-3, its shared memory carved out of the A operand images, which
+        //      are idle between this tile's last GEMM and the hand-over of the next tile's encoding
+        if (((range & 0xffffu) >= 0x7bffu) || ((range >> 16) >= 0x7bffu)) ovf[row] = 1;
+        if (tid == 0) *fixn = 0;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (h == 0 && fb == 0 && grow < n_rows && ovf[row]) {
+          const int k = atomicAdd(fixn, 1);
+          atomicAdd(a.fix_total, 1);
+          fixl[k] = row_i;
+          fixl[TROWS + k] = row_j;
+          fixl[2 * TROWS + k] = grow;            // re-scored straight into the output rows
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const int nfix = *fixn;
+        if (nfix > 0) {
+          if (tid < exact_tile::nthreads(8)) {
+            exact_tile::TileSmem<8> ts(reinterpret_cast<float*>(smem + OFF_AHI));
+            exact_tile::WeightStream ws;
+            const int passes = (nfix + 31) / 32;
+            exact_tile::stream_begin<true, exact_tile::nthreads(8)>(ws, &a.net, ts.ring, passes);
+            RowSrc fs{};
+            fs.mode = ROWS_LIST;
+            fs.M = a.src.M;
+            fs.n_rows = nfix;
+            fs.row_sample = fixl;
+            fs.row_obs = fixl + TROWS;
+            fs.out_row = fixl + 2 * TROWS;
+            int stage = 0;
+            for (int r0 = 0; r0 < nfix; r0 += 32) {
+              exact_tile::mlp_tile<true, 8, 8>(a.net, fs, r0, nfix, a.q, a.q_stride, a.obs, a.ignore_mask, a.out_m,
+                                              a.out_dist, a.out_grad, ts, ws, stage);
+              exact_tile::tile_sync<exact_tile::nthreads(8)>();
+            }
+          }
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+        }
+      }
       // ---- tile end: the next tile's encoding (prepared above) goes out first, then this tile's rows
       if (TCX_ENC_PIPE && MODE != 2 && tile + npairs < n_tiles) {
         enc_store();
@@ -857,7 +899,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_exac
       } else {
         enc_stored = false;
       }
-      if ((TCX_DEFER_STG || MODE == 2) && h == 0 && fb == 0 && grow < n_rows) {
+      if ((TCX_DEFER_STG || MODE == 2) && h == 0 && fb == 0 && grow < n_rows && !(MODE == 1 && ovf[row])) {
         if (out_m) out_m[orow] = o_m;
         if (BWD) {
           out_dist[orow] = o_dist;
@@ -867,10 +909,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_exac
         }
       }
       if (q4 == 0) TCX_PROF(h, 63);
-      // ---- rows whose activations or gradients saturated fp16 are handed to the FFMA arithmetic
+      // ---- rows whose activations saturated fp16 are handed to the FFMA arithmetic (forward-only launches: a
+      //      device-wide list re-scored by launch_exact_fixup; whole-horizon: this CTA's list, re-scored below)
+      if constexpr (MODE != 1) {
       if (((range & 0xffffu) >= 0x7bffu) || ((range >> 16) >= 0x7bffu)) ovf[row] = 1;
-      int* fixn = reinterpret_cast<int*>(smem + OFF_FIXN);
-      int* fixl = reinterpret_cast<int*>(smem + OFF_FIXL);
       if (MODE == 2 && tid == 0) *fixn = 0;
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (h == 0 && fb == 0 && grow < n_rows && ovf[row]) {
@@ -891,6 +933,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_exac
           fixl[TROWS + k] = row_j;
           fixl[2 * TROWS + k] = row;           // re-scored into the staged rows
         }
+      }
       }
       if constexpr (MODE == 2) {
         asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -1315,6 +1358,7 @@ int launch_tc_exact(dsmppi_ctx* c, const float* q, int q_stride, const RowSrc& s
     }
   }
 #endif
+  if (bwd) return 0;       // (forward + VJP launches re-score their flagged rows inside the kernel)
   // the flagged rows again, in IEEE fp32, written over the tensor-core results
   RowSrc fix{};
   fix.mode = ROWS_LIST;
