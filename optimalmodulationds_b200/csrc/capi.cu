@@ -206,6 +206,7 @@ int dsmppi_ctx_create(dsmppi_ctx** out, const dsmppi_net* net, const float* dh_p
   if (tc_build_images(c, net)) { delete c; return 1; }
   if (tcx_build_images(c, net)) { delete c; return 1; }
   if (const char* e = std::getenv("DSMPPI_HALF_TILES")) c->half_tiles = std::atoi(e) != 0;
+  if (const char* e = std::getenv("DSMPPI_PASS1_ACC")) c->pass1_hacc = std::strcmp(e, "f32") != 0;
   c->upd_blocks = c->sm_count * 4;       // update_partial_kernel: four 256-thread CTAs per SM (56 registers per thread)
   CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c->upd_partials),
                       (size_t)c->upd_blocks * dsmppi_update_packed_len(NKMAX, MAXD) * sizeof(float)));
@@ -460,6 +461,12 @@ static int prefilter_verdict(dsmppi_ctx* c, int n_max, cudaStream_t st, int* ver
   const int* h = c->counters_host;
   REQUIRE(h[7] == 0, "tensor-core scoring: rows left the fp16 range and did not fit the FFMA re-scoring list "
                      "(use dsmppi_set_score_mode(DSMPPI_SCORE_FFMA) for this network)");
+  if (h[9] != 0) {       // prefilter outputs that were inf / NaN (activations beyond fp16): nothing to rank them by
+    *verdict = 1;
+    *exact_mode = 1;
+    c->exact_fallbacks++;
+    return 0;
+  }
   const size_t high = (size_t)(unsigned)h[8];
   if (high <= cand_list_cap(c, n_max)) return 0;
   *verdict = 1;
@@ -582,7 +589,7 @@ int dsmppi_rollout(dsmppi_ctx* c, const dsmppi_rollout_args* a, void* stream) {
     c->ev_used = ev_start;
     c->prefilter_used = 0;
     if (!c->keep_counters || attempt > 0) CUDA_TRY(cudaMemsetAsync(c->counters + 1, 0, 3 * sizeof(int), st));
-    CUDA_TRY(cudaMemsetAsync(c->counters + 8, 0, sizeof(int), st));
+    CUDA_TRY(cudaMemsetAsync(c->counters + 8, 0, 2 * sizeof(int), st));
     if (rollout_once(c, a, st)) return 1;
     int verdict = 0, exact = 0;
     if (prefilter_verdict(c, n_max, st, &verdict, &exact)) return 1;
@@ -615,7 +622,7 @@ int dsmppi_distance_grad(dsmppi_ctx* c, const float* q_dev, int32_t n, int32_t n
     const int nb = (int)(n - off < block ? n - off : block);
     for (int attempt = 0;; ++attempt) {                 // same exactness protocol as dsmppi_rollout, per block
       c->prefilter_used = 0;
-      CUDA_TRY(cudaMemsetAsync(c->counters + 8, 0, sizeof(int), st));
+      CUDA_TRY(cudaMemsetAsync(c->counters + 8, 0, 2 * sizeof(int), st));
       int rc = distance_pipeline(c, q_dev + off * c->d, c->d, nb, n_closest, ignored_link_mask, st);
       if (!rc) rc = launch_blend(c, nb, n_closest, distance_dev + off, nn_grad_dev + off * c->d, st);
       int verdict = 0, exact = 0;

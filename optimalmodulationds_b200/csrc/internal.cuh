@@ -98,6 +98,7 @@ struct dsmppi_ctx {
   size_t cand_rows_want = 0;          // row-list capacity asked for after a rollout ran out of candidate rows
   int* counters_host = nullptr;       // pinned mirror of `counters` for the end-of-rollout exactness check
   int obs_tables_dirty = 1;           // c->obs changed since tc_set_obstacles built the per-obstacle layer-1 table
+  int pass1_hacc = 1;                 // fp16 prefilter: hidden layers accumulate in fp16 (DSMPPI_PASS1_ACC=f32: in fp32)
   int half_tiles = 1;                 // whole-horizon tensor-core rollout: 64-row tiles while one wave covers the batch
   int table_valid = 0;                // c->enc_q holds the layer-1 table of the states the next prefilter launch scores
   int prefilter_used = 0;             // set by distance_pipeline when a call went through the tensor-core prefilter
@@ -117,7 +118,8 @@ struct dsmppi_ctx {
                                       // than CAND_MAX obstacles (informational), [2..3] rescored pairs (u64), [4..5]
                                       // range-fixup row counts (ping-pong), [6] rows re-scored in FFMA so far, [7] rows
                                       // that did not fit the range-fixup list, [8] largest [0] of any step of this
-                                      // rollout (> capacity: the rollout is repeated with a larger list)
+                                      // rollout (> capacity: the rollout is repeated with a larger list), [9] prefilter
+                                      // outputs that were inf / NaN (> 0: the call is repeated with all pairs in fp32)
   int* sel = nullptr;                 // (n, K) selected obstacle indices (two-launch fp32 path)
   int* sel_rows = nullptr;            // (n, K) rows of row_dist / row_grad holding the K closest, ranked
   float* row_dist = nullptr;          // pass-2 distance of every differentiated row
@@ -194,7 +196,8 @@ int launch_max_abs_diff(dsmppi_ctx* c, const float* a, const float* b, long long
 int exact_set_attributes();
 // rows the candidate list of the prefilter path can hold for a batch of n samples
 inline size_t cand_list_cap(const dsmppi_ctx* c, int n) {
-  const size_t base = (size_t)n * CAND_MAX;
+  // (fp16 accumulators double the prefilter's error and with it the calibrated band: half a list more per sample)
+  const size_t base = (size_t)n * (CAND_MAX + (c->pass1_hacc ? CAND_MAX / 2 : 0));
   return base > c->cand_rows_want ? base : c->cand_rows_want;
 }
 int launch_rank_candidates(dsmppi_ctx* c, int n, int K, cudaStream_t st);

@@ -63,7 +63,10 @@ constexpr int OFF_TMEMPTR = OFF_BAR + NBAR * 8;
 // hand-over of a tile's 128 distances from the row warps of a slot to that slot's writer warp (warp 9 / 10): two
 // buffers per slot, so the row warps never wait for the writer
 constexpr int OFF_MBUF = OFF_TMEMPTR + 16;         // [slot][buffer][128] floats
-constexpr int SMEM_BYTES = OFF_MBUF + 2 * 2 * ROWS * 4;
+constexpr int OFF_BIASH = OFF_MBUF + 2 * 2 * ROWS * 4;   // hidden-layer biases as fp16 pairs (fp16-accumulator build)
+// staging of the two table-A rows a row warp's 32 pair-rows can touch: [warp][2][32] groups of 8 halves
+constexpr int OFF_ABUF = OFF_BIASH + NHID * HID * 2;
+constexpr int SMEM_BYTES = OFF_ABUF + 8 * 2 * 32 * 16;
 static_assert(IMG_BYTES % 16 == 0, "bulk copies need 16-byte granularity");
 static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB shared-memory budget");
 
@@ -213,6 +216,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "r"(taddr)
       : "memory");
 }
+// 64 consecutive columns holding one fp16 accumulator element each (32-bit containers), two per register
+__device__ __forceinline__ void tmem_ld32p(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.pack::16b.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : R8(v, 0), R8(v, 8), R8(v, 16), R8(v, 24)
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
@@ -265,9 +277,9 @@ __device__ __forceinline__ uint64_t make_b_desc(uint32_t smem_addr, uint32_t lbo
   d |= (uint64_t)1 << 46;   // descriptor version (Blackwell)
   return d;                 // base_offset 0, lbo_mode 0, layout_type 0 = SWIZZLE_NONE
 }
-__host__ __device__ constexpr uint32_t make_idesc(int fmt /*0 f16, 1 bf16*/, int M, int N) {
-  return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(N >> 3) << 17) |
-         ((uint32_t)(M >> 4) << 24);   // fp32 accumulate, K-major A and B, dense
+__host__ __device__ constexpr uint32_t make_idesc(int fmt /*0 f16, 1 bf16*/, int M, int N, bool acc_f32 = true) {
+  return (acc_f32 ? (1u << 4) : 0u) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);   // fp32 (or fp16) accumulate, K-major A and B, dense
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -311,6 +323,7 @@ struct TcArgs {
   uint32_t zero;                               // 0 (an opaque zero for scheduling dependencies, see first_layer)
   int use_writers;                             // 1: warps 9 / 10 store the distances (0: the row warps do, see there)
   long long* prof;                             // DSMPPI_TC_PROF builds only: [block][warp][8] cycle counters
+  int* nonfinite;                              // counts pair-rows whose prefilter output is inf / NaN (see the epilogue)
 };
 
 // Per-phase cycle accounting of the kernel's own pipeline (tools/tc_microbench.cu builds with
@@ -340,6 +353,23 @@ __device__ __forceinline__ void relu_pack32(const uint32_t (&v)[32], const float
     add2(v[4 * k + 2], v[4 * k + 3], bb.z, bb.w, s2, s3);
     pk[OFF + 2 * k + 0] = pack2_relu<BF16>(s0, s1);
     pk[OFF + 2 * k + 1] = pack2_relu<BF16>(s2, s3);
+  }
+}
+
+// fp16-accumulator build: 64 accumulator values arrive as 32 packed pairs; bias + ReLU is one HFMA2.RELU per pair.
+// No saturation here (a clamping HMNMX2 per pair cost 3.5 % of the kernel): an accumulator that overflowed is inf,
+// stays inf / NaN through the remaining layers, and is caught at the output.  The biases come from shared memory as
+// fp16 pairs (passed as kernel parameters -- constant bank -- they turned into 192 LDC.64 per tile and cost 4 %).
+template <int OFF, int NPK>
+__device__ __forceinline__ void relu_h2_32(const uint32_t (&v)[32], const uint4* __restrict__ bias_h2, uint32_t (&pk)[NPK]) {
+  const uint32_t one = 0x3c003c00u;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const uint4 bb = bias_h2[k];
+    asm("fma.rn.relu.f16x2 %0, %1, %2, %3;" : "=r"(pk[OFF + 4 * k + 0]) : "r"(v[4 * k + 0]), "r"(one), "r"(bb.x));
+    asm("fma.rn.relu.f16x2 %0, %1, %2, %3;" : "=r"(pk[OFF + 4 * k + 1]) : "r"(v[4 * k + 1]), "r"(one), "r"(bb.y));
+    asm("fma.rn.relu.f16x2 %0, %1, %2, %3;" : "=r"(pk[OFF + 4 * k + 2]) : "r"(v[4 * k + 2]), "r"(one), "r"(bb.z));
+    asm("fma.rn.relu.f16x2 %0, %1, %2, %3;" : "=r"(pk[OFF + 4 * k + 3]) : "r"(v[4 * k + 3]), "r"(one), "r"(bb.w));
   }
 }
 
@@ -403,6 +433,54 @@ __device__ __forceinline__ void first_layer(const TcArgs& a, int i, int j, uint3
     for (int k = 0; k < 128; ++k) pk[k] = 0u;
   }
 }
+// The same, with the per-sample half read through shared memory: the 32 consecutive pair-rows of a warp belong to at
+// most two samples (M >= 32), so the warp copies those two 512-byte rows once (one coalesced 16-byte load per lane and
+// row) instead of every lane loading its own copy -- 2 instead of 32 global loads per thread, and the whole per-obstacle
+// half (32 loads, 128 registers) fits in flight at once: one L2 latency per tile instead of two.
+// Issued in two parts so that the loads are in flight while the caller drains the output layer.
+struct TableLoads {
+  uint4 y[32];        // this thread's per-obstacle half (256 features)
+  uint4 a0, a1;       // lane-th 16-byte group of the warp's two per-sample rows
+  int i0;
+};
+__device__ __forceinline__ void first_layer_issue(const TcArgs& a, int i, int j, uint32_t dep, int lane, TableLoads& t) {
+  t.i0 = __shfl_sync(0xffffffffu, i, 0);
+  const uint4* ta = a.tabA + dep;
+  t.a0 = make_uint4(0u, 0u, 0u, 0u);
+  t.a1 = t.a0;
+  if (t.i0 < a.n) t.a0 = ldg_nc_v4(ta + (size_t)t.i0 * 32 + lane);
+  if (t.i0 + 1 < a.n) t.a1 = ldg_nc_v4(ta + (size_t)(t.i0 + 1) * 32 + lane);
+  if (i < a.n) {
+    const uint4* tb = a.tabB + j + dep;
+    const uint32_t strideM = (uint32_t)a.M + dep;
+#pragma unroll
+    for (int kb = 0; kb < 32; ++kb) t.y[kb] = ldg_nc_v4(tb + (size_t)(kb * strideM));
+  } else {
+#pragma unroll
+    for (int kb = 0; kb < 32; ++kb) t.y[kb] = make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+template <bool BF16>
+__device__ __forceinline__ void first_layer_finish(const TcArgs& a, int i, const TableLoads& t, uint4* abuf, int lane,
+                                                   uint32_t (&pk)[128]) {
+  abuf[lane] = t.a0;
+  abuf[32 + lane] = t.a1;
+  __syncwarp();
+  const uint4* ar = abuf + (i < a.n ? (i - t.i0) * 32 : 0);
+#pragma unroll
+  for (int kb = 0; kb < 32; ++kb) {
+    const uint4 x = ar[kb];
+    pk[4 * kb + 0] = add_relu_h2<BF16>(x.x, t.y[kb].x);
+    pk[4 * kb + 1] = add_relu_h2<BF16>(x.y, t.y[kb].y);
+    pk[4 * kb + 2] = add_relu_h2<BF16>(x.z, t.y[kb].z);
+    pk[4 * kb + 3] = add_relu_h2<BF16>(x.w, t.y[kb].w);
+  }
+  if (!(i < a.n)) {
+#pragma unroll
+    for (int k = 0; k < 128; ++k) pk[k] = 0u;
+  }
+  __syncwarp();
+}
 __device__ __forceinline__ void store_operand(uint32_t tA, const uint32_t (&pk)[128]) {
   tmem_st32<0>(tA, pk);
   tmem_st32<32>(tA + 32, pk);
@@ -410,8 +488,14 @@ __device__ __forceinline__ void store_operand(uint32_t tA, const uint32_t (&pk)[
   tmem_st32<96>(tA + 96, pk);
 }
 
-template <bool BF16>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_pass1_kernel(TcArgs a) {
+// HACC: the hidden layers accumulate in fp16 (tcgen05 D format f16) instead of fp32.  The prefilter only has to be
+// right to within its calibrated guard band, and an fp16 accumulator halves the epilogue (half the tcgen05.ld
+// traffic, one HFMA2.RELU instead of an FADD2 + a converting ReLU per two features) and costs the tensor pipe less
+// energy per MMA -- which is what this power-capped kernel is short of.  The output layer keeps fp32 accumulators.
+template <bool BF16, bool HACC = false, bool ASM = false>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
+tc_pass1_kernel(const __grid_constant__ TcArgs a) {
+  static_assert(!(BF16 && HACC), "bf16 operands accumulate in fp32");
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bar0 = sbase + OFF_BAR;
@@ -454,6 +538,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_pass
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   mbar_wait(BAR(BAR_W), 0);            // this CTA's weights have landed
+  if constexpr (HACC) {
+    uint32_t* bh = reinterpret_cast<uint32_t*>(smem + OFF_BIASH);
+    for (int k = tid; k < NHID * HID / 2; k += NTHREADS) bh[k] = pack2<false>(bias[2 * k], bias[2 * k + 1]);
+    __syncthreads();
+  }
   cluster_sync_all();                  // ... and so have the peer's; barrier inits visible cluster-wide
 
   const long long n_tiles = (a.n_rows + 2 * ROWS - 1) / (2 * ROWS);     // 256 pair-rows per tile
@@ -473,6 +562,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_pass
     const uint32_t bar_aready = BAR(slot ? BAR_AREADY1 : BAR_AREADY0);
     const uint32_t bar_full_lo = BAR(slot ? BAR_DFULL10 : BAR_DFULL00);
     const uint32_t bar_full_hi = BAR(slot ? BAR_DFULL11 : BAR_DFULL01);
+    uint4* abuf = reinterpret_cast<uint4*>(smem + OFF_ABUF) + warp * 64;
 
     auto signal = [&](uint32_t bar) {       // one arrival per warp on the leader CTA's barrier
       tc_fence_before();
@@ -487,7 +577,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_pass
     int i_cur = (int)min(r0 / a.M, (long long)a.n), j_cur = (int)(r0 % a.M);
     if ((long long)pair < n_tiles) {
       uint32_t pk[128];
-      first_layer<BF16>(a, i_cur, j_cur, a.zero, pk);
+      if constexpr (ASM) {
+        TableLoads t;
+        first_layer_issue(a, i_cur, j_cur, a.zero, lane, t);
+        first_layer_finish<BF16>(a, i_cur, t, abuf, lane, pk);
+      } else {
+        first_layer<BF16>(a, i_cur, j_cur, a.zero, pk);
+      }
       store_operand(tA, pk);
       tc_wait_st();
       signal(bar_aready);
@@ -500,11 +596,52 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_pass
       int i_next = min(i_cur + di, a.n), j_next = j_cur + dj;
       if (j_next >= a.M) { j_next -= a.M; i_next = min(i_next + 1, a.n); }
       uint32_t tile_dep = 0;
+      // fp16-accumulator build: one hidden layer's epilogue
+      auto hacc_layer = [&](auto L) {
+        constexpr int l = decltype(L)::value;
+        PROF_ADD(7);
+          uint32_t pk[64], raw[2][32];
+        mbar_wait(bar_full_lo, (uint32_t)(l & 1));
+        tc_fence_after();
+        PROF_ADD(0);
+        tmem_ld32p(tDlo, raw[0]);
+        tmem_ld32p(tDlo + 64, raw[1]);
+        tc_wait_ld();
+        signal(BAR(BAR_DFREE0));
+        PROF_ADD(1);
+        relu_h2_32<0>(raw[0], reinterpret_cast<const uint4*>(smem + OFF_BIASH) + l * (HID / 8) + 0, pk);
+        relu_h2_32<32>(raw[1], reinterpret_cast<const uint4*>(smem + OFF_BIASH) + l * (HID / 8) + 8, pk);
+        PROF_ADD(2);
+        mbar_wait(bar_full_hi, (uint32_t)((it + l) & 1));
+        tc_fence_after();
+        PROF_ADD(3);
+        tmem_ld32p(tDhi, raw[0]);
+        tmem_ld32p(tDhi + 64, raw[1]);
+        tmem_st32<0>(tA, pk);
+        tmem_st32<32>(tA + 32, pk);
+        tc_wait_ld();
+        signal(BAR(BAR_DFREE1));
+        PROF_ADD(4);
+        relu_h2_32<0>(raw[0], reinterpret_cast<const uint4*>(smem + OFF_BIASH) + l * (HID / 8) + 16, pk);
+        relu_h2_32<32>(raw[1], reinterpret_cast<const uint4*>(smem + OFF_BIASH) + l * (HID / 8) + 24, pk);
+        tmem_st32<0>(tA + 64, pk);
+        tmem_st32<32>(tA + 96, pk);
+        tc_wait_st();
+        signal(bar_aready);
+        if (l == NHID - 1) tile_dep = (pk[7] | pk[23] | pk[39] | pk[63]) & a.zero;
+        PROF_ADD(5);
+      };
+      if constexpr (HACC) {
+        hacc_layer(std::integral_constant<int, 0>{});
+        hacc_layer(std::integral_constant<int, 1>{});
+        hacc_layer(std::integral_constant<int, 2>{});
+        static_assert(NHID == 3, "three hidden GEMMs");
+      } else {
 #pragma unroll
       for (int l = 0; l < NHID; ++l) {       // network layers 2..4
         const float* bl = bias + l * HID;
-        uint32_t pk[64], raw[4][32];
         PROF_ADD(7);
+        uint32_t pk[64], raw[4][32];
         // ---- D_lo (features 0..127) while the tensor core is still producing D_hi.  Per tile a slot uses D_lo four
         //      times (three hidden layers + the output layer) and D_hi three times: phase parities below
         mbar_wait(bar_full_lo, (uint32_t)(l & 1));
@@ -546,17 +683,64 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_pass
         if (l == NHID - 1) tile_dep = (pk[7] | pk[23] | pk[39] | pk[63]) & a.zero;
         PROF_ADD(5);
       }
+      }
       // ---- output layer of this tile; under its MMAs (and the other tile's last hidden layer) the NEXT tile's
       //      first activation is read from the tables, so that the tile boundary costs one tcgen05.st
       const bool valid = i_cur < a.n;
       float rad = 0.f;
       if (valid) rad = __ldg(a.obs + (size_t)j_cur * 4 + 3);
+      // the tile's result: masked minimum link distance (MPPI.py:236-242), handed to the writer warp
+      auto finish_tile = [&](const uint32_t (&v)[16]) {
+        float m = 3.0e38f;
+        if (valid) {
+          bool finite = true;
+#pragma unroll
+          for (int o = 0; o < 16; ++o) {
+            if (o < a.O) {
+              float y = __uint_as_float(v[o]) + bias[NHID * HID + o];
+              finite = finite && (fabsf(y) <= 3.0e38f);
+              y = y / a.inv_scale_div - rad;
+              if ((a.ignore_mask >> o) & 1u) y = 1e6f;
+              m = fminf(m, y);
+            }
+          }
+          // An activation beyond the fp16 range (an fp16 accumulator that overflowed, or a saturated conversion feeding
+          // inf - inf) surfaces here as inf / NaN.  Such a value says nothing about the pair: it is counted, and the
+          // host repeats the whole call with every pair scored in fp32 (prefilter_verdict); the finite stand-in only
+          // keeps the selection kernel's arithmetic defined until then.
+          if (!finite) {
+            m = -3.0e38f;
+            atomicAdd(a.nonfinite, 1);
+          }
+        }
+        if (a.use_writers) {
+          // hand the distance to this slot's writer warp through shared memory (one st.shared + one mbarrier arrival
+          // per warp): this warp is on the tensor core's critical path, a global store and its address arithmetic are
+          // not free there (2.51 -> 2.39 ms per launch)
+          const int b = (int)(it & 1);
+          if (it >= 2) mbar_wait(BAR(BAR_MEMPTY + slot * 2 + b), (uint32_t)(((it >> 1) - 1) & 1));
+          mbuf[(slot * 2 + b) * ROWS + row] = m;
+          __syncwarp();
+          if (lane == 0) mbar_arrive_local(BAR(BAR_MFULL + slot * 2 + b));
+        } else if (valid) {
+          a.mdist[(size_t)i_cur * a.M + j_cur] = m;
+        }
+      };
       uint32_t v[16];
       // (one branch holds the whole life of the 128-register operand: split into two `if (more)` blocks around the
       // wait, the compiler kept it conditionally live through the hidden-layer epilogues and spilled 3 KB per thread)
       if (more) {
+        // (the output-layer MMA sits behind the other tile's layer in the issuer's order and completes late: draining
+        // it BEFORE the table loads are consumed -- to release D_lo sooner -- put that wait in front of the next
+        // tile's operand and cost 5 %)
         uint32_t nxt[128];
-        first_layer<BF16>(a, i_next, j_next, tile_dep, nxt);
+        if constexpr (ASM) {
+          TableLoads t;
+          first_layer_issue(a, i_next, j_next, tile_dep, lane, t);
+          first_layer_finish<BF16>(a, i_next, t, abuf, lane, nxt);
+        } else {
+          first_layer<BF16>(a, i_next, j_next, tile_dep, nxt);
+        }
         PROF_ADD(6);
         mbar_wait(bar_full_lo, 1u);                                 // fourth use of D_lo in this tile
         tc_fence_after();
@@ -567,6 +751,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_pass
         signal(BAR(BAR_DFREE0));
         tc_wait_st();
         signal(bar_aready);
+        finish_tile(v);
       } else {
         PROF_ADD(6);
         mbar_wait(bar_full_lo, 1u);
@@ -575,30 +760,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_pass
         tmem_ld16(tDlo, v);
         tc_wait_ld();
         signal(BAR(BAR_DFREE0));
-      }
-      float m = 3.0e38f;                     // masked minimum link distance (MPPI.py:236-242)
-      if (valid) {
-#pragma unroll
-        for (int o = 0; o < 16; ++o) {
-          if (o < a.O) {
-            float y = __uint_as_float(v[o]) + bias[NHID * HID + o];
-            y = y / a.inv_scale_div - rad;
-            if ((a.ignore_mask >> o) & 1u) y = 1e6f;
-            m = fminf(m, y);
-          }
-        }
-      }
-      if (a.use_writers) {
-        // hand the distance to this slot's writer warp through shared memory (one st.shared + one mbarrier arrival
-        // per warp): this warp is on the tensor core's critical path, a global store and its address arithmetic are
-        // not free there (2.51 -> 2.39 ms per launch)
-        const int b = (int)(it & 1);
-        if (it >= 2) mbar_wait(BAR(BAR_MEMPTY + slot * 2 + b), (uint32_t)(((it >> 1) - 1) & 1));
-        mbuf[(slot * 2 + b) * ROWS + row] = m;
-        __syncwarp();
-        if (lane == 0) mbar_arrive_local(BAR(BAR_MFULL + slot * 2 + b));
-      } else if (valid) {
-        a.mdist[(size_t)i_cur * a.M + j_cur] = m;
+        finish_tile(v);
       }
       i_cur = i_next;
       j_cur = j_next;
@@ -615,7 +777,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_pass
     // first version issued from a single divergent thread inside rolled loops: ~18 dependent instructions per
     // MMA, and the issue loop -- not the tensor pipe, not the epilogue -- set the pace of the whole kernel.)
     constexpr int fmt = BF16 ? 1 : 0;
-    constexpr uint32_t idesc128 = make_idesc(fmt, 256, 128);
+    constexpr uint32_t idesc128 = make_idesc(fmt, 256, 128, !HACC);
     constexpr uint32_t idesc32 = make_idesc(fmt, 256, 32);
     const uint32_t sb4 = sbase >> 4;
     uint32_t ph_a[2] = {0, 0}, ph_free[2] = {0, 0};
@@ -785,8 +947,15 @@ int tc_build_images(dsmppi_ctx* c, const dsmppi_net* net) {
   t->img[1] = nullptr;
   c->tc_blob = t;
   c->tc_blob_bytes = host.size();
-  CUDA_TRY(cudaFuncSetAttribute(tc_pass1_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-  CUDA_TRY(cudaFuncSetAttribute(tc_pass1_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  auto opt_in = [](auto kernel) {
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  };
+  CUDA_TRY(opt_in(tc_pass1_kernel<false, false, false>));
+  CUDA_TRY(opt_in(tc_pass1_kernel<false, false, true>));
+  CUDA_TRY(opt_in(tc_pass1_kernel<true, false, false>));
+  CUDA_TRY(opt_in(tc_pass1_kernel<true, false, true>));
+  CUDA_TRY(opt_in(tc_pass1_kernel<false, true, false>));
+  CUDA_TRY(opt_in(tc_pass1_kernel<false, true, true>));
   return 0;
 }
 
@@ -866,6 +1035,7 @@ int tc_pass1(dsmppi_ctx* c, const float* q, int q_stride, int n, uint32_t ignore
   a.inv_scale_div = (c->O == 9) ? 100.f : 1.f;
   a.zero = 0u;
   a.use_writers = 1;
+  a.nonfinite = c->counters + 9;
   a.prof = nullptr;
 #ifdef DSMPPI_TC_PROF
   a.prof = reinterpret_cast<long long*>(c->stage);   // the micro-benchmark parks its counter buffer here
@@ -875,8 +1045,12 @@ int tc_pass1(dsmppi_ctx* c, const float* q, int q_stride, int n, uint32_t ignore
   if (pairs > (n_tiles + 1) / 2) pairs = (n_tiles + 1) / 2;     // each pair takes two tiles per iteration
   if (pairs < 1) pairs = 1;
   const dim3 grid((unsigned)(2 * pairs));
-  if (bf16) tc_pass1_kernel<true><<<grid, NTHREADS, SMEM_BYTES, st>>>(a);
-  else tc_pass1_kernel<false><<<grid, NTHREADS, SMEM_BYTES, st>>>(a);
+  // (the shared-memory staging of table A needs a warp's 32 consecutive pair-rows to span at most two samples)
+  const bool stage_a = c->M >= 32;
+  auto launch = [&](auto kernel) { kernel<<<grid, NTHREADS, SMEM_BYTES, st>>>(a); };
+  if (bf16) stage_a ? launch(tc_pass1_kernel<true, false, true>) : launch(tc_pass1_kernel<true, false, false>);
+  else if (c->pass1_hacc) stage_a ? launch(tc_pass1_kernel<false, true, true>) : launch(tc_pass1_kernel<false, true, false>);
+  else stage_a ? launch(tc_pass1_kernel<false, false, true>) : launch(tc_pass1_kernel<false, false, false>);
   CUDA_TRY(cudaGetLastError());
   c->launches++;
   return 0;

@@ -277,8 +277,10 @@ def test_tensor_core_mode_is_bitwise_identical_to_fp32_mode(tag, N, H, factory):
         cost = m.get_cost()
         outs[mode] = (traj.clone(), dist.clone(), dots.clone(), acts.clone(), cost.clone())
         if mode == "tc_f16":
-            st = m.pass1_stats()
-            assert st["mode"] == 1 and st["band_overflows"] == 0, st
+            # (`band_overflows` counts samples whose guard band held more than 16 obstacles: they take more of the shared
+            # candidate list, nothing is truncated -- what must hold is that no call fell back to all-pairs fp32)
+            st, xs = m.pass1_stats(), m.exactness_stats()
+            assert st["mode"] == 1 and xs["exact_fallbacks"] == 0, (st, xs)
             print(f"{tag}: re-scored pairs per state-step = {st['rescored_pairs'] / (N * H):.2f} (K = {int(c['K'])})")
     for a, b2 in zip(outs["exact"], outs["tc_f16"]):
         assert torch.equal(a, b2)
@@ -400,8 +402,8 @@ def test_franka_large_batch_is_blockwise_consistent(factory):
     q = c["q0"] + 0.25 * torch.randn(N, 7, generator=gen)
     idx = torch.cat((torch.tensor([0, 262143, 262144, N - 1]), torch.randint(0, N, (300,), generator=gen))).unique()
     big, _ = _subset_matches_big_run(c, factory, N, H, q, idx, "tc_f16")
-    st = big.pass1_stats()
-    assert st["mode"] == 1 and st["band_overflows"] == 0, st
+    st, xs = big.pass1_stats(), big.exactness_stats()
+    assert st["mode"] == 1 and xs["exact_fallbacks"] == 0, (st, xs)     # crowded bands are re-scored, not truncated
 
 
 @pytest.mark.parametrize("tag", case_names())

@@ -8,6 +8,7 @@
 //              -I include -I optimalmodulationds_b200/csrc tools/tc_microbench.cu -o tools/tc_microbench
 #include <cstdio>
 #include <random>
+#include <string>
 
 #include "../optimalmodulationds_b200/csrc/tc_pass1.cu"
 
@@ -28,7 +29,12 @@ mb_kernel(int mode, int iters, int nwarps, int per_wait, long long* out) {
   volatile int* stop = reinterpret_cast<volatile int*>(smem + 2 * SZ_WHH + 128);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = cluster_ctarank();
-  for (int i = tid; i < 2 * SZ_WHH / 4; i += NTHREADS) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;  // fp16 1.0
+  // operands: pseudo-random fp16 in (-1, 1) (a constant operand toggles few wires and understates the power draw)
+  for (int i = tid; i < 2 * SZ_WHH / 4; i += NTHREADS) {
+    uint32_t x = (uint32_t)i * 2654435761u + blockIdx.x * 40503u;
+    x ^= x >> 13; x *= 0x5bd1e995u; x ^= x >> 15;
+    reinterpret_cast<uint32_t*>(smem)[i] = (x & 0x83ff83ffu) | 0x38003800u;   // sign + mantissa, exponent of 0.5..1
+  }
   if (tid == 0) *stop = 0;
   if (warp == MMA_WARP) {
     if (lane == 0) {
@@ -47,6 +53,22 @@ mb_kernel(int mode, int iters, int nwarps, int per_wait, long long* out) {
   const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
   long long cyc = 0;
   uint32_t sink = 0;
+  if (mode >= 2 && warp < 4) {            // the A operand (TMEM) gets the same kind of data
+    uint32_t v[32];
+    for (int g = 0; g < 4; ++g) {
+#pragma unroll
+      for (int k = 0; k < 32; ++k) {
+        uint32_t x = (uint32_t)(tid * 131 + g * 32 + k) * 2654435761u;
+        x ^= x >> 13; x *= 0x5bd1e995u; x ^= x >> 15;
+        v[k] = (x & 0x83ff83ffu) | 0x38003800u;
+      }
+      tmem_st32<0>(tmem_base + lane_addr + TM_A0 + g * 32, v);
+    }
+    tc_wait_st();
+    tc_fence_before();
+  }
+  __syncthreads();
+  tc_fence_after();
   if (mode <= 1 && warp < nwarps) {
     const uint32_t t0 = tmem_base + lane_addr + (warp >> 2) * 128;
     uint32_t v[32];
@@ -72,7 +94,9 @@ mb_kernel(int mode, int iters, int nwarps, int per_wait, long long* out) {
   }
   if (mode >= 2) {
     if (warp == MMA_WARP && rank == 0 && lane == 0) {
-      const uint32_t idesc128 = make_idesc(0, 256, 128), idesc256 = make_idesc(0, 256, 256);
+      // modes 5 / 6: the loop of mode 2 with an fp16 (instead of fp32) accumulator, for the power comparison below
+      const uint32_t acc_bit = (mode == 5) ? (1u << 4) : 0u;
+      const uint32_t idesc128 = make_idesc(0, 256, 128) ^ acc_bit, idesc256 = make_idesc(0, 256, 256);
       const long long c0 = clock64();
       for (int it = 0; it < iters; ++it) {
         if (mode == 3) {
@@ -118,6 +142,22 @@ mb_kernel(int mode, int iters, int nwarps, int per_wait, long long* out) {
   }
 }
 
+// Sustained rate under the power cap: the MMA loop alone on every SM for a few seconds, fp32 against fp16 accumulators.
+void run_power(const char* name, int mode, int iters, long long* dout) {
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  mb_kernel<<<148, NTHREADS, MB_SMEM>>>(mode, iters / 20, 0, 0, dout);   // warm-up
+  cudaEventRecord(e0);
+  mb_kernel<<<148, NTHREADS, MB_SMEM>>>(mode, iters, 0, 0, dout);
+  cudaEventRecord(e1);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("%s: %s\n", name, cudaGetErrorString(e)); exit(1); }
+  float ms;
+  cudaEventElapsedTime(&ms, e0, e1);
+  const double flops = (double)iters * 32 * 2.0 * 256 * 128 * 16 * 74;
+  printf("%-44s : %8.1f ms -> %.1f TFLOP/s sustained\n", name, ms, flops / ms * 1e-9);
+}
+
 void run_mb(const char* name, int mode, int iters, int nwarps, int per_wait, long long* dout, double unit_bytes_or_mma) {
   cudaMemset(dout, 0, 2 * 148 * 9 * sizeof(long long));
   mb_kernel<<<2, NTHREADS, MB_SMEM>>>(mode, iters, nwarps, per_wait, dout);
@@ -146,6 +186,13 @@ int main(int argc, char** argv) {
   cudaFuncSetAttribute(mb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MB_SMEM);
   long long* dout;
   cudaMalloc(&dout, 2 * 148 * 9 * sizeof(long long));
+  if (argc > 1 && std::string(argv[1]) == "power") {
+    for (int rep = 0; rep < 2; ++rep) {
+      run_power("MMA loop, fp32 accumulators, 148 SMs", 2, 2500000, dout);
+      run_power("MMA loop, fp16 accumulators, 148 SMs", 5, 2500000, dout);
+    }
+    return 0;
+  }
   for (int nw : {4, 8})
     for (int pw : {1, 2, 4}) run_mb("tcgen05.ld 32x32b.x32", 0, 2000, nw, pw, dout, 0);
   for (int nw : {4, 8}) run_mb("tcgen05.st 32x32b.x32", 1, 2000, nw, 4, dout, 0);
