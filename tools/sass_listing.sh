@@ -20,5 +20,5 @@ list() {   # object, start pattern, stop pattern, output
   } > "$4"
   echo "$4: $(wc -l < "$4") lines"
 }
-list tc_pass1.o 'tc_pass1_kernelILb0' x profiles/sass_tc_pass1.txt
-list tc_exact.o 'tc_exact_kernelILi1' x profiles/sass_tc_exact.txt
+list tc_pass1.o 'tc_pass1_kernelILb0ELb1ELb1' x profiles/sass_tc_pass1.txt
+list tc_exact.o 'tc_exact_kernelILi1ELb0' x profiles/sass_tc_exact.txt
