@@ -239,6 +239,35 @@ def test_guard_band_is_calibrated_per_network(factory):
         assert torch.equal(a, b), f"random-init net: {name} differs from the all-pairs fp32 rollout"
 
 
+@pytest.mark.parametrize("variant", ["f16_fp32acc", "bf16", "f16_few_obstacles", "bf16_few_obstacles"])
+def test_prefilter_variants_are_bitwise_the_all_pairs_rollout(factory, variant, monkeypatch):
+    """The prefilter kernel has six instantiations (fp16 operands with fp16 or fp32 accumulators, bf16 operands; the
+    per-sample table staged through shared memory from 32 obstacles on, read per lane below).  The default one is
+    covered by every tensor-core test; here the others: each gets its own calibrated band and must reproduce the
+    all-pairs fp32 rollout bit for bit."""
+    c = load_npz("case_franka_shelf")
+    if variant == "f16_fp32acc":
+        monkeypatch.setenv("DSMPPI_PASS1_ACC", "f32")           # read when the context is created
+    mode = "tc_bf16" if variant.startswith("bf16") else "tc_f16"
+    obs = c["obs"][:24] if variant.endswith("few_obstacles") else c["obs"]
+    torch.manual_seed(17)
+    N, H = 160, 4
+    q_cur = c["q0"] + 0.2 * torch.randn(N, 7)
+    outs, bands = {}, {}
+    for m_ in ("exact", mode):
+        m = factory.make_mppi(dict(c, obs=obs), device="cuda", N=N, H=H, q_cur=q_cur, pass1=m_, copy_policy=False)
+        torch.manual_seed(11)
+        m.Policy.sample_policy()
+        outs[m_] = _rollout_outputs(m) + [m.get_cost().clone()]
+        bands[m_] = (m.pass1_stats(), m.exactness_stats())
+    p1, xs = bands[mode]
+    print(f"{variant}: {p1}, {xs}")
+    assert p1["mode"] == (2 if mode == "tc_bf16" else 1) and xs["exact_fallbacks"] == 0
+    assert xs["guard_band"] > 0
+    for a, b in zip(outs["exact"], outs[mode]):
+        assert torch.equal(a, b)
+
+
 def test_prefilter_overflow_falls_back_to_all_pairs_fp32(factory):
     """A network whose hidden activations leave the fp16 range (layer 3 scaled by 1e5, layer 4 by 1e-5: the fp32
     function is an ordinary one) makes the prefilter's fp16 accumulators overflow.  The kernel reports the inf / NaN

@@ -245,8 +245,9 @@ def test_gradient_error_vs_fp64(name, factory):
 
 
 def test_tensor_core_prefilter_error_bound(factory):
-    """tcgen05 fp16 pass 1 vs fp32 pass 1 on the Franka shelf: the error must stay well inside the default
-    6 mm guard band (measured max 1.3 mm / 2.3 mm emulated over 2e5 random pairs)."""
+    """tcgen05 fp16 / bf16 pass 1 vs fp32 pass 1 on the Franka shelf as shipped: a sanity bound on the prefilter's
+    error (the guard band itself is calibrated per network and obstacle set: DESIGN.md section 3; measured here
+    ~1.5 mm with fp16 accumulators in the hidden layers, ~1 mm with fp32 ones)."""
     c = load_npz("case_franka_shelf")
     m = factory.make_mppi(c, device="cuda", N=32, H=1)
     torch.manual_seed(0)
