@@ -176,7 +176,11 @@ void dsmppi_modulation_toy(dsmppi_modulation* out);       /* MPPI_toy.py constan
 int dsmppi_ctx_create(dsmppi_ctx** out, const dsmppi_net* net, const float* dh_params_host,
                       int32_t capacity, int32_t device);
 int dsmppi_ctx_destroy(dsmppi_ctx* ctx);
-/* guard_band > 0 fixes the prefilter's guard band (metres); 0 = calibrate it for the network (dsmppi_exactness_stats) */
+/* guard_band > 0 fixes the prefilter's guard band (metres); 0 = calibrate it for the network (dsmppi_exactness_stats).
+ * Environment, read by dsmppi_ctx_create: DSMPPI_PASS1_ACC=f32 makes the fp16 prefilter accumulate its hidden layers
+ * in fp32 (default: fp16 accumulators -- twice the prefilter error, a wider calibrated band, the same results bit for
+ * bit, 8 % less time per prefilter launch); DSMPPI_HALF_TILES=0 keeps the whole-horizon kernel on 128-row tiles;
+ * DSMPPI_DISABLE_TC=1 builds no tensor-core images (every mode resolves to the FFMA kernels). */
 int dsmppi_set_pass1_mode(dsmppi_ctx* ctx, int32_t mode, float guard_band);
 int dsmppi_set_score_mode(dsmppi_ctx* ctx, int32_t mode);     /* DSMPPI_SCORE_*; default AUTO */
 /* Small obstacle sets scored in fp32 (M <= 16, or M <= 32 with a latency-bound batch) are rolled out over the whole
@@ -353,7 +357,8 @@ int dsmppi_pass1_stats(dsmppi_ctx* ctx, int64_t* rescored_pairs, int64_t* band_o
 /* The prefilter path is exact by construction: EVERY obstacle within the guard band of the K-th smallest approximate
  * distance is re-scored in fp32; when a step's candidates do not fit the shared row list the rollout is repeated with
  * a larger list (`capacity_retries`), past 2^27 rows with every pair scored in fp32 (`exact_fallbacks`) -- never
- * truncated.  `guard_band` is the band in effect (metres): the caller's (dsmppi_set_pass1_mode) or the one
+ * truncated; the same repeat in fp32 happens when the prefilter produced inf / NaN for any pair (activations beyond the
+ * fp16 range).  `guard_band` is the band in effect (metres): the caller's (dsmppi_set_pass1_mode) or the one
  * calibrated for this network and obstacle set = 3 x `calibration_error`, the largest |prefilter - fp32 scoring|
  * over 256 random joint vectors + the first states of the calling batch x every obstacle. */
 int dsmppi_exactness_stats(dsmppi_ctx* ctx, int64_t* capacity_retries, int64_t* exact_fallbacks, float* guard_band,
