@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdsmppi_b200.so")
+# DSMPPI_LIB=<path>: another build of the same library (A/B measurements of two builds on one box)
+LIB_PATH = os.environ.get("DSMPPI_LIB") or os.path.join(_HERE, "libdsmppi_b200.so")
 
 N_KERNEL_MAX = 50
 MAX_DOF = 8
