@@ -360,28 +360,36 @@ __device__ __forceinline__ void relu_pack32(const uint32_t (&v)[32], const float
 // No saturation here (a clamping HMNMX2 per pair cost 3.5 % of the kernel): an accumulator that overflowed is inf,
 // stays inf / NaN through the remaining layers, and is caught at the output.  The biases come from shared memory as
 // fp16 pairs (passed as kernel parameters -- constant bank -- they turned into 192 LDC.64 per tile and cost 4 %).
-template <int OFF, int NPK>
-__device__ __forceinline__ void relu_h2_32(const uint32_t (&v)[32], const uint4* __restrict__ bias_h2, uint32_t (&pk)[NPK]) {
+template <int OFF, int BOFF, int NPK>
+__device__ __forceinline__ void relu_h2_32(const uint32_t (&v)[32], const uint4 (&b)[16], uint32_t (&pk)[NPK]) {
   const uint32_t one = 0x3c003c00u;
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
-    const uint4 bb = bias_h2[k];
+    const uint4 bb = b[BOFF + k];
     asm("fma.rn.relu.f16x2 %0, %1, %2, %3;" : "=r"(pk[OFF + 4 * k + 0]) : "r"(v[4 * k + 0]), "r"(one), "r"(bb.x));
     asm("fma.rn.relu.f16x2 %0, %1, %2, %3;" : "=r"(pk[OFF + 4 * k + 1]) : "r"(v[4 * k + 1]), "r"(one), "r"(bb.y));
     asm("fma.rn.relu.f16x2 %0, %1, %2, %3;" : "=r"(pk[OFF + 4 * k + 2]) : "r"(v[4 * k + 2]), "r"(one), "r"(bb.z));
     asm("fma.rn.relu.f16x2 %0, %1, %2, %3;" : "=r"(pk[OFF + 4 * k + 3]) : "r"(v[4 * k + 3]), "r"(one), "r"(bb.w));
   }
 }
+// 16 x 16 bytes of fp16 bias pairs, read BEFORE the wait for the accumulator they belong to: the loads are then off
+// the chain accumulator ready -> operand stored (the asm waits carry memory clobbers, nothing moves across them)
+__device__ __forceinline__ void load_bias16(const uint4* __restrict__ src, uint4 (&b)[16]) {
+  const uint32_t sa = smem_u32(src);
+#pragma unroll
+  for (int k = 0; k < 16; ++k)      // volatile: the compiler would sink plain loads back to their uses, behind the wait
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(b[k].x), "=r"(b[k].y), "=r"(b[k].z), "=r"(b[k].w) : "r"(sa + 16u * k));
+}
 
 // relu(a + b) on two packed half-precision values: the first hidden activation from the layer-1 tables
 template <bool BF16>
 __device__ __forceinline__ uint32_t add_relu_h2(uint32_t a, uint32_t b) {
+  // one HFMA2.RELU: a * 1 is exact, so fma(a, 1, b) rounds exactly like a + b (an add + a max was two issue slots per
+  // feature pair on the tile boundary's critical path)
   uint32_t r;
-  if (BF16) {
-    asm("{\n\t.reg .b32 t;\n\tadd.rn.bf16x2 t, %1, %2;\n\tmax.bf16x2 %0, t, %3;\n\t}" : "=r"(r) : "r"(a), "r"(b), "r"(0u));
-  } else {
-    asm("{\n\t.reg .b32 t;\n\tadd.rn.f16x2 t, %1, %2;\n\tmax.f16x2 %0, t, %3;\n\t}" : "=r"(r) : "r"(a), "r"(b), "r"(0u));
-  }
+  if (BF16) asm("fma.rn.relu.bf16x2 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(0x3f803f80u), "r"(b));
+  else asm("fma.rn.relu.f16x2 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(0x3c003c00u), "r"(b));
   return r;
 }
 
@@ -444,21 +452,17 @@ struct TableLoads {
   int i0;
 };
 __device__ __forceinline__ void first_layer_issue(const TcArgs& a, int i, int j, uint32_t dep, int lane, TableLoads& t) {
+  // Every load is unconditional: pair-rows past the end of the batch (i == n; only in the last tile) read the tables
+  // of sample n - 1 and of their own, valid, obstacle index, and compute a row nobody stores.  (Predicated loads made
+  // the compiler zero all 132 destination registers first, on every tile.)
   t.i0 = __shfl_sync(0xffffffffu, i, 0);
   const uint4* ta = a.tabA + dep;
-  t.a0 = make_uint4(0u, 0u, 0u, 0u);
-  t.a1 = t.a0;
-  if (t.i0 < a.n) t.a0 = ldg_nc_v4(ta + (size_t)t.i0 * 32 + lane);
-  if (t.i0 + 1 < a.n) t.a1 = ldg_nc_v4(ta + (size_t)(t.i0 + 1) * 32 + lane);
-  if (i < a.n) {
-    const uint4* tb = a.tabB + j + dep;
-    const uint32_t strideM = (uint32_t)a.M + dep;
+  t.a0 = ldg_nc_v4(ta + (size_t)min(t.i0, a.n - 1) * 32 + lane);
+  t.a1 = ldg_nc_v4(ta + (size_t)min(t.i0 + 1, a.n - 1) * 32 + lane);
+  const uint4* tb = a.tabB + j + dep;
+  const uint32_t strideM = (uint32_t)a.M + dep;
 #pragma unroll
-    for (int kb = 0; kb < 32; ++kb) t.y[kb] = ldg_nc_v4(tb + (size_t)(kb * strideM));
-  } else {
-#pragma unroll
-    for (int kb = 0; kb < 32; ++kb) t.y[kb] = make_uint4(0u, 0u, 0u, 0u);
-  }
+  for (int kb = 0; kb < 32; ++kb) t.y[kb] = ldg_nc_v4(tb + (size_t)(kb * strideM));
 }
 template <bool BF16>
 __device__ __forceinline__ void first_layer_finish(const TcArgs& a, int i, const TableLoads& t, uint4* abuf, int lane,
@@ -466,7 +470,7 @@ __device__ __forceinline__ void first_layer_finish(const TcArgs& a, int i, const
   abuf[lane] = t.a0;
   abuf[32 + lane] = t.a1;
   __syncwarp();
-  const uint4* ar = abuf + (i < a.n ? (i - t.i0) * 32 : 0);
+  const uint4* ar = abuf + (i - t.i0) * 32;          // 0 or 1: a warp's rows span at most two samples
 #pragma unroll
   for (int kb = 0; kb < 32; ++kb) {
     const uint4 x = ar[kb];
@@ -474,10 +478,6 @@ __device__ __forceinline__ void first_layer_finish(const TcArgs& a, int i, const
     pk[4 * kb + 1] = add_relu_h2<BF16>(x.y, t.y[kb].y);
     pk[4 * kb + 2] = add_relu_h2<BF16>(x.z, t.y[kb].z);
     pk[4 * kb + 3] = add_relu_h2<BF16>(x.w, t.y[kb].w);
-  }
-  if (!(i < a.n)) {
-#pragma unroll
-    for (int k = 0; k < 128; ++k) pk[k] = 0u;
   }
   __syncwarp();
 }
@@ -600,7 +600,10 @@ tc_pass1_kernel(const __grid_constant__ TcArgs a) {
       auto hacc_layer = [&](auto L) {
         constexpr int l = decltype(L)::value;
         PROF_ADD(7);
-          uint32_t pk[64], raw[2][32];
+        uint32_t pk[64], raw[2][32];
+        const uint4* bsm = reinterpret_cast<const uint4*>(smem + OFF_BIASH) + l * (HID / 8);
+        uint4 bq[16];
+        load_bias16(bsm, bq);
         mbar_wait(bar_full_lo, (uint32_t)(l & 1));
         tc_fence_after();
         PROF_ADD(0);
@@ -609,9 +612,10 @@ tc_pass1_kernel(const __grid_constant__ TcArgs a) {
         tc_wait_ld();
         signal(BAR(BAR_DFREE0));
         PROF_ADD(1);
-        relu_h2_32<0>(raw[0], reinterpret_cast<const uint4*>(smem + OFF_BIASH) + l * (HID / 8) + 0, pk);
-        relu_h2_32<32>(raw[1], reinterpret_cast<const uint4*>(smem + OFF_BIASH) + l * (HID / 8) + 8, pk);
+        relu_h2_32<0, 0>(raw[0], bq, pk);
+        relu_h2_32<32, 8>(raw[1], bq, pk);
         PROF_ADD(2);
+        load_bias16(bsm + 16, bq);
         mbar_wait(bar_full_hi, (uint32_t)((it + l) & 1));
         tc_fence_after();
         PROF_ADD(3);
@@ -622,8 +626,8 @@ tc_pass1_kernel(const __grid_constant__ TcArgs a) {
         tc_wait_ld();
         signal(BAR(BAR_DFREE1));
         PROF_ADD(4);
-        relu_h2_32<0>(raw[0], reinterpret_cast<const uint4*>(smem + OFF_BIASH) + l * (HID / 8) + 16, pk);
-        relu_h2_32<32>(raw[1], reinterpret_cast<const uint4*>(smem + OFF_BIASH) + l * (HID / 8) + 24, pk);
+        relu_h2_32<0, 0>(raw[0], bq, pk);
+        relu_h2_32<32, 8>(raw[1], bq, pk);
         tmem_st32<0>(tA + 64, pk);
         tmem_st32<32>(tA + 96, pk);
         tc_wait_st();
