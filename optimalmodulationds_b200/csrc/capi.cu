@@ -228,7 +228,7 @@ int dsmppi_ctx_destroy(dsmppi_ctx* c) {
   tc_free_images(c);
   tcx_free_images(c);
   void* ptrs[] = {c->weights_blob, c->seds, c->obs, c->obs_raw, c->obs_enc, c->q_work, c->m_rows, c->mdist, c->enc_q,
-                  c->cand_obs, c->cand_cnt, c->row_base, c->row_sample, c->row_obs, c->counters, c->sel, c->fix_list,
+                  c->cand_cnt, c->row_base, c->row_sample, c->row_obs, c->counters, c->sel, c->fix_list,
                   c->sel_rows, c->row_dist, c->row_grad, c->dist_tmp, c->grad_tmp, c->upd_partials, c->stats_tmp, c->stats_part,
                   c->stats_ticket,
                   c->packed_tmp, c->stage};

@@ -110,7 +110,6 @@ struct dsmppi_ctx {
   float* mdist = nullptr;             // tensor path: approximate (n, M)
   size_t mdist_cap = 0;
   void* enc_q = nullptr; size_t enc_q_cap = 0;       // tensor path: per-sample packed encodings
-  int* cand_obs = nullptr;            // (n, CAND_MAX)
   int* cand_cnt = nullptr;            // (n)
   int* row_base = nullptr;            // (n)
   int* row_sample = nullptr; int* row_obs = nullptr; size_t rowlist_cap = 0;

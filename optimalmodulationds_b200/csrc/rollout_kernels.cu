@@ -135,7 +135,8 @@ __global__ void __launch_bounds__(128) step_kernel(StepArgs s) {
 // Prefilter path, ONE launch after the scoring kernel: a WARP per sample
 //   1. ranks the sample's re-scored candidate rows -- the K closest, ascending by (fp32 key, obstacle index): the
 //      second half of MPPI.py:245-253's sort (the body of rank_kernel);
-//   2. lane 0 runs the modulation / policy / Euler step (step_sample, MPPI.py:101-223) on those rows;
+//   2. the group's lanes run the modulation / policy / Euler step (step_group_t, MPPI.py:101-223) on those rows: lane a
+//      owns joint a, lane k row k and the policy kernels k, k + GL, ... -- bit-identical to the one-thread step_sample;
 //   3. all lanes write the layer-1 table row of the NEXT state for the next step's prefilter (l1_table.cuh).
 // Replaces rank_kernel + step_kernel + l1_table_kernel.  The step is a 5 k-instruction dependent chain per sample:
 // with one sample per warp an SM holds ~28 such chains on 28 warps instead of one warp with 28 active lanes, so the
@@ -187,9 +188,21 @@ __global__ void __launch_bounds__(128) rank_step_kernel(StepArgs s, RankStepArgs
     }
   }
   __syncwarp();
-  if (gl == 0 && live) step_sample(s, w, s.t, StepIO{s.row_dist, s.row_grad, rows_s[g], nullptr, qn_s[g]});
+  // the step: on all GL lanes where the lane-parallel form exists (bit-identical, step_device.cuh), else on lane 0
+  const bool grouped = s.mod.ds_kind == DSMPPI_DS_LINEAR_ATTRACTOR && s.p == 2.f && (s.d == 7 || s.d == 2);
+  if (grouped) {
+    if (s.d == 7) step_group_t<7, GL>(s, live ? w : 0, s.t, rows_s[g], qn_s[g], gl, live);
+    else step_group_t<2, GL>(s, live ? w : 0, s.t, rows_s[g], qn_s[g], gl, live);
+  } else if (gl == 0 && live) {
+    step_sample(s, w, s.t, StepIO{s.row_dist, s.row_grad, rows_s[g], nullptr, qn_s[g]});
+  }
   __syncwarp();
-  if (r.tabA != nullptr && s.t < s.H && live) {
+  // ---- the next state's layer-1 table rows, by the whole CTA: a thread owns two adjacent features, keeps their 3 d
+  //      weights in registers and walks the CTA's samples (inputs broadcast from shared memory).  (Each group writing
+  //      its own row -- 32 features per lane, the weights re-read from L2 inside every feature's dependent FMA chain --
+  //      took 29 of this kernel's 39 us.)  Same FMA order as l1_feature, so a table does not depend on who wrote it.
+  const bool table = r.tabA != nullptr && s.t < s.H;
+  if (table && live) {
     const int d = s.d;
     if (gl < d) {
       const float v = qn_s[g][gl];
@@ -198,13 +211,35 @@ __global__ void __launch_bounds__(128) rank_step_kernel(StepArgs s, RankStepArgs
       xs_s[g][3 * gl] = v; xs_s[g][3 * gl + 1] = sn; xs_s[g][3 * gl + 2] = cs;
     }
   }
-  __syncwarp();
-  if (r.tabA != nullptr && s.t < s.H && live) {
+  __syncthreads();
+  if (table) {
     const int d = s.d;
-#pragma unroll 2
-    for (int u = 0; u < HID / GL; ++u) {
-      const int k = gl + GL * u;
-      r.tabA[(size_t)w * HID + k] = l1_to_half_bits(l1_feature(r.Wf0, r.b0, k, xs_s[g], d, 0, r.nin), r.bf16 != 0);
+    static_assert(HID == 2 * 128, "two features per thread of a 128-thread CTA");
+    const int k = 2 * threadIdx.x;
+    float2 wq[MAXD], ws[MAXD], wc[MAXD];
+#pragma unroll
+    for (int c = 0; c < MAXD; ++c) {
+      if (c < d) {
+        wq[c] = *reinterpret_cast<const float2*>(r.Wf0 + (size_t)c * HID + k);
+        ws[c] = *reinterpret_cast<const float2*>(r.Wf0 + (size_t)(r.nin + c) * HID + k);
+        wc[c] = *reinterpret_cast<const float2*>(r.Wf0 + (size_t)(2 * r.nin + c) * HID + k);
+      }
+    }
+    const float2 bias = r.b0 ? *reinterpret_cast<const float2*>(r.b0 + k) : make_float2(0.f, 0.f);
+    const int n_here = min(SPB, s.N - blockIdx.x * SPB);
+    for (int gg = 0; gg < n_here; ++gg) {
+      float a0 = bias.x, a1 = bias.y;
+#pragma unroll
+      for (int c = 0; c < MAXD; ++c) {
+        if (c < d) {
+          const float x = xs_s[gg][3 * c], sn = xs_s[gg][3 * c + 1], cs = xs_s[gg][3 * c + 2];
+          a0 = fmaf(wq[c].x, x, a0); a1 = fmaf(wq[c].y, x, a1);
+          a0 = fmaf(ws[c].x, sn, a0); a1 = fmaf(ws[c].y, sn, a1);
+          a0 = fmaf(wc[c].x, cs, a0); a1 = fmaf(wc[c].y, cs, a1);
+        }
+      }
+      const uint32_t packed = (uint32_t)l1_to_half_bits(a0, r.bf16 != 0) | ((uint32_t)l1_to_half_bits(a1, r.bf16 != 0) << 16);
+      *reinterpret_cast<uint32_t*>(r.tabA + ((size_t)(blockIdx.x * SPB + gg)) * HID + k) = packed;
     }
   }
 }

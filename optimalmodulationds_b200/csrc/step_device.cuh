@@ -335,6 +335,134 @@ __device__ __forceinline__ void step_sample_t(const StepArgs& s, int i, int t, c
 }
 
 
+// ------------------------------------------------------------------------------------------------
+// The same step on a GROUP of GL lanes (rank_step_kernel): lane a owns joint a, lane k owns candidate row k and the
+// policy kernels k, k + GL, ...  step_sample_t is one thread walking ~5 k dependent instructions and two dozen dependent
+// loads; here the loads of a phase are issued together and the per-joint / per-row / per-kernel arithmetic runs side
+// by side.  EVERY floating-point operation is the one step_sample_t performs, on the same operands, and every sum is
+// accumulated in the same order (the library is built with -fmad=false; a sum over joints is re-played sequentially
+// from shuffled terms), so the result is bit-identical -- the tests that compare the prefilter path with the
+// all-pairs path (which steps with step_sample_t) hold the two together.
+// Covers what the shipped robots use: linear-attractor nominal DS, p = 2, d = D in {2, 7}; rank_step_kernel keeps the
+// one-thread form for everything else.  All GL lanes of every group of the warp must call it (live or not).
+// ------------------------------------------------------------------------------------------------
+template <int DD, int GL>
+__device__ __forceinline__ float group_ordered_sum(float term) {
+  float acc = 0.f;
+#pragma unroll
+  for (int a = 0; a < DD; ++a) acc += __shfl_sync(0xffffffffu, term, a, GL);
+  return acc;
+}
+
+template <int D, int GL>
+__device__ __forceinline__ void step_group_t(const StepArgs& s, int i, int t, const int* rows, float* q_next, int gl,
+                                             bool live) {
+  static_assert(D >= 1 && D <= GL && GL <= 32, "one lane per joint");
+  constexpr int d = D;
+  const size_t st = (size_t)i * s.H + (t - 1);
+  const bool mine = gl < d;                                   // this lane owns a joint
+  const int K = s.K;
+  // ---- loads of the whole step's row / state inputs, issued together
+  const float q = mine ? s.traj[st * d + gl] : 0.f;
+  const int row_k = gl < K ? rows[gl] : rows[0];
+  const float dist_k = s.row_dist[row_k];
+  float gk[MAXK];
+#pragma unroll
+  for (int k = 0; k < MAXK; ++k) gk[k] = (k < K && mine) ? s.row_grad[(size_t)rows[k] * d + gl] : 0.f;
+  const float goal = mine ? s.goal[gl] : 0.f;
+  // S0 nominal DS: unit-speed attractor, linear inside lin_thr (LinDS.py:11-21), and its norm (MPPI.py:106-108)
+  float v = mine ? -(q - goal) : 0.f;
+  {
+    const float dst = sqrtf(group_ordered_sum<D, GL>(v * v));
+    if (dst > s.lin_thr) v = v / dst;
+  }
+  const float vn = sqrtf(group_ordered_sum<D, GL>(v * v));
+  const float vhat = mine ? v / vn : 0.f;
+  // S2e blended distance / gradient (MPPI.py:270-280): lane k holds row k's softmax weight
+  float mx = gl < K ? -10.f * dist_k : -FLT_MAX;
+#pragma unroll
+  for (int off = GL / 2; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off, GL));
+  const float ek = expf(-10.f * dist_k - mx);
+  float den = 0.f;
+#pragma unroll
+  for (int k = 0; k < MAXK; ++k) {
+    const float e = __shfl_sync(0xffffffffu, ek, k, GL);
+    if (k < K) den += e;
+  }
+  const float wk = ek / den;
+  float g = 0.f;
+#pragma unroll
+  for (int k = 0; k < MAXK; ++k) {
+    const float w = __shfl_sync(0xffffffffu, wk, k, GL);
+    if (k < K) g += gk[k] * w;
+  }
+  float dist = __shfl_sync(0xffffffffu, dist_k, 0, GL);
+  dist -= s.dst_thr;                                          // MPPI.py:117
+  if (live && gl == 0) s.closest[st] = dist;
+  if (live && mine) s.grads[st * d + gl] = g;
+  const float gn = sqrtf(group_ordered_sum<D, GL>(g * g));
+  const float e0 = mine ? g / gn : 0.f;                       // MPPI.py:126
+  const float dot = group_ordered_sum<D, GL>(e0 * vhat);      // MPPI.py:129
+  if (live && gl == 0) s.dots[st] = dot;
+  // S3 modulation coefficients (MPPI.py:132,149-155) and activation (MPPI.py:191-196): scalars, every lane the same
+  const float l_vel = gsigmoid(dot, 0.f, 1.f, s.mod.lvel_mid, s.mod.lvel_k);
+  const float l_n = gsigmoid(dist, 0.f, 1.f, s.mod.dist_mid, s.mod.dist_k);
+  const float l_tau = gsigmoid(dist, s.mod.ltau_max, 1.f, s.mod.dist_mid, s.mod.dist_k);
+  const float l_nv = l_vel * 1.f + (1.f - l_vel) * l_n;
+  float ga = group_ordered_sum<D, GL>(mine ? sqrtf(fabsf(q - goal)) : 0.f);
+  ga = ga * ga;
+  ga = fminf(fmaxf(ga, 0.f), 1.f);
+  if (ga < s.mod.goal_act_thr) ga = 0.f;
+  const float act = (1.f - l_n) * (1.f - l_vel) * ga;
+  if (live && gl == 0) s.acts[st] = act;
+  const float kv_scale = s.mod.fold_activation ? act : 1.f;   // MPPI_toy.py:178-179
+  // S4 RBF policy (policy.py:186-199, MPPI.py:165-186): lane j evaluates kernels j, j + GL, ...; lane a accumulates
+  // joint a's velocity over the kernels in ascending order
+  float qa[D];
+#pragma unroll
+  for (int a = 0; a < D; ++a) qa[a] = __shfl_sync(0xffffffffu, q, a, GL);
+  float u = 0.f;
+  for (int k0 = 0; k0 < s.nk; k0 += GL) {
+    const int k = k0 + gl;
+    const bool has = k < s.nk;
+    const float* mu = s.mu + ((size_t)i * NKMAX + (has ? k : 0)) * d;
+    float muv[D], alv[GL];
+#pragma unroll
+    for (int a = 0; a < D; ++a) muv[a] = __ldg(mu + a);
+    const float sg = __ldg(s.sigma + (size_t)i * NKMAX + (has ? k : 0));
+#pragma unroll
+    for (int j = 0; j < GL; ++j)
+      alv[j] = (mine && k0 + j < s.nk) ? __ldg(s.alpha + ((size_t)i * NKMAX + k0 + j) * d + gl) : 0.f;
+    float acc = 0.f;
+#pragma unroll
+    for (int a = 0; a < D; ++a) { const float df = qa[a] - muv[a]; acc += df * df; }
+    acc = sqrtf(acc);
+    const float num = acc * acc;                              // norm ** 2
+    const float phi = expf(-sg * num);
+    if (live && has) s.kval[st * NKMAX + k] = s.mod.fold_activation ? phi * kv_scale : phi;   // MPPI.py:184
+#pragma unroll
+    for (int j = 0; j < GL; ++j) {
+      const float ph = __shfl_sync(0xffffffffu, phi, j, GL);
+      if (k0 + j < s.nk) u += alv[j] * ph;                    // MPPI.py:174-177
+    }
+  }
+  // total velocity and modulation M = l_tau I + (l_nv - l_tau) e0 e0^T  (MPPI.py:158-161,197-209)
+  const float vt = v + act * u * vn;
+  const float proj = group_ordered_sum<D, GL>(e0 * vt);
+  float m = l_tau * vt + (l_nv - l_tau) * e0 * proj;
+  if (!mine) m = 0.f;
+  float mn = sqrtf(group_ordered_sum<D, GL>(m * m));
+  if (mn <= 0.5f) mn = 1.f;                                   // MPPI.py:211-212
+  float mv = nan_to_num(m / mn);                              // MPPI.py:213
+  if (dist < 0.f) mv = mv * 0.1f + e0 * vn * s.mod.repulsion; // MPPI.py:215-217
+  if (live && mine) {
+    const float qn = q + s.dt * mv;                           // MPPI.py:220-221
+    if (t < s.H) s.traj[(st + 1) * d + gl] = qn;
+    if (q_next) q_next[gl] = qn;
+    if (t == 1) s.qdot[(size_t)i * d + gl] = mv;              // MPPI.py:222-223
+  }
+}
+
 // dispatch on the joint counts the shipped robots have (planar 2-DoF, planar / Franka 7-DoF); anything else runs generic
 __device__ __forceinline__ void step_sample(const StepArgs& s, int i, int t, const StepIO& io) {
   if (s.d == 7) step_sample_t<7>(s, i, t, io);
