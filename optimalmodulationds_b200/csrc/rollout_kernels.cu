@@ -189,10 +189,10 @@ __global__ void __launch_bounds__(128) rank_step_kernel(StepArgs s, RankStepArgs
   }
   __syncwarp();
   // the step: on all GL lanes where the lane-parallel form exists (bit-identical, step_device.cuh), else on lane 0
-  const bool grouped = s.mod.ds_kind == DSMPPI_DS_LINEAR_ATTRACTOR && s.p == 2.f && (s.d == 7 || s.d == 2);
-  if (grouped) {
-    if (s.d == 7) step_group_t<7, GL>(s, live ? w : 0, s.t, rows_s[g], qn_s[g], gl, live);
-    else step_group_t<2, GL>(s, live ? w : 0, s.t, rows_s[g], qn_s[g], gl, live);
+  if (step_group_supported(s)) {
+    const StepIO io{s.row_dist, s.row_grad, rows_s[g], nullptr, qn_s[g]};
+    if (s.d == 7) step_group_t<7, GL>(s, live ? w : 0, s.t, io, gl, live);
+    else step_group_t<2, GL>(s, live ? w : 0, s.t, io, gl, live);
   } else if (gl == 0 && live) {
     step_sample(s, w, s.t, StepIO{s.row_dist, s.row_grad, rows_s[g], nullptr, qn_s[g]});
   }

@@ -343,9 +343,14 @@ __device__ __forceinline__ void step_sample_t(const StepArgs& s, int i, int t, c
 // accumulated in the same order (the library is built with -fmad=false; a sum over joints is re-played sequentially
 // from shuffled terms), so the result is bit-identical -- the tests that compare the prefilter path with the
 // all-pairs path (which steps with step_sample_t) hold the two together.
-// Covers what the shipped robots use: linear-attractor nominal DS, p = 2, d = D in {2, 7}; rank_step_kernel keeps the
-// one-thread form for everything else.  All GL lanes of every group of the warp must call it (live or not).
+// Covers what the shipped robots use: linear-attractor nominal DS, p = 2, d = D in {2, 7} (step_group_supported); the
+// callers keep the one-thread form for everything else.  All GL lanes of every group of the warp must call it (live
+// or not).
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool step_group_supported(const StepArgs& s) {
+  return s.mod.ds_kind == DSMPPI_DS_LINEAR_ATTRACTOR && s.p == 2.f && (s.d == 7 || s.d == 2);
+}
+
 template <int DD, int GL>
 __device__ __forceinline__ float group_ordered_sum(float term) {
   float acc = 0.f;
@@ -354,21 +359,25 @@ __device__ __forceinline__ float group_ordered_sum(float term) {
   return acc;
 }
 
+// io: as for step_sample_t (rows / state from global or shared memory); a group that is not `live` (padding of the
+// last CTA) computes on sample i's state and row 0 and stores nothing.
 template <int D, int GL>
-__device__ __forceinline__ void step_group_t(const StepArgs& s, int i, int t, const int* rows, float* q_next, int gl,
-                                             bool live) {
+// q_lane (optional): this lane's joint of the state, carried in a register by a caller that steps the same sample again
+// (the whole-horizon kernel): read instead of io.q_in / all_traj, and updated.
+__device__ __forceinline__ void step_group_t(const StepArgs& s, int i, int t, const StepIO& io, int gl, bool live,
+                                             float* q_lane = nullptr) {
   static_assert(D >= 1 && D <= GL && GL <= 32, "one lane per joint");
   constexpr int d = D;
   const size_t st = (size_t)i * s.H + (t - 1);
   const bool mine = gl < d;                                   // this lane owns a joint
   const int K = s.K;
   // ---- loads of the whole step's row / state inputs, issued together
-  const float q = mine ? s.traj[st * d + gl] : 0.f;
-  const int row_k = gl < K ? rows[gl] : rows[0];
-  const float dist_k = s.row_dist[row_k];
+  const float q = mine ? (q_lane ? *q_lane : io.q_in ? io.q_in[gl] : s.traj[st * d + gl]) : 0.f;
+  const int row_k = live ? io.rows[gl < K ? gl : 0] : 0;
+  const float dist_k = io.row_dist[row_k];
   float gk[MAXK];
 #pragma unroll
-  for (int k = 0; k < MAXK; ++k) gk[k] = (k < K && mine) ? s.row_grad[(size_t)rows[k] * d + gl] : 0.f;
+  for (int k = 0; k < MAXK; ++k) gk[k] = (k < K && mine) ? io.row_grad[(size_t)(live ? io.rows[k] : 0) * d + gl] : 0.f;
   const float goal = mine ? s.goal[gl] : 0.f;
   // S0 nominal DS: unit-speed attractor, linear inside lin_thr (LinDS.py:11-21), and its norm (MPPI.py:106-108)
   float v = mine ? -(q - goal) : 0.f;
@@ -458,7 +467,8 @@ __device__ __forceinline__ void step_group_t(const StepArgs& s, int i, int t, co
   if (live && mine) {
     const float qn = q + s.dt * mv;                           // MPPI.py:220-221
     if (t < s.H) s.traj[(st + 1) * d + gl] = qn;
-    if (q_next) q_next[gl] = qn;
+    if (io.q_next) io.q_next[gl] = qn;
+    if (q_lane) *q_lane = qn;
     if (t == 1) s.qdot[(size_t)i * d + gl] = mv;              // MPPI.py:222-223
   }
 }

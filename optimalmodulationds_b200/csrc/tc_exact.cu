@@ -485,6 +485,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_exac
       if (TCX_ENC_PIPE) enc_compute(nx_i, nx_j, nx_valid, a.q, a.q_stride);
     }
     uint32_t pass = 0;                                      // (tile, step) passes done: locates the output layer's stage
+    float qlane[TROWS / 32] = {0.f, 0.f, 0.f, 0.f};         // whole-horizon kernel, lane-parallel step: this lane's joint
+    static_assert(TROWS == 128, "four batches of 32 sample slots");
     float qreg[MAXD];                                       // whole-horizon kernel: the state of this thread's sample
 #pragma unroll
     for (int c = 0; c < MAXD; ++c) qreg[c] = 0.f;
@@ -995,9 +997,51 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_exac
           }
           asm volatile("bar.sync 1, 256;" ::: "memory");
         }
-        // ---- one thread per sample: (ranking of a few obstacles,) then the modulation / policy / Euler step of
-        //      step_device.cuh
-        if (tid < a.S) {
+        // ---- eight lanes per sample: (ranking of a few obstacles on the first,) then the modulation / policy / Euler
+        //      step in its lane-parallel form (step_group_t: a lane per joint / ranked row / policy kernel, bit-identical
+        //      to the one-thread step_sample): the step was 13 k of a planar-7 rollout step's 65 k cycles on ONE warp
+        if (step_group_supported(a.sa)) {
+#pragma unroll
+         for (int sb = 0; sb < TROWS / 32; ++sb) {            // 32 sample slots (256 threads) at a time; S <= 128
+          if (32 * sb + (warp << 2) < a.S) {                  // warps holding at least one of the CTA's sample slots
+            const int g = 32 * sb + (tid >> 3), gl = tid & 7;
+            const int i = (tile * 2 + (int)rank) * a.S + g;
+            const bool live = g < a.S && i < a.sa.N;
+            const int K = a.sa.K, M = a.M;
+            int* rows = reinterpret_cast<int*>(stg + STG_ROWS) + (live ? g : 0) * MAXK;
+            if (live && gl == 0) {
+              asm volatile("prefetch.global.L1 [%0];" ::"l"(a.sa.sigma + (size_t)i * NKMAX));
+              for (int b = 0; b < a.sa.nk * d * 4; b += 128) {
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char*>(a.sa.mu + (size_t)i * NKMAX * d) + b));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char*>(a.sa.alpha + (size_t)i * NKMAX * d) + b));
+              }
+              const float* mr = stg + STG_M + g * M;
+              float last_v = -3.4e38f;
+              int last_j = -1;
+#pragma unroll 1
+              for (int kk = 0; kk < K && !warp_rank; ++kk) {
+                float bv = 3.4e38f;
+                int bj = -1;
+#pragma unroll 1
+                for (int j = 0; j < M; ++j) {
+                  const float v = mr[j];
+                  const bool after = kk == 0 || v > last_v || (v == last_v && j > last_j);
+                  if (after && (bj < 0 || v < bv)) { bv = v; bj = j; }
+                }
+                if (bj < 0) bj = last_j < 0 ? 0 : last_j;
+                rows[kk] = g * M + bj;
+                last_v = bv; last_j = bj;
+              }
+            }
+            __syncwarp();
+            if (tid == 0) TCX_PROF(0, 83);
+            if (t == 1) qlane[sb] = (live && gl < d) ? a.sa.traj[(size_t)i * a.sa.H * d + gl] : 0.f;
+            const StepIO io{stg + STG_DIST, stg + STG_GRAD, rows, nullptr, live ? stg + STG_Q + g * MAXD : nullptr};
+            if (d == 7) step_group_t<7, 8>(a.sa, live ? i : 0, t, io, gl, live, &qlane[sb]);
+            else step_group_t<2, 8>(a.sa, live ? i : 0, t, io, gl, live, &qlane[sb]);
+          }
+         }
+        } else if (tid < a.S) {
           const int i = (tile * 2 + (int)rank) * a.S + tid;
           if (i < a.sa.N) {
             const int K = a.sa.K, M = a.M;
