@@ -431,12 +431,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_exac
         // a rolled loop over the joints (the arrays it indexes live in local memory): seven inlined sincosf + 21 splits
         // are ~1000 instructions of straight-line code, and at the step boundary of the whole-horizon kernel this
         // runs un-overlapped on warps that are bound by instruction fetch
-#pragma unroll 1
-        for (int c = 0; c < d; ++c) {
-          float sn_, cs_;
-          sincosf(xq[c], &sn_, &cs_);                       // same bits as sinf / cosf (tools/tcx_regress.py)
-          en_sn[c] = sn_; en_cs[c] = cs_;
-          en_v[3 * c] = prep(xq[c]); en_v[3 * c + 1] = prep(sn_); en_v[3 * c + 2] = prep(cs_);
+#pragma unroll
+        for (int c = 0; c < MAXD; ++c) {
+          if (c < d) {
+            float sn_, cs_;
+            sincosf(xq[c], &sn_, &cs_);                     // same bits as sinf / cosf (tools/tcx_regress.py)
+            en_sn[c] = sn_; en_cs[c] = cs_;
+            en_v[3 * c] = prep(xq[c]); en_v[3 * c + 1] = prep(sn_); en_v[3 * c + 2] = prep(cs_);
+          }
         }
       } else {
         float xp[3];                                        // nin - d obstacle coordinates: 3, or 2 for the toy variant
