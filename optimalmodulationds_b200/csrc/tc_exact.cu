@@ -626,27 +626,33 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc_exac
         tmem_ld16(tD + D2B, r2);
         tc_wait_ld();
         if (q4 == 0) TCX_PROF(h, 64);
-        // straight-line and branch-free: the same operations on every link, the unused ones masked by o < O
+        // straight-line; the links the network does not have (o >= O, a launch-wide constant: uniform branches) are
+        // skipped -- their IEEE divisions were half of this epilogue for the 7- and 9-link networks
         const float comp_o = (a.dbg & 4) ? 0.f : COMP_K256;
         const float* b4s = reinterpret_cast<const float*>(smem + OFF_B4);
         const bool scaled = net.scale != 1.f;
         float v[16];
 #pragma unroll
-        for (int o = 0; o < 16; ++o) v[o] = combine(r1[o], r2[o], comp_o) + b4s[o];
+        for (int o = 0; o < 16; ++o)
+          if (o < O) v[o] = combine(r1[o], r2[o], comp_o) + b4s[o];
         int best = 0;
         float bv = v[0], m = 3.0e38f;
 #pragma unroll
         for (int o = 1; o < 16; ++o) {                        // argmin of the RAW output (robot_sdf.py:155)
-          const bool lt = o < O && v[o] < bv;
-          bv = lt ? v[o] : bv;
-          best = lt ? o : best;
+          if (o < O) {
+            const bool lt = v[o] < bv;
+            bv = lt ? v[o] : bv;
+            best = lt ? o : best;
+          }
         }
 #pragma unroll
         for (int o = 0; o < 16; ++o) {                        // MPPI.py:236-242: /100, minus radius, ignored := 1e6
-          float y = scaled ? v[o] / 100.f : v[o];
-          y -= rad;
-          if ((a.ignore_mask >> o) & 1u) y = 1e6f;
-          m = o < O ? fminf(m, y) : m;
+          if (o < O) {
+            float y = scaled ? v[o] / 100.f : v[o];
+            y -= rad;
+            if ((a.ignore_mask >> o) & 1u) y = 1e6f;
+            m = fminf(m, y);
+          }
         }
         o_m = m;
         if (BWD) {
