@@ -242,6 +242,8 @@ int main(int argc, char** argv) {
   cudaMalloc(&dq, q.size() * 4);
   cudaMemcpy(dq, q.data(), q.size() * 4, cudaMemcpyHostToDevice);
   cudaMalloc(&c.mdist, (size_t)n * M * 4);
+  cudaMalloc(reinterpret_cast<void**>(&c.counters), N_COUNTERS * sizeof(int));   // (the kernel counts non-finite outputs)
+  cudaMemset(c.counters, 0, N_COUNTERS * sizeof(int));
   const size_t prof_n = (size_t)c.sm_count * 9 * 8;
   cudaMalloc(reinterpret_cast<void**>(&c.stage), prof_n * sizeof(long long));
   cudaMemset(c.stage, 0, prof_n * sizeof(long long));
