@@ -1,9 +1,10 @@
 // Tensor-core prefilter for obstacle ranking (pass 1 of MPPI.distance_repulsion_nn, MPPI.py:231-247).
 //
 // Every (sample, obstacle) pair is pushed through the 5-layer distance MLP on the 5th-generation tensor
-// cores (tcgen05.mma, kind::f16, fp32 accumulation in TMEM) to get an APPROXIMATE masked minimum link
-// distance; the fp32-accurate scoring path then re-scores only the obstacles inside a guard band of
-// the K-th smallest, so the final ranking, distances and gradients are fp32-exact.
+// cores (tcgen05.mma, kind::f16; by default fp16 accumulators in the hidden layers and fp32 ones in the output
+// layer, see HACC below) to get an APPROXIMATE masked minimum link distance; the fp32-accurate scoring path then
+// re-scores only the obstacles inside a (calibrated) guard band of the K-th smallest, so the final ranking,
+// distances and gradients are fp32-exact.
 //
 // Design (B200, one CTA pair per TPC, persistent):
 //   * layer 1 is SEPARABLE in its input [q, p]:  W1 enc([q, p]) + b1 = (W1q enc(q) + b1) + W1p enc(p).  The
@@ -18,8 +19,9 @@
 //     matrix resident in shared memory for the whole kernel (3 x 64 + 8 KB of fp16 + 3 KB of biases = 203 KB),
 //     loaded once with bulk TMA copies (cp.async.bulk, UBLKCP) -- no weight traffic afterwards.
 //   * activations never touch shared memory or HBM: the A operand of every layer lives in TMEM
-//     (tcgen05.mma "ts" form); the epilogue warps read the fp32 accumulator with tcgen05.ld, add bias, ReLU,
-//     convert to fp16 pairs and write the next layer's A operand back with tcgen05.st.
+//     (tcgen05.mma "ts" form); the epilogue warps read the accumulator with tcgen05.ld (fp16 accumulators: two
+//     packed features per register), add bias + ReLU (one HFMA2.RELU per feature pair) and write the next layer's
+//     A operand back with tcgen05.st.
 //   * TMEM (512 columns): A operands of two row tiles X,Y (2 x 128 columns) + two 128-column accumulator
 //     halves D_lo/D_hi shared by both tiles.  While the epilogue warps of X drain D_lo/D_hi, the tensor core
 //     already works on Y, so in steady state the MMA pipe never waits for an epilogue.
