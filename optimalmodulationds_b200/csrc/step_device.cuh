@@ -367,6 +367,7 @@ template <int D, int GL>
 __device__ __forceinline__ void step_group_t(const StepArgs& s, int i, int t, const StepIO& io, int gl, bool live,
                                              float* q_lane = nullptr) {
   static_assert(D >= 1 && D <= GL && GL <= 32, "one lane per joint");
+  static_assert(MAXK <= GL, "one lane per ranked row");
   constexpr int d = D;
   const size_t st = (size_t)i * s.H + (t - 1);
   const bool mine = gl < d;                                   // this lane owns a joint
